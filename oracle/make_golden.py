@@ -1,0 +1,198 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz with the REAL reference code.
+
+Runs in the build container only (needs /root/reference).  For every case it builds the
+reference's own FitConfiguration -> VoigtModel -> vfit objects (through oracle/refshim.py) and
+records, for a seeded batch of theta:
+    * the lowered model arrays (atomic_lambda0, atomic_gamma[f32], atomic_f[f32], z_factors,
+      N_indices) and the LSF taps the reference applied,
+    * the observed spectra handed to vfit,
+    * reference model flux for a few walkers and reference lnprob for every walker.
+The fixtures are committed; tests compare the oracle AND the CUDA path against them.
+
+    python -m oracle.make_golden          # regenerate everything
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.normpath(os.path.join(HERE, ".."))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim, voigt_oracle as vo          # noqa: E402
+from rbvfit_b200 import workloads as wl                  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+N_FLUX_ROWS = 2
+
+
+def _ref_models(w, voigt_method="wofz"):
+    FitConfiguration, VoigtModel, mc, vm = refshim.import_reference()
+    from astropy.convolution import CustomKernel
+    config = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        config.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+    models = {}
+    for name, inst in w["instruments"].items():
+        m = VoigtModel(config, FWHM=inst["FWHM"], voigt_method=voigt_method)
+        if inst.get("lsf") == "cos_like":
+            # the reference's COS branch needs linetools; inject the table the same way
+            # _setup_kernel would (core/voigt_model.py:458-460)
+            m.kernel = CustomKernel(vo.cos_like_lsf(321))
+        models[name] = m
+    return config, models, mc
+
+
+def build_case(case_name, w, voigt_method="wofz", error_dtype=np.float64, nwalkers=None,
+               extra_thetas=None):
+    config, models, mc = _ref_models(w, voigt_method)
+    compiled = {n: m.compile() for n, m in models.items()}
+    spectra = wl.make_spectra(w, lambda n, th, wave: compiled[n].model_flux(th, wave),
+                              error_dtype=error_dtype)
+    thetas = wl.make_ensemble(w, nwalkers)
+    if extra_thetas is not None:
+        thetas = np.vstack([thetas, extra_thetas])
+    inst_data = {n: dict(model=models[n], wave=s["wave"], flux=s["flux"], error=s["error"])
+                 for n, s in spectra.items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = mc.vfit(inst_data, w["theta_true"], w["lb"], w["ub"])
+    with np.errstate(all="ignore"):
+        ref_lnprob = np.array([fitter.lnprob(t) for t in thetas])
+    finite = np.flatnonzero(np.isfinite(ref_lnprob))[:N_FLUX_ROWS]
+    out = dict(
+        meta=json.dumps(dict(case=case_name, workload=w["name"], voigt_method=voigt_method,
+                             error_dtype=np.dtype(error_dtype).name,
+                             instruments=list(w["instruments"].keys()),
+                             systems=[(z, ion, list(t), c) for (z, ion, t, c) in w["systems"]])),
+        thetas=thetas, lb=w["lb"], ub=w["ub"], ref_lnprob=ref_lnprob, flux_rows=finite)
+    for n, m in models.items():
+        d = compiled[n].data
+        out[f"{n}__lambda0"] = d.atomic_lambda0
+        out[f"{n}__gamma"] = d.atomic_gamma
+        out[f"{n}__f"] = d.atomic_f
+        out[f"{n}__zfac"] = d.z_factors
+        out[f"{n}__N_indices"] = d.N_indices
+        out[f"{n}__taps"] = (np.zeros(0) if d.kernel is None else np.asarray(d.kernel.array))
+        out[f"{n}__kernel_kind"] = np.array(
+            "none" if d.kernel is None else
+            ("gaussian" if type(d.kernel).__name__ == "Gaussian1DKernel" else "custom"))
+        out[f"{n}__wave"] = spectra[n]["wave"]
+        out[f"{n}__flux"] = spectra[n]["flux"]
+        out[f"{n}__error"] = spectra[n]["error"]
+        out[f"{n}__ref_flux"] = np.array([compiled[n].model_flux(thetas[i], spectra[n]["wave"])
+                                          for i in finite])
+        out[f"{n}__ref_flux_unconvolved"] = np.array(
+            [m.evaluate(thetas[i], spectra[n]["wave"], return_unconvolved=True) for i in finite[:1]])
+    path = os.path.join(GOLDEN_DIR, f"{case_name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{case_name}: W={len(thetas)} finite={np.isfinite(ref_lnprob).sum()} "
+          f"lnprob[0]={ref_lnprob[0]!r} -> {os.path.relpath(path, ROOT)} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def build_test_script_case():
+    """examples/test_script.py:38-63 + examples/cos_data.npz (float32 flux/error)."""
+    FitConfiguration, VoigtModel, mc, vm = refshim.import_reference()
+    d = np.load(os.path.join(refshim.REFERENCE_SRC, "rbvfit", "examples", "cos_data.npz"))
+    systems = [(0.0, "SiII", [1190.416, 1193.290], 1), (0.162005, "HI", [1025.722], 1)]
+    config = FitConfiguration()
+    for (z, ion, trans, comps) in systems:
+        config.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    fwhm = 2.394991274145626
+    model = VoigtModel(config, FWHM=fwhm)
+    theta0 = np.array([14.4228, 14.5105, 46.4066, 46.7789, -28.2628, -6.743])
+    lb = np.array([10., 10., 1., 1., -500., -500.])
+    ub = np.array([20., 20., 100., 100., 500., 500.])
+    rng = np.random.default_rng(20260)
+    thetas = np.vstack([theta0,
+                        theta0 + np.array([0.1, 0.1, 3, 3, 4, 4]) * rng.standard_normal((14, 6)),
+                        theta0 + np.array([100.0, 0, 0, 0, 0, 0])])
+    inst = {"COS": dict(model=model, wave=d["wave"], flux=d["flux"], error=d["error"])}
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = mc.vfit(inst, theta0, lb, ub)
+    ref_lnprob = np.array([fitter.lnprob(t) for t in thetas])
+    comp = model.compile()
+    rows = np.array([0, 1])
+    out = dict(
+        meta=json.dumps(dict(case="test_script", workload="test_script", voigt_method="wofz",
+                             error_dtype="float32", instruments=["COS"], systems=systems,
+                             FWHM=fwhm)),
+        thetas=thetas, lb=lb, ub=ub, ref_lnprob=ref_lnprob, flux_rows=rows)
+    cd = comp.data
+    out.update({"COS__lambda0": cd.atomic_lambda0, "COS__gamma": cd.atomic_gamma, "COS__f": cd.atomic_f,
+                "COS__zfac": cd.z_factors, "COS__N_indices": cd.N_indices,
+                "COS__taps": np.asarray(cd.kernel.array), "COS__kernel_kind": np.array("gaussian"),
+                "COS__wave": d["wave"], "COS__flux": d["flux"], "COS__error": d["error"],
+                "COS__ref_flux": np.array([comp.model_flux(thetas[i], d["wave"]) for i in rows]),
+                "COS__ref_flux_unconvolved": np.array(
+                    [model.evaluate(thetas[0], d["wave"], return_unconvolved=True)]),
+                "COS__inv_sigma2": fitter.instrument_data["COS"]["inv_sigma2"],
+                "COS__log_inv_sigma2": fitter.instrument_data["COS"]["log_inv_sigma2"]})
+    path = os.path.join(GOLDEN_DIR, "test_script.npz")
+    np.savez_compressed(path, **out)
+    print(f"test_script: lnprob(theta0)={ref_lnprob[0]!r} last={ref_lnprob[-1]!r} "
+          f"min flux={out['COS__ref_flux'][0].min()!r}")
+
+
+def build_wofz_lattice():
+    """Known-answer lattice for Re w(x + i a): scipy.special.wofz (the reference's call) and
+    mpmath at 40 digits.  Covers core, mid, far wings and the whole a range."""
+    import mpmath as mp
+    from scipy.special import wofz
+    mp.mp.dps = 40
+    xs = np.concatenate([np.linspace(0, 9, 37), np.geomspace(9.5, 3e4, 28)])
+    As = np.array([1e-8, 1e-6, 5e-6, 1.5e-4, 2.8e-3, 1e-2, 3.4e-2, 5e-2, 7e-2, 0.3, 1.0, 4.0, 20.0])
+    X, A = np.meshgrid(xs, As)
+    ref_scipy = wofz(X + 1j * A).real
+    ref_mp = np.zeros_like(X)
+    for i in range(X.shape[0]):
+        for j in range(X.shape[1]):
+            z = mp.mpc(X[i, j], A[i, j])
+            ref_mp[i, j] = float((mp.exp(-z * z) * mp.erfc(-1j * z)).real)
+    path = os.path.join(GOLDEN_DIR, "wofz_lattice.npz")
+    np.savez_compressed(path, x=X, a=A, scipy=ref_scipy, mpmath=ref_mp)
+    print("wofz lattice: max rel |scipy-mpmath| =", np.max(np.abs(ref_scipy - ref_mp) / ref_mp))
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    build_test_script_case()
+    build_wofz_lattice()
+    c1 = wl.get_workload("C1")
+    # extra rows: exact-bound rows (inclusive bounds), a tiny-b row (a > A_FAST path), NaN row
+    extra = np.vstack([c1["theta_true"], c1["theta_true"], c1["theta_true"], c1["theta_true"]])
+    extra[0, 0] = c1["ub"][0]            # on the bound -> allowed
+    extra[1, 2] = c1["lb"][2]            # b on its lower bound
+    extra[2, 4] = np.nextafter(c1["ub"][4], np.inf)   # one ulp outside -> -inf
+    extra[3, 1] = np.nan                 # NaN passes the prior and poisons the likelihood
+    build_case("C1", c1, extra_thetas=extra)
+    build_case("C1_f32err", c1, error_dtype=np.float32)
+    build_case("C1_fast", c1, voigt_method="fast")
+    c1n = wl.get_workload("C1")
+    c1n["instruments"]["COS"]["FWHM"] = None
+    build_case("C1_nolsf", c1n, nwalkers=8)
+    c1c = wl.get_workload("C1")
+    c1c["instruments"]["COS"].update(FWHM=None, lsf="cos_like")
+    build_case("C1_coslsf", c1c, nwalkers=16)
+    build_case("C2", wl.get_workload("C2"), nwalkers=24)
+    build_case("C3", wl.get_workload("C3"), nwalkers=16)
+    build_case("C4", wl.get_workload("C4"), nwalkers=16)
+    build_case("C4w", wl.get_workload("C4w"), nwalkers=8)
+    # small-b / large-a stress: bounds opened so that b down to 0.05 km/s is legal
+    cs = wl.get_workload("C1")
+    cs["lb"] = cs["lb"].copy(); cs["lb"][2:4] = 0.01
+    th = np.tile(cs["theta_true"], (6, 1))
+    th[:, 2] = [0.02, 0.1, 0.5, 1.0, 1.9, 3.0]
+    th[:, 3] = [3.0, 1.9, 1.0, 0.5, 0.1, 0.05]
+    build_case("C1_smallb", cs, nwalkers=4, extra_thetas=th)
+
+
+if __name__ == "__main__":
+    main()
