@@ -1,0 +1,143 @@
+/* rbvfit_b200 -- C ABI of the B200-native rbvfit likelihood hot path.
+ *
+ * This is the drop-in boundary: everything the reference does between
+ *     theta  ->  CompiledVoigtModel.model_flux  ->  vfit.lnlike / lnprior / lnprob
+ * (reference: src/rbvfit/core/voigt_model.py:100-323, src/rbvfit/vfit_mcmc.py:234-259, 291-353)
+ * happens behind these entry points, for a whole batch of theta rows ("walkers") per call.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = RBV_OK, otherwise an RBV_E* code; the text of the
+ *     most recent failure on the calling thread is available from rbv_last_error().
+ *   - "device" pointers are CUDA device pointers owned by the CALLER (PyTorch tensors in the Python
+ *     host layer) and must stay alive for as long as the context may use them; "host" pointers are
+ *     only read during the call.
+ *   - the library owns the opaque context and its small constant tables (line tables, LSF taps,
+ *     tile map, Faddeeva coefficient tables).  No *_batch call allocates memory.
+ *   - one context = one device; calls on one context must not overlap (one stream at a time).
+ *   - no CPU fallback exists: without a usable CUDA device rbv_create() fails.
+ */
+#ifndef RBVFIT_B200_H
+#define RBVFIT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBV_OK 0
+#define RBV_EINVAL 1   /* bad argument / shape */
+#define RBV_ECUDA 2    /* CUDA runtime error (text in rbv_last_error) */
+#define RBV_ENOMEM 3   /* caller-provided workspace too small */
+#define RBV_ESTATE 4   /* call order violated (e.g. lnprob before bounds were set) */
+
+#define RBV_VOIGT_WOFZ 0 /* H = Re w(x + i a), voigt_model.py:156 (scipy.special.wofz) */
+#define RBV_VOIGT_FAST 1 /* Tepper-Garcia 2006 variant, voigt_approx.py:35-86 */
+
+#define RBV_PRECISION_FP64 0
+#define RBV_PRECISION_FP32_GATED 1 /* FP32 far-wing arithmetic, used only when the gate passes */
+
+typedef struct RbvContext RbvContext;
+
+/* The lowered model of one instrument.
+ * Replaces CompiledModelData, voigt_model.py:265-280 (built by _cache_atomic_parameters :386-412 and
+ * _setup_fast_mapping :414-442).  All arrays are HOST arrays of length n_lines.
+ * gamma and f must carry the reference's float32 rounding (rb_setline.py:42,44) promoted to double. */
+typedef struct RbvLineTable {
+  int n_lines;         /* L = sum over ion groups of transitions x components            */
+  int n_components;    /* C; theta = [logN_1..C | b_1..C | v_1..C]  (parameter_manager.py:123-126) */
+  const double* lambda0; /* rest wavelength [Angstrom]                                    */
+  const double* gamma;   /* damping constant [1/s]                                        */
+  const double* f;       /* oscillator strength                                           */
+  const double* zfac;    /* 1 + z_system  (z_factors, voigt_model.py:407)                 */
+  const int* comp;       /* component slot c(l) = N_indices[l]; b and v slots are c+C, c+2C */
+  int voigt_method;      /* RBV_VOIGT_WOFZ | RBV_VOIGT_FAST                                */
+} RbvLineTable;
+
+/* One instrument's spectrum and line-spread function.
+ * Replaces the per-instrument dict built by vfit._compile_models, vfit_mcmc.py:249-257.
+ * wave/flux/inv_sigma2/log_inv_sigma2 are DEVICE arrays of n_pixels doubles; the weights must have been
+ * computed by the caller with the reference's expressions and dtype (1.0/error**2, log(1.0/error**2) in
+ * error's dtype) and then promoted to double.  flux/inv_sigma2/log_inv_sigma2 may be NULL for an instrument
+ * that is only used with rbv_model_flux_batch().
+ * inv_wave is a DEVICE scratch array of n_pixels doubles that the library fills with 1/wave.
+ * taps is a HOST array of n_taps (odd) LSF taps exactly as the reference would apply them
+ * (Gaussian1DKernel.array for ndimage.convolve1d(mode='nearest'), voigt_model.py:222-224, or the
+ * CustomKernel array for astropy convolve(boundary='extend'), :225-230); NULL / 0 = no convolution.
+ * normalize_taps != 0 divides the taps by their sum first (astropy convolve's normalize_kernel=True). */
+typedef struct RbvSpectrum {
+  int n_pixels;
+  const double* wave;
+  const double* flux;
+  const double* inv_sigma2;
+  const double* log_inv_sigma2;
+  double* inv_wave;
+  const double* taps;
+  int n_taps;
+  int normalize_taps;
+} RbvSpectrum;
+
+/* Create / destroy a likelihood context on CUDA device `device`. */
+int rbv_create(int device, RbvContext** out);
+void rbv_destroy(RbvContext* ctx);
+
+/* Select the arithmetic of the far-wing tier (default RBV_PRECISION_FP64). */
+int rbv_set_precision(RbvContext* ctx, int precision);
+
+/* Append an instrument (model + spectrum).  *out_index receives its index (0, 1, ...).
+ * Replaces one iteration of the loop in vfit._compile_models (vfit_mcmc.py:238-257). */
+int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lines, const RbvSpectrum* spec, int* out_index);
+
+/* Uniform prior bounds (HOST arrays of ndim doubles); vfit.lnprior, vfit_mcmc.py:291-295.
+ * ndim must be >= 3 * n_components of every instrument. */
+int rbv_set_bounds(RbvContext* ctx, const double* lb, const double* ub, int ndim);
+
+/* Bytes of caller-owned device workspace needed by rbv_lnprob_batch for up to n_walkers rows.
+ * The workspace must be ZERO-FILLED once before its first use (it holds self-resetting counters). */
+int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
+
+/* lnprob for a batch of walkers; vfit.lnprob, vfit_mcmc.py:348-353, vectorised over rows.
+ *   theta   DEVICE [n_walkers, ndim] row-major doubles
+ *   lnprob  DEVICE [n_walkers] doubles (out): -inf where a row violates the bounds, NaN where the
+ *           reference's numpy arithmetic would give NaN
+ *   stream  cudaStream_t (as void*), NULL = default stream.  Asynchronous. */
+int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int n_walkers, double* lnprob,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, from HOST buffers (pinned for full speed): copies theta in, runs, copies lnprob out and
+ * synchronises the stream.  theta_dev / lnprob_dev are caller-owned device staging buffers of at least
+ * n_walkers*ndim / n_walkers doubles.  This is the call the Python lnprob(theta) makes. */
+int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int n_walkers, double* lnprob_host,
+                          double* theta_dev, double* lnprob_dev, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Model flux for a batch of walkers on instrument `inst`; CompiledVoigtModel.model_flux,
+ * voigt_model.py:295-311 (convolve != 0) or VoigtModel.evaluate(return_unconvolved=True), :509-558.
+ *   out_flux DEVICE [n_walkers, n_pixels] row-major doubles.  Asynchronous. */
+int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int n_walkers, int convolve,
+                         double* out_flux, void* stream);
+
+/* Introspection used by the host layer and the tests. */
+int rbv_num_instruments(const RbvContext* ctx);
+int rbv_num_tiles(const RbvContext* ctx);          /* CTAs per walker in rbv_lnprob_batch */
+int rbv_ndim(const RbvContext* ctx);
+long long rbv_launch_count(const RbvContext* ctx); /* kernels launched by this context so far */
+
+/* Device Voigt-Hjerting function on a lattice (test hook): out[i] = H(a[i], x[i]); all DEVICE arrays. */
+int rbv_voigt_h(RbvContext* ctx, const double* x, const double* a, double* out, int n, int method,
+                void* stream);
+
+/* FP64 FMA throughput of the device (roofline denominator measured on the box): runs a dependent-chain
+ * DFMA kernel for about `millis` ms and returns TFLOP/s (2 flops per FMA). */
+int rbv_measure_fp64_peak(RbvContext* ctx, double millis, double* tflops);
+
+/* Text of the last error raised on this thread ("" if none). */
+const char* rbv_last_error(void);
+
+/* Library version string. */
+const char* rbv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBVFIT_B200_H */

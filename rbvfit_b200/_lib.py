@@ -1,0 +1,77 @@
+"""ctypes binding of include/rbvfit_b200.h.  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+
+class RbvError(RuntimeError):
+    pass
+
+
+class RbvLineTable(C.Structure):
+    _fields_ = [("n_lines", C.c_int), ("n_components", C.c_int),
+                ("lambda0", C.POINTER(C.c_double)), ("gamma", C.POINTER(C.c_double)),
+                ("f", C.POINTER(C.c_double)), ("zfac", C.POINTER(C.c_double)),
+                ("comp", C.POINTER(C.c_int)), ("voigt_method", C.c_int)]
+
+
+class RbvSpectrum(C.Structure):
+    _fields_ = [("n_pixels", C.c_int), ("wave", C.c_void_p), ("flux", C.c_void_p),
+                ("inv_sigma2", C.c_void_p), ("log_inv_sigma2", C.c_void_p), ("inv_wave", C.c_void_p),
+                ("taps", C.POINTER(C.c_double)), ("n_taps", C.c_int), ("normalize_taps", C.c_int)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "rbv_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "rbv_destroy": (None, [C.c_void_p]),
+    "rbv_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "rbv_add_instrument": (C.c_int, [C.c_void_p, C.POINTER(RbvLineTable), C.POINTER(RbvSpectrum),
+                                     C.POINTER(C.c_int)]),
+    "rbv_set_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
+    "rbv_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "rbv_lnprob_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
+    "rbv_lnprob_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rbv_model_flux_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "rbv_num_instruments": (C.c_int, [C.c_void_p]),
+    "rbv_num_tiles": (C.c_int, [C.c_void_p]),
+    "rbv_ndim": (C.c_int, [C.c_void_p]),
+    "rbv_launch_count": (C.c_longlong, [C.c_void_p]),
+    "rbv_voigt_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "rbv_measure_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_double)]),
+    "rbv_selftest_rcp": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "rbv_last_error": (C.c_char_p, []),
+    "rbv_version": (C.c_char_p, []),
+}
+
+
+def load():
+    """Load the in-tree CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RbvError(
+            f"{LIB_PATH} is missing: build it with `python -m rbvfit_b200.build` "
+            "(or __graft_entry__.build()).  rbvfit_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)     # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().rbv_last_error().decode("utf-8", "replace")
+        raise RbvError(f"{what or 'rbvfit_b200'} failed (status {status}): {msg}")

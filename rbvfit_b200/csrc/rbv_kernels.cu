@@ -1,0 +1,807 @@
+// rbvfit_b200 -- fused Voigt forward model + likelihood kernels for sm_100a, and their C ABI.
+//
+// One CTA = one (walker, pixel tile).  Per CTA:
+//   prep    theta row -> per-line constants in shared memory (A, B, a^2, kappa-scaled series
+//           coefficients; _evaluate_compiled_model :192-200 and _vectorized_voigt_tau :142-150)
+//   phase 1 tau_p = sum_l coef_l H(a_l, x_lp) for the tile's pixels + LSF halo, flux = exp(-tau) into
+//           shared memory (edge pixels replicated = ndimage 'nearest' / astropy 'extend')
+//   phase 2 LSF convolution from shared memory with R outputs per thread (register-blocked sliding
+//           window), then either the chi^2 partial of vfit.lnlike (vfit_mcmc.py:309-311) reduced with
+//           warp shuffles, or the model flux written out
+//   final   the last CTA of a walker (atomic ticket) adds the tile partials in fixed order, applies
+//           -0.5 per instrument, and writes lnprob; rows outside [lb, ub] get -inf without evaluation
+//           (vfit.lnprior :291-295, lnprob :348-353).
+//
+// Data layout in HBM (all float64): per instrument 1/wave, flux, inv_sigma2, log_inv_sigma2 [P] shared by
+// every walker (L2-resident); theta [W, ndim] row-major; lnprob [W]; workspace = tile partials
+// [W, n_tiles] + tickets [W].  No per-line optical depth is ever materialised.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rbvfit_b200.h"
+#include "rbv_device.cuh"
+
+namespace rbv {
+
+// ------------------------------------------------------------------------------------------ device structs
+struct InstDev {
+  const double* inv_wave;
+  const double* flux;
+  const double* inv_sigma2;
+  const double* log_inv_sigma2;
+  const double* lambda0;   // [L]
+  const double* gamma;     // [L]
+  const double* f;         // [L]
+  const double* zfac;      // [L]
+  const int* comp;         // [L]
+  const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
+  int P, K, Kpad, L, C, method;
+  int tile, ext_alloc, R;  // outputs per tile, smem flux slots, register blocking
+  int first_tile, n_tiles; // tile range of this instrument in the global tile list
+};
+
+struct TileDesc {
+  int inst;
+  int p0;  // first output pixel
+};
+
+struct LaunchParams {
+  const InstDev* inst;
+  const TileDesc* tiles;
+  const double* theta;   // [W, ndim]
+  const double* lb;
+  const double* ub;
+  const double* core_tab;
+  double* lnprob;        // [W]
+  double* partials;      // [W, n_tiles]
+  unsigned int* tickets; // [W]
+  double* out_flux;      // flux mode: [W, P]
+  int ndim, n_tiles, n_inst, W;
+  int tile_base;         // flux mode: first tile of the instrument
+  int precision;
+};
+
+__device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
+
+// ------------------------------------------------------------------------------------------ prep
+// per-line constants for the wofz method
+__device__ __forceinline__ void prep_line_wofz(const InstDev& I, int l, const double* __restrict__ th,
+                                               double* __restrict__ lc) {
+  int c = I.comp[l];
+  double logN = th[c], b = th[I.C + c], v = th[2 * I.C + c];
+  double lam0 = I.lambda0[l], gam = I.gamma[l], f = I.f[l], zf = I.zfac[l];
+  double N = pow(10.0, logN);                       // 10**theta[N_indices], voigt_model.py:192
+  double b_f = b / lam0 * 1e13;                     // :142
+  double nu0 = kCFreq / lam0;                       // :143
+  double konst = kAtomicConst / (nu0 * b);          // :146
+  double a = gam / (kFourPi * b_f);                 // :149
+  double zt = zf * (1.0 + v / kCkms) - 1.0;         // :200
+  double opz = 1.0 + zt;                            // :204
+  double coef = N * f * konst;                      // :158  ((N*f)*constant)
+  double A = kCFreq * opz / b_f;                    // x = (c/(lambda/(1+zt)) - nu0)/b_f = A/lambda - B
+  double B = nu0 / b_f;
+  if (!(b > 0.0)) {  // b <= 0 or NaN: outside the model's domain (documented: NaN)
+    A = B = a = coef = CUDART_NAN;
+  }
+  double a2 = a * a;
+  lc[LC_A] = A;
+  lc[LC_B] = B;
+  lc[LC_A2] = a2;
+  lc[LC_a] = a;
+  lc[LC_COEF] = coef;
+  lc[LC_COEF_EA2] = 0.0;
+  lc[LC_AUX] = coef * a * kInvSqrtPi;  // kappa
+}
+
+// per-line constants for the Tepper-Garcia method (voigt_approx.py:69-86)
+__device__ __forceinline__ void prep_line_fast(const InstDev& I, int l, const double* __restrict__ th,
+                                               double* __restrict__ lc) {
+  prep_line_wofz(I, l, th, lc);
+  double a = lc[LC_a];
+  lc[LC_A2] = fmax(1e-2, 100.0 * fabs(a) / kSqrtPi);  // eps
+  lc[LC_a] = a / kSqrtPi;                             // a / sqrt_pi
+  lc[LC_AUX] = 1.0 - 2.0 * a / kSqrtPi;               // core factor
+}
+
+// ------------------------------------------------------------------------------------------ phase 1
+template <int NQ>
+__device__ __forceinline__ void accum_asym(const double* __restrict__ lc, const double (&d)[kPixPerThread],
+                                           double (&tau)[kPixPerThread]) {
+  double Q[NQ];
+#pragma unroll
+  for (int p = 0; p < NQ; ++p) Q[p] = lc[LC_Q + p];
+#pragma unroll
+  for (int j = 0; j < kPixPerThread; ++j) {
+    double rho = rcp_pos(d[j]);
+    double s = Q[NQ - 1];
+#pragma unroll
+    for (int p = NQ - 2; p >= 0; --p) s = fma(s, rho, Q[p]);
+    tau[j] = fma(s, rho, tau[j]);
+  }
+}
+
+__device__ __forceinline__ void tau_wofz(const double* __restrict__ s_lc, int L, const double (&u)[kPixPerThread],
+                                         double (&tau)[kPixPerThread], const double* __restrict__ core_tab) {
+  for (int l = 0; l < L; ++l) {
+    const double* lc = s_lc + l * LC_STRIDE;
+    const double A = lc[LC_A], B = lc[LC_B], a2 = lc[LC_A2];
+    double d[kPixPerThread];
+    if (a2 > kABig * kABig) {   // per-line (CTA-uniform): damping beyond the series' rearrangement
+      const double a = lc[LC_a], coef = lc[LC_COEF];
+#pragma unroll 1
+      for (int j = 0; j < kPixPerThread; ++j) {
+        double x = fma(A, u[j], -B);
+        tau[j] = fma(coef, general_H(x, a, fma(x, x, a2)), tau[j]);
+      }
+      continue;
+    }
+    int hmin = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kPixPerThread; ++j) {
+      double x = fma(A, u[j], -B);
+      d[j] = fma(x, x, a2);
+      hmin = min(hmin, __double2hiint(d[j]));
+    }
+    hmin = __reduce_min_sync(0xffffffffu, hmin);
+    if (hmin >= kHiFar) {
+      accum_asym<kNQFar>(lc, d, tau);
+    } else if (hmin >= kHiNear) {
+      accum_asym<kNQMid>(lc, d, tau);
+    } else if (hmin >= kHiCore) {
+      accum_asym<kNQNear>(lc, d, tau);
+    } else {
+      const double a = lc[LC_a], coef = lc[LC_COEF];
+#pragma unroll 1
+      for (int j = 0; j < kPixPerThread; ++j) {
+        if (d[j] < kDCore) {
+          double x = fma(A, u[j], -B);
+          tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
+        } else {
+          tau[j] += asym_series<kNQNear>(lc + LC_Q, d[j]);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tau_fast(const double* __restrict__ s_lc, int L, const double (&u)[kPixPerThread],
+                                         double (&tau)[kPixPerThread]) {
+  for (int l = 0; l < L; ++l) {
+    const double* lc = s_lc + l * LC_STRIDE;
+    const double A = lc[LC_A], B = lc[LC_B], eps = lc[LC_A2], aos = lc[LC_a], cf = lc[LC_AUX],
+                 coef = lc[LC_COEF];
+#pragma unroll
+    for (int j = 0; j < kPixPerThread; ++j) {
+      double x = fma(A, u[j], -B);
+      tau[j] = fma(coef, tg_H(x, aos, eps, cf), tau[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+// MODE 0: lnprob (chi^2 partial + ticket finalisation); MODE 1: model flux out.
+template <int LOGR, int MODE>
+__global__ void __launch_bounds__(kThreads, 3) voigt_tile_kernel(const LaunchParams prm) {
+  constexpr int R = 1 << LOGR;
+  extern __shared__ double smem[];
+  __shared__ double s_red[kThreads / 32];
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = blockIdx.x;
+  const int tile_id = (MODE == 0) ? blockIdx.y : prm.tile_base + blockIdx.y;
+  const TileDesc td = prm.tiles[tile_id];
+  const InstDev I = prm.inst[td.inst];
+  const int ndim = prm.ndim;
+
+  double* s_theta = smem;                              // [ndim]
+  double* s_lc = s_theta + ((ndim + 1) & ~1);          // [L * LC_STRIDE]
+  double* s_taps = s_lc + I.L * LC_STRIDE;             // [Kpad]
+  double* s_flux = s_taps + I.Kpad;                    // [smem_pos(ext_alloc)]
+
+  // ---- theta row + prior
+  const double* th_g = prm.theta + (size_t)w * ndim;
+  int oob = 0;
+  for (int i = tid; i < ndim; i += kThreads) {
+    double t = th_g[i];
+    s_theta[i] = t;
+    if (MODE == 0) oob |= (t < prm.lb[i]) || (t > prm.ub[i]);   // vfit_mcmc.py:293
+  }
+  for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
+  if (MODE == 0) {
+    oob = __syncthreads_or(oob);
+  } else {
+    __syncthreads();
+  }
+
+  double part = 0.0;
+  if (!oob) {
+    // ---- per-line constants
+    const bool fast = (I.method == RBV_VOIGT_FAST);
+    for (int l = tid; l < I.L; l += kThreads) {
+      if (fast) prep_line_fast(I, l, s_theta, s_lc + l * LC_STRIDE);
+      else prep_line_wofz(I, l, s_theta, s_lc + l * LC_STRIDE);
+    }
+    __syncthreads();
+    if (!fast) {
+      for (int t = tid; t < I.L * kNQNear; t += kThreads) {
+        int l = t / kNQNear, p = t - l * kNQNear;
+        const double* lc = s_lc + l * LC_STRIDE;
+        s_lc[l * LC_STRIDE + LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 1: flux for the tile + halo into shared memory
+    const int h = I.K >> 1;
+    const int p0 = td.p0;
+    const int n_out = min(I.tile, I.P - p0);
+    const int ext = n_out + I.K - 1;
+    for (int base = 0; base < ext; base += kPass) {
+      const int i0 = base + warp * kWarpPix;
+      if (i0 >= ext) continue;  // warp-uniform
+      double u[kPixPerThread], tau[kPixPerThread];
+#pragma unroll
+      for (int j = 0; j < kPixPerThread; ++j) {
+        int i = i0 + j * 32 + lane;
+        int p = min(max(p0 - h + i, 0), I.P - 1);   // edge replication
+        u[j] = __ldg(I.inv_wave + p);
+        tau[j] = 0.0;
+      }
+      if (fast) tau_fast(s_lc, I.L, u, tau);
+      else tau_wofz(s_lc, I.L, u, tau, prm.core_tab);
+#pragma unroll
+      for (int j = 0; j < kPixPerThread; ++j) {
+        int i = i0 + j * 32 + lane;
+        if (i < ext) s_flux[smem_pos(i, LOGR)] = exp(-tau[j]);   // voigt_model.py:217
+      }
+    }
+    // zero the slack the register-blocked window may touch (taps there are zero, values must be finite)
+    for (int i = ext + tid; i < I.ext_alloc; i += kThreads) s_flux[smem_pos(i, LOGR)] = 0.0;
+    __syncthreads();
+
+    // ---- phase 2: LSF + chi^2 (or flux out).  M_p = sum_m taps_rev[m] * E[o + m]
+    const int n_groups = (n_out + R - 1) >> LOGR;
+    for (int g = tid; g < n_groups; g += kThreads) {
+      double acc[R], win[2 * R - 1];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.0;
+      const int e0 = g << LOGR;
+#pragma unroll
+      for (int q = 0; q < R - 1; ++q) win[q] = s_flux[smem_pos(e0 + q, LOGR)];
+      for (int m0 = 0; m0 < I.Kpad; m0 += R) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) win[R - 1 + q] = s_flux[smem_pos(e0 + m0 + R - 1 + q, LOGR)];
+#pragma unroll
+        for (int mm = 0; mm < R; ++mm) {
+          const double tap = s_taps[m0 + mm];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fma(tap, win[mm + r], acc[r]);
+        }
+#pragma unroll
+        for (int q = 0; q < R - 1; ++q) win[q] = win[R + q];
+      }
+      const int pbase = p0 + e0;
+      if (MODE == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int p = pbase + r;
+          if (e0 + r < n_out) {
+            double resid = __ldg(I.flux + p) - acc[r];
+            double sq = resid * resid;
+            part += sq * __ldg(I.inv_sigma2 + p) - __ldg(I.log_inv_sigma2 + p);   // vfit_mcmc.py:310
+          }
+        }
+      } else {
+        double* out = prm.out_flux + (size_t)w * I.P;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (e0 + r < n_out) out[pbase + r] = acc[r];
+      }
+    }
+  }
+
+  if (MODE == 0) {
+    // ---- CTA reduction of the chi^2 partial (fixed order -> reproducible)
+    part = warp_sum(part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < kThreads / 32; ++k) s += s_red[k];
+      prm.partials[(size_t)w * prm.n_tiles + tile_id] = s;
+      __threadfence();
+      unsigned int prev = atomicAdd(prm.tickets + w, 1u);
+      s_flag = (prev == (unsigned int)(prm.n_tiles - 1));
+    }
+    __syncthreads();
+    if (s_flag && tid == 0) {
+      __threadfence();
+      double total;
+      if (oob) {
+        total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
+      } else {
+        total = 0.0;
+        const volatile double* pp = prm.partials + (size_t)w * prm.n_tiles;
+        for (int k = 0; k < prm.n_inst; ++k) {
+          const InstDev& J = prm.inst[k];
+          double s = 0.0;
+          for (int t = 0; t < J.n_tiles; ++t) s += pp[J.first_tile + t];
+          total += -0.5 * s;                                          // vfit_mcmc.py:309-313
+        }
+      }
+      prm.lnprob[w] = total;
+      prm.tickets[w] = 0u;   // self-reset for the next launch
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+__global__ void reciprocal_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 1.0 / in[i];
+}
+
+// H(a,x) on a lattice through the same device functions the tile kernel uses (test hook).
+__global__ void voigt_h_kernel(const double* __restrict__ x, const double* __restrict__ a, double* __restrict__ out,
+                               int n, int method, const double* __restrict__ core_tab) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xv = x[i], av = a[i];
+  if (method == RBV_VOIGT_FAST) {
+    out[i] = tg_H(xv, av / kSqrtPi, fmax(1e-2, 100.0 * fabs(av) / kSqrtPi), 1.0 - 2.0 * av / kSqrtPi);
+    return;
+  }
+  double a2 = av * av;
+  double d = fma(xv, xv, a2);
+  double H;
+  if (av > kABig) {
+    H = general_H(xv, av, d);
+  } else if (d < kDCore) {
+    H = core_H(xv, av, a2, core_tab);
+  } else {
+    double Q[kNQNear];
+    double kappa = av * kInvSqrtPi;
+    for (int p = 0; p < kNQNear; ++p) Q[p] = asym_coef(p + 1, a2, kappa);
+    if (d >= kDFar) H = asym_series<kNQFar>(Q, d);
+    else if (d >= kDNear) H = asym_series<kNQMid>(Q, d);
+    else H = asym_series<kNQNear>(Q, d);
+  }
+  out[i] = H;
+}
+
+// max relative error of rcp_pos over a sweep of positive doubles (self-test of the MUFU seed accuracy)
+__global__ void rcp_selftest_kernel(double* out_max) {
+  double worst = 0.0;
+  for (int k = threadIdx.x; k < (1 << 16); k += blockDim.x) {
+    double d = 64.0 * exp2(k * (40.0 / 65536.0)) * (1.0 + 1e-3 * (k % 7));
+    double r = rcp_pos(d);
+    double err = fabs(fma(r, d, -1.0));
+    worst = fmax(worst, err);
+  }
+  worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 16));
+  worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 8));
+  worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 4));
+  worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 2));
+  worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, 1));
+  if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)out_max, (unsigned long long)__double_as_longlong(worst));
+}
+
+// dependent-chain DFMA throughput probe: 8 chains per thread
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace rbv
+
+// =============================================================================================== host / C ABI
+using namespace rbv;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define RBV_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(RBV_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+  } while (0)
+
+struct HostInst {
+  InstDev dev;
+  std::vector<double> taps;  // LSF taps as applied by the reference (normalised if requested), length K
+  double* d_taps = nullptr;  // flipped + zero-padded copy on the device (rebuilt when R changes)
+  std::vector<void*> owned;  // device allocations owned by the library for this instrument
+};
+
+struct RbvContext {
+  int device = 0;
+  int sm_count = 148;
+  int ndim = 0;
+  int n_tiles = 0;
+  int precision = RBV_PRECISION_FP64;
+  long long launches = 0;
+  std::vector<HostInst> inst;
+  std::vector<TileDesc> tiles;
+  InstDev* d_inst = nullptr;
+  TileDesc* d_tiles = nullptr;
+  double* d_lb = nullptr;
+  double* d_ub = nullptr;
+  double* d_core_tab = nullptr;
+  size_t max_smem_lnprob[2] = {0, 0};  // per LOGR in {2,3}
+};
+
+template <typename T>
+static cudaError_t upload(T** dst, const T* src, size_t n) {
+  cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (n) e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+static size_t smem_bytes_for(const InstDev& I, int ndim) {
+  int logR = (I.R == 8) ? 3 : 2;
+  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (I.ext_alloc + (I.ext_alloc >> logR)) + 2;
+  return n * sizeof(double);
+}
+
+extern "C" {
+
+const char* rbv_last_error(void) { return g_last_error.c_str(); }
+const char* rbv_version(void) { return "rbvfit_b200 0.1 (sm_100a)"; }
+
+int rbv_create(int device, RbvContext** out) {
+  if (!out) return fail(RBV_EINVAL, "rbv_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(RBV_ECUDA, std::string("rbv_create: no CUDA device (") + cudaGetErrorString(e) +
+                               "); this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail(RBV_EINVAL, "rbv_create: bad device index");
+  RBV_CUDA(cudaSetDevice(device));
+  RbvContext* ctx = new RbvContext();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  RBV_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  RBV_CUDA(cudaMemcpyToSymbol(c_ctab, RBV_ASYM_CTAB_HOST, sizeof(RBV_ASYM_CTAB_HOST)));
+  RBV_CUDA(cudaMemcpyToSymbol(c_weid, RBV_WEID_COEF_HOST, sizeof(RBV_WEID_COEF_HOST)));
+  RBV_CUDA(upload(&ctx->d_core_tab, RBV_CORE_TABLE_HOST, (size_t)RBV_CORE_TABLE_LEN));
+  const int max_dyn = (int)prop.sharedMemPerBlockOptin - 2048;
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  *out = ctx;
+  return RBV_OK;
+}
+
+void rbv_destroy(RbvContext* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& hi : ctx->inst) {
+    for (void* p : hi.owned) cudaFree(p);
+    cudaFree(hi.d_taps);
+  }
+  cudaFree(ctx->d_inst);
+  cudaFree(ctx->d_tiles);
+  cudaFree(ctx->d_lb);
+  cudaFree(ctx->d_ub);
+  cudaFree(ctx->d_core_tab);
+  delete ctx;
+}
+
+int rbv_set_precision(RbvContext* ctx, int precision) {
+  if (!ctx) return fail(RBV_EINVAL, "null context");
+  if (precision != RBV_PRECISION_FP64 && precision != RBV_PRECISION_FP32_GATED)
+    return fail(RBV_EINVAL, "rbv_set_precision: unknown precision");
+  ctx->precision = precision;
+  return RBV_OK;
+}
+
+// Tile geometry + tap upload for every instrument.  The register blocking R is context-wide (8 as soon as
+// one instrument has a wide LSF) so that all instruments run in ONE launch.
+static int rebuild_tables(RbvContext* ctx) {
+  ctx->tiles.clear();
+  int R = 4;
+  for (auto& hi : ctx->inst)
+    if ((int)hi.taps.size() > 64) R = 8;
+  for (size_t k = 0; k < ctx->inst.size(); ++k) {
+    HostInst& hi = ctx->inst[k];
+    InstDev& I = hi.dev;
+    I.K = (int)hi.taps.size();
+    I.R = R;
+    I.Kpad = (I.K + R - 1) / R * R;
+    std::vector<double> rev(I.Kpad, 0.0);
+    for (int m = 0; m < I.K; ++m) rev[m] = hi.taps[I.K - 1 - m];   // true convolution -> correlation
+    cudaFree(hi.d_taps);
+    hi.d_taps = nullptr;
+    RBV_CUDA(upload(&hi.d_taps, rev.data(), rev.size()));
+    I.taps_rev = hi.d_taps;
+    // ext = n_pass * kPass flux slots per CTA; halo overhead <= ~8 % for wide LSFs
+    int n_pass = 1;
+    if (I.K - 1 > 64) n_pass = (int)std::ceil((I.K - 1) / (0.08 * kPass));
+    n_pass = std::min(n_pass, 8);
+    int need = (I.P + I.K - 1 + kPass - 1) / kPass;
+    n_pass = std::max(1, std::min(n_pass, need));
+    I.tile = n_pass * kPass - (I.K - 1);
+    I.ext_alloc = n_pass * kPass + 2 * R;
+    I.first_tile = (int)ctx->tiles.size();
+    I.n_tiles = (I.P + I.tile - 1) / I.tile;
+    for (int t = 0; t < I.n_tiles; ++t) ctx->tiles.push_back(TileDesc{(int)k, t * I.tile});
+  }
+  ctx->n_tiles = (int)ctx->tiles.size();
+  std::vector<InstDev> flat;
+  for (auto& hi : ctx->inst) flat.push_back(hi.dev);
+  cudaFree(ctx->d_inst);
+  cudaFree(ctx->d_tiles);
+  ctx->d_inst = nullptr;
+  ctx->d_tiles = nullptr;
+  RBV_CUDA(upload(&ctx->d_inst, flat.data(), flat.size()));
+  RBV_CUDA(upload(&ctx->d_tiles, ctx->tiles.data(), ctx->tiles.size()));
+  return RBV_OK;
+}
+
+int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectrum* sp, int* out_index) {
+  if (!ctx || !lt || !sp) return fail(RBV_EINVAL, "rbv_add_instrument: null argument");
+  if (lt->n_lines <= 0 || lt->n_components <= 0) return fail(RBV_EINVAL, "rbv_add_instrument: empty line table");
+  if (sp->n_pixels <= 0 || !sp->wave || !sp->inv_wave)
+    return fail(RBV_EINVAL, "rbv_add_instrument: empty spectrum (n_pixels, wave and inv_wave are required)");
+  if (lt->voigt_method != RBV_VOIGT_WOFZ && lt->voigt_method != RBV_VOIGT_FAST)
+    return fail(RBV_EINVAL, "rbv_add_instrument: voigt_method must be RBV_VOIGT_WOFZ or RBV_VOIGT_FAST");
+  if (sp->n_taps < 0 || (sp->n_taps > 0 && (sp->n_taps % 2 == 0 || !sp->taps)))
+    return fail(RBV_EINVAL, "rbv_add_instrument: the LSF needs an odd number of taps");
+  for (int l = 0; l < lt->n_lines; ++l)
+    if (lt->comp[l] < 0 || lt->comp[l] >= lt->n_components)
+      return fail(RBV_EINVAL, "rbv_add_instrument: component index out of range");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+
+  HostInst hi;
+  InstDev& I = hi.dev;
+  memset(&I, 0, sizeof(I));
+  I.P = sp->n_pixels;
+  I.L = lt->n_lines;
+  I.C = lt->n_components;
+  I.method = lt->voigt_method;
+  I.inv_wave = sp->inv_wave;
+  I.flux = sp->flux;
+  I.inv_sigma2 = sp->inv_sigma2;
+  I.log_inv_sigma2 = sp->log_inv_sigma2;
+
+  // LSF taps as the reference applies them; "no kernel" = the single tap 1.0
+  hi.taps.assign(sp->n_taps > 0 ? sp->n_taps : 1, 1.0);
+  if (sp->n_taps > 0) {
+    std::copy(sp->taps, sp->taps + sp->n_taps, hi.taps.begin());
+    if (sp->normalize_taps) {
+      double s = 0.0;
+      for (double t : hi.taps) s += t;
+      for (double& t : hi.taps) t /= s;
+    }
+  }
+  if ((int)hi.taps.size() - 1 > 4 * kPass) return fail(RBV_EINVAL, "rbv_add_instrument: LSF too wide (max 4097 taps)");
+
+  double *d_l0, *d_g, *d_f, *d_z;
+  int* d_c;
+  RBV_CUDA(upload(&d_l0, lt->lambda0, (size_t)I.L)); hi.owned.push_back(d_l0);
+  RBV_CUDA(upload(&d_g, lt->gamma, (size_t)I.L));    hi.owned.push_back(d_g);
+  RBV_CUDA(upload(&d_f, lt->f, (size_t)I.L));        hi.owned.push_back(d_f);
+  RBV_CUDA(upload(&d_z, lt->zfac, (size_t)I.L));     hi.owned.push_back(d_z);
+  RBV_CUDA(upload(&d_c, lt->comp, (size_t)I.L));     hi.owned.push_back(d_c);
+  I.lambda0 = d_l0; I.gamma = d_g; I.f = d_f; I.zfac = d_z; I.comp = d_c;
+
+  reciprocal_kernel<<<(I.P + 255) / 256, 256>>>(sp->wave, sp->inv_wave, I.P);
+  RBV_CUDA(cudaGetLastError());
+  RBV_CUDA(cudaDeviceSynchronize());
+  ctx->launches++;
+
+  ctx->inst.push_back(hi);
+  int rc = rebuild_tables(ctx);
+  if (rc != RBV_OK) return rc;
+  if (out_index) *out_index = (int)ctx->inst.size() - 1;
+  return RBV_OK;
+}
+
+int rbv_set_bounds(RbvContext* ctx, const double* lb, const double* ub, int ndim) {
+  if (!ctx || !lb || !ub || ndim <= 0) return fail(RBV_EINVAL, "rbv_set_bounds: bad argument");
+  for (auto& hi : ctx->inst)
+    if (3 * hi.dev.C > ndim) return fail(RBV_EINVAL, "rbv_set_bounds: ndim smaller than 3 * n_components");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  cudaFree(ctx->d_lb);
+  cudaFree(ctx->d_ub);
+  ctx->d_lb = ctx->d_ub = nullptr;
+  RBV_CUDA(upload(&ctx->d_lb, lb, (size_t)ndim));
+  RBV_CUDA(upload(&ctx->d_ub, ub, (size_t)ndim));
+  ctx->ndim = ndim;
+  return RBV_OK;
+}
+
+int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes) {
+  if (!ctx || !bytes || n_walkers < 0) return fail(RBV_EINVAL, "rbv_workspace_bytes: bad argument");
+  size_t tickets = ((size_t)n_walkers * sizeof(unsigned int) + 255) & ~(size_t)255;
+  *bytes = tickets + (size_t)n_walkers * std::max(ctx->n_tiles, 1) * sizeof(double);
+  return RBV_OK;
+}
+
+int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, "rbv_lnprob_batch: null argument");
+  if (W < 0) return fail(RBV_EINVAL, "rbv_lnprob_batch: negative n_walkers");
+  if (W == 0) return RBV_OK;
+  if (ctx->inst.empty()) return fail(RBV_ESTATE, "rbv_lnprob_batch: no instrument added");
+  if (ctx->ndim == 0) return fail(RBV_ESTATE, "rbv_lnprob_batch: bounds not set (rbv_set_bounds)");
+  for (auto& hi : ctx->inst) {
+    if (!hi.dev.flux || !hi.dev.inv_sigma2 || !hi.dev.log_inv_sigma2)
+      return fail(RBV_ESTATE, "rbv_lnprob_batch: an instrument has no observed spectrum (flux-only instrument)");
+    if (3 * hi.dev.C > ctx->ndim) return fail(RBV_EINVAL, "rbv_lnprob_batch: ndim smaller than 3 * n_components");
+  }
+  size_t need = 0;
+  rbv_workspace_bytes(ctx, W, &need);
+  if (!workspace || workspace_bytes < need) return fail(RBV_ENOMEM, "rbv_lnprob_batch: workspace too small");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+
+  size_t tickets_bytes = ((size_t)W * sizeof(unsigned int) + 255) & ~(size_t)255;
+  LaunchParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.inst = ctx->d_inst;
+  prm.tiles = ctx->d_tiles;
+  prm.theta = theta;
+  prm.lb = ctx->d_lb;
+  prm.ub = ctx->d_ub;
+  prm.core_tab = ctx->d_core_tab;
+  prm.lnprob = lnprob;
+  prm.tickets = (unsigned int*)workspace;
+  prm.partials = (double*)((char*)workspace + tickets_bytes);
+  prm.ndim = ctx->ndim;
+  prm.n_tiles = ctx->n_tiles;
+  prm.n_inst = (int)ctx->inst.size();
+  prm.W = W;
+  prm.precision = ctx->precision;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // ONE launch covers every instrument: grid = (walkers, all tiles); R is context-wide.
+  size_t smem = 0;
+  for (auto& hi : ctx->inst) smem = std::max(smem, smem_bytes_for(hi.dev, ctx->ndim));
+  const bool r8 = ctx->inst[0].dev.R == 8;
+  dim3 grid((unsigned)W, (unsigned)ctx->n_tiles);
+  if (ctx->n_tiles > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 tiles per walker");
+  if (r8) voigt_tile_kernel<3, 0><<<grid, kThreads, smem, st>>>(prm);
+  else voigt_tile_kernel<2, 0><<<grid, kThreads, smem, st>>>(prm);
+  RBV_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return RBV_OK;
+}
+
+int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, double* lnprob_host,
+                          double* theta_dev, double* lnprob_dev, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (!ctx || !theta_host || !lnprob_host || !theta_dev || !lnprob_dev)
+    return fail(RBV_EINVAL, "rbv_lnprob_batch_host: null argument");
+  if (W <= 0) return W == 0 ? RBV_OK : fail(RBV_EINVAL, "negative n_walkers");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RBV_CUDA(cudaMemcpyAsync(theta_dev, theta_host, (size_t)W * ctx->ndim * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = rbv_lnprob_batch(ctx, theta_dev, W, lnprob_dev, workspace, workspace_bytes, stream);
+  if (rc != RBV_OK) return rc;
+  RBV_CUDA(cudaMemcpyAsync(lnprob_host, lnprob_dev, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RBV_CUDA(cudaStreamSynchronize(st));
+  return RBV_OK;
+}
+
+int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, int convolve, double* out_flux,
+                         void* stream) {
+  if (!ctx || !theta || !out_flux) return fail(RBV_EINVAL, "rbv_model_flux_batch: null argument");
+  if (inst < 0 || inst >= (int)ctx->inst.size()) return fail(RBV_EINVAL, "rbv_model_flux_batch: bad instrument index");
+  if (W <= 0) return W == 0 ? RBV_OK : fail(RBV_EINVAL, "negative n_walkers");
+  if (!convolve) return fail(RBV_EINVAL, "rbv_model_flux_batch: convolve=0 needs an instrument added without taps");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  const InstDev& I = ctx->inst[inst].dev;
+  int ndim = ctx->ndim ? ctx->ndim : 3 * I.C;
+  LaunchParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.inst = ctx->d_inst;
+  prm.tiles = ctx->d_tiles;
+  prm.theta = theta;
+  prm.core_tab = ctx->d_core_tab;
+  prm.out_flux = out_flux;
+  prm.ndim = ndim;
+  prm.n_tiles = ctx->n_tiles;
+  prm.n_inst = (int)ctx->inst.size();
+  prm.W = W;
+  prm.tile_base = I.first_tile;
+  prm.precision = ctx->precision;
+  size_t smem = smem_bytes_for(I, ndim);
+  dim3 grid((unsigned)W, (unsigned)I.n_tiles);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (I.R == 8) voigt_tile_kernel<3, 1><<<grid, kThreads, smem, st>>>(prm);
+  else voigt_tile_kernel<2, 1><<<grid, kThreads, smem, st>>>(prm);
+  RBV_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return RBV_OK;
+}
+
+int rbv_num_instruments(const RbvContext* ctx) { return ctx ? (int)ctx->inst.size() : 0; }
+int rbv_num_tiles(const RbvContext* ctx) { return ctx ? ctx->n_tiles : 0; }
+int rbv_ndim(const RbvContext* ctx) { return ctx ? ctx->ndim : 0; }
+long long rbv_launch_count(const RbvContext* ctx) { return ctx ? ctx->launches : 0; }
+
+int rbv_voigt_h(RbvContext* ctx, const double* x, const double* a, double* out, int n, int method, void* stream) {
+  if (!ctx || !x || !a || !out || n < 0) return fail(RBV_EINVAL, "rbv_voigt_h: bad argument");
+  if (n == 0) return RBV_OK;
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  voigt_h_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, a, out, n, method, ctx->d_core_tab);
+  RBV_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return RBV_OK;
+}
+
+int rbv_measure_fp64_peak(RbvContext* ctx, double millis, double* tflops) {
+  if (!ctx || !tflops) return fail(RBV_EINVAL, "rbv_measure_fp64_peak: bad argument");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  double* d_out;
+  RBV_CUDA(cudaMalloc(&d_out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  RBV_CUDA(cudaEventCreate(&e0));
+  RBV_CUDA(cudaEventCreate(&e1));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  int iters = 2000;
+  double best = 0.0, spent = 0.0;
+  dfma_peak_kernel<<<blocks, threads>>>(d_out, 200, 1.0);  // warm-up
+  RBV_CUDA(cudaDeviceSynchronize());
+  while (spent < millis) {
+    RBV_CUDA(cudaEventRecord(e0));
+    dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0);
+    RBV_CUDA(cudaEventRecord(e1));
+    RBV_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RBV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->launches++;
+    double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    spent += ms;
+    if (ms < 5.0f) iters *= 2;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
+  return RBV_OK;
+}
+
+// max relative error of the device reciprocal used in the asymptotic tiers (test hook)
+int rbv_selftest_rcp(RbvContext* ctx, double* max_rel_err) {
+  if (!ctx || !max_rel_err) return fail(RBV_EINVAL, "rbv_selftest_rcp: bad argument");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  double* d;
+  RBV_CUDA(cudaMalloc(&d, sizeof(double)));
+  RBV_CUDA(cudaMemset(d, 0, sizeof(double)));
+  rcp_selftest_kernel<<<1, 256>>>(d);
+  RBV_CUDA(cudaGetLastError());
+  RBV_CUDA(cudaMemcpy(max_rel_err, d, sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  ctx->launches++;
+  return RBV_OK;
+}
+
+}  // extern "C"

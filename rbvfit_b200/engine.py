@@ -1,0 +1,208 @@
+"""Thin owner of one ``RbvContext`` (C ABI) and of the PyTorch tensors it points at.
+
+PyTorch is used for exactly three things here: device / pinned-host buffer ownership, the CUDA stream
+handle, and (in ``rbvfit_b200.dist``) torch.distributed.  All arithmetic happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import RbvError, RbvLineTable, RbvSpectrum, check
+
+VOIGT_METHODS = {"wofz": 0, "fast": 1}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RbvError("rbvfit_b200 needs a CUDA device: torch.cuda.is_available() is False and there is "
+                       "no CPU fallback")
+    return torch
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Engine:
+    """One likelihood context on one device."""
+
+    def __init__(self, device: Optional[int] = None):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self._h = C.c_void_p()
+        check(self.lib.rbv_create(self.device, C.byref(self._h)), "rbv_create")
+        self._keep: List[object] = []        # device tensors the context points at
+        self.pixels: List[int] = []
+        self.components: List[int] = []
+        self.ndim = 0
+        self._cap = 0                         # walker capacity of the staging buffers
+        self._theta_dev = self._lnp_dev = self._ws = None
+        self._theta_pin = self._lnp_pin = None
+        self._ws_bytes = 0
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.rbv_destroy(self._h)
+            self._h = C.c_void_p()
+        self._keep = []
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ set-up
+    def add_instrument(self, lowered, wave, flux=None, inv_sigma2=None, log_inv_sigma2=None,
+                       taps=None, normalize_taps=False) -> int:
+        """``lowered``: object with atomic_lambda0/atomic_gamma/atomic_f/z_factors/N_indices/
+        total_components/voigt_method (CompiledModelData layout, voigt_model.py:265-280)."""
+        torch = _torch()
+        lam = np.ascontiguousarray(lowered.atomic_lambda0, dtype=np.float64)
+        gam = np.ascontiguousarray(np.asarray(lowered.atomic_gamma), dtype=np.float64)   # f32 -> f64 promotion
+        fos = np.ascontiguousarray(np.asarray(lowered.atomic_f), dtype=np.float64)
+        zf = np.ascontiguousarray(lowered.z_factors, dtype=np.float64)
+        comp = np.ascontiguousarray(lowered.N_indices, dtype=np.int32)
+        lt = RbvLineTable(len(lam), int(lowered.total_components), _dptr(lam), _dptr(gam), _dptr(fos), _dptr(zf),
+                          comp.ctypes.data_as(C.POINTER(C.c_int)), VOIGT_METHODS[lowered.voigt_method])
+
+        def dev(a):
+            if a is None:
+                return None
+            t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.tdev)
+            self._keep.append(t)
+            return t
+
+        wave_t = dev(wave)
+        P = int(wave_t.numel())
+        inv_wave_t = torch.empty(P, dtype=torch.float64, device=self.tdev)
+        self._keep.append(inv_wave_t)
+        flux_t, w_t, l_t = dev(flux), dev(inv_sigma2), dev(log_inv_sigma2)
+        if taps is not None:
+            taps = np.ascontiguousarray(taps, dtype=np.float64)
+            taps_p, n_taps = _dptr(taps), int(taps.size)
+        else:
+            taps_p, n_taps = None, 0
+        sp = RbvSpectrum(P, wave_t.data_ptr(),
+                         flux_t.data_ptr() if flux_t is not None else None,
+                         w_t.data_ptr() if w_t is not None else None,
+                         l_t.data_ptr() if l_t is not None else None,
+                         inv_wave_t.data_ptr(), taps_p, n_taps, int(bool(normalize_taps)))
+        idx = C.c_int(-1)
+        check(self.lib.rbv_add_instrument(self._h, C.byref(lt), C.byref(sp), C.byref(idx)), "rbv_add_instrument")
+        self.pixels.append(P)
+        self.components.append(int(lowered.total_components))
+        self._cap = 0   # tile count changed -> workspace must be re-sized
+        return idx.value
+
+    def set_bounds(self, lb, ub):
+        lb = np.ascontiguousarray(lb, dtype=np.float64)
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        if lb.shape != ub.shape or lb.ndim != 1:
+            raise ValueError("lb and ub must be 1-D arrays of equal length")
+        check(self.lib.rbv_set_bounds(self._h, _dptr(lb), _dptr(ub), lb.size), "rbv_set_bounds")
+        self.ndim = int(lb.size)
+        self._cap = 0
+
+    def set_precision(self, precision: str):
+        check(self.lib.rbv_set_precision(self._h, {"fp64": 0, "fp32-gated": 1}[precision]), "rbv_set_precision")
+
+    # ------------------------------------------------------------------ buffers
+    def _reserve(self, W: int, ndim: int):
+        torch = _torch()
+        if W <= self._cap and self._theta_dev is not None and self._theta_dev.shape[1] == ndim:
+            return
+        cap = max(W, 64, int(self._cap * 1.5))
+        nbytes = C.c_size_t(0)
+        check(self.lib.rbv_workspace_bytes(self._h, cap, C.byref(nbytes)), "rbv_workspace_bytes")
+        self._ws_bytes = int(nbytes.value)
+        self._ws = torch.zeros(max(self._ws_bytes, 8), dtype=torch.uint8, device=self.tdev)   # zero-filled once
+        self._theta_dev = torch.empty((cap, ndim), dtype=torch.float64, device=self.tdev)
+        self._lnp_dev = torch.empty(cap, dtype=torch.float64, device=self.tdev)
+        self._theta_pin = torch.empty((cap, ndim), dtype=torch.float64, pin_memory=True)
+        self._lnp_pin = torch.empty(cap, dtype=torch.float64, pin_memory=True)
+        self._theta_pin_np = self._theta_pin.numpy()
+        self._lnp_pin_np = self._lnp_pin.numpy()
+        self._cap = cap
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.tdev).cuda_stream
+
+    # ------------------------------------------------------------------ hot path
+    def lnprob_host(self, theta: np.ndarray) -> np.ndarray:
+        """HOST theta [W, ndim] -> HOST lnprob [W]; H2D, kernel, D2H and the sync happen inside the C call."""
+        W, ndim = theta.shape
+        if ndim != self.ndim:
+            raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
+        self._reserve(W, ndim)
+        self._theta_pin_np[:W] = theta
+        check(self.lib.rbv_lnprob_batch_host(self._h, self._theta_pin.data_ptr(), W, self._lnp_pin.data_ptr(),
+                                             self._theta_dev.data_ptr(), self._lnp_dev.data_ptr(),
+                                             self._ws.data_ptr(), self._ws_bytes, self._stream()),
+              "rbv_lnprob_batch_host")
+        return self._lnp_pin_np[:W].copy()
+
+    def lnprob_device(self, theta_t, out_t=None):
+        """DEVICE theta tensor [W, ndim] (float64, contiguous) -> DEVICE lnprob tensor [W]; asynchronous."""
+        torch = _torch()
+        if theta_t.dtype != torch.float64 or not theta_t.is_contiguous() or theta_t.device != self.tdev:
+            raise ValueError("theta must be a contiguous float64 tensor on the engine's device")
+        W, ndim = theta_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
+        self._reserve(W, ndim)
+        if out_t is None:
+            out_t = torch.empty(W, dtype=torch.float64, device=self.tdev)
+        check(self.lib.rbv_lnprob_batch(self._h, theta_t.data_ptr(), W, out_t.data_ptr(), self._ws.data_ptr(),
+                                        self._ws_bytes, self._stream()), "rbv_lnprob_batch")
+        return out_t
+
+    def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:
+        """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``."""
+        torch = _torch()
+        cols = self.ndim if self.ndim else 3 * self.components[inst]
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim != 2 or theta.shape[1] < cols:
+            raise ValueError(f"theta must be [W, >= {cols}]")
+        th = torch.as_tensor(np.ascontiguousarray(theta[:, :cols]), device=self.tdev)
+        W = th.shape[0]
+        out = torch.empty((W, self.pixels[inst]), dtype=torch.float64, device=self.tdev)
+        check(self.lib.rbv_model_flux_batch(self._h, inst, th.data_ptr(), W, 1, out.data_ptr(), self._stream()),
+              "rbv_model_flux_batch")
+        return out.cpu().numpy()
+
+    def voigt_h(self, x: np.ndarray, a: np.ndarray, method: str = "wofz") -> np.ndarray:
+        torch = _torch()
+        xs = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64).ravel(), device=self.tdev)
+        as_ = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).ravel(), device=self.tdev)
+        out = torch.empty_like(xs)
+        check(self.lib.rbv_voigt_h(self._h, xs.data_ptr(), as_.data_ptr(), out.data_ptr(), xs.numel(),
+                                   VOIGT_METHODS[method], self._stream()), "rbv_voigt_h")
+        return out.cpu().numpy().reshape(np.shape(x))
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def n_tiles(self) -> int:
+        return self.lib.rbv_num_tiles(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rbv_launch_count(self._h))
+
+    def measure_fp64_peak(self, millis: float = 200.0) -> float:
+        out = C.c_double(0.0)
+        check(self.lib.rbv_measure_fp64_peak(self._h, float(millis), C.byref(out)), "rbv_measure_fp64_peak")
+        return out.value
+
+    def selftest_rcp(self) -> float:
+        out = C.c_double(0.0)
+        check(self.lib.rbv_selftest_rcp(self._h, C.byref(out)), "rbv_selftest_rcp")
+        return out.value

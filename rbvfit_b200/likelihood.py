@@ -1,0 +1,94 @@
+"""Batched GPU likelihood: the B200 replacement of ``vfit._compile_models`` + ``lnprior/lnlike/lnprob``
+(reference: src/rbvfit/vfit_mcmc.py:234-259, 291-353).
+
+``GpuLikelihood.lnprob`` honours emcee's / zeus's ``vectorize=True`` contract -- ``(n, ndim) -> (n,)`` --
+and still returns a plain float for a single ``(ndim,)`` row, so it can be handed to either sampler or
+called by an optimiser exactly like the reference's bound method.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from ._lib import RbvError
+from .engine import Engine
+from .model import GpuCompiledVoigtModel, GpuVoigtModel
+
+
+def _weights(error):
+    """inv_sigma2 / log_inv_sigma2 with the reference's expressions AND dtype (vfit_mcmc.py:255-256):
+    a float32 error array gives float32-rounded weights, which are then promoted to float64."""
+    err = np.asarray(error)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv_sigma2 = 1.0 / (err ** 2)
+        log_inv_sigma2 = np.log(1.0 / (err ** 2))
+    return inv_sigma2, log_inv_sigma2
+
+
+class GpuLikelihood:
+    """All instruments of one fit on one GPU."""
+
+    def __init__(self, instrument_data: Dict[str, dict], lb, ub, device: Optional[int] = None):
+        if not isinstance(instrument_data, dict):
+            raise TypeError("instrument_data must be a dictionary")
+        if len(instrument_data) == 0:
+            raise ValueError("instrument_data cannot be empty")
+        self.engine = Engine(device)
+        self.names = []
+        self.pixels = []
+        self.instrument_data = {}
+        for name, d in instrument_data.items():
+            model = d["model"]
+            if isinstance(model, GpuVoigtModel):                 # vfit_mcmc.py:241-245
+                compiled = model.compile(verbose=False)
+            elif isinstance(model, GpuCompiledVoigtModel):
+                compiled = model
+            else:
+                raise TypeError(
+                    f"instrument_data['{name}']['model'] must be a GpuVoigtModel / GpuCompiledVoigtModel: "
+                    "arbitrary Python callables cannot run on the device and rbvfit_b200 has no CPU fallback")
+            wave, flux, error = (np.asarray(d[k]) for k in ("wave", "flux", "error"))
+            if len(flux) != len(wave) or len(error) != len(wave):
+                raise ValueError(f"instrument_data['{name}']: wave, flux, and error must have same length")
+            inv_sigma2, log_inv_sigma2 = _weights(error)
+            data = compiled.data
+            self.engine.add_instrument(data, wave, flux=flux, inv_sigma2=inv_sigma2,
+                                       log_inv_sigma2=log_inv_sigma2, taps=data.kernel,
+                                       normalize_taps=data.kernel_normalize)
+            self.names.append(name)
+            self.pixels.append(len(wave))
+            self.instrument_data[name] = {"model": compiled.model_flux, "wave": wave, "flux": flux,
+                                          "error": error, "inv_sigma2": inv_sigma2,
+                                          "log_inv_sigma2": log_inv_sigma2}
+        self.lb = np.asarray(lb, dtype=np.float64)
+        self.ub = np.asarray(ub, dtype=np.float64)
+        self.engine.set_bounds(self.lb, self.ub)
+        self.ndim = self.lb.size
+        self.total_pixels = int(sum(self.pixels))
+
+    # ------------------------------------------------------------------ reference-shaped API
+    def lnprob(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim == 1:
+            return float(self.engine.lnprob_host(theta[None, :])[0])
+        if theta.ndim != 2:
+            raise ValueError("theta must be (ndim,) or (n, ndim)")
+        if theta.shape[0] == 0:
+            return np.zeros(0)
+        return self.engine.lnprob_host(np.ascontiguousarray(theta))
+
+    __call__ = lnprob
+
+    def lnprior(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        bad = np.any(theta < self.lb, axis=-1) | np.any(theta > self.ub, axis=-1)
+        out = np.where(bad, -np.inf, 0.0)
+        return float(out) if out.ndim == 0 else out
+
+    def lnprob_device(self, theta_t, out_t=None):
+        """Device-resident variant (torch tensors in / out, asynchronous)."""
+        return self.engine.lnprob_device(theta_t, out_t)
+
+    def close(self):
+        self.engine.close()
