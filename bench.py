@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the rbvfit likelihood hot path on B200 (BASELINE.json metric: walker.pixel lnprob evals/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C5a] [--impl reference]
+
+One "step" = one lnprob evaluation of the whole walker ensemble of the workload (default C5a: 8192 walkers x
+100 000 px, L = 33 lines, K = 23 LSF taps -- the configuration the metric is quoted on; it fits one GPU).
+With N > 1 (launched by torchrun, one rank per GPU) the ensemble is split by walkers (strong scaling: the
+total work per step is fixed) and every step ends with the NCCL all-gather of lnprob.
+
+`value`  device-resident throughput: theta already in HBM, CUDA events around each step on the launch
+         stream, L2 flushed (untimed) between steps, max over ranks.
+`e2e`    the same metric through the public API `lnprob(theta_host)` -> numpy: per step H2D of the theta rows
+         from pinned memory, the kernel, the gather and the D2H of lnprob, timed by wall clock around
+         synchronous calls.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "walker_pixel_lnprob_evals_per_sec"
+UNIT = "walker*pixel/s"
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def build_problem(workload: str, device: int):
+    """Synthetic spectra (model(theta_true) + noise, generated with the GPU model itself), the likelihood
+    object and the walker ensemble."""
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200 import lsf
+    from rbvfit_b200.likelihood import GpuLikelihood
+    from rbvfit_b200.model import GpuVoigtModel
+    w = wl.get_workload(workload)
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    models = {}
+    for name, inst in w["instruments"].items():
+        taps = lsf.cos_like_taps(321) if inst.get("lsf") == "cos_like" else None
+        models[name] = GpuVoigtModel(cfg, FWHM=inst["FWHM"], device=device, lsf_taps=taps)
+    compiled = {n: m.compile() for n, m in models.items()}
+    spectra = wl.make_spectra(w, lambda n, th, wave: compiled[n].model_flux(th, wave))
+    inst_data = {n: dict(model=models[n], **spectra[n]) for n in models}
+    like = GpuLikelihood(inst_data, w["lb"], w["ub"], device=device)
+    thetas = wl.make_ensemble(w)
+    return w, models, like, thetas, spectra
+
+
+def oracle_problem(workload: str):
+    """The same workload for the CPU arm (oracle port of the reference, numpy + scipy.special.wofz)."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import workloads as wl
+    w = wl.get_workload(workload)
+    cfg = vo.OracleConfig()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z, ion, trans, comps)
+    models = {}
+    for name, inst in w["instruments"].items():
+        taps = vo.cos_like_lsf(321) if inst.get("lsf") == "cos_like" else None
+        models[name] = vo.lower(cfg, FWHM=inst["FWHM"], custom_taps=taps)
+    spectra = wl.make_spectra(w, lambda n, th, wave: vo.model_flux(models[n], th, wave))
+    comp = vo.compile_instruments({n: dict(model=models[n], **spectra[n]) for n in models})
+    return w, comp, wl.make_ensemble(w)
+
+
+def cpu_arm(workload: str, steps: int, warmup: int, sample_walkers=None):
+    """Times the reference's CPU implementation of the path (oracle port; `use_pool=True` equivalent: fork
+    pool over all host cores, vfit_mcmc.py:41-45, 413) on a bounded walker sample of the workload."""
+    from oracle import voigt_oracle as vo
+    cores = len(os.sched_getaffinity(0))
+    w, comp, thetas = oracle_problem(workload)
+    total_px = sum(len(d["wave"]) for d in comp.values())
+    if sample_walkers is None:
+        # ~140 ns per (line, pixel) wofz on one core -> aim at ~2 s of wall clock per pool call
+        per_walker = 1.4e-7 * sum(len(d["wave"]) * d["model"].n_lines for d in comp.values())
+        sample_walkers = int(min(len(thetas), max(cores, round(cores * 2.0 / max(per_walker, 1e-4)))))
+    sample = thetas[:sample_walkers]
+    times = []
+    pool = vo.make_pool(comp, w["lb"], w["ub"], processes=cores)      # lives across steps, like emcee's
+    try:
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            vo.lnprob_pool(comp, sample, w["lb"], w["ub"], pool=pool)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    finally:
+        pool.close()
+        pool.join()
+    best = min(times)
+    mean = sum(times) / len(times)
+    return {"value": sample_walkers * total_px / mean, "best": sample_walkers * total_px / best,
+            "ms_per_step": mean * 1e3, "cores": cores, "sample_walkers": sample_walkers,
+            "total_px": total_px,
+            "sample": f"{sample_walkers} of {len(thetas)} walkers x {total_px} px of {workload} per step, "
+                      f"fork pool over {cores} cores (oracle port: numpy + scipy.special.wofz)"}
+
+
+# --------------------------------------------------------------------------------------------- arms
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    r = cpu_arm(args.workload, steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args, rank, world, local):
+    import torch
+    from rbvfit_b200 import dist as rdist
+    from rbvfit_b200 import roofline as rf
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w, models, like, thetas, spectra = build_problem(args.workload, local)
+    part = rdist.WalkerPartition(rank, world)
+    dlike = rdist.DistributedLikelihood(like, part)
+    W, ndim = thetas.shape
+    total_px = like.total_pixels
+    lo, hi = part.rows(W)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+
+    # ---------------- roofline denominators
+    fp64_peak = like.engine.measure_fp64_peak(300.0)          # TFLOP/s, DFMA chain, measured on this box
+    name0 = like.names[0]
+    data0 = models[name0].compile().data
+    n_taps = 1 if data0.kernel is None else len(data0.kernel)
+    F, tiers = 0.0, {}
+    for n in like.names:                                        # pixel-weighted over instruments
+        d = models[n].compile().data
+        k = 1 if d.kernel is None else len(d.kernel)
+        Fn, tn = rf.flops_per_walker_pixel(d, w["theta_true"], spectra[n]["wave"], k)
+        F += Fn * len(spectra[n]["wave"]) / total_px
+        tiers[n] = tn
+
+    # ---------------- device-resident timing
+    theta_dev = torch.as_tensor(thetas, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    for _ in range(args.warmup):
+        out = dlike.lnprob_device(theta_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = like.engine.launch_count
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                                     # untimed L2 flush
+        ev[k][0].record()
+        if hi > lo:
+            kev[k][0].record()
+            local_out = like.lnprob_device(theta_dev[lo:hi])          # the tile kernel (1 launch)
+            kev[k][1].record()
+        else:
+            local_out = theta_dev.new_empty(0)
+        out = part.gather(local_out, W)                   # NCCL all-gather of lnprob (N > 1)
+        ev[k][1].record()
+    barrier()
+    launches = like.engine.launch_count - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kern_ms = [a.elapsed_time(b) for a, b in kev] if hi > lo else [0.0]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = W * total_px / (ms_per_step * 1e-3)
+    lnp = out.cpu().numpy()
+
+    # ---------------- e2e through the public API (host buffers)
+    for _ in range(min(args.warmup, 3)):
+        dlike.lnprob(thetas)
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = dlike.lnprob(thetas)
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
+    e2e_value = W * total_px / (e2e_ms * 1e-3)
+    assert np.array_equal(np.asarray(res), lnp, equal_nan=True), "e2e and device-resident results differ"
+
+    if rank != 0:
+        return
+    # ---------------- roofline of the dominant (only) kernel on this rank
+    k_ms = sum(kern_ms) / len(kern_ms)
+    n_local = hi - lo
+    n_inb = int(np.count_nonzero(np.isfinite(lnp[lo:hi]) | np.isnan(lnp[lo:hi])))   # rows actually evaluated
+    achieved = F * n_inb * total_px / (k_ms * 1e-3) / 1e12
+    peaks, peaks_kind = _peaks()
+    hbm_alg_bytes = n_local * ndim * 8 + n_local * 8 + 4 * 8 * total_px
+    prof = {}
+    ppath = os.path.join(ROOT, "profiles", "latest_ncu_summary.json")
+    if os.path.exists(ppath):
+        with open(ppath) as fh:
+            prof = json.load(fh)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "walkers": W, "pixels": total_px, "ndim": ndim,
+                   "lines": int(data0.n_lines), "lsf_taps": n_taps, "partition": f"walkers/{world}",
+                   "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                   "walkers_out_of_bounds": int(np.count_nonzero(np.isneginf(lnp)))},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "traffic": prof.get("dram_bytes_per_launch"),
+                     "peak_source": "DFMA dependent-chain probe measured in this run (rbv_measure_fp64_peak); "
+                                    "MEASURED_PEAKS.json has no FP64 entry (spec: 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
+                     "kernel": "voigt_tile_kernel", "kernel_ms": k_ms,
+                     "algorithmic_flops_per_walker_pixel": F, "tiers": tiers,
+                     "hbm_sanity": {"algorithmic_gbs": hbm_alg_bytes / (k_ms * 1e-3) / 1e9,
+                                    "peak_gbs": peaks.get("hbm_gbs"), "peaks": peaks_kind}},
+    }
+    if not args.no_cpu and world >= 1:
+        r = cpu_arm(args.workload, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C5a")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world_env == 1 and args.impl == "ours":
+        # not under torchrun: relaunch ourselves with one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+    from rbvfit_b200 import dist as rdist
+    rank, world, local = rdist.init_from_env("nccl" if world_env > 1 else None)
+    try:
+        run_gpu(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -301,15 +301,26 @@ def _pool_eval(theta):
     return lnprob(s["compiled"], theta, s["lb"], s["ub"])
 
 
-def lnprob_pool(compiled, thetas, lb, ub, processes=None):
-    """``use_pool=True`` equivalent (vfit_mcmc.py:41-45, 413): fork pool, map lnprob over rows.
-    The state is inherited by fork instead of being pickled per task, which is *kinder* to
-    the CPU arm than emcee's pickling of the bound method."""
+def make_pool(compiled, lb, ub, processes=None):
+    """``use_pool=True`` equivalent (vfit_mcmc.py:41-45, 413): a fork pool that lives for the whole run.
+    The likelihood state is inherited by fork instead of being pickled per task, which is *kinder* to the
+    CPU arm than emcee's pickling of the bound method per chunk."""
     import multiprocessing as mp
     _POOL_STATE.update(compiled=compiled, lb=np.asarray(lb), ub=np.asarray(ub))
-    ctx = mp.get_context("fork")
-    with ctx.Pool(processes) as pool:
+    return mp.get_context("fork").Pool(processes)
+
+
+def lnprob_pool(compiled, thetas, lb, ub, processes=None, pool=None):
+    """Map lnprob over the rows of ``thetas`` with a fork pool (what emcee does per half-step)."""
+    own = pool is None
+    if own:
+        pool = make_pool(compiled, lb, ub, processes)
+    try:
         out = pool.map(_pool_eval, list(np.atleast_2d(thetas)))
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     return np.array(out)
 
 

@@ -1,0 +1,239 @@
+"""Batched affine-invariant ensemble sampler with emcee's semantics and sampler-object contract.
+
+The reference hands ``vfit.lnprob`` to ``emcee.EnsembleSampler(nwalkers, ndim, lnprob, pool=pool)``
+(src/rbvfit/vfit_mcmc.py:408-423) and later reads ``get_chain(discard, flat)``, ``acceptance_fraction``
+and ``get_autocorr_time()`` from it (:563-655; core/unified_results.py:163-299).  emcee is a third-party
+dependency that is not vendored in the reference (requirements.txt:5, ``emcee>=3.0.0``) and is not
+installed here, so the algorithm is restated from its published description (Goodman & Weare 2010;
+Foreman-Mackey et al. 2013, emcee 3 ``RedBlueMove`` + ``StretchMove``):
+
+  per step: shuffle the walkers into two halves; for each half S with complement C
+      z_k   = ((a - 1) u_k + 1)^2 / a,  u_k ~ U(0,1),  a = 2
+      Y_k   = C_{j(k)} - (C_{j(k)} - S_k) z_k,          j(k) uniform over the complement
+      ln q  = (ndim - 1) ln z_k + lnp(Y_k) - lnp(S_k);  accept when ln U < ln q
+
+The only structural change: ``lnp`` is evaluated for the whole half-ensemble in ONE call
+(``vectorize=True`` contract) -- that call is the GPU batch.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+
+class AutocorrError(Exception):
+    """Raised when the chain is too short for a reliable autocorrelation-time estimate (emcee's name)."""
+
+    def __init__(self, tau, *args, **kwargs):
+        self.tau = tau
+        super().__init__(*args, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------ autocorrelation
+def _next_pow_two(n):
+    i = 1
+    while i < n:
+        i <<= 1
+    return i
+
+
+def function_1d(x):
+    """Normalised autocorrelation function of a 1-D series (FFT based)."""
+    x = np.atleast_1d(x)
+    if x.ndim != 1:
+        raise ValueError("invalid dimensions for 1D autocorrelation function")
+    n = _next_pow_two(len(x))
+    f = np.fft.fft(x - np.mean(x), n=2 * n)
+    acf = np.fft.ifft(f * np.conjugate(f))[: len(x)].real
+    acf /= acf[0]
+    return acf
+
+
+def _auto_window(taus, c):
+    m = np.arange(len(taus)) < c * taus
+    if np.any(m):
+        return int(np.argmin(m))
+    return len(taus) - 1
+
+
+def integrated_time(x, c=5, tol=50, quiet=False):
+    """Integrated autocorrelation time per dimension; ``x`` is [nsteps, nwalkers, ndim] (Sokal windowing)."""
+    x = np.atleast_1d(x)
+    if x.ndim == 1:
+        x = x[:, None, None]
+    if x.ndim == 2:
+        x = x[:, :, None]
+    if x.ndim != 3:
+        raise ValueError("invalid dimensions")
+    n_t, n_w, n_d = x.shape
+    tau_est = np.empty(n_d)
+    windows = np.empty(n_d, dtype=int)
+    for d in range(n_d):
+        f = np.zeros(n_t)
+        for k in range(n_w):
+            f += function_1d(x[:, k, d])
+        f /= n_w
+        taus = 2.0 * np.cumsum(f) - 1.0
+        windows[d] = _auto_window(taus, c)
+        tau_est[d] = taus[windows[d]]
+    flag = tol * tau_est > n_t
+    if np.any(flag):
+        msg = ("The chain is shorter than {0} times the integrated autocorrelation time for {1} parameter(s). "
+               "Use this estimate with caution and run a longer chain!\n").format(tol, np.sum(flag))
+        msg += "N/{0} = {1:.0f};\ntau: {2}".format(tol, n_t / tol, tau_est)
+        if not quiet:
+            raise AutocorrError(tau_est, msg)
+    return tau_est
+
+
+def walkers_independent(coords) -> bool:
+    """emcee's initial-state check: the ensemble must span the parameter space."""
+    if not np.all(np.isfinite(coords)):
+        return False
+    C = coords - np.mean(coords, axis=0)[None, :]
+    C_colmax = np.amax(np.abs(C), axis=0)
+    if np.any(C_colmax == 0):
+        return False
+    C /= C_colmax
+    C_colsum = np.sqrt(np.sum(C ** 2, axis=0))
+    C /= C_colsum
+    return np.linalg.cond(C.astype(float)) <= 1e8
+
+
+# ------------------------------------------------------------------------------------------ sampler
+class EnsembleSampler:
+    """Stretch-move ensemble sampler; ``log_prob_fn`` must map ``(n, ndim) -> (n,)``."""
+
+    def __init__(self, nwalkers: int, ndim: int, log_prob_fn: Callable, a: float = 2.0, pool=None,
+                 vectorize: bool = True, seed: Optional[int] = None):
+        if nwalkers < 2 * ndim:
+            # emcee refuses this only for the live check below; keep the same spirit
+            pass
+        if nwalkers % 2 != 0 and nwalkers < 2:
+            raise ValueError("need at least two walkers")
+        self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
+        self.log_prob_fn = log_prob_fn
+        self.vectorize = vectorize
+        self.pool = pool          # accepted for API compatibility; batches run on the device instead
+        self._random = np.random.default_rng(seed)
+        self.reset()
+
+    def reset(self):
+        self._chain = np.empty((0, self.nwalkers, self.ndim))
+        self._log_prob = np.empty((0, self.nwalkers))
+        self._accepted = np.zeros(self.nwalkers)
+        self.iteration = 0
+        self._last = None
+        self.n_logp_calls = 0
+        self.n_logp_rows = 0
+
+    # -- likelihood plumbing
+    def compute_log_prob(self, coords):
+        if np.any(np.isinf(coords)):
+            raise ValueError("At least one parameter value was infinite")
+        if np.any(np.isnan(coords)):
+            raise ValueError("At least one parameter value was NaN")
+        if self.vectorize:
+            lp = np.asarray(self.log_prob_fn(coords), dtype=np.float64)
+        else:
+            lp = np.array([float(self.log_prob_fn(c)) for c in coords])
+        self.n_logp_calls += 1
+        self.n_logp_rows += len(coords)
+        if np.any(np.isnan(lp)):
+            raise ValueError("Probability function returned NaN")
+        return lp
+
+    # -- one full step (two half-steps)
+    def _step(self, coords, log_prob):
+        nw, nd, a = self.nwalkers, self.ndim, self.a
+        inds = np.arange(nw) % 2
+        self._random.shuffle(inds)
+        accepted = np.zeros(nw, dtype=bool)
+        for split in range(2):
+            S1 = inds == split
+            s = coords[S1]
+            c = coords[~S1]
+            Ns, Nc = len(s), len(c)
+            zz = ((a - 1.0) * self._random.random(Ns) + 1.0) ** 2.0 / a
+            factors = (nd - 1.0) * np.log(zz)
+            rint = self._random.integers(Nc, size=Ns)
+            q = c[rint] - (c[rint] - s) * zz[:, None]
+            new_lp = self.compute_log_prob(q)
+            lnpdiff = factors + new_lp - log_prob[S1]
+            acc = np.log(self._random.random(Ns)) < lnpdiff
+            idx = np.flatnonzero(S1)[acc]
+            coords[idx] = q[acc]
+            log_prob[idx] = new_lp[acc]
+            accepted[idx] = True
+        return coords, log_prob, accepted
+
+    def run_mcmc(self, initial_state, nsteps, progress=False, skip_initial_state_check=False, **_ignored):
+        if initial_state is None:
+            if self._last is None:
+                raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
+            coords, log_prob = self._last
+        else:
+            coords = np.array(initial_state, dtype=np.float64, copy=True)
+            if coords.shape != (self.nwalkers, self.ndim):
+                raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+            if not skip_initial_state_check and not walkers_independent(coords):
+                raise ValueError("Initial state has a large condition number. Make sure that your walkers are "
+                                 "linearly independent for the best performance")
+            log_prob = self.compute_log_prob(coords)
+        chain = np.empty((nsteps, self.nwalkers, self.ndim))
+        lps = np.empty((nsteps, self.nwalkers))
+        it = range(nsteps)
+        if progress:
+            try:
+                from tqdm import tqdm
+                it = tqdm(it, total=nsteps)
+            except ImportError:
+                pass
+        for i in it:
+            coords, log_prob, acc = self._step(coords, log_prob)
+            self._accepted += acc
+            chain[i] = coords
+            lps[i] = log_prob
+        self._chain = np.concatenate([self._chain, chain], axis=0)
+        self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self.iteration += nsteps
+        self._last = (coords, log_prob)
+        return coords, log_prob
+
+    # -- emcee-shaped accessors (what UnifiedResults and vfit read)
+    def _get(self, arr, discard=0, thin=1, flat=False):
+        v = arr[discard + thin - 1:: thin]
+        if flat:
+            s = list(v.shape[1:])
+            s[0] = np.prod(v.shape[:2])
+            return v.reshape(s)
+        return v
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self._get(self._chain, discard, thin, flat)
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        return self._get(self._log_prob, discard, thin, flat)
+
+    @property
+    def chain(self):
+        return np.swapaxes(self._chain, 0, 1)
+
+    @property
+    def flatchain(self):
+        return self.get_chain(flat=True)
+
+    @property
+    def lnprobability(self):
+        return self._log_prob.T
+
+    @property
+    def acceptance_fraction(self):
+        return self._accepted / max(self.iteration, 1)
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
+
+    def get_last_sample(self):
+        return self._last
