@@ -1,0 +1,241 @@
+"""GPU drop-in for rbvfit's ``vfit`` fitter (reference: src/rbvfit/vfit_mcmc.py:102-692) and ``set_bounds``
+(:695-787, traditional branch).
+
+Same constructor, attributes and methods as the reference for the likelihood path and its immediate
+callers: ``lnprior / lnlike / lnprob``, ``optimize_guess``, ``_initialize_walkers``, ``runmcmc``,
+``compute_best_theta``, ``get_samples``.  What changes is *where the batch is*: every place the reference
+loops over theta rows one at a time (walker initialisation :442-466, the finite-difference gradient of
+L-BFGS-B :355-360, the sampler's half-steps :536-540) hands the whole batch to the GPU in one call.
+``use_pool=True`` is accepted and ignored -- a CUDA context must not be forked; the device batch replaces
+the process pool.
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+from typing import Dict
+
+import numpy as np
+
+from .likelihood import GpuLikelihood
+from .sampler import EnsembleSampler
+
+
+class vfit:
+    def __init__(self, instrument_data: Dict, theta, lb, ub, no_of_Chain=50, no_of_steps=1000,
+                 perturbation=1e-4, sampler="emcee", skip_initial_state_check=False, device=None, seed=None):
+        self._validate_unified_instrument_data(instrument_data)
+        self._validate_guesses(theta, lb, ub)
+        self.theta = np.asarray(theta)
+        self.lb = np.asarray(lb)
+        self.ub = np.asarray(ub)
+        self._like = GpuLikelihood(instrument_data, self.lb, self.ub, device=device)   # _compile_models
+        self.instrument_data = self._like.instrument_data
+        self.instrument_configs = self._extract_configs(instrument_data)
+        self.multi_instrument = len(instrument_data) > 1
+        self.no_of_Chain = no_of_Chain
+        self.no_of_steps = no_of_steps
+        self.perturbation = perturbation
+        self.skip_initial_state_check = skip_initial_state_check
+        self.sampler_name = sampler.lower()
+        if self.sampler_name not in ["emcee", "zeus"]:
+            raise ValueError(f"Unknown sampler '{sampler}'. Use 'emcee' or 'zeus'.")
+        self.mcmc_flag = False
+        self.sampler = None
+        self.best_theta = None
+        self.samples = None
+        self.ndim = len(self.theta)
+        self.nwalkers = no_of_Chain
+        self._rng = np.random.default_rng(seed)
+        self._seed = seed
+
+    # ------------------------------------------------------------------ validation (vfit_mcmc.py:199-229)
+    def _validate_unified_instrument_data(self, instrument_data):
+        if not isinstance(instrument_data, dict):
+            raise TypeError("instrument_data must be a dictionary")
+        if len(instrument_data) == 0:
+            raise ValueError("instrument_data cannot be empty")
+        required = {"model", "wave", "flux", "error"}
+        for name, data in instrument_data.items():
+            if not isinstance(data, dict):
+                raise TypeError(f"instrument_data['{name}'] must be a dictionary")
+            missing = required - set(data.keys())
+            if missing:
+                raise ValueError(f"instrument_data['{name}'] missing keys: {missing}")
+            n = len(data["wave"])
+            if len(data["flux"]) != n or len(data["error"]) != n:
+                raise ValueError(f"instrument_data['{name}']: wave, flux, and error must have same length")
+
+    def _validate_guesses(self, theta, lb, ub):
+        theta, lb, ub = np.asarray(theta), np.asarray(lb), np.asarray(ub)
+        if len(theta) != len(lb) or len(theta) != len(ub):
+            raise ValueError("theta, lb, and ub must have the same length")
+        if np.any(theta < lb) or np.any(theta > ub):
+            raise ValueError("Initial guess theta must be within bounds lb and ub")
+
+    def _extract_configs(self, instrument_data):
+        configs = {}
+        for name, data in instrument_data.items():
+            model = data["model"]
+            if hasattr(model, "config"):
+                cfg = copy.deepcopy(model.config)
+                if not hasattr(cfg, "instrumental_params"):
+                    cfg.instrumental_params = {}
+                if getattr(model, "FWHM", None) is not None:
+                    cfg.instrumental_params["FWHM"] = model.FWHM
+                for p in ("grating", "life_position", "cen_wave"):
+                    if getattr(model, p, None) is not None:
+                        cfg.instrumental_params[p] = getattr(model, p)
+                configs[name] = cfg
+        return configs
+
+    # ------------------------------------------------------------------ likelihood (vfit_mcmc.py:291-353)
+    def lnprior(self, theta):
+        return self._like.lnprior(theta)
+
+    def lnprob(self, theta):
+        """(ndim,) -> float, (n, ndim) -> (n,): prior and likelihood are fused on the device."""
+        return self._like.lnprob(theta)
+
+    def lnlike(self, theta):
+        """lnlike alone (no prior): evaluated with the bounds opened, exceptions -> -inf as in the reference."""
+        theta = np.asarray(theta, dtype=np.float64)
+        lp = self.lnprob(theta)
+        prior = self.lnprior(theta)
+        if np.all(np.isfinite(prior)):
+            return lp
+        # out-of-bounds rows: the reference's lnlike still evaluates them
+        eng = self._like.engine
+        try:
+            eng.set_bounds(np.full(self.ndim, -np.inf), np.full(self.ndim, np.inf))
+            return self._like.lnprob(theta)
+        finally:
+            eng.set_bounds(self.lb, self.ub)
+
+    # ------------------------------------------------------------------ optimiser (vfit_mcmc.py:355-360)
+    def optimize_guess(self, theta):
+        """L-BFGS-B on -lnprob with scipy's 2-point finite differences (absolute step 1e-8, flipped at the
+        upper bound), exactly what ``op.minimize(nll, theta, method='L-BFGS-B', bounds=bounds)`` does -- but
+        f(x) and its ndim forward-difference probes are ONE device batch per iteration instead of ndim+1
+        serial calls."""
+        import scipy.optimize as op
+        lb, ub = self.lb.astype(float), self.ub.astype(float)
+        h = 1e-8
+
+        def fun_and_grad(x):
+            x = np.asarray(x, dtype=np.float64)
+            steps = np.full(self.ndim, h)
+            steps[x + h > ub] = -h                      # one-sided step stays inside the bounds
+            batch = np.vstack([x, x[None, :] + np.diag(steps)])
+            vals = -np.asarray(self.lnprob(batch))
+            return vals[0], (vals[1:] - vals[0]) / steps
+
+        result = op.minimize(fun_and_grad, np.asarray(theta, dtype=np.float64), jac=True, method="L-BFGS-B",
+                             bounds=list(zip(lb, ub)))
+        return result.x
+
+    # ------------------------------------------------------------------ walkers (vfit_mcmc.py:442-466)
+    def _initialize_walkers(self, popt):
+        """Same distribution and bounds clipping as the reference; validity is checked for all walkers in one
+        batch and only the invalid ones are redrawn."""
+        guesses = np.empty((self.nwalkers, self.ndim))
+        todo = np.arange(self.nwalkers)
+        for _attempt in range(1000):
+            g = popt + self.perturbation * self._rng.standard_normal((len(todo), self.ndim))
+            g = np.clip(g, self.lb + 1e-10, self.ub - 1e-10)
+            ok = np.isfinite(np.atleast_1d(self.lnprob(g)))
+            guesses[todo[ok]] = g[ok]
+            todo = todo[~ok]
+            if len(todo) == 0:
+                return guesses
+        raise RuntimeError(f"Could not initialize walker {todo[0]} after 1000 attempts")
+
+    # ------------------------------------------------------------------ MCMC (vfit_mcmc.py:492-561)
+    def runmcmc(self, optimize=True, verbose=True, use_pool=True, progress=True):
+        if optimize:
+            if verbose:
+                print("  Optimizing starting guess...")
+            self.theta = self.optimize_guess(self.theta)
+            if verbose:
+                print("✓ Starting guess optimized")
+        guesses = self._initialize_walkers(self.theta)
+        if self.sampler_name == "zeus":
+            from .slice_sampler import EnsembleSliceSampler
+            sampler = EnsembleSliceSampler(self.nwalkers, self.ndim, self.lnprob, seed=self._seed)
+        else:
+            sampler = EnsembleSampler(self.nwalkers, self.ndim, self.lnprob, seed=self._seed)
+        if verbose:
+            print(f"  Starting {self.sampler_name} MCMC (device batches)...")
+            print(f"   Walkers: {self.nwalkers}")
+            print(f"   Steps: {self.no_of_steps}")
+            print(f"   Instruments: {len(self.instrument_data)}")
+        try:
+            if self.sampler_name == "emcee":
+                sampler.run_mcmc(guesses, self.no_of_steps, progress=progress,
+                                 skip_initial_state_check=self.skip_initial_state_check)
+            else:
+                sampler.run_mcmc(guesses, self.no_of_steps, progress=progress)
+        except Exception as e:
+            raise RuntimeError(f"MCMC sampling failed: {e}")
+        self.sampler = sampler
+        self.mcmc_flag = True
+        self.samples = None
+        self.compute_best_theta()
+        if verbose:
+            print("  MCMC completed")
+            self._print_diagnostics()
+
+    def compute_best_theta(self, burntime=100):
+        if self.samples is None:
+            self.samples = self._extract_samples(self.sampler, burntime)
+        self.best_theta = np.percentile(self.samples, 50, axis=0)
+        self.low_theta = np.percentile(self.samples, 16, axis=0)
+        self.high_theta = np.percentile(self.samples, 84, axis=0)
+
+    def _extract_samples(self, sampler, burntime):
+        try:
+            return sampler.get_chain(discard=burntime, flat=True)
+        except Exception as e:   # pragma: no cover
+            warnings.warn(f"Could not extract samples: {e}")
+            return np.array([])
+
+    def _get_acceptance_fraction(self, sampler):
+        return sampler.acceptance_fraction
+
+    def _print_diagnostics(self):
+        print("\n" + "=" * 60 + "\nMCMC DIAGNOSTICS\n" + "=" * 60)
+        af = np.mean(self._get_acceptance_fraction(self.sampler))
+        print(f"Mean acceptance fraction: {af:.3f}")
+        try:
+            tau = self.sampler.get_autocorr_time()
+            print(f"Mean auto-correlation time: {np.nanmean(tau):.3f} steps")
+        except Exception:
+            print("⚠️  Warning: Could not calculate auto-correlation time")
+        print("=" * 60)
+
+    def get_samples(self, flat=True, burn_in=0.5):
+        if not self.mcmc_flag:
+            raise RuntimeError("MCMC has not been run")
+        return self.sampler.get_chain(discard=int(burn_in * self.no_of_steps), flat=flat)
+
+
+def set_bounds(nguess, bguess, vguess, **kwargs):
+    """Traditional branch of the reference's ``set_bounds`` (vfit_mcmc.py:760-787): N +- 2 dex,
+    b in [max(2, b-40), min(150, b+40)], v +- 50 km/s, with the same keyword overrides.
+    (The reference's ``ions=`` branch is mis-indented and leaves most bounds at zero -- SURVEY.md appendix B;
+    it is not replicated.)"""
+    if kwargs.get("ions") is not None:
+        raise NotImplementedError("ion-aware bounds are outside the hot path (and broken in the reference)")
+    nguess, bguess, vguess = np.asarray(nguess), np.asarray(bguess), np.asarray(vguess)
+    Nlow, NHI = nguess - 2.0, nguess + 2.0
+    blow, bHI = np.clip(bguess - 40.0, 2.0, None), np.clip(bguess + 40.0, None, 150.0)
+    vlow, vHI = vguess - 50.0, vguess + 50.0
+    Nlow = np.asarray(kwargs.get("Nlow", Nlow))
+    blow = np.asarray(kwargs.get("blow", blow))
+    vlow = np.asarray(kwargs.get("vlow", vlow))
+    NHI = np.asarray(kwargs.get("Nhi", NHI))
+    bHI = np.asarray(kwargs.get("bhi", bHI))
+    vHI = np.asarray(kwargs.get("vhi", vHI))
+    lb = np.concatenate([Nlow, blow, vlow])
+    ub = np.concatenate([NHI, bHI, vHI])
+    return [lb, ub], lb, ub

@@ -1,0 +1,107 @@
+"""CPU tests of the host layer: configuration mirror, line table, LSF taps, workloads, sampler."""
+import numpy as np
+import pytest
+
+from golden_util import Golden
+
+
+def test_line_table_float32_rounding():
+    from rbvfit_b200 import rb_setline
+    r = rb_setline(2796.3, "closest")
+    assert r["wave"][0] == 2796.3543 or abs(r["wave"][0] - 2796.35) < 0.01
+    assert r["fval"].dtype == np.float32 and r["gamma"].dtype == np.float32
+    assert float(r["fval"][0]) == 0.6122999787330627
+    assert r["name"][0].startswith("MgII")
+    with pytest.raises(ValueError):
+        rb_setline(1000.0, "nearest")
+    assert len(rb_setline(1215.6701, "Exact")["wave"]) == 1
+
+
+def test_config_snaps_and_ties():
+    from rbvfit_b200 import FitConfiguration
+    g = Golden("C2")
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in g.meta["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    cfg.validate()
+    assert len(cfg.systems) == 3 and [len(s.ion_groups) for s in cfg.systems] == [3, 3, 3]
+    assert cfg.systems[0].ion_groups[0].transitions[0] == 1548.2049 or \
+        abs(cfg.systems[0].ion_groups[0].transitions[0] - 1548.2) < 0.01
+    with pytest.raises(ValueError):
+        cfg.add_system(z=2.0, ion="CIV", transitions=[1548.2], components=1)     # duplicate ion
+    with pytest.raises(ValueError):
+        FitConfiguration().add_system(z=0.1, ion="MgII", transitions=[1548.2])    # wrong ion
+    with pytest.raises(ValueError):
+        FitConfiguration().validate()
+
+
+def test_gaussian_taps_match_reference_fixture():
+    from rbvfit_b200 import lsf
+    assert np.array_equal(lsf.gaussian_taps("6.5"), Golden("C1").inst("COS", "taps"))
+    assert np.array_equal(lsf.gaussian_taps(2.394991274145626), Golden("test_script").inst("COS", "taps"))
+    assert lsf.gaussian_taps("3.0").size == 11 and lsf.gaussian_taps("4.0").size == 15
+    with pytest.raises(ImportError):
+        lsf.cos_taps("G130M", "1", "1300A")       # linetools absent -> same error type as the reference
+    from oracle import voigt_oracle as vo
+    assert np.array_equal(lsf.cos_like_taps(321), vo.cos_like_lsf(321))
+
+
+def test_workloads_are_deterministic():
+    from rbvfit_b200 import workloads as wl
+    a, b = wl.get_workload("C2"), wl.get_workload("C2")
+    assert np.array_equal(a["theta_true"], b["theta_true"]) and a["theta_true"].size == 36
+    e1, e2 = wl.make_ensemble(a), wl.make_ensemble(b)
+    assert np.array_equal(e1, e2)
+    out = np.any((e1 < a["lb"]) | (e1 > a["ub"]), axis=1)
+    assert out.sum() >= 1                       # the -inf path is exercised
+    assert wl.get_workload("C5a")["nwalkers"] == 8192
+    s = wl.c5b_sightline(3)
+    assert 0.3 <= s["systems"][0][0] <= 0.4 and s["nwalkers"] == 64
+
+
+def test_set_bounds_traditional():
+    from rbvfit_b200.vfit_mcmc import set_bounds
+    _, lb, ub = set_bounds([14.0], [20.0], [0.0])
+    assert list(lb) == [12.0, 2.0, -50.0] and list(ub) == [16.0, 60.0, 50.0]
+    _, lb, ub = set_bounds([14.0], [130.0], [0.0], vlow=[-10.0])
+    assert ub[1] == 150.0 and lb[2] == -10.0
+
+
+def test_stretch_sampler_recovers_gaussian():
+    from rbvfit_b200.sampler import EnsembleSampler, integrated_time
+    mu = np.array([1.0, -2.0, 0.5])
+    sig = np.array([0.5, 2.0, 1.0])
+    calls = []
+
+    def lnp(x):
+        calls.append(x.shape)
+        return -0.5 * np.sum(((x - mu) / sig) ** 2, axis=1)
+
+    rng = np.random.default_rng(1)
+    s = EnsembleSampler(32, 3, lnp, seed=2)
+    s.run_mcmc(mu + 1e-2 * rng.standard_normal((32, 3)), 1500)
+    assert all(c[1] == 3 and c[0] in (16, 32) for c in calls)      # batched half-ensembles
+    flat = s.get_chain(discard=300, flat=True)
+    assert flat.shape == (1200 * 32, 3)
+    assert np.all(np.abs(flat.mean(0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(0) / sig - 1) < 0.1)
+    af = s.acceptance_fraction
+    assert af.shape == (32,) and 0.3 < af.mean() < 0.85
+    tau = s.get_autocorr_time(quiet=True)
+    assert tau.shape == (3,) and np.all(tau > 1) and np.all(tau < 200)
+    assert s.get_chain().shape == (1500, 32, 3) and s.get_log_prob().shape == (1500, 32)
+    with pytest.raises(ValueError):
+        EnsembleSampler(8, 3, lnp).run_mcmc(np.zeros((8, 3)), 1)     # degenerate initial state
+
+
+def test_roofline_flops_rule():
+    from rbvfit_b200 import roofline as rf, workloads as wl
+    from oracle import voigt_oracle as vo
+    w = wl.get_workload("C1")
+    cfg = vo.OracleConfig()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z, ion, trans, comps)
+    m = vo.lower(cfg)
+    F, tiers = rf.flops_per_walker_pixel(m, w["theta_true"], w["instruments"]["COS"]["wave"], 23)
+    assert abs(sum(tiers.values()) - 1) < 1e-12
+    assert 150 < F < 398            # ~280 for C1, upper bound 80 L + 2 K + 32 = 398
