@@ -44,6 +44,7 @@ struct InstDev {
   int P, K, Kpad, L, C, method;
   int tile, ext_alloc, R;  // outputs per tile, smem flux slots, register blocking
   int first_tile, n_tiles; // tile range of this instrument in the global tile list
+  int line_base;           // first row of this instrument in the per-walker line-constant block
 };
 
 struct TileDesc {
@@ -61,8 +62,10 @@ struct LaunchParams {
   double* lnprob;        // [W]
   double* partials;      // [W, n_tiles]
   unsigned int* tickets; // [W]
+  int* oob;              // [W] 1 = row violates the prior bounds (written by prep_kernel)
+  double* lc;            // [W, n_lines_total, LC_STRIDE] per-walker line constants (written by prep_kernel)
   double* out_flux;      // flux mode: [W, P]
-  int ndim, n_tiles, n_inst, W;
+  int ndim, n_tiles, n_inst, W, n_lines_total;
   int tile_base;         // flux mode: first tile of the instrument
   int precision;
 };
@@ -134,8 +137,8 @@ __device__ __forceinline__ void tau_wofz(const double* __restrict__ s_lc, int L,
     double d[kPixPerThread];
     if (a2 > kABig * kABig) {   // per-line (CTA-uniform): damping beyond the series' rearrangement
       const double a = lc[LC_a], coef = lc[LC_COEF];
-#pragma unroll 1
-      for (int j = 0; j < kPixPerThread; ++j) {
+#pragma unroll
+      for (int j = 0; j < kPixPerThread; ++j) {   // unrolled: tau/u must stay in registers
         double x = fma(A, u[j], -B);
         tau[j] = fma(coef, general_H(x, a, fma(x, x, a2)), tau[j]);
       }
@@ -157,8 +160,8 @@ __device__ __forceinline__ void tau_wofz(const double* __restrict__ s_lc, int L,
       accum_asym<kNQNear>(lc, d, tau);
     } else {
       const double a = lc[LC_a], coef = lc[LC_COEF];
-#pragma unroll 1
-      for (int j = 0; j < kPixPerThread; ++j) {
+#pragma unroll
+      for (int j = 0; j < kPixPerThread; ++j) {   // unrolled: no dynamic indexing of register arrays
         if (d[j] < kDCore) {
           double x = fma(A, u[j], -B);
           tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
@@ -184,6 +187,41 @@ __device__ __forceinline__ void tau_fast(const double* __restrict__ s_lc, int L,
   }
 }
 
+// ------------------------------------------------------------------------------------------ prep kernel
+// One thread per (walker, line of any instrument): theta row -> the 20-double line-constant record, once per
+// walker instead of once per tile (pow, five divisions and the 13 series coefficients are ~400 dependent
+// FP64 instructions -- as long as a tile's whole phase 1 when done by 33 threads of every CTA).
+// Thread 0 of each walker also evaluates the uniform prior (vfit.lnprior, vfit_mcmc.py:291-295).
+__global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
+  const int w = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* th = prm.theta + (size_t)w * prm.ndim;
+  if (g == 0) {
+    int bad = 0;
+    for (int i = 0; i < prm.ndim; ++i) {
+      double t = th[i];
+      bad |= (t < prm.lb[i]) || (t > prm.ub[i]);
+    }
+    prm.oob[w] = bad;
+  }
+  if (g >= prm.n_lines_total) return;
+  int k = 0;
+  while (k + 1 < prm.n_inst && g >= prm.inst[k + 1].line_base) ++k;
+  const InstDev& I = prm.inst[k];
+  const int l = g - I.line_base;
+  double lc[LC_STRIDE];
+  if (I.method == RBV_VOIGT_FAST) {
+    prep_line_fast(I, l, th, lc);
+  } else {
+    prep_line_wofz(I, l, th, lc);
+#pragma unroll
+    for (int p = 0; p < kNQNear; ++p) lc[LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
+  }
+  double2* dst = reinterpret_cast<double2*>(prm.lc + ((size_t)w * prm.n_lines_total + g) * LC_STRIDE);
+#pragma unroll
+  for (int i = 0; i < LC_STRIDE / 2; ++i) dst[i] = make_double2(lc[2 * i], lc[2 * i + 1]);
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 // MODE 0: lnprob (chi^2 partial + ticket finalisation); MODE 1: model flux out.
 template <int LOGR, int MODE>
@@ -205,25 +243,24 @@ __global__ void __launch_bounds__(kThreads, 3) voigt_tile_kernel(const LaunchPar
   double* s_taps = s_lc + I.L * LC_STRIDE;             // [Kpad]
   double* s_flux = s_taps + I.Kpad;                    // [smem_pos(ext_alloc)]
 
-  // ---- theta row + prior
-  const double* th_g = prm.theta + (size_t)w * ndim;
-  int oob = 0;
-  for (int i = tid; i < ndim; i += kThreads) {
-    double t = th_g[i];
-    s_theta[i] = t;
-    if (MODE == 0) oob |= (t < prm.lb[i]) || (t > prm.ub[i]);   // vfit_mcmc.py:293
-  }
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
+  int oob = 0;
+  const bool fast = (I.method == RBV_VOIGT_FAST);
   if (MODE == 0) {
-    oob = __syncthreads_or(oob);
-  } else {
+    // ---- per-line constants and the prior flag were computed once per walker by prep_kernel
+    oob = prm.oob[w];
+    if (!oob) {
+      const double2* src =
+          reinterpret_cast<const double2*>(prm.lc + ((size_t)w * prm.n_lines_total + I.line_base) * LC_STRIDE);
+      double2* dst = reinterpret_cast<double2*>(s_lc);
+      for (int i = tid; i < I.L * (LC_STRIDE / 2); i += kThreads) dst[i] = src[i];
+    }
     __syncthreads();
-  }
-
-  double part = 0.0;
-  if (!oob) {
-    // ---- per-line constants
-    const bool fast = (I.method == RBV_VOIGT_FAST);
+  } else {
+    // ---- flux mode: the CTA prepares its own constants (no workspace in this entry point)
+    const double* th_g = prm.theta + (size_t)w * ndim;
+    for (int i = tid; i < ndim; i += kThreads) s_theta[i] = th_g[i];
+    __syncthreads();
     for (int l = tid; l < I.L; l += kThreads) {
       if (fast) prep_line_fast(I, l, s_theta, s_lc + l * LC_STRIDE);
       else prep_line_wofz(I, l, s_theta, s_lc + l * LC_STRIDE);
@@ -237,7 +274,10 @@ __global__ void __launch_bounds__(kThreads, 3) voigt_tile_kernel(const LaunchPar
       }
       __syncthreads();
     }
+  }
 
+  double part = 0.0;
+  if (!oob) {
     // ---- phase 1: flux for the tile + halo into shared memory
     const int h = I.K >> 1;
     const int p0 = td.p0;
@@ -441,6 +481,7 @@ struct RbvContext {
   int sm_count = 148;
   int ndim = 0;
   int n_tiles = 0;
+  int n_lines_total = 0;
   int precision = RBV_PRECISION_FP64;
   long long launches = 0;
   std::vector<HostInst> inst;
@@ -549,10 +590,13 @@ static int rebuild_tables(RbvContext* ctx) {
     I.tile = n_pass * kPass - (I.K - 1);
     I.ext_alloc = n_pass * kPass + 2 * R;
     I.first_tile = (int)ctx->tiles.size();
+    I.line_base = (k == 0) ? 0 : ctx->inst[k - 1].dev.line_base + ctx->inst[k - 1].dev.L;
     I.n_tiles = (I.P + I.tile - 1) / I.tile;
     for (int t = 0; t < I.n_tiles; ++t) ctx->tiles.push_back(TileDesc{(int)k, t * I.tile});
   }
   ctx->n_tiles = (int)ctx->tiles.size();
+  ctx->n_lines_total = 0;
+  for (auto& hi : ctx->inst) ctx->n_lines_total += hi.dev.L;
   std::vector<InstDev> flat;
   for (auto& hi : ctx->inst) flat.push_back(hi.dev);
   cudaFree(ctx->d_inst);
@@ -637,10 +681,26 @@ int rbv_set_bounds(RbvContext* ctx, const double* lb, const double* ub, int ndim
   return RBV_OK;
 }
 
+struct WorkspaceLayout {
+  size_t tickets, oob, partials, lc, total;   // byte offsets
+};
+
+// [tickets u32 x W][oob i32 x W][partials f64 x W x n_tiles][line constants f64 x W x n_lines x LC_STRIDE]
+static WorkspaceLayout workspace_layout(const RbvContext* ctx, int W) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  WorkspaceLayout lay;
+  lay.tickets = 0;
+  lay.oob = up((size_t)W * sizeof(unsigned int));
+  lay.partials = lay.oob + up((size_t)W * sizeof(int));
+  lay.lc = lay.partials + up((size_t)W * std::max(ctx->n_tiles, 1) * sizeof(double));
+  lay.total = lay.lc + up((size_t)W * std::max(ctx->n_lines_total, 1) * LC_STRIDE * sizeof(double));
+  return lay;
+}
+
 int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes) {
   if (!ctx || !bytes || n_walkers < 0) return fail(RBV_EINVAL, "rbv_workspace_bytes: bad argument");
-  size_t tickets = ((size_t)n_walkers * sizeof(unsigned int) + 255) & ~(size_t)255;
-  *bytes = tickets + (size_t)n_walkers * std::max(ctx->n_tiles, 1) * sizeof(double);
+  WorkspaceLayout lay = workspace_layout(ctx, n_walkers);
+  *bytes = lay.total;
   return RBV_OK;
 }
 
@@ -661,7 +721,7 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   if (!workspace || workspace_bytes < need) return fail(RBV_ENOMEM, "rbv_lnprob_batch: workspace too small");
   RBV_CUDA(cudaSetDevice(ctx->device));
 
-  size_t tickets_bytes = ((size_t)W * sizeof(unsigned int) + 255) & ~(size_t)255;
+  WorkspaceLayout lay = workspace_layout(ctx, W);
   LaunchParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.inst = ctx->d_inst;
@@ -671,8 +731,11 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   prm.ub = ctx->d_ub;
   prm.core_tab = ctx->d_core_tab;
   prm.lnprob = lnprob;
-  prm.tickets = (unsigned int*)workspace;
-  prm.partials = (double*)((char*)workspace + tickets_bytes);
+  prm.tickets = (unsigned int*)((char*)workspace + lay.tickets);
+  prm.oob = (int*)((char*)workspace + lay.oob);
+  prm.partials = (double*)((char*)workspace + lay.partials);
+  prm.lc = (double*)((char*)workspace + lay.lc);
+  prm.n_lines_total = ctx->n_lines_total;
   prm.ndim = ctx->ndim;
   prm.n_tiles = ctx->n_tiles;
   prm.n_inst = (int)ctx->inst.size();
@@ -686,6 +749,11 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   const bool r8 = ctx->inst[0].dev.R == 8;
   dim3 grid((unsigned)W, (unsigned)ctx->n_tiles);
   if (ctx->n_tiles > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 tiles per walker");
+  if (W > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 walkers per call (split the batch)");
+  dim3 pgrid((unsigned)((ctx->n_lines_total + 127) / 128), (unsigned)W);
+  prep_kernel<<<pgrid, 128, 0, st>>>(prm);
+  RBV_CUDA(cudaGetLastError());
+  ctx->launches++;
   if (r8) voigt_tile_kernel<3, 0><<<grid, kThreads, smem, st>>>(prm);
   else voigt_tile_kernel<2, 0><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
