@@ -58,11 +58,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("RBVFIT_B200_LIB", LIB_PATH)    # override = tuning experiments only
+    if not os.path.exists(path):
         raise RbvError(
-            f"{LIB_PATH} is missing: build it with `python -m rbvfit_b200.build` "
+            f"{path} is missing: build it with `python -m rbvfit_b200.build` "
             "(or __graft_entry__.build()).  rbvfit_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)     # AttributeError if the symbol is not exported
         fn.restype = res

@@ -26,8 +26,14 @@
 
 namespace rbv {
 
+#ifndef RBV_PPT
+#define RBV_PPT 8
+#endif
+#ifndef RBV_MIN_CTAS
+#define RBV_MIN_CTAS 2
+#endif
 constexpr int kThreads = 256;
-constexpr int kPixPerThread = 4;
+constexpr int kPixPerThread = RBV_PPT;
 constexpr int kPass = kThreads * kPixPerThread;  // pixels per phase-1 pass
 constexpr int kWarpPix = 32 * kPixPerThread;     // pixels covered by one warp per pass
 

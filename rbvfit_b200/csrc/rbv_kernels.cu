@@ -113,15 +113,58 @@ __device__ __forceinline__ void prep_line_fast(const InstDev& I, int l, const do
 }
 
 // ------------------------------------------------------------------------------------------ phase 1
+extern __shared__ double smem[];   // every hot-loop access indexes this array directly (shared-space addressing)
+
+// Tier codes of a (warp chunk, line) pair
+constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGeneral = 4;
+
+// Classify every line once per warp chunk from the chunk's range of 1/lambda (lane l handles line l):
+// far lines go to the front of the warp's list, everything else to the back with its tier in the top bits.
+// Returns (n_far, n_other).  Conservative: uses the smallest |z|^2 any pixel of the chunk can reach.
+__device__ __forceinline__ int2 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
+                                               double umin, double umax, int lane) {
+  int n_far = 0, n_oth = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const bool valid = l < L;
+    int tier = kTierCore;
+    if (valid) {
+      const double* lc = smem + lc_off + l * LC_STRIDE;
+      const double A = lc[LC_A], B = lc[LC_B], a2 = lc[LC_A2];
+      const double x1 = fma(A, umin, -B), x2 = fma(A, umax, -B);
+      const double m = (x1 * x2 <= 0.0) ? 0.0 : fmin(fabs(x1), fabs(x2));
+      const double dmin = fma(m, m, a2);
+      tier = (a2 > kABig * kABig) ? kTierGeneral
+             : (dmin >= kDFar)    ? kTierFar
+             : (dmin >= kDNear)   ? kTierMid
+             : (dmin >= kDCore)   ? kTierNear
+                                  : kTierCore;   // NaN lands here and propagates through the arithmetic
+    }
+    const unsigned far_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFar);
+    const unsigned oth_mask = __ballot_sync(0xffffffffu, valid && tier != kTierFar);
+    if (valid) {
+      if (tier == kTierFar) list[n_far + __popc(far_mask & lt)] = (unsigned short)l;
+      else list[L - 1 - (n_oth + __popc(oth_mask & lt))] = (unsigned short)(l | (tier << 12));
+    }
+    n_far += __popc(far_mask);
+    n_oth += __popc(oth_mask);
+  }
+  __syncwarp();
+  return make_int2(n_far, n_oth);
+}
+
 template <int NQ>
-__device__ __forceinline__ void accum_asym(const double* __restrict__ lc, const double (&d)[kPixPerThread],
-                                           double (&tau)[kPixPerThread]) {
+__device__ __forceinline__ void accum_asym_line(int off, const double (&u)[kPixPerThread],
+                                                double (&tau)[kPixPerThread]) {
+  const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2];
   double Q[NQ];
 #pragma unroll
-  for (int p = 0; p < NQ; ++p) Q[p] = lc[LC_Q + p];
+  for (int p = 0; p < NQ; ++p) Q[p] = smem[off + LC_Q + p];
 #pragma unroll
   for (int j = 0; j < kPixPerThread; ++j) {
-    double rho = rcp_pos(d[j]);
+    const double x = fma(A, u[j], -B);
+    const double rho = rcp_pos(fma(x, x, a2));
     double s = Q[NQ - 1];
 #pragma unroll
     for (int p = NQ - 2; p >= 0; --p) s = fma(s, rho, Q[p]);
@@ -129,56 +172,64 @@ __device__ __forceinline__ void accum_asym(const double* __restrict__ lc, const 
   }
 }
 
-__device__ __forceinline__ void tau_wofz(const double* __restrict__ s_lc, int L, const double (&u)[kPixPerThread],
-                                         double (&tau)[kPixPerThread], const double* __restrict__ core_tab) {
-  for (int l = 0; l < L; ++l) {
-    const double* lc = s_lc + l * LC_STRIDE;
-    const double A = lc[LC_A], B = lc[LC_B], a2 = lc[LC_A2];
-    double d[kPixPerThread];
-    if (a2 > kABig * kABig) {   // per-line (CTA-uniform): damping beyond the series' rearrangement
-      const double a = lc[LC_a], coef = lc[LC_COEF];
+__device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __restrict__ list,
+                                         const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
+                                         const double* __restrict__ core_tab, int lane) {
+  // range of 1/lambda over the warp's chunk (no monotonicity assumed)
+  double umin = u[0], umax = u[0];
 #pragma unroll
-      for (int j = 0; j < kPixPerThread; ++j) {   // unrolled: tau/u must stay in registers
-        double x = fma(A, u[j], -B);
-        tau[j] = fma(coef, general_H(x, a, fma(x, x, a2)), tau[j]);
-      }
-      continue;
-    }
-    int hmin = 0x7fffffff;
+  for (int j = 1; j < kPixPerThread; ++j) {
+    umin = fmin(umin, u[j]);
+    umax = fmax(umax, u[j]);
+  }
 #pragma unroll
-    for (int j = 0; j < kPixPerThread; ++j) {
-      double x = fma(A, u[j], -B);
-      d[j] = fma(x, x, a2);
-      hmin = min(hmin, __double2hiint(d[j]));
-    }
-    hmin = __reduce_min_sync(0xffffffffu, hmin);
-    if (hmin >= kHiFar) {
-      accum_asym<kNQFar>(lc, d, tau);
-    } else if (hmin >= kHiNear) {
-      accum_asym<kNQMid>(lc, d, tau);
-    } else if (hmin >= kHiCore) {
-      accum_asym<kNQNear>(lc, d, tau);
+  for (int o = 16; o > 0; o >>= 1) {
+    umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+  }
+  const int2 n = classify_lines(lc_off, L, list, umin, umax, lane);
+
+  // far lines: branch-free body, 8 FP64 instructions per (line, pixel)
+#pragma unroll 2
+  for (int k = 0; k < n.x; ++k) accum_asym_line<kNQFar>(lc_off + (int)list[k] * LC_STRIDE, u, tau);
+
+  // everything else (a few lines per chunk at most)
+  for (int k = 0; k < n.y; ++k) {
+    const int e = list[L - 1 - k];
+    const int off = lc_off + (e & 0xfff) * LC_STRIDE;
+    const int tier = e >> 12;
+    if (tier == kTierMid) {
+      accum_asym_line<kNQMid>(off, u, tau);
+    } else if (tier == kTierNear) {
+      accum_asym_line<kNQNear>(off, u, tau);
     } else {
-      const double a = lc[LC_a], coef = lc[LC_COEF];
+      const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2], a = smem[off + LC_a],
+                   coef = smem[off + LC_COEF];
+      if (tier == kTierGeneral) {
 #pragma unroll
-      for (int j = 0; j < kPixPerThread; ++j) {   // unrolled: no dynamic indexing of register arrays
-        if (d[j] < kDCore) {
-          double x = fma(A, u[j], -B);
-          tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
-        } else {
-          tau[j] += asym_series<kNQNear>(lc + LC_Q, d[j]);
+        for (int j = 0; j < kPixPerThread; ++j) {   // unrolled: tau/u must stay in registers
+          const double x = fma(A, u[j], -B);
+          tau[j] = fma(coef, general_H(x, a, fma(x, x, a2)), tau[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kPixPerThread; ++j) {
+          const double x = fma(A, u[j], -B);
+          const double d = fma(x, x, a2);
+          if (d < kDCore) tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
+          else tau[j] += asym_series<kNQNear>(smem + off + LC_Q, d);
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ void tau_fast(const double* __restrict__ s_lc, int L, const double (&u)[kPixPerThread],
+__device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[kPixPerThread],
                                          double (&tau)[kPixPerThread]) {
   for (int l = 0; l < L; ++l) {
-    const double* lc = s_lc + l * LC_STRIDE;
-    const double A = lc[LC_A], B = lc[LC_B], eps = lc[LC_A2], aos = lc[LC_a], cf = lc[LC_AUX],
-                 coef = lc[LC_COEF];
+    const int off = lc_off + l * LC_STRIDE;
+    const double A = smem[off + LC_A], B = smem[off + LC_B], eps = smem[off + LC_A2], aos = smem[off + LC_a],
+                 cf = smem[off + LC_AUX], coef = smem[off + LC_COEF];
 #pragma unroll
     for (int j = 0; j < kPixPerThread; ++j) {
       double x = fma(A, u[j], -B);
@@ -225,9 +276,8 @@ __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
 // ------------------------------------------------------------------------------------------ main kernel
 // MODE 0: lnprob (chi^2 partial + ticket finalisation); MODE 1: model flux out.
 template <int LOGR, int MODE>
-__global__ void __launch_bounds__(kThreads, 3) voigt_tile_kernel(const LaunchParams prm) {
+__global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(const LaunchParams prm) {
   constexpr int R = 1 << LOGR;
-  extern __shared__ double smem[];
   __shared__ double s_red[kThreads / 32];
   __shared__ int s_flag;
 
@@ -238,10 +288,15 @@ __global__ void __launch_bounds__(kThreads, 3) voigt_tile_kernel(const LaunchPar
   const InstDev I = prm.inst[td.inst];
   const int ndim = prm.ndim;
 
-  double* s_theta = smem;                              // [ndim]
-  double* s_lc = s_theta + ((ndim + 1) & ~1);          // [L * LC_STRIDE]
-  double* s_taps = s_lc + I.L * LC_STRIDE;             // [Kpad]
-  double* s_flux = s_taps + I.Kpad;                    // [smem_pos(ext_alloc)]
+  const int lc_off = (ndim + 1) & ~1;                  // smem layout (doubles): theta | line consts | taps |
+  const int taps_off = lc_off + I.L * LC_STRIDE;       //   flux tile | per-warp line lists (u16)
+  const int flux_off = taps_off + I.Kpad;
+  const int list_off = flux_off + ((smem_pos(I.ext_alloc, LOGR) + 1) & ~1);
+  double* s_theta = smem;
+  double* s_lc = smem + lc_off;
+  double* s_taps = smem + taps_off;
+  double* s_flux = smem + flux_off;
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + list_off) + warp * ((I.L + 3) & ~3);
 
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
   int oob = 0;
@@ -294,8 +349,8 @@ __global__ void __launch_bounds__(kThreads, 3) voigt_tile_kernel(const LaunchPar
         u[j] = __ldg(I.inv_wave + p);
         tau[j] = 0.0;
       }
-      if (fast) tau_fast(s_lc, I.L, u, tau);
-      else tau_wofz(s_lc, I.L, u, tau, prm.core_tab);
+      if (fast) tau_fast(lc_off, I.L, u, tau);
+      else tau_wofz(lc_off, I.L, s_list, u, tau, prm.core_tab, lane);
 #pragma unroll
       for (int j = 0; j < kPixPerThread; ++j) {
         int i = i0 + j * 32 + lane;
@@ -504,8 +559,9 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 
 static size_t smem_bytes_for(const InstDev& I, int ndim) {
   int logR = (I.R == 8) ? 3 : 2;
-  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (I.ext_alloc + (I.ext_alloc >> logR)) + 2;
-  return n * sizeof(double);
+  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (I.ext_alloc + (I.ext_alloc >> logR)) + 4;
+  size_t lists = (size_t)(kThreads / 32) * ((I.L + 3) & ~3) * sizeof(unsigned short);
+  return n * sizeof(double) + ((lists + 15) & ~(size_t)15);
 }
 
 extern "C" {
@@ -611,6 +667,7 @@ static int rebuild_tables(RbvContext* ctx) {
 int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectrum* sp, int* out_index) {
   if (!ctx || !lt || !sp) return fail(RBV_EINVAL, "rbv_add_instrument: null argument");
   if (lt->n_lines <= 0 || lt->n_components <= 0) return fail(RBV_EINVAL, "rbv_add_instrument: empty line table");
+  if (lt->n_lines > 4095) return fail(RBV_EINVAL, "rbv_add_instrument: more than 4095 lines per instrument");
   if (sp->n_pixels <= 0 || !sp->wave || !sp->inv_wave)
     return fail(RBV_EINVAL, "rbv_add_instrument: empty spectrum (n_pixels, wave and inv_wave are required)");
   if (lt->voigt_method != RBV_VOIGT_WOFZ && lt->voigt_method != RBV_VOIGT_FAST)
