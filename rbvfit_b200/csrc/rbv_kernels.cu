@@ -42,19 +42,23 @@ struct InstDev {
   const int* comp;         // [L]
   const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
   int P, K, Kpad, L, C, method;
-  int tile, ext_alloc, R;  // outputs per tile, smem flux slots, register blocking
-  int first_tile, n_tiles; // tile range of this instrument in the global tile list
+  int R;                   // register blocking of the LSF stage (context-wide)
   int line_base;           // first row of this instrument in the per-walker line-constant block
 };
 
-struct TileDesc {
-  int inst;
-  int p0;  // first output pixel
+// Tile geometry of one instrument for ONE launch (chosen per launch from the batch size: big tiles when
+// there are plenty of walkers, small ones when the grid would otherwise not fill the GPU).
+struct TileGeom {
+  int tile;        // output pixels per CTA
+  int ext_alloc;   // flux slots per CTA in shared memory (tile + halo + slack)
+  int first_tile;  // index of this instrument's first tile in the launch's tile list
+  int n_tiles;
 };
+constexpr int kMaxInst = 16;
 
 struct LaunchParams {
   const InstDev* inst;
-  const TileDesc* tiles;
+  TileGeom geom[kMaxInst];
   const double* theta;   // [W, ndim]
   const double* lb;
   const double* ub;
@@ -280,18 +284,22 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   constexpr int R = 1 << LOGR;
   __shared__ double s_red[kThreads / 32];
   __shared__ int s_flag;
+  __shared__ int s_next;   // dynamic chunk counter of phase 1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int w = blockIdx.x;
   const int tile_id = (MODE == 0) ? blockIdx.y : prm.tile_base + blockIdx.y;
-  const TileDesc td = prm.tiles[tile_id];
-  const InstDev I = prm.inst[td.inst];
+  int inst_id = 0;
+  while (inst_id + 1 < prm.n_inst && tile_id >= prm.geom[inst_id + 1].first_tile) ++inst_id;
+  const TileGeom G = prm.geom[inst_id];
+  const InstDev I = prm.inst[inst_id];
   const int ndim = prm.ndim;
+  if (tid == 0) s_next = 0;
 
   const int lc_off = (ndim + 1) & ~1;                  // smem layout (doubles): theta | line consts | taps |
   const int taps_off = lc_off + I.L * LC_STRIDE;       //   flux tile | per-warp line lists (u16)
   const int flux_off = taps_off + I.Kpad;
-  const int list_off = flux_off + ((smem_pos(I.ext_alloc, LOGR) + 1) & ~1);
+  const int list_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1);
   double* s_theta = smem;
   double* s_lc = smem + lc_off;
   double* s_taps = smem + taps_off;
@@ -335,12 +343,18 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   if (!oob) {
     // ---- phase 1: flux for the tile + halo into shared memory
     const int h = I.K >> 1;
-    const int p0 = td.p0;
-    const int n_out = min(I.tile, I.P - p0);
+    const int p0 = (tile_id - G.first_tile) * G.tile;
+    const int n_out = min(G.tile, I.P - p0);
     const int ext = n_out + I.K - 1;
-    for (int base = 0; base < ext; base += kPass) {
-      const int i0 = base + warp * kWarpPix;
-      if (i0 >= ext) continue;  // warp-uniform
+    const int n_chunks = (ext + kWarpPix - 1) / kWarpPix;
+    // warps pull 32*kPixPerThread-pixel chunks from a CTA-wide counter: chunks that contain a line core cost
+    // several times a far-wing chunk, and static assignment would leave the other warps waiting at the barrier
+    while (true) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_next, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= n_chunks) break;
+      const int i0 = c * kWarpPix;
       double u[kPixPerThread], tau[kPixPerThread];
 #pragma unroll
       for (int j = 0; j < kPixPerThread; ++j) {
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       }
     }
     // zero the slack the register-blocked window may touch (taps there are zero, values must be finite)
-    for (int i = ext + tid; i < I.ext_alloc; i += kThreads) s_flux[smem_pos(i, LOGR)] = 0.0;
+    for (int i = ext + tid; i < G.ext_alloc; i += kThreads) s_flux[smem_pos(i, LOGR)] = 0.0;
     __syncthreads();
 
     // ---- phase 2: LSF + chi^2 (or flux out).  M_p = sum_m taps_rev[m] * E[o + m]
@@ -368,6 +382,16 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.0;
       const int e0 = g << LOGR;
+      double obs[R], wgt[R], lgw[R];   // observed spectrum: issue the global loads before the tap loop
+      if (MODE == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int p = min(p0 + e0 + r, I.P - 1);
+          obs[r] = __ldg(I.flux + p);
+          wgt[r] = __ldg(I.inv_sigma2 + p);
+          lgw[r] = __ldg(I.log_inv_sigma2 + p);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < R - 1; ++q) win[q] = s_flux[smem_pos(e0 + q, LOGR)];
       for (int m0 = 0; m0 < I.Kpad; m0 += R) {
@@ -386,11 +410,10 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       if (MODE == 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          int p = pbase + r;
           if (e0 + r < n_out) {
-            double resid = __ldg(I.flux + p) - acc[r];
+            double resid = obs[r] - acc[r];
             double sq = resid * resid;
-            part += sq * __ldg(I.inv_sigma2 + p) - __ldg(I.log_inv_sigma2 + p);   // vfit_mcmc.py:310
+            part += sq * wgt[r] - lgw[r];   // vfit_mcmc.py:310
           }
         }
       } else {
@@ -426,9 +449,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         total = 0.0;
         const volatile double* pp = prm.partials + (size_t)w * prm.n_tiles;
         for (int k = 0; k < prm.n_inst; ++k) {
-          const InstDev& J = prm.inst[k];
           double s = 0.0;
-          for (int t = 0; t < J.n_tiles; ++t) s += pp[J.first_tile + t];
+          for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
           total += -0.5 * s;                                          // vfit_mcmc.py:309-313
         }
       }
@@ -540,9 +562,8 @@ struct RbvContext {
   int precision = RBV_PRECISION_FP64;
   long long launches = 0;
   std::vector<HostInst> inst;
-  std::vector<TileDesc> tiles;
   InstDev* d_inst = nullptr;
-  TileDesc* d_tiles = nullptr;
+  int max_dyn_smem = 0;
   double* d_lb = nullptr;
   double* d_ub = nullptr;
   double* d_core_tab = nullptr;
@@ -557,9 +578,9 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
   return e;
 }
 
-static size_t smem_bytes_for(const InstDev& I, int ndim) {
+static size_t smem_bytes_for(const InstDev& I, const TileGeom& G, int ndim) {
   int logR = (I.R == 8) ? 3 : 2;
-  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (I.ext_alloc + (I.ext_alloc >> logR)) + 4;
+  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (G.ext_alloc + (G.ext_alloc >> logR)) + 4;
   size_t lists = (size_t)(kThreads / 32) * ((I.L + 3) & ~3) * sizeof(unsigned short);
   return n * sizeof(double) + ((lists + 15) & ~(size_t)15);
 }
@@ -587,6 +608,7 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaMemcpyToSymbol(c_weid, RBV_WEID_COEF_HOST, sizeof(RBV_WEID_COEF_HOST)));
   RBV_CUDA(upload(&ctx->d_core_tab, RBV_CORE_TABLE_HOST, (size_t)RBV_CORE_TABLE_LEN));
   const int max_dyn = (int)prop.sharedMemPerBlockOptin - 2048;
+  ctx->max_dyn_smem = max_dyn;
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
@@ -603,7 +625,6 @@ void rbv_destroy(RbvContext* ctx) {
     cudaFree(hi.d_taps);
   }
   cudaFree(ctx->d_inst);
-  cudaFree(ctx->d_tiles);
   cudaFree(ctx->d_lb);
   cudaFree(ctx->d_ub);
   cudaFree(ctx->d_core_tab);
@@ -618,10 +639,53 @@ int rbv_set_precision(RbvContext* ctx, int precision) {
   return RBV_OK;
 }
 
-// Tile geometry + tap upload for every instrument.  The register blocking R is context-wide (8 as soon as
-// one instrument has a wide LSF) so that all instruments run in ONE launch.
+// Tile geometry of every instrument for one launch.  ``scale`` multiplies the base tile (1, 2, 4, ...):
+// big tiles amortise the per-CTA preamble and halo and make the dynamic chunk scheduling effective, small
+// tiles keep the grid full when there are few walkers.  Returns the total tile count and the dynamic smem.
+static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, size_t* smem_out) {
+  int total = 0;
+  size_t smem = 0;
+  int ndim = ctx->ndim;
+  for (size_t k = 0; k < ctx->inst.size(); ++k) {
+    const InstDev& I = ctx->inst[k].dev;
+    int n_pass = 1;
+    if (I.K - 1 > 64) n_pass = (int)std::ceil((I.K - 1) / (0.08 * kPass));   // halo overhead <= ~8 %
+    n_pass = std::min(n_pass, 8) * scale;
+    int need = (I.P + I.K - 1 + kPass - 1) / kPass;
+    n_pass = std::max(1, std::min(n_pass, need));
+    TileGeom g;
+    g.tile = n_pass * kPass - (I.K - 1);
+    g.ext_alloc = n_pass * kPass + 2 * I.R;
+    g.first_tile = total;
+    g.n_tiles = (I.P + g.tile - 1) / g.tile;
+    total += g.n_tiles;
+    geom[k] = g;
+    smem = std::max(smem, smem_bytes_for(I, g, ndim ? ndim : 3 * I.C));
+  }
+  if (smem_out) *smem_out = smem;
+  return total;
+}
+
+// Picks the largest tile scale that still gives every SM several CTAs and fits two CTAs per SM.
+static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t* smem_out) {
+  const long long want = 4LL * 2 * ctx->sm_count;   // >= 4 waves at 2 CTAs / SM
+  int total = 0;
+  for (int scale = 4; scale >= 1; scale >>= 1) {
+    size_t smem = 0;
+    total = compute_geometry(ctx, scale, geom, &smem);
+    bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, 100 * 1024);
+    if (scale == 1 || (fits && (long long)W * total >= want)) {
+      if (smem_out) *smem_out = smem;
+      return total;
+    }
+  }
+  return total;
+}
+
+// Tap upload + line bases for every instrument.  The register blocking R is context-wide (8 as soon as one
+// instrument has a wide LSF) so that all instruments run in ONE launch.
 static int rebuild_tables(RbvContext* ctx) {
-  ctx->tiles.clear();
+  if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "at most 16 instruments per context");
   int R = 4;
   for (auto& hi : ctx->inst)
     if ((int)hi.taps.size() > 64) R = 8;
@@ -637,30 +701,17 @@ static int rebuild_tables(RbvContext* ctx) {
     hi.d_taps = nullptr;
     RBV_CUDA(upload(&hi.d_taps, rev.data(), rev.size()));
     I.taps_rev = hi.d_taps;
-    // ext = n_pass * kPass flux slots per CTA; halo overhead <= ~8 % for wide LSFs
-    int n_pass = 1;
-    if (I.K - 1 > 64) n_pass = (int)std::ceil((I.K - 1) / (0.08 * kPass));
-    n_pass = std::min(n_pass, 8);
-    int need = (I.P + I.K - 1 + kPass - 1) / kPass;
-    n_pass = std::max(1, std::min(n_pass, need));
-    I.tile = n_pass * kPass - (I.K - 1);
-    I.ext_alloc = n_pass * kPass + 2 * R;
-    I.first_tile = (int)ctx->tiles.size();
     I.line_base = (k == 0) ? 0 : ctx->inst[k - 1].dev.line_base + ctx->inst[k - 1].dev.L;
-    I.n_tiles = (I.P + I.tile - 1) / I.tile;
-    for (int t = 0; t < I.n_tiles; ++t) ctx->tiles.push_back(TileDesc{(int)k, t * I.tile});
   }
-  ctx->n_tiles = (int)ctx->tiles.size();
+  TileGeom geom[kMaxInst];
+  ctx->n_tiles = compute_geometry(ctx, 1, geom, nullptr);   // smallest tiles = most tiles: sizes the workspace
   ctx->n_lines_total = 0;
   for (auto& hi : ctx->inst) ctx->n_lines_total += hi.dev.L;
   std::vector<InstDev> flat;
   for (auto& hi : ctx->inst) flat.push_back(hi.dev);
   cudaFree(ctx->d_inst);
-  cudaFree(ctx->d_tiles);
   ctx->d_inst = nullptr;
-  ctx->d_tiles = nullptr;
   RBV_CUDA(upload(&ctx->d_inst, flat.data(), flat.size()));
-  RBV_CUDA(upload(&ctx->d_tiles, ctx->tiles.data(), ctx->tiles.size()));
   return RBV_OK;
 }
 
@@ -782,7 +833,6 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   LaunchParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.inst = ctx->d_inst;
-  prm.tiles = ctx->d_tiles;
   prm.theta = theta;
   prm.lb = ctx->d_lb;
   prm.ub = ctx->d_ub;
@@ -794,17 +844,17 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   prm.lc = (double*)((char*)workspace + lay.lc);
   prm.n_lines_total = ctx->n_lines_total;
   prm.ndim = ctx->ndim;
-  prm.n_tiles = ctx->n_tiles;
   prm.n_inst = (int)ctx->inst.size();
   prm.W = W;
   prm.precision = ctx->precision;
   cudaStream_t st = (cudaStream_t)stream;
 
-  // ONE launch covers every instrument: grid = (walkers, all tiles); R is context-wide.
+  // ONE launch covers every instrument: grid = (walkers, all tiles); R is context-wide; the tile size is
+  // chosen per launch from the batch size.
   size_t smem = 0;
-  for (auto& hi : ctx->inst) smem = std::max(smem, smem_bytes_for(hi.dev, ctx->ndim));
+  prm.n_tiles = choose_geometry(ctx, W, prm.geom, &smem);
   const bool r8 = ctx->inst[0].dev.R == 8;
-  dim3 grid((unsigned)W, (unsigned)ctx->n_tiles);
+  dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (ctx->n_tiles > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 tiles per walker");
   if (W > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 walkers per call (split the batch)");
   dim3 pgrid((unsigned)((ctx->n_lines_total + 127) / 128), (unsigned)W);
@@ -846,18 +896,17 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   LaunchParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.inst = ctx->d_inst;
-  prm.tiles = ctx->d_tiles;
   prm.theta = theta;
   prm.core_tab = ctx->d_core_tab;
   prm.out_flux = out_flux;
   prm.ndim = ndim;
-  prm.n_tiles = ctx->n_tiles;
   prm.n_inst = (int)ctx->inst.size();
   prm.W = W;
-  prm.tile_base = I.first_tile;
   prm.precision = ctx->precision;
-  size_t smem = smem_bytes_for(I, ndim);
-  dim3 grid((unsigned)W, (unsigned)I.n_tiles);
+  prm.n_tiles = compute_geometry(ctx, 1, prm.geom, nullptr);
+  prm.tile_base = prm.geom[inst].first_tile;
+  size_t smem = smem_bytes_for(I, prm.geom[inst], ndim);
+  dim3 grid((unsigned)W, (unsigned)prm.geom[inst].n_tiles);
   cudaStream_t st = (cudaStream_t)stream;
   if (I.R == 8) voigt_tile_kernel<3, 1><<<grid, kThreads, smem, st>>>(prm);
   else voigt_tile_kernel<2, 1><<<grid, kThreads, smem, st>>>(prm);
