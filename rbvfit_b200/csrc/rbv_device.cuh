@@ -192,6 +192,28 @@ __device__ __forceinline__ double tg_H(double x, double a_over_sqrtpi, double ep
   return (x2 < eps) ? Hcore : Htg;
 }
 
+// exp(x) for the flux: Cody-Waite reduction x = k ln2 + r, |r| <= 0.347, degree-13 Taylor polynomial
+// (truncation 4e-18), scaling by an exponent-field add.  Coefficients sit in constant memory so that every
+// DFMA takes its constant as a c[][] operand (CUDA's exp() spends 23 UMOVs per call on them).
+// Results below 2^-1020 flush to 0 (np.exp would return a denormal < 1e-307: irrelevant at |dflux| <= 1e-10).
+__constant__ double c_exp[14] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                                 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+
+__device__ __forceinline__ double exp_flux(double x) {
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);   // round(x log2 e) in the low word
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = c_exp[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = fma(p, r, c_exp[i]);
+  double y = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  if (!(x >= -707.0)) y = (x != x) ? x : 0.0;     // underflow (and NaN passes through)
+  if (x > 709.0) y = CUDART_INF;
+  return y;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

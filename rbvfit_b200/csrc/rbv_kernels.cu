@@ -124,7 +124,9 @@ constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGen
 
 // Classify every line once per warp chunk from the chunk's range of 1/lambda (lane l handles line l):
 // far lines go to the front of the warp's list, everything else to the back with its tier in the top bits.
-// Returns (n_far, n_other).  Conservative: uses the smallest |z|^2 any pixel of the chunk can reach.
+// Returns (n_far, n_other).  Conservative: uses the smallest |z|^2 any pixel of the chunk can reach; the
+// comparisons run on the high words of the doubles (integer pipe, thresholds have zero low words).
+// A NaN line lands in the far list and its NaN propagates through the arithmetic.
 __device__ __forceinline__ int2 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
                                                double umin, double umax, int lane) {
   int n_far = 0, n_oth = 0;
@@ -134,16 +136,18 @@ __device__ __forceinline__ int2 classify_lines(int lc_off, int L, unsigned short
     const bool valid = l < L;
     int tier = kTierCore;
     if (valid) {
-      const double* lc = smem + lc_off + l * LC_STRIDE;
-      const double A = lc[LC_A], B = lc[LC_B], a2 = lc[LC_A2];
+      const int off = lc_off + l * LC_STRIDE;
+      const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2];
       const double x1 = fma(A, umin, -B), x2 = fma(A, umax, -B);
-      const double m = (x1 * x2 <= 0.0) ? 0.0 : fmin(fabs(x1), fabs(x2));
-      const double dmin = fma(m, m, a2);
-      tier = (a2 > kABig * kABig) ? kTierGeneral
-             : (dmin >= kDFar)    ? kTierFar
-             : (dmin >= kDNear)   ? kTierMid
-             : (dmin >= kDCore)   ? kTierNear
-                                  : kTierCore;   // NaN lands here and propagates through the arithmetic
+      const int h1 = __double2hiint(fma(x1, x1, a2)), h2 = __double2hiint(fma(x2, x2, a2));
+      const int ha = __double2hiint(a2);
+      const bool crosses = ((__double2hiint(x1) ^ __double2hiint(x2)) < 0);   // line centre inside the chunk
+      const int hmin = crosses ? ha : min(h1, h2);
+      tier = (ha >= 0x3ff00000) ? kTierGeneral      // a >= 1
+             : (hmin >= kHiFar) ? kTierFar
+             : (hmin >= kHiNear) ? kTierMid
+             : (hmin >= kHiCore) ? kTierNear
+                                 : kTierCore;
     }
     const unsigned far_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFar);
     const unsigned oth_mask = __ballot_sync(0xffffffffu, valid && tier != kTierFar);
@@ -179,18 +183,18 @@ __device__ __forceinline__ void accum_asym_line(int off, const double (&u)[kPixP
 __device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __restrict__ list,
                                          const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
                                          const double* __restrict__ core_tab, int lane) {
-  // range of 1/lambda over the warp's chunk (no monotonicity assumed)
-  double umin = u[0], umax = u[0];
+  // range of 1/lambda over the warp's chunk (no monotonicity assumed): integer min/max of the high words
+  // (1/lambda > 0, so the bit patterns order like the values), widened to the enclosing doubles
+  int hlo = __double2hiint(u[0]), hhi = hlo;
 #pragma unroll
   for (int j = 1; j < kPixPerThread; ++j) {
-    umin = fmin(umin, u[j]);
-    umax = fmax(umax, u[j]);
+    const int hj = __double2hiint(u[j]);
+    hlo = min(hlo, hj);
+    hhi = max(hhi, hj);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-    umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-  }
+  hlo = __reduce_min_sync(0xffffffffu, hlo);
+  hhi = __reduce_max_sync(0xffffffffu, hhi);
+  const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
   const int2 n = classify_lines(lc_off, L, list, umin, umax, lane);
 
   // far lines: branch-free body, 8 FP64 instructions per (line, pixel)
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 #pragma unroll
       for (int j = 0; j < kPixPerThread; ++j) {
         int i = i0 + j * 32 + lane;
-        if (i < ext) s_flux[smem_pos(i, LOGR)] = exp(-tau[j]);   // voigt_model.py:217
+        if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_flux(-tau[j]);   // voigt_model.py:217
       }
     }
     // zero the slack the register-blocked window may touch (taps there are zero, values must be finite)
@@ -686,9 +690,7 @@ static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t*
 // instrument has a wide LSF) so that all instruments run in ONE launch.
 static int rebuild_tables(RbvContext* ctx) {
   if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "at most 16 instruments per context");
-  int R = 4;
-  for (auto& hi : ctx->inst)
-    if ((int)hi.taps.size() > 64) R = 8;
+  const int R = 8;   // outputs per thread in the LSF stage (64 FMAs per 8 flux + 8 tap loads)
   for (size_t k = 0; k < ctx->inst.size(); ++k) {
     HostInst& hi = ctx->inst[k];
     InstDev& I = hi.dev;
