@@ -93,7 +93,7 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lines, const RbvSpec
 int rbv_set_bounds(RbvContext* ctx, const double* lb, const double* ub, int ndim);
 
 /* Bytes of caller-owned device workspace needed by rbv_lnprob_batch for up to n_walkers rows.
- * The workspace must be ZERO-FILLED once before its first use (it holds self-resetting counters). */
+ * Its contents need no initialisation and do not have to survive between calls. */
 int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
 
 /* lnprob for a batch of walkers; vfit.lnprob, vfit_mcmc.py:348-353, vectorised over rows.

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
       bad |= (t < prm.lb[i]) || (t > prm.ub[i]);
     }
     prm.oob[w] = bad;
+    prm.tickets[w] = 0u;   // the workspace layout depends on W: never trust ticket state from an earlier call
   }
   if (g >= prm.n_lines_total) return;
   int k = 0;
@@ -459,7 +460,6 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         }
       }
       prm.lnprob[w] = total;
-      prm.tickets[w] = 0u;   // self-reset for the next launch
     }
   }
 }

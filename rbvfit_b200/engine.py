@@ -124,7 +124,7 @@ class Engine:
         nbytes = C.c_size_t(0)
         check(self.lib.rbv_workspace_bytes(self._h, cap, C.byref(nbytes)), "rbv_workspace_bytes")
         self._ws_bytes = int(nbytes.value)
-        self._ws = torch.zeros(max(self._ws_bytes, 8), dtype=torch.uint8, device=self.tdev)   # zero-filled once
+        self._ws = torch.empty(max(self._ws_bytes, 8), dtype=torch.uint8, device=self.tdev)
         self._theta_dev = torch.empty((cap, ndim), dtype=torch.float64, device=self.tdev)
         self._lnp_dev = torch.empty(cap, dtype=torch.float64, device=self.tdev)
         self._theta_pin = torch.empty((cap, ndim), dtype=torch.float64, pin_memory=True)

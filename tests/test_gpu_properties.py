@@ -1,0 +1,132 @@
+"""GPU: size-independent properties at BASELINE.json's full sizes (C5a: 100 000 px, L = 33; C3: two instruments;
+C4w: 321-tap LSF), where the CPU oracle would take minutes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(workload, nwalkers, voigt_method="wofz"):
+    from rbvfit_b200 import FitConfiguration, lsf, workloads as wl
+    from rbvfit_b200.likelihood import GpuLikelihood
+    from rbvfit_b200.model import GpuVoigtModel
+    w = wl.get_workload(workload)
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    models = {}
+    for name, inst in w["instruments"].items():
+        taps = lsf.cos_like_taps(321) if inst.get("lsf") == "cos_like" else None
+        models[name] = GpuVoigtModel(cfg, FWHM=inst["FWHM"], lsf_taps=taps, voigt_method=voigt_method)
+    compiled = {n: m.compile() for n, m in models.items()}
+    spectra = wl.make_spectra(w, lambda n, th, wave: compiled[n].model_flux(th, wave))
+    like = GpuLikelihood({n: dict(model=models[n], **spectra[n]) for n in models}, w["lb"], w["ub"])
+    return w, models, compiled, spectra, like, wl.make_ensemble(w, nwalkers)
+
+
+def _host_lnprob_from_flux(compiled, spectra, like, thetas, lb, ub):
+    """lnprob recomputed on the host with the reference's numpy formula (vfit_mcmc.py:309-311) from the GPU's
+    model flux -- ties the flux kernel, the chi^2 kernel and the finalisation together."""
+    out = np.zeros(len(thetas))
+    for n, c in compiled.items():
+        d = like.instrument_data[n]
+        m = c.model_flux(thetas, spectra[n]["wave"])
+        out += -0.5 * np.sum((d["flux"][None, :] - m) ** 2 * d["inv_sigma2"][None, :] - d["log_inv_sigma2"][None, :],
+                             axis=1)
+    bad = np.any((thetas < lb) | (thetas > ub), axis=1)
+    out[bad] = -np.inf
+    return out
+
+
+@pytest.mark.parametrize("workload,nw", [("C5a", 48), ("C3", 64), ("C4w", 32), ("C2", 80)])
+def test_lnprob_equals_host_formula_on_gpu_flux(workload, nw):
+    w, models, compiled, spectra, like, thetas = _problem(workload, nw)
+    got = like.lnprob(thetas)
+    ref = _host_lnprob_from_flux(compiled, spectra, like, thetas, w["lb"], w["ub"])
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    assert fin.sum() >= nw - 3
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-11
+
+
+def test_c5a_batching_permutation_and_tile_geometry_invariance():
+    w, models, compiled, spectra, like, thetas = _problem("C5a", 700)
+    full = like.lnprob(thetas)                       # 700 walkers -> big tiles (scale 4)
+    assert np.isneginf(full).sum() >= 1
+    # sub-batches of 5 walkers use the smallest tiles: different tile sizes, same answer
+    idx = np.arange(0, 700, 70)
+    small = np.concatenate([like.lnprob(thetas[i:i + 5]) for i in idx])
+    ref = np.concatenate([full[i:i + 5] for i in idx])
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isneginf(small), np.isneginf(ref))
+    assert np.max(np.abs(small[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-12
+    perm = np.random.default_rng(1).permutation(700)
+    assert np.array_equal(like.lnprob(thetas[perm]), full[perm], equal_nan=True)     # bit-exact
+    assert np.array_equal(like.lnprob(thetas), full, equal_nan=True)                 # run-to-run
+
+
+def test_additivity_over_pixel_ranges_without_lsf():
+    """Without an LSF the likelihood is a plain sum over pixels: lnL(spectrum) = lnL(left) + lnL(right)."""
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.likelihood import GpuLikelihood
+    from rbvfit_b200.model import GpuVoigtModel
+    w = wl.get_workload("C2")
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    model = GpuVoigtModel(cfg, FWHM=None)
+    wave = w["instruments"]["SPEC"]["wave"]
+    rng = np.random.default_rng(3)
+    flux = 1.0 + 0.05 * rng.standard_normal(wave.size)
+    err = np.full(wave.size, 0.05)
+    thetas = wl.make_ensemble(w, 16, frac_out_of_bounds=0.0)
+    cut = 7777
+
+    def like_for(sl):
+        return GpuLikelihood({"S": dict(model=model, wave=wave[sl], flux=flux[sl], error=err[sl])}, w["lb"], w["ub"])
+
+    whole = like_for(slice(None)).lnprob(thetas)
+    parts = like_for(slice(0, cut)).lnprob(thetas) + like_for(slice(cut, None)).lnprob(thetas)
+    assert np.max(np.abs(whole - parts) / np.abs(whole)) <= 1e-12
+
+
+def test_flux_bounds_and_monotonicity_in_column_density():
+    """0 <= flux <= 1 everywhere and more column density never increases the (unconvolved) flux."""
+    w, models, compiled, spectra, like, thetas = _problem("C4w", 4)
+    m = models["SPEC"]
+    wave = spectra["SPEC"]["wave"]
+    th = w["theta_true"].copy()
+    f0 = m.evaluate(th, wave, return_unconvolved=True)
+    th2 = th.copy()
+    th2[:3] += 0.3
+    f1 = m.evaluate(th2, wave, return_unconvolved=True)
+    assert f0.min() >= 0.0 and f0.max() <= 1.0
+    assert np.all(f1 <= f0 + 1e-15)
+    assert f0.min() == 0.0          # the DLA core is black: exp(-tau) underflows cleanly
+
+
+def test_error_zero_gives_nan_and_empty_batch():
+    w, models, compiled, spectra, like, thetas = _problem("C1", 8)
+    assert like.lnprob(np.zeros((0, like.ndim))).shape == (0,)
+    from rbvfit_b200.likelihood import GpuLikelihood
+    s = spectra["COS"]
+    err = s["error"].copy()
+    err[100] = 0.0                  # examples/example_voigt_fitter.py:42-44 masks pixels this way
+    bad = GpuLikelihood({"COS": dict(model=models["COS"], wave=s["wave"], flux=s["flux"], error=err)},
+                        w["lb"], w["ub"])
+    with np.errstate(all="ignore"):
+        out = bad.lnprob(thetas)
+    inb = ~np.any((thetas < w["lb"]) | (thetas > w["ub"]), axis=1)
+    assert np.all(np.isnan(out[inb]))            # inf - inf, as numpy would give
+
+
+def test_components_are_unconvolved_per_line_fluxes():
+    w, models, compiled, spectra, like, thetas = _problem("C1", 4)
+    m = models["COS"]
+    wave = spectra["COS"]["wave"]
+    res = m.evaluate(w["theta_true"], wave, return_components=True)
+    assert set(res) == {"flux", "components", "component_info"} and len(res["components"]) == 4
+    prod = np.prod(np.array(res["components"]), axis=0)          # exp(-sum tau_i) = prod exp(-tau_i)
+    unc = m.evaluate(w["theta_true"], wave, return_unconvolved=True)
+    assert np.max(np.abs(prod - unc)) <= 1e-13
+    assert res["component_info"][0]["lambda0"] == float(m.atomic_lambda0[0])

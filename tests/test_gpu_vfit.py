@@ -1,0 +1,108 @@
+"""GPU: the ``vfit`` mirror end to end -- batched optimiser, walker initialisation, stretch-move sampling --
+and its sampler-object contract; chain parity against the same sampler driven by the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _c1_fitter(nwalkers=32, nsteps=60, seed=5, sampler="emcee"):
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.model import GpuVoigtModel
+    from rbvfit_b200.vfit_mcmc import vfit
+    w = wl.get_workload("C1")
+    cfg, ocfg = FitConfiguration(), vo.OracleConfig()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+        ocfg.add_system(z, ion, trans, comps)
+    omodel = vo.lower(ocfg, FWHM="6.5")
+    spectra = wl.make_spectra(w, lambda n, th, wave: vo.model_flux(omodel, th, wave))
+    s = spectra["COS"]
+    model = GpuVoigtModel(cfg, FWHM="6.5")
+    theta0 = np.clip(w["theta_true"] + np.array([0.05, -0.05, 2, -2, 3, -3.0]), w["lb"], w["ub"])
+    fitter = vfit({"COS": dict(model=model, wave=s["wave"], flux=s["flux"], error=s["error"])}, theta0,
+                  w["lb"], w["ub"], no_of_Chain=nwalkers, no_of_steps=nsteps, seed=seed, sampler=sampler)
+    comp = vo.compile_instruments({"COS": dict(model=omodel, **s)})
+    return w, fitter, comp, theta0
+
+
+def test_vfit_validation_errors():
+    from rbvfit_b200.vfit_mcmc import vfit
+    with pytest.raises(TypeError):
+        vfit([], [0.0], [0.0], [1.0])
+    with pytest.raises(ValueError):
+        vfit({}, [0.0], [0.0], [1.0])
+    with pytest.raises(ValueError):
+        vfit({"a": {"model": None, "wave": [1], "flux": [1]}}, [0.0], [0.0], [1.0])
+    w, fitter, comp, theta0 = _c1_fitter()
+    from rbvfit_b200.vfit_mcmc import vfit as V
+    with pytest.raises(ValueError):
+        V({"COS": dict(model=lambda t, x: x, wave=[1.0], flux=[1.0], error=[1.0])}, w["ub"] + 1, w["lb"], w["ub"])
+    with pytest.raises(TypeError):       # arbitrary callables cannot run on the device; no CPU fallback
+        V({"COS": dict(model=lambda t, x: x, wave=[1.0], flux=[1.0], error=[1.0])}, theta0, w["lb"], w["ub"])
+
+
+def test_lnprob_lnlike_lnprior_match_oracle():
+    from oracle import voigt_oracle as vo
+    w, fitter, comp, theta0 = _c1_fitter()
+    ref = vo.lnprob(comp, theta0, w["lb"], w["ub"])
+    assert abs(fitter.lnprob(theta0) - ref) / abs(ref) <= 1e-9
+    out = theta0.copy()
+    out[0] = w["ub"][0] + 0.5
+    assert fitter.lnprior(out) == -np.inf and fitter.lnprob(out) == -np.inf
+    ll = fitter.lnlike(out)                      # lnlike ignores the prior, like the reference's
+    assert abs(ll - vo.lnlike(comp, out)) / abs(ll) <= 1e-9
+    assert fitter.lnprob(theta0) == fitter.lnprob(theta0[None, :])[0]
+
+
+def test_optimize_and_walker_init():
+    w, fitter, comp, theta0 = _c1_fitter(nwalkers=40)
+    before = fitter.lnprob(theta0)
+    popt = fitter.optimize_guess(theta0)
+    after = fitter.lnprob(popt)
+    assert after > before + 1.0
+    assert np.all(popt >= w["lb"]) and np.all(popt <= w["ub"])
+    # the optimum is at least as good as the truth the data were drawn from (up to the noise realisation);
+    # the two blended components make (N1, N2) nearly degenerate, so compare likelihoods, not parameters
+    assert after >= fitter.lnprob(w["theta_true"]) - 5.0
+    assert np.all(np.abs(popt - w["theta_true"]) < np.array([0.3, 0.3, 10, 10, 8, 8]))
+    g = fitter._initialize_walkers(popt)
+    assert g.shape == (40, 6) and np.all(g > w["lb"]) and np.all(g < w["ub"])
+    assert np.all(np.isfinite(fitter.lnprob(g)))
+
+
+def test_runmcmc_contract_and_posterior():
+    w, fitter, comp, theta0 = _c1_fitter(nwalkers=32, nsteps=400, seed=11)
+    fitter.runmcmc(optimize=True, verbose=False, use_pool=True, progress=False)
+    s = fitter.sampler
+    assert fitter.mcmc_flag and s.get_chain().shape == (400, 32, 6)
+    assert s.get_chain(discard=100, flat=True).shape == (300 * 32, 6)
+    assert fitter.samples.shape == (300 * 32, 6) and fitter.best_theta.shape == (6,)
+    af = s.acceptance_fraction
+    assert af.shape == (32,) and 0.15 < af.mean() < 0.8
+    tau = s.get_autocorr_time(quiet=True)
+    assert tau.shape == (6,) and np.all(np.isfinite(tau))
+    # the posterior brackets the truth the spectrum was generated from
+    lo, hi = np.percentile(fitter.samples, [0.5, 99.5], axis=0)
+    assert np.all(lo < w["theta_true"]) and np.all(w["theta_true"] < hi)
+    assert np.all(fitter.low_theta <= fitter.best_theta) and np.all(fitter.best_theta <= fitter.high_theta)
+    assert fitter.get_samples(burn_in=0.5).shape == (200 * 32, 6)
+    assert s.n_logp_rows == 32 + 400 * 32        # one batched call per half-step, one row per proposal
+
+
+def test_chain_matches_cpu_oracle_chain():
+    """Same sampler, same seed: driven by the GPU lnprob and by the CPU oracle the chains coincide (an
+    accept/reject flip needs |ln u - ln q| < 1e-9, i.e. essentially never in 1280 decisions)."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200.sampler import EnsembleSampler
+    w, fitter, comp, theta0 = _c1_fitter()
+    rng = np.random.default_rng(2)
+    p0 = np.clip(w["theta_true"] + 1e-3 * rng.standard_normal((16, 6)), w["lb"], w["ub"])
+    gpu = EnsembleSampler(16, 6, fitter.lnprob, seed=9)
+    cpu = EnsembleSampler(16, 6, lambda th: vo.lnprob_batch(comp, th, w["lb"], w["ub"]), seed=9)
+    cg, lg = gpu.run_mcmc(p0, 80)
+    cc, lc = cpu.run_mcmc(p0, 80)
+    assert np.allclose(cg, cc, rtol=0, atol=1e-9)
+    assert np.max(np.abs(lg - lc) / np.abs(lc)) <= 1e-9
+    assert np.array_equal(gpu.acceptance_fraction, cpu.acceptance_fraction)
