@@ -38,8 +38,9 @@ constexpr int kPass = kThreads * kPixPerThread;  // pixels per phase-1 pass
 constexpr int kWarpPix = 32 * kPixPerThread;     // pixels covered by one warp per pass
 
 // line-constant record (doubles)
-constexpr int LC_A = 0, LC_B = 1, LC_A2 = 2, LC_a = 3, LC_Q = 4 /* Q1..Q13 */, LC_COEF = 17, LC_COEF_EA2 = 18,
-              LC_AUX = 19, LC_STRIDE = 20;
+constexpr int LC_A = 0, LC_B = 1, LC_A2 = 2, LC_a = 3, LC_Q = 4 /* Q1..Q13 */, LC_COEF = 17,
+              LC_F32B = 18 /* float2: Q3, unused */, LC_AUX = 19 /* kappa */,
+              LC_F32A = 20 /* float4: A, a^2, Q1, Q2 in FP32 for the gated far-wing path */, LC_STRIDE = 22;
 
 constexpr double kAFast = 0.05;               // table path valid for a <= kAFast
 constexpr double kABig = 1.0;                 // rho-polynomial series valid for a <= kABig; beyond: complex series

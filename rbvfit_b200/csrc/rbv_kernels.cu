@@ -102,8 +102,17 @@ __device__ __forceinline__ void prep_line_wofz(const InstDev& I, int l, const do
   lc[LC_A2] = a2;
   lc[LC_a] = a;
   lc[LC_COEF] = coef;
-  lc[LC_COEF_EA2] = 0.0;
+  lc[LC_F32B] = 0.0;
+  lc[LC_F32A] = lc[LC_F32A + 1] = 0.0;
   lc[LC_AUX] = coef * a * kInvSqrtPi;  // kappa
+}
+
+// FP32 copies of the far-tier constants (A, a^2, Q1..Q3) for the gated FP32 path
+__device__ __forceinline__ void fill_fp32_constants(double* __restrict__ lc) {
+  float4 fa = make_float4((float)lc[LC_A], (float)lc[LC_A2], (float)lc[LC_Q], (float)lc[LC_Q + 1]);
+  float2 fb = make_float2((float)lc[LC_Q + 2], 0.f);
+  *reinterpret_cast<float4*>(lc + LC_F32A) = fa;
+  *reinterpret_cast<float2*>(lc + LC_F32B) = fb;
 }
 
 // per-line constants for the Tepper-Garcia method (voigt_approx.py:69-86)
@@ -120,16 +129,19 @@ __device__ __forceinline__ void prep_line_fast(const InstDev& I, int l, const do
 extern __shared__ double smem[];   // every hot-loop access indexes this array directly (shared-space addressing)
 
 // Tier codes of a (warp chunk, line) pair
-constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGeneral = 4;
+constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGeneral = 4, kTierFar32 = 5;
 
 // Classify every line once per warp chunk from the chunk's range of 1/lambda (lane l handles line l):
 // far lines go to the front of the warp's list, everything else to the back with its tier in the top bits.
 // Returns (n_far, n_other).  Conservative: uses the smallest |z|^2 any pixel of the chunk can reach; the
 // comparisons run on the high words of the doubles (integer pipe, thresholds have zero low words).
 // A NaN line lands in the far list and its NaN propagates through the arithmetic.
-__device__ __forceinline__ int2 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
+// With gate32 > 0, far lines whose largest possible contribution over the chunk, kappa / min|z|^2, is at most
+// gate32 go to a second list (list32) and are evaluated on the FP32 pipe; returns their count in .z.
+__device__ __forceinline__ int3 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
+                                               unsigned short* __restrict__ list32, double gate32,
                                                double umin, double umax, int lane) {
-  int n_far = 0, n_oth = 0;
+  int n_far = 0, n_oth = 0, n_32 = 0;
   const unsigned lt = (1u << lane) - 1u;
   for (int l0 = 0; l0 < L; l0 += 32) {
     const int l = l0 + lane;
@@ -148,18 +160,60 @@ __device__ __forceinline__ int2 classify_lines(int lc_off, int L, unsigned short
              : (hmin >= kHiNear) ? kTierMid
              : (hmin >= kHiCore) ? kTierNear
                                  : kTierCore;
+      if (gate32 > 0.0 && tier == kTierFar) {
+        // kappa / dmin with dmin rounded DOWN to its high word: an upper bound of the line's contribution
+        const double tmax = fabs(smem[off + LC_AUX]) / __hiloint2double(hmin, 0);
+        if (tmax <= gate32) tier = kTierFar32;     // NaN fails the comparison and stays on the FP64 path
+      }
     }
     const unsigned far_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFar);
-    const unsigned oth_mask = __ballot_sync(0xffffffffu, valid && tier != kTierFar);
+    const unsigned f32_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFar32);
+    const unsigned oth_mask = __ballot_sync(0xffffffffu, valid && tier != kTierFar && tier != kTierFar32);
     if (valid) {
       if (tier == kTierFar) list[n_far + __popc(far_mask & lt)] = (unsigned short)l;
+      else if (tier == kTierFar32) list32[n_32 + __popc(f32_mask & lt)] = (unsigned short)l;
       else list[L - 1 - (n_oth + __popc(oth_mask & lt))] = (unsigned short)(l | (tier << 12));
     }
     n_far += __popc(far_mask);
+    n_32 += __popc(f32_mask);
     n_oth += __popc(oth_mask);
   }
   __syncwarp();
-  return make_int2(n_far, n_oth);
+  return make_int3(n_far, n_oth, n_32);
+}
+
+// FP32 far-wing accumulation for the gated lines.  x = X0 + A du with X0 = A u_ref - B formed in FP64 once per
+// (line, chunk) and du = u - u_ref exact in FP64, both then rounded to FP32 (no cancellation left in FP32);
+// two pixels share one MUFU.RCP through 1/(d1 d2).  Error model: relative 3e-7 per
+// contribution + 6e-8 per FP32 accumulation step; the gate bounds the gated sum by 4e-6, i.e. |dtau| <= 1e-11.
+__device__ __forceinline__ void accum_far32(int lc_off, const unsigned short* __restrict__ list32, int n32,
+                                            const double (&u)[kPixPerThread], double (&tau)[kPixPerThread]) {
+  const double u_ref = __shfl_sync(0xffffffffu, u[0], 0);
+  float du[kPixPerThread], acc[kPixPerThread];
+#pragma unroll
+  for (int j = 0; j < kPixPerThread; ++j) {
+    du[j] = (float)(u[j] - u_ref);
+    acc[j] = 0.f;
+  }
+#pragma unroll 2
+  for (int k = 0; k < n32; ++k) {
+    const int off = lc_off + (int)list32[k] * LC_STRIDE;
+    const float X0 = (float)fma(smem[off + LC_A], u_ref, -smem[off + LC_B]);
+    const float4 c = *reinterpret_cast<const float4*>(smem + off + LC_F32A);   // A, a^2, Q1, Q2
+    const float q3 = reinterpret_cast<const float2*>(smem + off + LC_F32B)->x;
+#pragma unroll
+    for (int j = 0; j < kPixPerThread; j += 2) {
+      const float x0 = fmaf(c.x, du[j], X0), x1 = fmaf(c.x, du[j + 1], X0);
+      const float d0 = fmaf(x0, x0, c.y), d1 = fmaf(x1, x1, c.y);
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+      const float r0 = r * d1, r1 = r * d0;
+      acc[j] = fmaf(fmaf(fmaf(q3, r0, c.w), r0, c.z), r0, acc[j]);
+      acc[j + 1] = fmaf(fmaf(fmaf(q3, r1, c.w), r1, c.z), r1, acc[j + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPixPerThread; ++j) tau[j] += (double)acc[j];
 }
 
 template <int NQ>
@@ -181,6 +235,7 @@ __device__ __forceinline__ void accum_asym_line(int off, const double (&u)[kPixP
 }
 
 __device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __restrict__ list,
+                                         unsigned short* __restrict__ list32, double gate32,
                                          const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
                                          const double* __restrict__ core_tab, int lane) {
   // range of 1/lambda over the warp's chunk (no monotonicity assumed): integer min/max of the high words
@@ -195,7 +250,8 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __re
   hlo = __reduce_min_sync(0xffffffffu, hlo);
   hhi = __reduce_max_sync(0xffffffffu, hhi);
   const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
-  const int2 n = classify_lines(lc_off, L, list, umin, umax, lane);
+  const int3 n = classify_lines(lc_off, L, list, list32, gate32, umin, umax, lane);
+  if (n.z > 0) accum_far32(lc_off, list32, n.z, u, tau);
 
   // far lines: branch-free body, 8 FP64 instructions per (line, pixel)
 #pragma unroll 2
@@ -269,13 +325,14 @@ __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
   while (k + 1 < prm.n_inst && g >= prm.inst[k + 1].line_base) ++k;
   const InstDev& I = prm.inst[k];
   const int l = g - I.line_base;
-  double lc[LC_STRIDE];
+  __align__(16) double lc[LC_STRIDE];
   if (I.method == RBV_VOIGT_FAST) {
     prep_line_fast(I, l, th, lc);
   } else {
     prep_line_wofz(I, l, th, lc);
 #pragma unroll
     for (int p = 0; p < kNQNear; ++p) lc[LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
+    fill_fp32_constants(lc);
   }
   double2* dst = reinterpret_cast<double2*>(prm.lc + ((size_t)w * prm.n_lines_total + g) * LC_STRIDE);
 #pragma unroll
@@ -309,7 +366,11 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   double* s_lc = smem + lc_off;
   double* s_taps = smem + taps_off;
   double* s_flux = smem + flux_off;
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + list_off) + warp * ((I.L + 3) & ~3);
+  const int list_stride = (I.L + 3) & ~3;
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + list_off) + warp * 2 * list_stride;
+  unsigned short* s_list32 = s_list + list_stride;
+  // FP32 gate: the gated contributions of one pixel sum to <= 4e-6 (=> |dtau| <= 1e-11)
+  const double gate32 = (prm.precision == RBV_PRECISION_FP32_GATED) ? 4e-6 / (double)I.L : 0.0;
 
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
   int oob = 0;
@@ -341,6 +402,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         s_lc[l * LC_STRIDE + LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
       }
       __syncthreads();
+      for (int l = tid; l < I.L; l += kThreads) fill_fp32_constants(s_lc + l * LC_STRIDE);
+      __syncthreads();
     }
   }
 
@@ -369,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         tau[j] = 0.0;
       }
       if (fast) tau_fast(lc_off, I.L, u, tau);
-      else tau_wofz(lc_off, I.L, s_list, u, tau, prm.core_tab, lane);
+      else tau_wofz(lc_off, I.L, s_list, s_list32, gate32, u, tau, prm.core_tab, lane);
 #pragma unroll
       for (int j = 0; j < kPixPerThread; ++j) {
         int i = i0 + j * 32 + lane;
@@ -585,7 +648,7 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 static size_t smem_bytes_for(const InstDev& I, const TileGeom& G, int ndim) {
   int logR = (I.R == 8) ? 3 : 2;
   size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (G.ext_alloc + (G.ext_alloc >> logR)) + 4;
-  size_t lists = (size_t)(kThreads / 32) * ((I.L + 3) & ~3) * sizeof(unsigned short);
+  size_t lists = (size_t)(kThreads / 32) * 2 * ((I.L + 3) & ~3) * sizeof(unsigned short);
   return n * sizeof(double) + ((lists + 15) & ~(size_t)15);
 }
 

@@ -66,6 +66,8 @@ class GpuLikelihood:
         self.engine.set_bounds(self.lb, self.ub)
         self.ndim = self.lb.size
         self.total_pixels = int(sum(self.pixels))
+        self.precision = "fp64"
+        self.last_precision_check = None
 
     # ------------------------------------------------------------------ reference-shaped API
     def lnprob(self, theta):
@@ -89,6 +91,33 @@ class GpuLikelihood:
     def lnprob_device(self, theta_t, out_t=None):
         """Device-resident variant (torch tensors in / out, asynchronous)."""
         return self.engine.lnprob_device(theta_t, out_t)
+
+    def set_precision(self, precision: str = "fp64", check_thetas=None, rtol: float = 1e-9) -> bool:
+        """Select the far-wing arithmetic.  ``"fp32-gated"`` moves far-wing lines whose contribution is provably
+        tiny (a-priori bound: their sum stays <= 4e-6 per pixel, i.e. |dtau| <= 1e-11) to the FP32 pipe.
+        With ``check_thetas`` the gate is also verified a posteriori: the batch is evaluated in both modes and
+        the FP32 variant is kept only if every finite lnprob agrees to ``rtol``; otherwise the likelihood
+        falls back to FP64 (never to the CPU).  Returns True when the requested precision is active."""
+        if precision not in ("fp64", "fp32-gated"):
+            raise ValueError("precision must be 'fp64' or 'fp32-gated'")
+        self.engine.set_precision("fp64")
+        self.precision = "fp64"
+        if precision == "fp64":
+            return True
+        ref = None if check_thetas is None else self.lnprob(np.atleast_2d(check_thetas))
+        self.engine.set_precision("fp32-gated")
+        self.precision = "fp32-gated"
+        if ref is not None:
+            got = self.lnprob(np.atleast_2d(check_thetas))
+            fin = np.isfinite(ref)
+            same_pattern = np.array_equal(np.isfinite(got), fin)
+            err = np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) if fin.any() else 0.0
+            self.last_precision_check = float(err)
+            if not same_pattern or not (err <= rtol):
+                self.engine.set_precision("fp64")
+                self.precision = "fp64"
+                return False
+        return True
 
     def close(self):
         self.engine.close()

@@ -82,3 +82,27 @@ def test_lnprob_vs_golden(case):
     perm = np.random.default_rng(0).permutation(len(g.thetas))
     assert np.array_equal(like.lnprob(g.thetas[perm]), got[perm], equal_nan=True)
     like.close()
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c != "C1_fast"])
+def test_fp32_gated_variant_within_tolerance(case):
+    """The FP32-gated far-wing variant must meet the SAME tolerances as the FP64 kernel (gate: a-priori bound
+    |dtau| <= 1e-11, plus the a-posteriori check against the FP64 kernel)."""
+    from rbvfit_b200.likelihood import GpuLikelihood
+    g = Golden(case)
+    models = _gpu_models(g)
+    inst = {n: dict(model=models[n], wave=g.inst(n, "wave"), flux=g.inst(n, "flux"), error=g.inst(n, "error"))
+            for n in g.instruments}
+    like = GpuLikelihood(inst, g.lb, g.ub)
+    ref64 = like.lnprob(g.thetas)
+    assert like.set_precision("fp32-gated", check_thetas=g.thetas) is True
+    assert like.last_precision_check <= LNPROB_RTOL
+    got = like.lnprob(g.thetas)
+    ref = g.ref_lnprob
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.array_equal(np.isnan(got), np.isnan(ref))
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= LNPROB_RTOL
+    assert np.max(np.abs(got[fin] - ref64[fin]) / np.abs(ref64[fin])) <= 1e-10
+    assert like.set_precision("fp64") and like.precision == "fp64"
+    assert np.array_equal(like.lnprob(g.thetas), ref64, equal_nan=True)
+    like.close()

@@ -13,6 +13,7 @@ def main():
     ap.add_argument("--workload", default="C5a")
     ap.add_argument("--walkers", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--precision", default="fp64")
     args = ap.parse_args()
     import torch
     import bench
@@ -20,6 +21,7 @@ def main():
     w, models, like, thetas, spectra = bench.build_problem(args.workload, 0)
     if args.walkers and args.walkers != len(thetas):
         thetas = wl.make_ensemble(w, args.walkers)
+    like.set_precision(args.precision)
     th = torch.as_tensor(thetas, device="cuda:0")
     evs = []
     for _ in range(args.steps):
@@ -31,7 +33,7 @@ def main():
     torch.cuda.synchronize()
     ms = [a.elapsed_time(b) for a, b in evs]
     npx = like.total_pixels * len(thetas)
-    print(f"{args.workload} W={len(thetas)} px={like.total_pixels} ms={['%.3f' % m for m in ms]} "
+    print(f"[{args.precision}] {args.workload} W={len(thetas)} px={like.total_pixels} ms={['%.3f' % m for m in ms]} "
           f"-> {npx / (min(ms) * 1e-3):.4e} walker*px/s; finite={int(torch.isfinite(out).sum())}")
 
 
