@@ -298,7 +298,7 @@ def run_gpu(args, rank, world, local):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches),       # prep_kernel + voigt_tile_kernel per step
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": prof.get("dram_bytes_per_launch"),
                      "peak_source": "DFMA dependent-chain probe measured in this run (rbv_measure_fp64_peak); "
@@ -308,11 +308,93 @@ def run_gpu(args, rank, world, local):
                      "hbm_sanity": {"algorithmic_gbs": hbm_alg_bytes / (k_ms * 1e-3) / 1e9,
                                     "peak_gbs": peaks.get("hbm_gbs"), "peaks": peaks_kind}},
     }
+    if world == 1 and not args.no_extras:
+        line["fp32_gated"] = fp32_gated_leg(like, theta_dev, thetas, W, total_px, args.steps, flush)
+        line["mcmc"] = mcmc_leg(local, with_cpu=not args.no_cpu)
     if not args.no_cpu and world >= 1:
         r = cpu_arm(args.workload, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
     print(json.dumps(line))
+
+
+def fp32_gated_leg(like, theta_dev, thetas, W, total_px, steps, flush):
+    """The FP32-gated far-wing variant (north_star): kept only if it passes the tolerance check against the
+    FP64 kernel on a walker sample; timed exactly like `value`."""
+    import torch
+    ok = like.set_precision("fp32-gated", check_thetas=thetas[:256])
+    out = {"accepted": bool(ok), "max_rel_dev_vs_fp64": like.last_precision_check, "tolerance": 1e-9,
+           "gate": "per pixel the FP32-evaluated far-wing contributions sum to <= 4e-6 (|dtau| <= 1e-11)"}
+    if ok:
+        for _ in range(3):
+            like.lnprob_device(theta_dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for k in range(steps):
+            flush.zero_()
+            ev[k][0].record()
+            like.lnprob_device(theta_dev)
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        out.update(value=W * total_px / (ms * 1e-3), unit=UNIT, ms_per_step=ms)
+    like.set_precision("fp64")
+    return out
+
+
+def mcmc_leg(device, with_cpu=True, nsteps=300, cpu_steps=12):
+    """Second half of the metric: MCMC steps/s (one step = every walker updated once) on config C1
+    (MgII doublet, 2 components, 2048 px, 50 walkers, stretch move) -- GPU-batched sampler through the public
+    ``vfit`` API vs the same sampler driven by the CPU oracle (serial and fork pool)."""
+    import contextlib
+    import io
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.model import GpuVoigtModel
+    from rbvfit_b200.sampler import EnsembleSampler
+    from rbvfit_b200.vfit_mcmc import vfit
+    w = wl.get_workload("C1")
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    model = GpuVoigtModel(cfg, FWHM="6.5", device=device)
+    comp = model.compile()
+    spectra = wl.make_spectra(w, lambda n, th, wave: comp.model_flux(th, wave))
+    s = spectra["COS"]
+    fitter = vfit({"COS": dict(model=model, **s)}, w["theta_true"], w["lb"], w["ub"], no_of_Chain=50,
+                  no_of_steps=nsteps, seed=1, device=device)
+    p0 = fitter._initialize_walkers(w["theta_true"])
+    smp = EnsembleSampler(50, 6, fitter.lnprob, seed=2)
+    smp.run_mcmc(p0, 20)
+    t0 = time.perf_counter()
+    smp.run_mcmc(None, nsteps)
+    gpu_sps = nsteps / (time.perf_counter() - t0)
+    out = {"workload": "C1 (50 walkers x 2048 px, L=4, stretch move)", "steps_per_sec": gpu_sps,
+           "walker_pixel_per_sec": gpu_sps * 50 * 2048, "acceptance": float(smp.acceptance_fraction.mean())}
+    if with_cpu:
+        from oracle import voigt_oracle as vo
+        ocfg = vo.OracleConfig()
+        for (z, ion, trans, comps) in w["systems"]:
+            ocfg.add_system(z, ion, trans, comps)
+        om = vo.lower(ocfg, FWHM="6.5")
+        ocomp = vo.compile_instruments({"COS": dict(model=om, **s)})
+        cpu = EnsembleSampler(50, 6, lambda th: vo.lnprob_batch(ocomp, th, w["lb"], w["ub"]), seed=2)
+        cpu.run_mcmc(p0, 2)
+        t0 = time.perf_counter()
+        cpu.run_mcmc(None, cpu_steps)
+        out["cpu_serial_steps_per_sec"] = cpu_steps / (time.perf_counter() - t0)
+        cores = len(os.sched_getaffinity(0))
+        pool = vo.make_pool(ocomp, w["lb"], w["ub"], processes=cores)
+        try:
+            cpup = EnsembleSampler(50, 6, lambda th: vo.lnprob_pool(ocomp, th, w["lb"], w["ub"], pool=pool), seed=2)
+            cpup.run_mcmc(p0, 2)
+            t0 = time.perf_counter()
+            cpup.run_mcmc(None, cpu_steps)
+            out["cpu_pool_steps_per_sec"] = cpu_steps / (time.perf_counter() - t0)
+            out["cpu_cores"] = cores
+        finally:
+            pool.close()
+            pool.join()
+    return out
 
 
 def main():
@@ -323,6 +405,7 @@ def main():
     ap.add_argument("--workload", default="C5a")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-gated and MCMC legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

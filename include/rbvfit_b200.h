@@ -104,6 +104,15 @@ int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
 int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int n_walkers, double* lnprob,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Survey mode: the context holds S independent sightlines (instruments with identical n_pixels, n_taps,
+ * n_lines, n_components; their line tables -- e.g. redshifts -- and spectra differ) and theta holds
+ * walkers_per_sightline consecutive rows per sightline: row w is evaluated against sightline w / walkers_per_sightline
+ * only.  lnprob[w] = that sightline's lnprob (same bounds for all).  n_walkers = S * walkers_per_sightline.
+ * One launch for the whole batch; no limit of 16 instruments.  Workspace: rbv_workspace_bytes_sightlines(). */
+int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t* bytes);
+int rbv_lnprob_batch_sightlines(RbvContext* ctx, const double* theta, int n_walkers, int walkers_per_sightline,
+                                double* lnprob, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same, from HOST buffers (pinned for full speed): copies theta in, runs, copies lnprob out and
  * synchronises the stream.  theta_dev / lnprob_dev are caller-owned device staging buffers of at least
  * n_walkers*ndim / n_walkers doubles.  This is the call the Python lnprob(theta) makes. */

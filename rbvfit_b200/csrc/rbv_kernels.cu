@@ -72,6 +72,7 @@ struct LaunchParams {
   int ndim, n_tiles, n_inst, W, n_lines_total;
   int tile_base;         // flux mode: first tile of the instrument
   int precision;
+  int wps;               // sightline mode: walkers per sightline (walker w belongs to instrument w / wps); 0 = off
 };
 
 __device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
@@ -308,8 +309,8 @@ __device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[kP
 // FP64 instructions -- as long as a tile's whole phase 1 when done by 33 threads of every CTA).
 // Thread 0 of each walker also evaluates the uniform prior (vfit.lnprior, vfit_mcmc.py:291-295).
 __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
-  const int w = blockIdx.y;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = blockIdx.x;
+  const int g = blockIdx.y * blockDim.x + threadIdx.x;
   const double* th = prm.theta + (size_t)w * prm.ndim;
   if (g == 0) {
     int bad = 0;
@@ -321,10 +322,14 @@ __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
     prm.tickets[w] = 0u;   // the workspace layout depends on W: never trust ticket state from an earlier call
   }
   if (g >= prm.n_lines_total) return;
-  int k = 0;
-  while (k + 1 < prm.n_inst && g >= prm.inst[k + 1].line_base) ++k;
+  int k = 0, l = g;
+  if (prm.wps > 0) {
+    k = w / prm.wps;                       // sightline mode: the walker's own instrument, all L lines
+  } else {
+    while (k + 1 < prm.n_inst && g >= prm.inst[k + 1].line_base) ++k;
+    l = g - prm.inst[k].line_base;
+  }
   const InstDev& I = prm.inst[k];
-  const int l = g - I.line_base;
   __align__(16) double lc[LC_STRIDE];
   if (I.method == RBV_VOIGT_FAST) {
     prep_line_fast(I, l, th, lc);
@@ -352,8 +357,12 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   const int w = blockIdx.x;
   const int tile_id = (MODE == 0) ? blockIdx.y : prm.tile_base + blockIdx.y;
   int inst_id = 0;
-  while (inst_id + 1 < prm.n_inst && tile_id >= prm.geom[inst_id + 1].first_tile) ++inst_id;
-  const TileGeom G = prm.geom[inst_id];
+  if (prm.wps > 0) {
+    inst_id = w / prm.wps;                 // sightline mode: every instrument shares geom[0]
+  } else {
+    while (inst_id + 1 < prm.n_inst && tile_id >= prm.geom[inst_id + 1].first_tile) ++inst_id;
+  }
+  const TileGeom G = prm.geom[prm.wps > 0 ? 0 : inst_id];
   const InstDev I = prm.inst[inst_id];
   const int ndim = prm.ndim;
   if (tid == 0) s_next = 0;
@@ -380,7 +389,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     oob = prm.oob[w];
     if (!oob) {
       const double2* src =
-          reinterpret_cast<const double2*>(prm.lc + ((size_t)w * prm.n_lines_total + I.line_base) * LC_STRIDE);
+          reinterpret_cast<const double2*>(
+              prm.lc + ((size_t)w * prm.n_lines_total + (prm.wps > 0 ? 0 : I.line_base)) * LC_STRIDE);
       double2* dst = reinterpret_cast<double2*>(s_lc);
       for (int i = tid; i < I.L * (LC_STRIDE / 2); i += kThreads) dst[i] = src[i];
     }
@@ -516,7 +526,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       } else {
         total = 0.0;
         const volatile double* pp = prm.partials + (size_t)w * prm.n_tiles;
-        for (int k = 0; k < prm.n_inst; ++k) {
+        const int n_sum = (prm.wps > 0) ? 1 : prm.n_inst;   // a sightline walker sees one instrument only
+        for (int k = 0; k < n_sum; ++k) {
           double s = 0.0;
           for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
           total += -0.5 * s;                                          // vfit_mcmc.py:309-313
@@ -676,9 +687,7 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(upload(&ctx->d_core_tab, RBV_CORE_TABLE_HOST, (size_t)RBV_CORE_TABLE_LEN));
   const int max_dyn = (int)prop.sharedMemPerBlockOptin - 2048;
   ctx->max_dyn_smem = max_dyn;
-  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   *out = ctx;
   return RBV_OK;
@@ -709,11 +718,12 @@ int rbv_set_precision(RbvContext* ctx, int precision) {
 // Tile geometry of every instrument for one launch.  ``scale`` multiplies the base tile (1, 2, 4, ...):
 // big tiles amortise the per-CTA preamble and halo and make the dynamic chunk scheduling effective, small
 // tiles keep the grid full when there are few walkers.  Returns the total tile count and the dynamic smem.
-static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, size_t* smem_out) {
+static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, size_t* smem_out,
+                            size_t n_inst_used = (size_t)-1) {
   int total = 0;
   size_t smem = 0;
   int ndim = ctx->ndim;
-  for (size_t k = 0; k < ctx->inst.size(); ++k) {
+  for (size_t k = 0; k < std::min(ctx->inst.size(), n_inst_used); ++k) {
     const InstDev& I = ctx->inst[k].dev;
     int n_pass = 1;
     if (I.K - 1 > 64) n_pass = (int)std::ceil((I.K - 1) / (0.08 * kPass));   // halo overhead <= ~8 %
@@ -734,12 +744,13 @@ static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, si
 }
 
 // Picks the largest tile scale that still gives every SM several CTAs and fits two CTAs per SM.
-static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t* smem_out) {
+static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t* smem_out,
+                           size_t n_inst_used = (size_t)-1) {
   const long long want = 4LL * 2 * ctx->sm_count;   // >= 4 waves at 2 CTAs / SM
   int total = 0;
   for (int scale = 4; scale >= 1; scale >>= 1) {
     size_t smem = 0;
-    total = compute_geometry(ctx, scale, geom, &smem);
+    total = compute_geometry(ctx, scale, geom, &smem, n_inst_used);
     bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, 100 * 1024);
     if (scale == 1 || (fits && (long long)W * total >= want)) {
       if (smem_out) *smem_out = smem;
@@ -752,7 +763,6 @@ static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t*
 // Tap upload + line bases for every instrument.  The register blocking R is context-wide (8 as soon as one
 // instrument has a wide LSF) so that all instruments run in ONE launch.
 static int rebuild_tables(RbvContext* ctx) {
-  if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "at most 16 instruments per context");
   const int R = 8;   // outputs per thread in the LSF stage (64 FMAs per 8 flux + 8 tap loads)
   for (size_t k = 0; k < ctx->inst.size(); ++k) {
     HostInst& hi = ctx->inst[k];
@@ -769,7 +779,9 @@ static int rebuild_tables(RbvContext* ctx) {
     I.line_base = (k == 0) ? 0 : ctx->inst[k - 1].dev.line_base + ctx->inst[k - 1].dev.L;
   }
   TileGeom geom[kMaxInst];
-  ctx->n_tiles = compute_geometry(ctx, 1, geom, nullptr);   // smallest tiles = most tiles: sizes the workspace
+  // smallest tiles = most tiles: sizes the workspace (joint fits use <= 16 instruments; larger contexts are
+  // sightline batches, which size their workspace from one instrument)
+  ctx->n_tiles = compute_geometry(ctx, 1, geom, nullptr, kMaxInst);
   ctx->n_lines_total = 0;
   for (auto& hi : ctx->inst) ctx->n_lines_total += hi.dev.L;
   std::vector<InstDev> flat;
@@ -859,42 +871,64 @@ struct WorkspaceLayout {
 };
 
 // [tickets u32 x W][oob i32 x W][partials f64 x W x n_tiles][line constants f64 x W x n_lines x LC_STRIDE]
-static WorkspaceLayout workspace_layout(const RbvContext* ctx, int W) {
+static WorkspaceLayout workspace_layout_raw(int W, int tiles_per_walker, int lines_per_walker) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   WorkspaceLayout lay;
   lay.tickets = 0;
   lay.oob = up((size_t)W * sizeof(unsigned int));
   lay.partials = lay.oob + up((size_t)W * sizeof(int));
-  lay.lc = lay.partials + up((size_t)W * std::max(ctx->n_tiles, 1) * sizeof(double));
-  lay.total = lay.lc + up((size_t)W * std::max(ctx->n_lines_total, 1) * LC_STRIDE * sizeof(double));
+  lay.lc = lay.partials + up((size_t)W * std::max(tiles_per_walker, 1) * sizeof(double));
+  lay.total = lay.lc + up((size_t)W * std::max(lines_per_walker, 1) * LC_STRIDE * sizeof(double));
   return lay;
+}
+static WorkspaceLayout workspace_layout(const RbvContext* ctx, int W, bool sightlines) {
+  if (!sightlines) return workspace_layout_raw(W, ctx->n_tiles, ctx->n_lines_total);
+  TileGeom g[1];
+  int tiles = compute_geometry(ctx, 1, g, nullptr, 1);
+  return workspace_layout_raw(W, tiles, ctx->inst.empty() ? 1 : ctx->inst[0].dev.L);
 }
 
 int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes) {
   if (!ctx || !bytes || n_walkers < 0) return fail(RBV_EINVAL, "rbv_workspace_bytes: bad argument");
-  WorkspaceLayout lay = workspace_layout(ctx, n_walkers);
+  WorkspaceLayout lay = workspace_layout(ctx, n_walkers, false);
   *bytes = lay.total;
   return RBV_OK;
 }
 
-int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob, void* workspace,
-                     size_t workspace_bytes, void* stream) {
-  if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, "rbv_lnprob_batch: null argument");
-  if (W < 0) return fail(RBV_EINVAL, "rbv_lnprob_batch: negative n_walkers");
+int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t* bytes) {
+  if (!ctx || !bytes || n_walkers < 0) return fail(RBV_EINVAL, "rbv_workspace_bytes_sightlines: bad argument");
+  *bytes = workspace_layout(ctx, n_walkers, true).total;
+  return RBV_OK;
+}
+
+static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, double* lnprob, void* workspace,
+                         size_t workspace_bytes, void* stream, const char* who) {
+  if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, std::string(who) + ": null argument");
+  if (W < 0) return fail(RBV_EINVAL, std::string(who) + ": negative n_walkers");
   if (W == 0) return RBV_OK;
-  if (ctx->inst.empty()) return fail(RBV_ESTATE, "rbv_lnprob_batch: no instrument added");
-  if (ctx->ndim == 0) return fail(RBV_ESTATE, "rbv_lnprob_batch: bounds not set (rbv_set_bounds)");
+  if (ctx->inst.empty()) return fail(RBV_ESTATE, std::string(who) + ": no instrument added");
+  if (ctx->ndim == 0) return fail(RBV_ESTATE, std::string(who) + ": bounds not set (rbv_set_bounds)");
   for (auto& hi : ctx->inst) {
     if (!hi.dev.flux || !hi.dev.inv_sigma2 || !hi.dev.log_inv_sigma2)
-      return fail(RBV_ESTATE, "rbv_lnprob_batch: an instrument has no observed spectrum (flux-only instrument)");
-    if (3 * hi.dev.C > ctx->ndim) return fail(RBV_EINVAL, "rbv_lnprob_batch: ndim smaller than 3 * n_components");
+      return fail(RBV_ESTATE, std::string(who) + ": an instrument has no observed spectrum (flux-only instrument)");
+    if (3 * hi.dev.C > ctx->ndim) return fail(RBV_EINVAL, std::string(who) + ": ndim smaller than 3 * n_components");
   }
-  size_t need = 0;
-  rbv_workspace_bytes(ctx, W, &need);
-  if (!workspace || workspace_bytes < need) return fail(RBV_ENOMEM, "rbv_lnprob_batch: workspace too small");
+  const bool sl = wps > 0;
+  if (sl) {
+    if ((long long)wps * (long long)ctx->inst.size() != (long long)W)
+      return fail(RBV_EINVAL, std::string(who) + ": n_walkers must equal n_sightlines * walkers_per_sightline");
+    const InstDev& A = ctx->inst[0].dev;
+    for (auto& hi : ctx->inst)
+      if (hi.dev.P != A.P || hi.dev.K != A.K || hi.dev.L != A.L || hi.dev.C != A.C)
+        return fail(RBV_EINVAL, std::string(who) + ": sightlines must share n_pixels, n_taps, n_lines, n_components");
+  } else if (ctx->inst.size() > (size_t)kMaxInst) {
+    return fail(RBV_EINVAL, std::string(who) + ": at most 16 instruments in a joint fit (use the sightline entry "
+                            "point for batches of independent spectra)");
+  }
+  WorkspaceLayout lay = workspace_layout(ctx, W, sl);
+  if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, std::string(who) + ": workspace too small");
   RBV_CUDA(cudaSetDevice(ctx->device));
 
-  WorkspaceLayout lay = workspace_layout(ctx, W);
   LaunchParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.inst = ctx->d_inst;
@@ -907,30 +941,40 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   prm.oob = (int*)((char*)workspace + lay.oob);
   prm.partials = (double*)((char*)workspace + lay.partials);
   prm.lc = (double*)((char*)workspace + lay.lc);
-  prm.n_lines_total = ctx->n_lines_total;
+  prm.n_lines_total = sl ? ctx->inst[0].dev.L : ctx->n_lines_total;
   prm.ndim = ctx->ndim;
   prm.n_inst = (int)ctx->inst.size();
   prm.W = W;
   prm.precision = ctx->precision;
+  prm.wps = wps;
   cudaStream_t st = (cudaStream_t)stream;
 
-  // ONE launch covers every instrument: grid = (walkers, all tiles); R is context-wide; the tile size is
-  // chosen per launch from the batch size.
+  // ONE launch covers every instrument: grid = (walkers, tiles per walker); the tile size is chosen per launch
+  // from the batch size.  Sightline mode: each walker sees only its own instrument (identical geometry).
   size_t smem = 0;
-  prm.n_tiles = choose_geometry(ctx, W, prm.geom, &smem);
-  const bool r8 = ctx->inst[0].dev.R == 8;
+  prm.n_tiles = choose_geometry(ctx, W, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
-  if (ctx->n_tiles > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 tiles per walker");
-  if (W > 65535) return fail(RBV_EINVAL, "rbv_lnprob_batch: more than 65535 walkers per call (split the batch)");
-  dim3 pgrid((unsigned)((ctx->n_lines_total + 127) / 128), (unsigned)W);
+  if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
+  dim3 pgrid((unsigned)W, (unsigned)((prm.n_lines_total + 127) / 128));
   prep_kernel<<<pgrid, 128, 0, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
-  if (r8) voigt_tile_kernel<3, 0><<<grid, kThreads, smem, st>>>(prm);
-  else voigt_tile_kernel<2, 0><<<grid, kThreads, smem, st>>>(prm);
+  voigt_tile_kernel<3, 0><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   return RBV_OK;
+}
+
+int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return launch_lnprob(ctx, theta, W, 0, lnprob, workspace, workspace_bytes, stream, "rbv_lnprob_batch");
+}
+
+int rbv_lnprob_batch_sightlines(RbvContext* ctx, const double* theta, int W, int walkers_per_sightline,
+                                double* lnprob, void* workspace, size_t workspace_bytes, void* stream) {
+  if (walkers_per_sightline <= 0) return fail(RBV_EINVAL, "rbv_lnprob_batch_sightlines: walkers_per_sightline <= 0");
+  return launch_lnprob(ctx, theta, W, walkers_per_sightline, lnprob, workspace, workspace_bytes, stream,
+                       "rbv_lnprob_batch_sightlines");
 }
 
 int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, double* lnprob_host,
@@ -968,13 +1012,13 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   prm.n_inst = (int)ctx->inst.size();
   prm.W = W;
   prm.precision = ctx->precision;
+  if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "rbv_model_flux_batch: more than 16 instruments");
   prm.n_tiles = compute_geometry(ctx, 1, prm.geom, nullptr);
   prm.tile_base = prm.geom[inst].first_tile;
   size_t smem = smem_bytes_for(I, prm.geom[inst], ndim);
   dim3 grid((unsigned)W, (unsigned)prm.geom[inst].n_tiles);
   cudaStream_t st = (cudaStream_t)stream;
-  if (I.R == 8) voigt_tile_kernel<3, 1><<<grid, kThreads, smem, st>>>(prm);
-  else voigt_tile_kernel<2, 1><<<grid, kThreads, smem, st>>>(prm);
+  voigt_tile_kernel<3, 1><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   return RBV_OK;

@@ -46,6 +46,7 @@ class Engine:
         self._theta_dev = self._lnp_dev = self._ws = None
         self._theta_pin = self._lnp_pin = None
         self._ws_bytes = 0
+        self._ws_sightlines = False
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -116,13 +117,16 @@ class Engine:
         check(self.lib.rbv_set_precision(self._h, {"fp64": 0, "fp32-gated": 1}[precision]), "rbv_set_precision")
 
     # ------------------------------------------------------------------ buffers
-    def _reserve(self, W: int, ndim: int):
+    def _reserve(self, W: int, ndim: int, sightlines: bool = False):
         torch = _torch()
-        if W <= self._cap and self._theta_dev is not None and self._theta_dev.shape[1] == ndim:
+        if (W <= self._cap and self._theta_dev is not None and self._theta_dev.shape[1] == ndim
+                and self._ws_sightlines == sightlines):
             return
         cap = max(W, 64, int(self._cap * 1.5))
         nbytes = C.c_size_t(0)
-        check(self.lib.rbv_workspace_bytes(self._h, cap, C.byref(nbytes)), "rbv_workspace_bytes")
+        fn = self.lib.rbv_workspace_bytes_sightlines if sightlines else self.lib.rbv_workspace_bytes
+        check(fn(self._h, cap, C.byref(nbytes)), "rbv_workspace_bytes")
+        self._ws_sightlines = sightlines
         self._ws_bytes = int(nbytes.value)
         self._ws = torch.empty(max(self._ws_bytes, 8), dtype=torch.uint8, device=self.tdev)
         self._theta_dev = torch.empty((cap, ndim), dtype=torch.float64, device=self.tdev)
@@ -142,7 +146,7 @@ class Engine:
         W, ndim = theta.shape
         if ndim != self.ndim:
             raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
-        self._reserve(W, ndim)
+        self._reserve(W, ndim, sightlines=False)
         self._theta_pin_np[:W] = theta
         check(self.lib.rbv_lnprob_batch_host(self._h, self._theta_pin.data_ptr(), W, self._lnp_pin.data_ptr(),
                                              self._theta_dev.data_ptr(), self._lnp_dev.data_ptr(),
@@ -158,11 +162,30 @@ class Engine:
         W, ndim = theta_t.shape
         if ndim != self.ndim:
             raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
-        self._reserve(W, ndim)
+        self._reserve(W, ndim, sightlines=False)
         if out_t is None:
             out_t = torch.empty(W, dtype=torch.float64, device=self.tdev)
         check(self.lib.rbv_lnprob_batch(self._h, theta_t.data_ptr(), W, out_t.data_ptr(), self._ws.data_ptr(),
                                         self._ws_bytes, self._stream()), "rbv_lnprob_batch")
+        return out_t
+
+    def lnprob_sightlines_host(self, theta: np.ndarray, wps: int) -> np.ndarray:
+        """HOST theta [S * wps, ndim] (wps consecutive rows per sightline) -> HOST lnprob [S * wps]."""
+        out = self.lnprob_sightlines_device(_torch().as_tensor(np.ascontiguousarray(theta, dtype=np.float64),
+                                                               device=self.tdev), wps)
+        return out.cpu().numpy()
+
+    def lnprob_sightlines_device(self, theta_t, wps: int, out_t=None):
+        torch = _torch()
+        W, ndim = theta_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
+        self._reserve(W, ndim, sightlines=True)
+        if out_t is None:
+            out_t = torch.empty(W, dtype=torch.float64, device=self.tdev)
+        check(self.lib.rbv_lnprob_batch_sightlines(self._h, theta_t.data_ptr(), W, int(wps), out_t.data_ptr(),
+                                                   self._ws.data_ptr(), self._ws_bytes, self._stream()),
+              "rbv_lnprob_batch_sightlines")
         return out_t
 
     def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:

@@ -121,3 +121,49 @@ class GpuLikelihood:
 
     def close(self):
         self.engine.close()
+
+
+class SightlineBatch:
+    """Survey mode (BASELINE.json config 5, "1024 independent sightlines batched"): S independent fits that share
+    the model *structure* (same number of lines / components / pixels / LSF taps) but have their own redshift,
+    spectrum and walker ensemble.  One launch evaluates every walker of every sightline; walker row
+    ``s * walkers_per_sightline + k`` belongs to sightline ``s``.  Sightlines shard across GPUs with no
+    collective (each rank builds a SightlineBatch over its own subset)."""
+
+    def __init__(self, sightlines, lb, ub, device: Optional[int] = None):
+        """``sightlines``: list of dicts {'model', 'wave', 'flux', 'error'} (one instrument each)."""
+        if len(sightlines) == 0:
+            raise ValueError("sightlines cannot be empty")
+        self.engine = Engine(device)
+        self.n_sightlines = len(sightlines)
+        for i, d in enumerate(sightlines):
+            model = d["model"]
+            compiled = model.compile(verbose=False) if isinstance(model, GpuVoigtModel) else model
+            if not isinstance(compiled, GpuCompiledVoigtModel):
+                raise TypeError(f"sightline {i}: 'model' must be a GpuVoigtModel / GpuCompiledVoigtModel")
+            wave, flux, error = (np.asarray(d[k]) for k in ("wave", "flux", "error"))
+            if len(flux) != len(wave) or len(error) != len(wave):
+                raise ValueError(f"sightline {i}: wave, flux, and error must have same length")
+            inv_sigma2, log_inv_sigma2 = _weights(error)
+            data = compiled.data
+            self.engine.add_instrument(data, wave, flux=flux, inv_sigma2=inv_sigma2, log_inv_sigma2=log_inv_sigma2,
+                                       taps=data.kernel, normalize_taps=data.kernel_normalize)
+        self.pixels = self.engine.pixels[0]
+        self.lb = np.asarray(lb, dtype=np.float64)
+        self.ub = np.asarray(ub, dtype=np.float64)
+        self.engine.set_bounds(self.lb, self.ub)
+        self.ndim = self.lb.size
+
+    def lnprob(self, theta):
+        """theta [S, Ws, ndim] -> lnprob [S, Ws]."""
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim != 3 or theta.shape[0] != self.n_sightlines or theta.shape[2] != self.ndim:
+            raise ValueError(f"theta must be [{self.n_sightlines}, walkers_per_sightline, {self.ndim}]")
+        S, Ws, nd = theta.shape
+        return self.engine.lnprob_sightlines_host(theta.reshape(S * Ws, nd), Ws).reshape(S, Ws)
+
+    def lnprob_device(self, theta_t, wps: int, out_t=None):
+        return self.engine.lnprob_sightlines_device(theta_t, wps, out_t)
+
+    def close(self):
+        self.engine.close()

@@ -130,3 +130,34 @@ def test_components_are_unconvolved_per_line_fluxes():
     unc = m.evaluate(w["theta_true"], wave, return_unconvolved=True)
     assert np.max(np.abs(prod - unc)) <= 1e-13
     assert res["component_info"][0]["lambda0"] == float(m.atomic_lambda0[0])
+
+
+def test_sightline_batch_equals_individual_fits():
+    """C5b-style survey batch: one launch over S sightlines == S separate single-sightline likelihoods."""
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.likelihood import GpuLikelihood, SightlineBatch
+    from rbvfit_b200.model import GpuVoigtModel
+    S, Ws = 24, 16
+    sight, thetas, singles = [], [], []
+    w0 = wl.c5b_sightline(0)
+    for s in range(S):
+        w = wl.c5b_sightline(s)
+        cfg = FitConfiguration()
+        for (z, ion, trans, comps) in w["systems"]:
+            cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+        m = GpuVoigtModel(cfg, FWHM="6.5")
+        c = m.compile()
+        sp = wl.make_spectra(w, lambda n, th, wave: c.model_flux(th, wave))["COS"]
+        sight.append(dict(model=m, **sp))
+        thetas.append(wl.make_ensemble(w, Ws, frac_out_of_bounds=0.1))
+        singles.append(GpuLikelihood({"COS": dict(model=m, **sp)}, w["lb"], w["ub"]))
+    thetas = np.array(thetas)
+    batch = SightlineBatch(sight, w0["lb"], w0["ub"])
+    got = batch.lnprob(thetas)
+    ref = np.array([singles[s].lnprob(thetas[s]) for s in range(S)])
+    assert got.shape == (S, Ws)
+    assert np.isneginf(ref).sum() >= S
+    assert np.array_equal(got, ref, equal_nan=True)          # same kernel, same tiles: bit-identical
+    assert len(set(np.round(ref[np.isfinite(ref)], 3))) > S     # sightlines really differ
+    with pytest.raises(ValueError):
+        batch.lnprob(thetas[:5])
