@@ -1,0 +1,195 @@
+"""Batched ensemble slice sampler with zeus's semantics and sampler-object contract.
+
+The reference hands ``vfit.lnprob`` to ``zeus.EnsembleSampler(nwalkers, ndim, lnprob, pool=pool)``
+(src/rbvfit/vfit_mcmc.py:425-440) when ``sampler='zeus'``.  zeus-mcmc is a third-party dependency that is not
+vendored (requirements.txt:11, ``zeus-mcmc>=2.3.0``) and is not installed here, so the algorithm is restated
+from its published description (Karamanis & Beutler 2021, "Ensemble slice sampling", Algorithm 2-3; zeus 2.x
+defaults: DifferentialMove, mu = 1 tuned by stochastic approximation, tolerance 0.05, patience 5):
+
+  per iteration, for each half of the (shuffled) ensemble with the other half as the complementary set C:
+      direction_k = 2 mu (C_j - C_l),  j != l drawn from C                       (differential move)
+      slice level  y_k = lnp(X_k) - Exp(1)
+      stepping out: [L, R] = [-U, 1 - U]; widen L (R) by 1 while lnp(X_k + L dir_k) > y_k, counting expansions
+      shrinking:   draw t ~ U(L, R); accept X_k + t dir_k if lnp >= y_k, else shrink the bracket towards 0
+      tuning:      mu <- mu * 2 n_exp / (n_exp + n_con) until the expansion fraction sits at 1/2 +- tolerance
+
+Every lnp evaluation inside the two loops is ONE device batch over the walkers that are still active in
+that loop (``vectorize=True`` contract) -- the long tail of small batches is latency-bound on the GPU
+(SURVEY.md section 7.3), which is why the stretch move remains the default.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+from .sampler import integrated_time
+
+
+class EnsembleSliceSampler:
+    def __init__(self, nwalkers: int, ndim: int, log_prob_fn: Callable, mu: float = 1.0, tune: bool = True,
+                 tolerance: float = 0.05, patience: int = 5, maxsteps: int = 10000, maxiter: int = 10000,
+                 pool=None, vectorize: bool = True, seed: Optional[int] = None):
+        if nwalkers < 2 * ndim or nwalkers % 2:
+            raise ValueError("Please provide at least (2 * ndim) walkers, and an even number of them.")
+        self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        self.log_prob_fn = log_prob_fn
+        self.vectorize = vectorize
+        self.pool = pool
+        self.mu, self.mu0 = float(mu), float(mu)
+        self.tune, self.tolerance, self.patience = bool(tune), float(tolerance), int(patience)
+        self.maxsteps, self.maxiter = int(maxsteps), int(maxiter)
+        self._random = np.random.default_rng(seed)
+        self.reset()
+
+    def reset(self):
+        self._chain = np.empty((0, self.nwalkers, self.ndim))
+        self._log_prob = np.empty((0, self.nwalkers))
+        self.iteration = 0
+        self.ncall = 0          # lnp evaluations (rows)
+        self.nbatches = 0       # lnp calls (device batches)
+        self.mus = []
+        self._last = None
+
+    def compute_log_prob(self, coords):
+        coords = np.atleast_2d(coords)
+        if self.vectorize:
+            lp = np.asarray(self.log_prob_fn(coords), dtype=np.float64)
+        else:
+            lp = np.array([float(self.log_prob_fn(c)) for c in coords])
+        self.ncall += len(coords)
+        self.nbatches += 1
+        if np.any(np.isnan(lp)):
+            raise ValueError("Probability function returned NaN")
+        return lp
+
+    # ------------------------------------------------------------------ one iteration
+    def _iterate(self, X, Z):
+        nw, rng = self.nwalkers, self._random
+        half = nw // 2
+        order = rng.permutation(nw)
+        nexp = ncon = 0
+        for split in range(2):
+            active = order[split * half:(split + 1) * half]
+            inactive = order[(1 - split) * half:(2 - split) * half] if split == 0 else order[:half]
+            n = len(active)
+            # differential move: two distinct complementary walkers per active walker
+            j = rng.integers(0, len(inactive), size=n)
+            l = (j + rng.integers(1, len(inactive), size=n)) % len(inactive)
+            directions = 2.0 * self.mu * (X[inactive[j]] - X[inactive[l]])
+            X0, Z0 = X[active].copy(), Z[active] - rng.exponential(size=n)
+            L = -rng.random(n)
+            R = L + 1.0
+            # stepping out, left then right (batched over the walkers still expanding)
+            J = np.floor(self.maxsteps * rng.random(n)).astype(int)
+            K = (self.maxsteps - 1) - J
+            for side, budget in ((L, J), (R, K)):
+                step = -1.0 if side is L else 1.0
+                mask = np.ones(n, dtype=bool)
+                while np.any(mask):
+                    idx = np.flatnonzero(mask)
+                    Zs = self.compute_log_prob(X0[idx] + side[idx, None] * directions[idx])
+                    grow = (Zs >= Z0[idx]) & (budget[idx] >= 1)
+                    side[idx[grow]] += step
+                    budget[idx[grow]] -= 1
+                    nexp += int(grow.sum())
+                    mask[idx[~grow]] = False
+            # shrinking
+            Xp, Zp = X0.copy(), np.empty(n)
+            mask = np.ones(n, dtype=bool)
+            it = 0
+            while np.any(mask):
+                idx = np.flatnonzero(mask)
+                t = L[idx] + rng.random(len(idx)) * (R[idx] - L[idx])
+                cand = X0[idx] + t[:, None] * directions[idx]
+                Zc = self.compute_log_prob(cand)
+                ok = Zc >= Z0[idx]
+                Xp[idx[ok]] = cand[ok]
+                Zp[idx[ok]] = Zc[ok]
+                mask[idx[ok]] = False
+                rej = idx[~ok]
+                tl = t[~ok]
+                L[rej[tl < 0]] = tl[tl < 0]
+                R[rej[tl >= 0]] = tl[tl >= 0]
+                ncon += len(rej)
+                it += 1
+                if it > self.maxiter:
+                    raise RuntimeError("Number of contractions exceeded maximum limit!")
+            X[active], Z[active] = Xp, Zp
+        return X, Z, nexp, ncon
+
+    def run_mcmc(self, start, nsteps, progress=False, **_ignored):
+        if start is None:
+            if self._last is None:
+                raise ValueError("Cannot have `start=None` if run_mcmc has never been called.")
+            X, Z = self._last
+        else:
+            X = np.array(start, dtype=np.float64, copy=True)
+            if X.shape != (self.nwalkers, self.ndim):
+                raise ValueError("Incompatible input dimensions! Please provide array of shape (nwalkers, ndim)")
+            Z = self.compute_log_prob(X)
+            if not np.all(np.isfinite(Z)):
+                raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite "
+                                 "log probability.")
+        chain = np.empty((nsteps, self.nwalkers, self.ndim))
+        lps = np.empty((nsteps, self.nwalkers))
+        it = range(nsteps)
+        if progress:
+            try:
+                from tqdm import tqdm
+                it = tqdm(it, total=nsteps)
+            except ImportError:
+                pass
+        good = 0
+        for i in it:
+            X, Z, nexp, ncon = self._iterate(X, Z)
+            if self.tune:
+                nexp = max(1, nexp)
+                self.mu *= 2.0 * nexp / (nexp + ncon)
+                self.mus.append(self.mu)
+                if abs(nexp / (nexp + ncon) - 0.5) < self.tolerance:
+                    good += 1
+                if good > self.patience:
+                    self.tune = False
+            chain[i], lps[i] = X, Z
+        self._chain = np.concatenate([self._chain, chain], axis=0)
+        self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self.iteration += nsteps
+        self._last = (X, Z)
+        return X, Z
+
+    # ------------------------------------------------------------------ zeus-shaped accessors
+    def _get(self, arr, discard=0, thin=1, flat=False):
+        v = arr[discard::thin]
+        if flat:
+            return v.reshape((-1,) + v.shape[2:])
+        return v
+
+    def get_chain(self, flat=False, thin=1, discard=0):
+        return self._get(self._chain, discard, thin, flat)
+
+    def get_log_prob(self, flat=False, thin=1, discard=0):
+        return self._get(self._log_prob, discard, thin, flat)
+
+    @property
+    def chain(self):
+        return self._chain
+
+    @property
+    def acceptance_fraction(self):
+        """Fraction of (walker, step) pairs that moved -- what the reference derives for zeus chains
+        (vfit_mcmc.py:470-486); slice sampling always moves, so this is ~1."""
+        c = self._chain
+        if len(c) < 2:
+            return np.ones(self.nwalkers)
+        return np.mean(np.any(c[1:] != c[:-1], axis=2), axis=0)
+
+    @property
+    def efficiency(self):
+        return self.iteration * self.nwalkers / max(self.ncall, 1)
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
+
+    def get_last_sample(self):
+        return self._last

@@ -94,6 +94,38 @@ def test_stretch_sampler_recovers_gaussian():
         EnsembleSampler(8, 3, lnp).run_mcmc(np.zeros((8, 3)), 1)     # degenerate initial state
 
 
+def test_slice_sampler_recovers_gaussian():
+    """zeus-style ensemble slice sampler (restated, rbvfit_b200/slice_sampler.py): statistical parity on a
+    correlated Gaussian, batched lnprob calls only, zeus's accessor contract."""
+    from rbvfit_b200.slice_sampler import EnsembleSliceSampler
+    mu = np.array([1.0, -2.0, 0.5])
+    cov = np.array([[0.25, 0.3, 0.0], [0.3, 4.0, 0.5], [0.0, 0.5, 1.0]])
+    icov = np.linalg.inv(cov)
+    shapes = []
+
+    def lnp(x):
+        shapes.append(x.shape)
+        d = x - mu
+        return -0.5 * np.einsum("ni,ij,nj->n", d, icov, d)
+
+    rng = np.random.default_rng(3)
+    s = EnsembleSliceSampler(16, 3, lnp, seed=4)
+    s.run_mcmc(mu + 1e-2 * rng.standard_normal((16, 3)), 700)
+    assert all(len(sh) == 2 and sh[1] == 3 and 1 <= sh[0] <= 16 for sh in shapes)
+    flat = s.get_chain(discard=100, flat=True)
+    assert flat.shape == (600 * 16, 3)
+    sig = np.sqrt(np.diag(cov))
+    assert np.all(np.abs(flat.mean(0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(0) / sig - 1) < 0.1)
+    assert abs(np.corrcoef(flat.T)[0, 1] - 0.3) < 0.08
+    assert s.acceptance_fraction.shape == (16,) and s.acceptance_fraction.min() > 0.95   # slice moves always move
+    assert 0.05 < s.efficiency < 1.0 and not s.tune                                       # mu tuning converged
+    tau = s.get_autocorr_time(quiet=True)
+    assert tau.shape == (3,) and np.all(tau < 50)
+    with pytest.raises(ValueError):
+        EnsembleSliceSampler(5, 3, lnp)           # zeus: >= 2*ndim walkers, even
+
+
 def test_roofline_flops_rule():
     from rbvfit_b200 import roofline as rf, workloads as wl
     from oracle import voigt_oracle as vo
