@@ -37,6 +37,10 @@ extern "C" {
 #define RBV_PRECISION_FP64 0
 #define RBV_PRECISION_FP32_GATED 1 /* FP32 far-wing arithmetic, used only when the gate passes */
 
+#define RBV_FARFIELD_DIRECT 0    /* every (line, pixel) pair evaluated on its own                          */
+#define RBV_FARFIELD_CHEBYSHEV 1 /* default: summed far wings of a 256-pixel chunk interpolated from 8 nodes, */
+                                 /* used per (line, chunk) only when an a-priori bound keeps |dtau| <= 1e-13  */
+
 typedef struct RbvContext RbvContext;
 
 /* The lowered model of one instrument.
@@ -83,6 +87,9 @@ void rbv_destroy(RbvContext* ctx);
 
 /* Select the arithmetic of the far-wing tier (default RBV_PRECISION_FP64). */
 int rbv_set_precision(RbvContext* ctx, int precision);
+
+/* Select how far line wings (|x| >= 200 Doppler widths) are accumulated (default RBV_FARFIELD_CHEBYSHEV). */
+int rbv_set_farfield(RbvContext* ctx, int mode);
 
 /* Append an instrument (model + spectrum).  *out_index receives its index (0, 1, ...).
  * Replaces one iteration of the loop in vfit._compile_models (vfit_mcmc.py:238-257). */

@@ -31,6 +31,7 @@ EXPORTS = {
     "rbv_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rbv_destroy": (None, [C.c_void_p]),
     "rbv_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "rbv_set_farfield": (C.c_int, [C.c_void_p, C.c_int]),
     "rbv_add_instrument": (C.c_int, [C.c_void_p, C.POINTER(RbvLineTable), C.POINTER(RbvSpectrum),
                                      C.POINTER(C.c_int)]),
     "rbv_set_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),

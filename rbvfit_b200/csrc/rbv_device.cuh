@@ -61,6 +61,8 @@ constexpr double kCkms = 299792.458;             // voigt_model.py:197
 
 __constant__ double c_ctab[(RBV_ASYM_PMAX + 1) * (RBV_ASYM_MMAX + 1)];
 __constant__ double c_weid[RBV_WEID_N];
+__constant__ double c_ff_nodes[RBV_FF_M];              // Chebyshev nodes of the far-field interpolant
+__constant__ double c_ff_minv[RBV_FF_M * RBV_FF_M];    // node values -> monomial coefficients, [power][node]
 
 // ---------------------------------------------------------------------------------------------- helpers
 // Full-precision reciprocal of a positive, normal double: MUFU seed + one cubically convergent step.

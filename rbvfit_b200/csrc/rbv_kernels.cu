@@ -72,6 +72,7 @@ struct LaunchParams {
   int ndim, n_tiles, n_inst, W, n_lines_total;
   int tile_base;         // flux mode: first tile of the instrument
   int precision;
+  int farfield;          // 1 = far wings of a chunk through the Chebyshev far-field interpolant (section 4c)
   int wps;               // sightline mode: walkers per sightline (walker w belongs to instrument w / wps); 0 = off
 };
 
@@ -130,7 +131,11 @@ __device__ __forceinline__ void prep_line_fast(const InstDev& I, int l, const do
 extern __shared__ double smem[];   // every hot-loop access indexes this array directly (shared-space addressing)
 
 // Tier codes of a (warp chunk, line) pair
-constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGeneral = 4, kTierFar32 = 5;
+constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGeneral = 4, kTierFar32 = 5,
+              kTierFF = 6;
+// Far-field budget: the interpolation errors of all lines of one pixel sum to <= kFFEps in optical depth
+// (flux error <= 1e-13, three decades inside the 1e-10 parity tolerance).
+constexpr double kFFEps = 1e-13;
 
 // Classify every line once per warp chunk from the chunk's range of 1/lambda (lane l handles line l):
 // far lines go to the front of the warp's list, everything else to the back with its tier in the top bits.
@@ -139,10 +144,18 @@ constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGen
 // A NaN line lands in the far list and its NaN propagates through the arithmetic.
 // With gate32 > 0, far lines whose largest possible contribution over the chunk, kappa / min|z|^2, is at most
 // gate32 go to a second list (list32) and are evaluated on the FP32 pipe; returns their count in .z.
-__device__ __forceinline__ int3 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
-                                               unsigned short* __restrict__ list32, double gate32,
+// With ff_eps > 0, far lines whose wing is smooth enough over the chunk go to listff (count in .w): the chunk
+// then evaluates their SUM at RBV_FF_M Chebyshev nodes and interpolates it.  A-priori error bound of the
+// degree-(m-1) Chebyshev interpolant of kappa/x^2 on [xm, xm + 2 hw] (m-th derivative (m+1)!/x^(m+2)):
+//     |err| <= 2 (m+1) kappa (hw / (2 xm))^m / xm^2;
+// the gate uses 8 (m+1) (4x margin covers the a^2 and rho^2, rho^3 corrections, all <= 1e-4 relative at
+// |z|^2 >= 4e4, a <= 1) and runs in FP32 with every rounding pushed to the conservative side.
+__device__ __forceinline__ int4 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
+                                               unsigned short* __restrict__ list32,
+                                               unsigned short* __restrict__ listff, double gate32, float ff_eps,
                                                double umin, double umax, int lane) {
-  int n_far = 0, n_oth = 0, n_32 = 0;
+  int n_far = 0, n_oth = 0, n_32 = 0, n_ff = 0;
+  const double du = umax - umin;
   const unsigned lt = (1u << lane) - 1u;
   for (int l0 = 0; l0 < L; l0 += 32) {
     const int l = l0 + lane;
@@ -161,6 +174,15 @@ __device__ __forceinline__ int3 classify_lines(int lc_off, int L, unsigned short
              : (hmin >= kHiNear) ? kTierMid
              : (hmin >= kHiCore) ? kTierNear
                                  : kTierCore;
+      if (ff_eps > 0.f && tier == kTierFar) {
+        const float xm = fminf(fabsf((float)x1), fabsf((float)x2)) * 0.99999f;     // rounded towards the line
+        const float hw = (float)(0.5 * fabs(A) * du) * 1.00001f;
+        const float r = __fdividef(hw, 2.f * xm) * 1.00001f;
+        const float r2 = r * r, r4 = r2 * r2;
+        const float bound = (8.f * (RBV_FF_M + 1) * 1.001f) * fabsf((float)smem[off + LC_AUX]) *
+                            __fdividef(r4 * r4, xm * xm);
+        if (bound <= ff_eps) tier = kTierFF;       // NaN fails the comparison and stays on the direct path
+      }
       if (gate32 > 0.0 && tier == kTierFar) {
         // kappa / dmin with dmin rounded DOWN to its high word: an upper bound of the line's contribution
         const double tmax = fabs(smem[off + LC_AUX]) / __hiloint2double(hmin, 0);
@@ -169,18 +191,22 @@ __device__ __forceinline__ int3 classify_lines(int lc_off, int L, unsigned short
     }
     const unsigned far_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFar);
     const unsigned f32_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFar32);
-    const unsigned oth_mask = __ballot_sync(0xffffffffu, valid && tier != kTierFar && tier != kTierFar32);
+    const unsigned ff_mask = __ballot_sync(0xffffffffu, valid && tier == kTierFF);
+    const unsigned oth_mask = __ballot_sync(0xffffffffu, valid && tier != kTierFar && tier != kTierFar32 &&
+                                                             tier != kTierFF);
     if (valid) {
       if (tier == kTierFar) list[n_far + __popc(far_mask & lt)] = (unsigned short)l;
       else if (tier == kTierFar32) list32[n_32 + __popc(f32_mask & lt)] = (unsigned short)l;
+      else if (tier == kTierFF) listff[n_ff + __popc(ff_mask & lt)] = (unsigned short)l;
       else list[L - 1 - (n_oth + __popc(oth_mask & lt))] = (unsigned short)(l | (tier << 12));
     }
     n_far += __popc(far_mask);
     n_32 += __popc(f32_mask);
+    n_ff += __popc(ff_mask);
     n_oth += __popc(oth_mask);
   }
   __syncwarp();
-  return make_int3(n_far, n_oth, n_32);
+  return make_int4(n_far, n_oth, n_32, n_ff);
 }
 
 // FP32 far-wing accumulation for the gated lines.  x = X0 + A du with X0 = A u_ref - B formed in FP64 once per
@@ -235,8 +261,89 @@ __device__ __forceinline__ void accum_asym_line(int off, const double (&u)[kPixP
   }
 }
 
+// Far field of one warp chunk.  The listed lines are all >= 200 Doppler widths away from
+// every pixel of the chunk, where their summed optical depth g(u) = sum_l kappa_l rho_l (q1 + q2 rho_l + q3 rho_l^2)
+// is an analytic, slowly varying function of u = 1/lambda.  Instead of n_ff * 256 series evaluations:
+//   1. lane = line: evaluate the line at the RBV_FF_M Chebyshev nodes of [umin, umax] (same 8-FMA body as the
+//      direct far tier, ILP 8 over the nodes);
+//   2. transpose-reduce over the lanes (9 shuffle-adds) -> node sums S_k;
+//   3. lanes 0..7: monomial coefficients c_j = sum_k MINV[j][k] S_k (constant matrix, generated in 60-digit
+//      arithmetic), published through 16 doubles of per-warp shared memory;
+//   4. every pixel: t = (u - um)/uh by one FMA, tau = Horner_7(t)  (8 FMAs, whatever the number of lines).
+// Fixed evaluation order -> bit-reproducible for a given chunk.
+__device__ __forceinline__ void tau_farfield(int lc_off, const unsigned short* __restrict__ listff, int n_ff,
+                                             double umin, double umax, int ffw_off,
+                                             const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
+                                             int lane) {
+  static_assert(RBV_FF_M == 8 && kPixPerThread == 8, "far-field code is written for 8 nodes and 8 pixels/lane");
+  const double um = 0.5 * (umin + umax), uh = 0.5 * (umax - umin);
+  double S[8];
+  {
+    double un[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      un[k] = fma(uh, c_ff_nodes[k], um);
+      S[k] = 0.0;
+    }
+    for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQFar>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
+  }
+  // transpose-reduce: after the three halving steps lane holds node (lane >> 2) & 7 summed over 8 lanes
+  double T4[4], T2[2], T1;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double send = hi ? S[i] : S[i + 4], keep = hi ? S[i + 4] : S[i];
+      T4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double send = hi ? T4[i] : T4[i + 2], keep = hi ? T4[i + 2] : T4[i];
+      T2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const double send = hi ? T2[0] : T2[1], keep = hi ? T2[1] : T2[0];
+    T1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  T1 += __shfl_xor_sync(0xffffffffu, T1, 2);
+  T1 += __shfl_xor_sync(0xffffffffu, T1, 1);
+  __syncwarp();                                        // earlier readers of the per-warp scratch are done
+  if ((lane & 3) == 0) smem[ffw_off + (lane >> 2)] = T1;   // S_k, k = lane >> 2
+  __syncwarp();
+  if (lane < 8) {
+    double c = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c = fma(c_ff_minv[lane * 8 + k], smem[ffw_off + k], c);
+    smem[ffw_off + 8 + lane] = c;
+  }
+  __syncwarp();
+  double c[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(smem + ffw_off + 8 + j);
+    c[j] = v.x;
+    c[j + 1] = v.y;
+  }
+  const double sc = 1.0 / uh, of = -um * sc;
+#pragma unroll
+  for (int j = 0; j < kPixPerThread; ++j) {
+    const double t = fma(u[j], sc, of);
+    double p = c[7];
+#pragma unroll
+    for (int q = 6; q >= 0; --q) p = fma(p, t, c[q]);
+    tau[j] = p;                                        // tau starts from the far field (was 0)
+  }
+}
+
 __device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __restrict__ list,
-                                         unsigned short* __restrict__ list32, double gate32,
+                                         unsigned short* __restrict__ list32,
+                                         unsigned short* __restrict__ listff, double gate32, float ff_eps,
+                                         int ffw_off,
                                          const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
                                          const double* __restrict__ core_tab, int lane) {
   // range of 1/lambda over the warp's chunk (no monotonicity assumed): integer min/max of the high words
@@ -251,7 +358,8 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __re
   hlo = __reduce_min_sync(0xffffffffu, hlo);
   hhi = __reduce_max_sync(0xffffffffu, hhi);
   const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
-  const int3 n = classify_lines(lc_off, L, list, list32, gate32, umin, umax, lane);
+  const int4 n = classify_lines(lc_off, L, list, list32, listff, gate32, ff_eps, umin, umax, lane);
+  if (n.w > 0) tau_farfield(lc_off, listff, n.w, umin, umax, ffw_off, u, tau, lane);
   if (n.z > 0) accum_far32(lc_off, list32, n.z, u, tau);
 
   // far lines: branch-free body, 8 FP64 instructions per (line, pixel)
@@ -370,16 +478,19 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   const int lc_off = (ndim + 1) & ~1;                  // smem layout (doubles): theta | line consts | taps |
   const int taps_off = lc_off + I.L * LC_STRIDE;       //   flux tile | per-warp line lists (u16)
   const int flux_off = taps_off + I.Kpad;
-  const int list_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1);
+  const int ffw_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1) + warp * 16;   // far-field scratch
+  const int list_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1) + (kThreads / 32) * 16;
   double* s_theta = smem;
   double* s_lc = smem + lc_off;
   double* s_taps = smem + taps_off;
   double* s_flux = smem + flux_off;
   const int list_stride = (I.L + 3) & ~3;
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + list_off) + warp * 2 * list_stride;
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + list_off) + warp * 3 * list_stride;
   unsigned short* s_list32 = s_list + list_stride;
+  unsigned short* s_listff = s_list32 + list_stride;
   // FP32 gate: the gated contributions of one pixel sum to <= 4e-6 (=> |dtau| <= 1e-11)
   const double gate32 = (prm.precision == RBV_PRECISION_FP32_GATED) ? 4e-6 / (double)I.L : 0.0;
+  const float ff_eps = prm.farfield ? (float)(kFFEps / (double)I.L) : 0.f;
 
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
   int oob = 0;
@@ -442,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         tau[j] = 0.0;
       }
       if (fast) tau_fast(lc_off, I.L, u, tau);
-      else tau_wofz(lc_off, I.L, s_list, s_list32, gate32, u, tau, prm.core_tab, lane);
+      else tau_wofz(lc_off, I.L, s_list, s_list32, s_listff, gate32, ff_eps, ffw_off, u, tau, prm.core_tab, lane);
 #pragma unroll
       for (int j = 0; j < kPixPerThread; ++j) {
         int i = i0 + j * 32 + lane;
@@ -638,6 +749,7 @@ struct RbvContext {
   int n_tiles = 0;
   int n_lines_total = 0;
   int precision = RBV_PRECISION_FP64;
+  int farfield = RBV_FARFIELD_CHEBYSHEV;
   long long launches = 0;
   std::vector<HostInst> inst;
   InstDev* d_inst = nullptr;
@@ -658,8 +770,9 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 
 static size_t smem_bytes_for(const InstDev& I, const TileGeom& G, int ndim) {
   int logR = (I.R == 8) ? 3 : 2;
-  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (G.ext_alloc + (G.ext_alloc >> logR)) + 4;
-  size_t lists = (size_t)(kThreads / 32) * 2 * ((I.L + 3) & ~3) * sizeof(unsigned short);
+  size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (G.ext_alloc + (G.ext_alloc >> logR)) + 4 +
+             (kThreads / 32) * 16;
+  size_t lists = (size_t)(kThreads / 32) * 3 * ((I.L + 3) & ~3) * sizeof(unsigned short);
   return n * sizeof(double) + ((lists + 15) & ~(size_t)15);
 }
 
@@ -684,6 +797,8 @@ int rbv_create(int device, RbvContext** out) {
   ctx->sm_count = prop.multiProcessorCount;
   RBV_CUDA(cudaMemcpyToSymbol(c_ctab, RBV_ASYM_CTAB_HOST, sizeof(RBV_ASYM_CTAB_HOST)));
   RBV_CUDA(cudaMemcpyToSymbol(c_weid, RBV_WEID_COEF_HOST, sizeof(RBV_WEID_COEF_HOST)));
+  RBV_CUDA(cudaMemcpyToSymbol(c_ff_nodes, RBV_FF_NODES_HOST, sizeof(RBV_FF_NODES_HOST)));
+  RBV_CUDA(cudaMemcpyToSymbol(c_ff_minv, RBV_FF_MINV_HOST, sizeof(RBV_FF_MINV_HOST)));
   RBV_CUDA(upload(&ctx->d_core_tab, RBV_CORE_TABLE_HOST, (size_t)RBV_CORE_TABLE_LEN));
   const int max_dyn = (int)prop.sharedMemPerBlockOptin - 2048;
   ctx->max_dyn_smem = max_dyn;
@@ -712,6 +827,14 @@ int rbv_set_precision(RbvContext* ctx, int precision) {
   if (precision != RBV_PRECISION_FP64 && precision != RBV_PRECISION_FP32_GATED)
     return fail(RBV_EINVAL, "rbv_set_precision: unknown precision");
   ctx->precision = precision;
+  return RBV_OK;
+}
+
+int rbv_set_farfield(RbvContext* ctx, int mode) {
+  if (!ctx) return fail(RBV_EINVAL, "null context");
+  if (mode != RBV_FARFIELD_DIRECT && mode != RBV_FARFIELD_CHEBYSHEV)
+    return fail(RBV_EINVAL, "rbv_set_farfield: unknown mode");
+  ctx->farfield = mode;
   return RBV_OK;
 }
 
@@ -946,6 +1069,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   prm.n_inst = (int)ctx->inst.size();
   prm.W = W;
   prm.precision = ctx->precision;
+  prm.farfield = ctx->farfield;
   prm.wps = wps;
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -1012,6 +1136,7 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   prm.n_inst = (int)ctx->inst.size();
   prm.W = W;
   prm.precision = ctx->precision;
+  prm.farfield = ctx->farfield;
   if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "rbv_model_flux_batch: more than 16 instruments");
   prm.n_tiles = compute_geometry(ctx, 1, prm.geom, nullptr);
   prm.tile_base = prm.geom[inst].first_tile;

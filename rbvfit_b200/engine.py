@@ -116,6 +116,10 @@ class Engine:
     def set_precision(self, precision: str):
         check(self.lib.rbv_set_precision(self._h, {"fp64": 0, "fp32-gated": 1}[precision]), "rbv_set_precision")
 
+    def set_farfield(self, mode: str):
+        """'chebyshev' (default) or 'direct' -- how far line wings are accumulated."""
+        check(self.lib.rbv_set_farfield(self._h, {"direct": 0, "chebyshev": 1}[mode]), "rbv_set_farfield")
+
     # ------------------------------------------------------------------ buffers
     def _reserve(self, W: int, ndim: int, sightlines: bool = False):
         torch = _torch()

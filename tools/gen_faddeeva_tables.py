@@ -23,6 +23,12 @@ Three ingredients (see DESIGN.md "Faddeeva"):
 3. GENERAL-a CORE (|z|^2 < 64, a > A_FAST): Weideman (1994) N = 40 rational approximation,
    coefficients from the FFT recipe of the paper.
 
+4. FAR FIELD: m = 8 Chebyshev nodes t_k = cos(pi (2k+1)/(2m)) on [-1,1] and the m x m matrix that maps
+   the values of a function at those nodes to the MONOMIAL coefficients of its interpolating polynomial
+   (discrete Chebyshev transform followed by the T_j -> monomial change of basis), in 60-digit arithmetic.
+   The tile kernel interpolates the summed far-wing optical depth of a 256-pixel chunk with it (DESIGN.md
+   section 4c).
+
 This is build tooling, not test infrastructure and not product code; the generated header is
 committed so that building needs only nvcc.
 """
@@ -44,6 +50,7 @@ ASYM_KMAX = 12            # k = 0..12  -> p = 1..13
 ASYM_PMAX = ASYM_KMAX + 1
 ASYM_MMAX = 6
 WEID_N = 40
+FF_M = 8                  # far-field interpolation nodes per chunk
 
 
 # ----------------------------------------------------------------------------- core tables
@@ -144,6 +151,24 @@ def build_weideman(N=WEID_N):
     return L, a
 
 
+# ----------------------------------------------------------------------------- far field
+def build_farfield(m=FF_M):
+    """(nodes[m], MINV[m][m]) with  coef_j = sum_k MINV[j][k] f(t_k)  (monomial coefficients, j = power)."""
+    import mpmath as mp
+    mp.mp.dps = 60
+    nodes = [mp.cos(mp.pi * (2 * k + 1) / (2 * m)) for k in range(m)]
+    T = _cheb_monomials(m, mp)
+    minv = [[mp.mpf(0)] * m for _ in range(m)]
+    for j in range(m):                      # Chebyshev coefficient c_j = (2/m) sum_k f_k T_j(t_k), c_0 halved
+        for k in range(m):
+            cjk = mp.cos(mp.pi * j * (2 * k + 1) / (2 * m)) * 2 / m
+            if j == 0:
+                cjk /= 2
+            for i, v in enumerate(T[j]):    # T_j = sum_i v t^i
+                minv[i][k] += cjk * v
+    return [float(t) for t in nodes], np.array([[float(v) for v in row] for row in minv])
+
+
 # ----------------------------------------------------------------------------- emit
 def _arr(name, values, per_line=4):
     vals = [f"{v:.17g}" for v in np.asarray(values, dtype=np.float64).ravel()]
@@ -158,6 +183,7 @@ def render_header():
     tabs = build_core_tables()
     ctab = build_ctab()
     L, wa = build_weideman()
+    ff_nodes, ff_minv = build_farfield()
     out = []
     out.append("// GENERATED by tools/gen_faddeeva_tables.py -- do not edit by hand.\n")
     out.append("// Tables for the device Voigt-Hjerting function; see the generator's docstring.\n")
@@ -174,13 +200,17 @@ def render_header():
     out.append(f"#define RBV_ASYM_PMAX {ASYM_PMAX}\n")
     out.append(f"#define RBV_ASYM_MMAX {ASYM_MMAX}\n")
     out.append(f"#define RBV_WEID_N {WEID_N}\n")
-    out.append(f"#define RBV_WEID_L {L:.17g}\n\n")
+    out.append(f"#define RBV_WEID_L {L:.17g}\n")
+    out.append(f"#define RBV_FF_M {FF_M}\n\n")
     out.append("// g_k tables, layout [k][degree][interval] (interval fastest), monomials in t in [-1,1]\n")
     out.append(_arr("RBV_CORE_TABLE_HOST", np.concatenate([t.ravel() for t in tabs])))
     out.append("\n// CTAB[p][m], p = 0..PMAX (row 0 unused), m = 0..MMAX\n")
     out.append(_arr("RBV_ASYM_CTAB_HOST", ctab, per_line=ASYM_MMAX + 1))
     out.append("\n// Weideman N=40 polynomial coefficients, highest power first\n")
     out.append(_arr("RBV_WEID_COEF_HOST", wa))
+    out.append("\n// far field: Chebyshev nodes on [-1,1] and the node-values -> monomial-coefficients matrix [power][node]\n")
+    out.append(_arr("RBV_FF_NODES_HOST", ff_nodes))
+    out.append(_arr("RBV_FF_MINV_HOST", ff_minv, per_line=FF_M))
     return "".join(out)
 
 
