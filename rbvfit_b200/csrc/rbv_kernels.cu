@@ -40,6 +40,7 @@ struct InstDev {
   const double* f;         // [L]
   const double* zfac;      // [L]
   const int* comp;         // [L]
+  const double2* ublk;     // [ceil(P / 256)] (min, max) of 1/wave over aligned 256-pixel blocks
   const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
   int P, K, Kpad, L, C, method;
   int R;                   // register blocking of the LSF stage (context-wide)
@@ -53,6 +54,7 @@ struct TileGeom {
   int ext_alloc;   // flux slots per CTA in shared memory (tile + halo + slack)
   int first_tile;  // index of this instrument's first tile in the launch's tile list
   int n_tiles;
+  int n_super;     // super-chunks (kSuperPix flux slots) per CTA
 };
 constexpr int kMaxInst = 16;
 
@@ -261,20 +263,22 @@ __device__ __forceinline__ void accum_asym_line(int off, const double (&u)[kPixP
   }
 }
 
-// Far field of one warp chunk.  The listed lines are all >= 200 Doppler widths away from
-// every pixel of the chunk, where their summed optical depth g(u) = sum_l kappa_l rho_l (q1 + q2 rho_l + q3 rho_l^2)
-// is an analytic, slowly varying function of u = 1/lambda.  Instead of n_ff * 256 series evaluations:
+// Far field of one super-chunk.  The listed lines are all >= 200 Doppler widths away from
+// every pixel of the super-chunk, where their summed optical depth
+//     g(u) = sum_l kappa_l rho_l (q1 + q2 rho_l + q3 rho_l^2)
+// is an analytic, slowly varying function of u = 1/lambda.  Instead of n_ff series evaluations per pixel:
+//   phase 0, once per super-chunk (one warp):
 //   1. lane = line: evaluate the line at the RBV_FF_M Chebyshev nodes of [umin, umax] (same 8-FMA body as the
 //      direct far tier, ILP 8 over the nodes);
 //   2. transpose-reduce over the lanes (9 shuffle-adds) -> node sums S_k;
 //   3. lanes 0..7: monomial coefficients c_j = sum_k MINV[j][k] S_k (constant matrix, generated in 60-digit
-//      arithmetic), published through 16 doubles of per-warp shared memory;
-//   4. every pixel: t = (u - um)/uh by one FMA, tau = Horner_7(t)  (8 FMAs, whatever the number of lines).
-// Fixed evaluation order -> bit-reproducible for a given chunk.
-__device__ __forceinline__ void tau_farfield(int lc_off, const unsigned short* __restrict__ listff, int n_ff,
-                                             double umin, double umax, int ffw_off,
-                                             const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
-                                             int lane) {
+//      arithmetic) -> the super-chunk's record in shared memory, with the affine map u -> t in [-1, 1];
+//   phase 1, every pixel: t = u * scale + offset (one FMA), tau = Horner_7(t): 8 FMAs whatever the number of lines.
+// Fixed evaluation order -> bit-reproducible for a given tile geometry.
+constexpr int SC_COEF = 0, SC_SCALE = 8, SC_OFFSET = 9, SC_COUNTS = 10 /* 4 ints */, SC_STRIDE = 12;
+
+__device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned short* __restrict__ listff,
+                                                      int n_ff, double umin, double umax, int rec_off, int lane) {
   static_assert(RBV_FF_M == 8 && kPixPerThread == 8, "far-field code is written for 8 nodes and 8 pixels/lane");
   const double um = 0.5 * (umin + umax), uh = 0.5 * (umax - umin);
   double S[8];
@@ -311,55 +315,68 @@ __device__ __forceinline__ void tau_farfield(int lc_off, const unsigned short* _
     T1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
   }
   T1 += __shfl_xor_sync(0xffffffffu, T1, 2);
-  T1 += __shfl_xor_sync(0xffffffffu, T1, 1);
-  __syncwarp();                                        // earlier readers of the per-warp scratch are done
-  if ((lane & 3) == 0) smem[ffw_off + (lane >> 2)] = T1;   // S_k, k = lane >> 2
-  __syncwarp();
-  if (lane < 8) {
-    double c = 0.0;
+  T1 += __shfl_xor_sync(0xffffffffu, T1, 1);       // every lane: S_k of node k = lane >> 2
+  double c = 0.0;                                   // lane j < 8: c_j = sum_k MINV[j][k] S_k
 #pragma unroll
-    for (int k = 0; k < 8; ++k) c = fma(c_ff_minv[lane * 8 + k], smem[ffw_off + k], c);
-    smem[ffw_off + 8 + lane] = c;
-  }
-  __syncwarp();
+  for (int k = 0; k < 8; ++k) c = fma(c_ff_minv[(lane & 7) * 8 + k], __shfl_sync(0xffffffffu, T1, 4 * k), c);
+  const double sc = 1.0 / uh;
+  if (lane < 8) smem[rec_off + SC_COEF + lane] = c;
+  if (lane == 8) smem[rec_off + SC_SCALE] = sc;
+  if (lane == 9) smem[rec_off + SC_OFFSET] = -um * sc;
+}
+
+__device__ __forceinline__ void farfield_eval(int rec_off, const double (&u)[kPixPerThread],
+                                              double (&tau)[kPixPerThread]) {
   double c[8];
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
-    const double2 v = *reinterpret_cast<const double2*>(smem + ffw_off + 8 + j);
+    const double2 v = *reinterpret_cast<const double2*>(smem + rec_off + SC_COEF + j);
     c[j] = v.x;
     c[j + 1] = v.y;
   }
-  const double sc = 1.0 / uh, of = -um * sc;
+  const double2 so = *reinterpret_cast<const double2*>(smem + rec_off + SC_SCALE);
 #pragma unroll
   for (int j = 0; j < kPixPerThread; ++j) {
-    const double t = fma(u[j], sc, of);
+    const double t = fma(u[j], so.x, so.y);
     double p = c[7];
 #pragma unroll
     for (int q = 6; q >= 0; --q) p = fma(p, t, c[q]);
-    tau[j] = p;                                        // tau starts from the far field (was 0)
+    tau[j] = p;                                        // tau starts from the far field
   }
 }
 
-__device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __restrict__ list,
-                                         unsigned short* __restrict__ list32,
-                                         unsigned short* __restrict__ listff, double gate32, float ff_eps,
-                                         int ffw_off,
-                                         const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
-                                         const double* __restrict__ core_tab, int lane) {
-  // range of 1/lambda over the warp's chunk (no monotonicity assumed): integer min/max of the high words
-  // (1/lambda > 0, so the bit patterns order like the values), widened to the enclosing doubles
-  int hlo = __double2hiint(u[0]), hhi = hlo;
-#pragma unroll
-  for (int j = 1; j < kPixPerThread; ++j) {
-    const int hj = __double2hiint(u[j]);
-    hlo = min(hlo, hj);
-    hhi = max(hhi, hj);
+// Phase 0 for one super-chunk (one warp): range of 1/lambda over the aligned 256-pixel blocks that cover its
+// pixels [plo, phi] (from the per-instrument block table: no monotonicity assumed), tier lists, far-field record.
+__device__ __forceinline__ void prepare_super_chunk(const InstDev& I, int lc_off, int rec_off,
+                                                    unsigned short* __restrict__ list,
+                                                    unsigned short* __restrict__ list32,
+                                                    unsigned short* __restrict__ listff, double gate32,
+                                                    float ff_eps, int plo, int phi, int lane) {
+  int hlo = 0x7fffffff, hhi = 0;
+  for (int b = (plo >> 8) + lane; b <= (phi >> 8); b += 32) {
+    const double2 mm = I.ublk[b];
+    hlo = min(hlo, __double2hiint(mm.x));
+    hhi = max(hhi, __double2hiint(mm.y));
   }
-  hlo = __reduce_min_sync(0xffffffffu, hlo);
+  hlo = __reduce_min_sync(0xffffffffu, hlo);       // 1/lambda > 0: the high words order like the values
   hhi = __reduce_max_sync(0xffffffffu, hhi);
   const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
-  const int4 n = classify_lines(lc_off, L, list, list32, listff, gate32, ff_eps, umin, umax, lane);
-  if (n.w > 0) tau_farfield(lc_off, listff, n.w, umin, umax, ffw_off, u, tau, lane);
+  const int4 n = classify_lines(lc_off, I.L, list, list32, listff, gate32, ff_eps, umin, umax, lane);
+  if (n.w > 0) farfield_coefficients(lc_off, listff, n.w, umin, umax, rec_off, lane);
+  if (lane == 0) *reinterpret_cast<int4*>(smem + rec_off + SC_COUNTS) = n;
+}
+
+__device__ __forceinline__ void tau_wofz(int lc_off, int L, const unsigned short* __restrict__ list,
+                                         const unsigned short* __restrict__ list32, int rec_off,
+                                         const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
+                                         const double* __restrict__ core_tab) {
+  const int4 n = *reinterpret_cast<const int4*>(smem + rec_off + SC_COUNTS);   // n_far, n_other, n_fp32, n_farfield
+  if (n.w > 0) {
+    farfield_eval(rec_off, u, tau);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kPixPerThread; ++j) tau[j] = 0.0;
+  }
   if (n.z > 0) accum_far32(lc_off, list32, n.z, u, tau);
 
   // far lines: branch-free body, 8 FP64 instructions per (line, pixel)
@@ -399,6 +416,8 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, unsigned short* __re
 
 __device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[kPixPerThread],
                                          double (&tau)[kPixPerThread]) {
+#pragma unroll
+  for (int j = 0; j < kPixPerThread; ++j) tau[j] = 0.0;
   for (int l = 0; l < L; ++l) {
     const int off = lc_off + l * LC_STRIDE;
     const double A = smem[off + LC_A], B = smem[off + LC_B], eps = smem[off + LC_A2], aos = smem[off + LC_a],
@@ -478,16 +497,16 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   const int lc_off = (ndim + 1) & ~1;                  // smem layout (doubles): theta | line consts | taps |
   const int taps_off = lc_off + I.L * LC_STRIDE;       //   flux tile | per-warp line lists (u16)
   const int flux_off = taps_off + I.Kpad;
-  const int ffw_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1) + warp * 16;   // far-field scratch
-  const int list_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1) + (kThreads / 32) * 16;
+  const int rec_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1);              // super-chunk records
+  const int list_off = rec_off + G.n_super * SC_STRIDE;
   double* s_theta = smem;
   double* s_lc = smem + lc_off;
   double* s_taps = smem + taps_off;
   double* s_flux = smem + flux_off;
   const int list_stride = (I.L + 3) & ~3;
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + list_off) + warp * 3 * list_stride;
-  unsigned short* s_list32 = s_list + list_stride;
-  unsigned short* s_listff = s_list32 + list_stride;
+  // u16 lists: [n_super][2][list_stride] (direct tiers, FP32-gated), then one far-field scratch list per warp
+  unsigned short* s_lists = reinterpret_cast<unsigned short*>(smem + list_off);
+  unsigned short* s_listff = s_lists + (G.n_super * 2 + warp) * list_stride;
   // FP32 gate: the gated contributions of one pixel sum to <= 4e-6 (=> |dtau| <= 1e-11)
   const double gate32 = (prm.precision == RBV_PRECISION_FP32_GATED) ? 4e-6 / (double)I.L : 0.0;
   const float ff_eps = prm.farfield ? (float)(kFFEps / (double)I.L) : 0.f;
@@ -536,6 +555,17 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     const int n_out = min(G.tile, I.P - p0);
     const int ext = n_out + I.K - 1;
     const int n_chunks = (ext + kWarpPix - 1) / kWarpPix;
+    // ---- phase 0: tier lists + far-field record of every super-chunk (one warp each)
+    if (!fast) {
+      const int n_sc = (ext + kSuperPix - 1) / kSuperPix;
+      for (int sc = warp; sc < n_sc; sc += kThreads / 32) {
+        const int plo = min(max(p0 - h + sc * kSuperPix, 0), I.P - 1);
+        const int phi = min(max(p0 - h + min((sc + 1) * kSuperPix, ext) - 1, 0), I.P - 1);
+        prepare_super_chunk(I, lc_off, rec_off + sc * SC_STRIDE, s_lists + sc * 2 * list_stride,
+                            s_lists + (sc * 2 + 1) * list_stride, s_listff, gate32, ff_eps, plo, phi, lane);
+      }
+      __syncthreads();
+    }
     // warps pull 32*kPixPerThread-pixel chunks from a CTA-wide counter: chunks that contain a line core cost
     // several times a far-wing chunk, and static assignment would leave the other warps waiting at the barrier
     while (true) {
@@ -550,10 +580,13 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         int i = i0 + j * 32 + lane;
         int p = min(max(p0 - h + i, 0), I.P - 1);   // edge replication
         u[j] = __ldg(I.inv_wave + p);
-        tau[j] = 0.0;
       }
       if (fast) tau_fast(lc_off, I.L, u, tau);
-      else tau_wofz(lc_off, I.L, s_list, s_list32, s_listff, gate32, ff_eps, ffw_off, u, tau, prm.core_tab, lane);
+      else {
+        const int sc = c / kSuperChunks;
+        tau_wofz(lc_off, I.L, s_lists + sc * 2 * list_stride, s_lists + (sc * 2 + 1) * list_stride,
+                 rec_off + sc * SC_STRIDE, u, tau, prm.core_tab);
+      }
 #pragma unroll
       for (int j = 0; j < kPixPerThread; ++j) {
         int i = i0 + j * 32 + lane;
@@ -653,6 +686,33 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 __global__ void reciprocal_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = 1.0 / in[i];
+}
+
+// (min, max) of 1/wave over aligned 256-pixel blocks: the tile kernel's phase 0 takes the range of a super-chunk
+// from this table instead of re-reading its pixels (no monotonicity of the wavelength grid is assumed).
+__global__ void __launch_bounds__(256) block_range_kernel(const double* __restrict__ inv_wave,
+                                                          double2* __restrict__ out, int n) {
+  __shared__ double s_lo[8], s_hi[8];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double v = inv_wave[min(i, n - 1)];
+  double lo = v, hi = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      lo = fmin(lo, s_lo[k]);
+      hi = fmax(hi, s_hi[k]);
+    }
+    out[blockIdx.x] = make_double2(lo, hi);
+  }
 }
 
 // H(a,x) on a lattice through the same device functions the tile kernel uses (test hook).
@@ -771,8 +831,8 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 static size_t smem_bytes_for(const InstDev& I, const TileGeom& G, int ndim) {
   int logR = (I.R == 8) ? 3 : 2;
   size_t n = ((ndim + 1) & ~1) + (size_t)I.L * LC_STRIDE + I.Kpad + (G.ext_alloc + (G.ext_alloc >> logR)) + 4 +
-             (kThreads / 32) * 16;
-  size_t lists = (size_t)(kThreads / 32) * 3 * ((I.L + 3) & ~3) * sizeof(unsigned short);
+             (size_t)G.n_super * SC_STRIDE;
+  size_t lists = (size_t)(G.n_super * 2 + kThreads / 32) * ((I.L + 3) & ~3) * sizeof(unsigned short);
   return n * sizeof(double) + ((lists + 15) & ~(size_t)15);
 }
 
@@ -856,6 +916,7 @@ static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, si
     TileGeom g;
     g.tile = n_pass * kPass - (I.K - 1);
     g.ext_alloc = n_pass * kPass + 2 * I.R;
+    g.n_super = (n_pass * kPass + kSuperPix - 1) / kSuperPix;
     g.first_tile = total;
     g.n_tiles = (I.P + g.tile - 1) / g.tile;
     total += g.n_tiles;
@@ -874,7 +935,7 @@ static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t*
   for (int scale = 4; scale >= 1; scale >>= 1) {
     size_t smem = 0;
     total = compute_geometry(ctx, scale, geom, &smem, n_inst_used);
-    bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, 100 * 1024);
+    bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, (227 * 1024) / RBV_MIN_CTAS - 2048);   // RBV_MIN_CTAS CTAs per SM
     if (scale == 1 || (fits && (long long)W * total >= want)) {
       if (smem_out) *smem_out = smem;
       return total;
@@ -965,8 +1026,15 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
 
   reciprocal_kernel<<<(I.P + 255) / 256, 256>>>(sp->wave, sp->inv_wave, I.P);
   RBV_CUDA(cudaGetLastError());
+  const int n_blk = (I.P + 255) / 256;
+  double2* d_blk;
+  RBV_CUDA(cudaMalloc((void**)&d_blk, (size_t)n_blk * sizeof(double2)));
+  hi.owned.push_back(d_blk);
+  block_range_kernel<<<n_blk, 256>>>(sp->inv_wave, d_blk, I.P);
+  RBV_CUDA(cudaGetLastError());
   RBV_CUDA(cudaDeviceSynchronize());
-  ctx->launches++;
+  I.ublk = d_blk;
+  ctx->launches += 2;
 
   ctx->inst.push_back(hi);
   int rc = rebuild_tables(ctx);
