@@ -219,6 +219,14 @@ __device__ __forceinline__ double exp_flux(double x) {
   return y;
 }
 
+// exp(x) for |x| < 2^-6: degree-7 Taylor polynomial, truncation x^8/8! <= 9e-20
+__device__ __forceinline__ double exp_small(double x) {
+  double p = c_exp[7];
+#pragma unroll
+  for (int i = 6; i >= 0; --i) p = fma(p, x, c_exp[i]);
+  return p;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

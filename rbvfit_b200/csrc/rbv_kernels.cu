@@ -42,6 +42,7 @@ struct InstDev {
   const int* comp;         // [L]
   const double2* ublk;     // [ceil(P / 256)] (min, max) of 1/wave over aligned 256-pixel blocks
   const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
+  double sum_log_inv_sigma2;   // sum_p log_inv_sigma2[p] (theta-independent part of lnlike), fixed order
   int P, K, Kpad, L, C, method;
   int R;                   // register blocking of the LSF stage (context-wide)
   int line_base;           // first row of this instrument in the per-walker line-constant block
@@ -587,10 +588,23 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         tau_wofz(lc_off, I.L, s_lists + sc * 2 * list_stride, s_lists + (sc * 2 + 1) * list_stride,
                  rec_off + sc * SC_STRIDE, u, tau, prm.core_tab);
       }
+      // flux = exp(-tau), voigt_model.py:217.  Away from line cores every pixel of the chunk has |tau| < 2^-6,
+      // where the degree-7 Taylor polynomial is exact to 9e-20 and needs no range reduction.
+      unsigned hmax = 0u;
 #pragma unroll
-      for (int j = 0; j < kPixPerThread; ++j) {
-        int i = i0 + j * 32 + lane;
-        if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_flux(-tau[j]);   // voigt_model.py:217
+      for (int j = 0; j < kPixPerThread; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]) & 0x7fffffffu);
+      if (__reduce_max_sync(0xffffffffu, hmax) < 0x3F900000u) {       // NaN has a larger high word: slow path
+#pragma unroll
+        for (int j = 0; j < kPixPerThread; ++j) {
+          const int i = i0 + j * 32 + lane;
+          if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_small(-tau[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kPixPerThread; ++j) {
+          const int i = i0 + j * 32 + lane;
+          if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_flux(-tau[j]);
+        }
       }
     }
     // zero the slack the register-blocked window may touch (taps there are zero, values must be finite)
@@ -604,26 +618,32 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.0;
       const int e0 = g << LOGR;
-      double obs[R], wgt[R], lgw[R];   // observed spectrum: issue the global loads before the tap loop
+      double obs[R], wgt[R];   // observed spectrum: issue the global loads before the tap loop
       if (MODE == 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int p = min(p0 + e0 + r, I.P - 1);
           obs[r] = __ldg(I.flux + p);
           wgt[r] = __ldg(I.inv_sigma2 + p);
-          lgw[r] = __ldg(I.log_inv_sigma2 + p);
         }
       }
+      // padded layout: slot(R g + j) = (R + 1) g + j for j < R, so every window position is the group's base
+      // plus a compile-time offset (block b of R taps starts (R + 1) b further on)
+      int fw = flux_off + (R + 1) * g;
 #pragma unroll
-      for (int q = 0; q < R - 1; ++q) win[q] = s_flux[smem_pos(e0 + q, LOGR)];
-      for (int m0 = 0; m0 < I.Kpad; m0 += R) {
+      for (int q = 0; q < R - 1; ++q) win[q] = smem[fw + q];
+#pragma unroll 3
+      for (int m0 = 0; m0 < I.Kpad; m0 += R, fw += R + 1) {
+        win[R - 1] = smem[fw + R - 1];
 #pragma unroll
-        for (int q = 0; q < R; ++q) win[R - 1 + q] = s_flux[smem_pos(e0 + m0 + R - 1 + q, LOGR)];
+        for (int q = 1; q < R; ++q) win[R - 1 + q] = smem[fw + R + q];
 #pragma unroll
-        for (int mm = 0; mm < R; ++mm) {
-          const double tap = s_taps[m0 + mm];
+        for (int mm = 0; mm < R; mm += 2) {
+          const double2 tap = *reinterpret_cast<const double2*>(smem + taps_off + m0 + mm);
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fma(tap, win[mm + r], acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = fma(tap.x, win[mm + r], acc[r]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fma(tap.y, win[mm + 1 + r], acc[r]);
         }
 #pragma unroll
         for (int q = 0; q < R - 1; ++q) win[q] = win[R + q];
@@ -633,9 +653,9 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (e0 + r < n_out) {
-            double resid = obs[r] - acc[r];
-            double sq = resid * resid;
-            part += sq * wgt[r] - lgw[r];   // vfit_mcmc.py:310
+            const double resid = obs[r] - acc[r];
+            part = fma(resid * resid, wgt[r], part);   // vfit_mcmc.py:310; the log_inv_sigma2 term is summed once
+                                                       // per instrument at set-up (InstDev::sum_log_inv_sigma2)
           }
         }
       } else {
@@ -674,7 +694,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         for (int k = 0; k < n_sum; ++k) {
           double s = 0.0;
           for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
-          total += -0.5 * s;                                          // vfit_mcmc.py:309-313
+          const int ki = (prm.wps > 0) ? inst_id : k;
+          total += -0.5 * (s - prm.inst[ki].sum_log_inv_sigma2);      // vfit_mcmc.py:309-313
         }
       }
       prm.lnprob[w] = total;
@@ -713,6 +734,20 @@ __global__ void __launch_bounds__(256) block_range_kernel(const double* __restri
     }
     out[blockIdx.x] = make_double2(lo, hi);
   }
+}
+
+// sum_p v[p] in a fixed order (one CTA; set-up only)
+__global__ void __launch_bounds__(256) fixed_order_sum_kernel(const double* __restrict__ v, int n, double* out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += v[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = s[0];
 }
 
 // H(a,x) on a lattice through the same device functions the tile kernel uses (test hook).
@@ -1035,6 +1070,15 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
   RBV_CUDA(cudaDeviceSynchronize());
   I.ublk = d_blk;
   ctx->launches += 2;
+  if (I.log_inv_sigma2) {
+    double* d_sum;
+    RBV_CUDA(cudaMalloc((void**)&d_sum, sizeof(double)));
+    fixed_order_sum_kernel<<<1, 256>>>(I.log_inv_sigma2, I.P, d_sum);
+    RBV_CUDA(cudaGetLastError());
+    RBV_CUDA(cudaMemcpy(&I.sum_log_inv_sigma2, d_sum, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_sum);
+    ctx->launches++;
+  }
 
   ctx->inst.push_back(hi);
   int rc = rebuild_tables(ctx);
