@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +44,7 @@ struct InstDev {
   const double2* ublk;     // [ceil(P / 256)] (min, max) of 1/wave over aligned 256-pixel blocks
   const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
   double sum_log_inv_sigma2;   // sum_p log_inv_sigma2[p] (theta-independent part of lnlike), fixed order
+  int vec16;                   // flux and inv_sigma2 are 16-byte aligned (vector loads in phase 2)
   int P, K, Kpad, L, C, method;
   int R;                   // register blocking of the LSF stage (context-wide)
   int line_base;           // first row of this instrument in the per-walker line-constant block
@@ -478,7 +480,6 @@ template <int LOGR, int MODE>
 __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(const LaunchParams prm) {
   constexpr int R = 1 << LOGR;
   __shared__ double s_red[kThreads / 32];
-  __shared__ int s_flag;
   __shared__ int s_next;   // dynamic chunk counter of phase 1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -569,11 +570,14 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     }
     // warps pull 32*kPixPerThread-pixel chunks from a CTA-wide counter: chunks that contain a line core cost
     // several times a far-wing chunk, and static assignment would leave the other warps waiting at the barrier
-    while (true) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&s_next, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= n_chunks) break;
+    // (the ticket for the NEXT chunk is drawn one iteration ahead, so that its 1/lambda lines can be prefetched
+    // into L1 while the current chunk is computed)
+    int c = 0;
+    if (lane == 0) c = atomicAdd(&s_next, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    while (c < n_chunks) {
+      int c_next = 0;
+      if (lane == 0) c_next = atomicAdd(&s_next, 1);
       const int i0 = c * kWarpPix;
       double u[kPixPerThread], tau[kPixPerThread];
 #pragma unroll
@@ -581,6 +585,11 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         int i = i0 + j * 32 + lane;
         int p = min(max(p0 - h + i, 0), I.P - 1);   // edge replication
         u[j] = __ldg(I.inv_wave + p);
+      }
+      c_next = __shfl_sync(0xffffffffu, c_next, 0);
+      if (c_next < n_chunks && lane < kWarpPix / 16) {          // 16 doubles per 128-byte line
+        const int p = min(max(p0 - h + c_next * kWarpPix + lane * 16, 0), I.P - 1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(I.inv_wave + p));
       }
       if (fast) tau_fast(lc_off, I.L, u, tau);
       else {
@@ -606,27 +615,43 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
           if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_flux(-tau[j]);
         }
       }
+      c = c_next;
     }
+    // observed spectrum of a group of R outputs: 16-byte loads (the R doubles of a thread are contiguous);
+    // the first group's loads are issued BEFORE the barrier so that their latency overlaps the wait
+    const int n_groups = (n_out + R - 1) >> LOGR;
+    double obs[R], wgt[R];
+    auto load_group = [&](int g) {
+      const int pg = p0 + (g << LOGR);
+      if (I.vec16 && pg + R <= I.P) {
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          const double2 o = __ldg(reinterpret_cast<const double2*>(I.flux + pg + r));
+          const double2 v = __ldg(reinterpret_cast<const double2*>(I.inv_sigma2 + pg + r));
+          obs[r] = o.x; obs[r + 1] = o.y;
+          wgt[r] = v.x; wgt[r + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int p = min(pg + r, I.P - 1);
+          obs[r] = __ldg(I.flux + p);
+          wgt[r] = __ldg(I.inv_sigma2 + p);
+        }
+      }
+    };
+    if (MODE == 0 && tid < n_groups) load_group(tid);
     // zero the slack the register-blocked window may touch (taps there are zero, values must be finite)
     for (int i = ext + tid; i < G.ext_alloc; i += kThreads) s_flux[smem_pos(i, LOGR)] = 0.0;
     __syncthreads();
 
     // ---- phase 2: LSF + chi^2 (or flux out).  M_p = sum_m taps_rev[m] * E[o + m]
-    const int n_groups = (n_out + R - 1) >> LOGR;
     for (int g = tid; g < n_groups; g += kThreads) {
       double acc[R], win[2 * R - 1];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.0;
       const int e0 = g << LOGR;
-      double obs[R], wgt[R];   // observed spectrum: issue the global loads before the tap loop
-      if (MODE == 0) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int p = min(p0 + e0 + r, I.P - 1);
-          obs[r] = __ldg(I.flux + p);
-          wgt[r] = __ldg(I.inv_sigma2 + p);
-        }
-      }
+      if (MODE == 0 && g != tid) load_group(g);
       // padded layout: slot(R g + j) = (R + 1) g + j for j < R, so every window position is the group's base
       // plus a compile-time offset (block b of R taps starts (R + 1) b further on)
       int fw = flux_off + (R + 1) * g;
@@ -677,13 +702,10 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 #pragma unroll
       for (int k = 0; k < kThreads / 32; ++k) s += s_red[k];
       prm.partials[(size_t)w * prm.n_tiles + tile_id] = s;
-      __threadfence();
-      unsigned int prev = atomicAdd(prm.tickets + w, 1u);
-      s_flag = (prev == (unsigned int)(prm.n_tiles - 1));
-    }
-    __syncthreads();
-    if (s_flag && tid == 0) {
-      __threadfence();
+      // release our partial / acquire the others' with ONE acq_rel ticket atomic; the walker's last CTA finalises
+      unsigned int prev;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(prm.tickets + w) : "memory");
+      if (prev != (unsigned int)(prm.n_tiles - 1)) return;
       double total;
       if (oob) {
         total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
@@ -1037,6 +1059,7 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
   I.flux = sp->flux;
   I.inv_sigma2 = sp->inv_sigma2;
   I.log_inv_sigma2 = sp->log_inv_sigma2;
+  I.vec16 = (((uintptr_t)sp->flux | (uintptr_t)sp->inv_sigma2) & 15) == 0;
 
   // LSF taps as the reference applies them; "no kernel" = the single tap 1.0
   hi.taps.assign(sp->n_taps > 0 ? sp->n_taps : 1, 1.0);
