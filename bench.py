@@ -48,7 +48,7 @@ def _peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons with NVML during the timed region."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -213,13 +213,21 @@ def run_gpu(args, rank, world, local):
     name0 = like.names[0]
     data0 = models[name0].compile().data
     n_taps = 1 if data0.kernel is None else len(data0.kernel)
-    F, tiers = 0.0, {}
+    # algorithmic flops per walker.pixel: of the far-field algorithm the default path runs (F), and of the
+    # direct evaluation of every (line, pixel) pair by SURVEY.md 8(d)'s rule (F_direct)
+    F, F_direct, tiers, tiers_direct = 0.0, 0.0, {}, {}
     for n in like.names:                                        # pixel-weighted over instruments
         d = models[n].compile().data
         k = 1 if d.kernel is None else len(d.kernel)
-        Fn, tn = rf.flops_per_walker_pixel(d, w["theta_true"], spectra[n]["wave"], k)
-        F += Fn * len(spectra[n]["wave"]) / total_px
-        tiers[n] = tn
+        share = len(spectra[n]["wave"]) / total_px
+        Fd, td = rf.flops_per_walker_pixel(d, w["theta_true"], spectra[n]["wave"], k)
+        Ff, tf = rf.flops_farfield(d, w["theta_true"], spectra[n]["wave"], k)
+        F_direct += Fd * share
+        F += Ff * share
+        tiers[n], tiers_direct[n] = tf, td
+    if args.far_field == "direct":
+        F, tiers = F_direct, tiers_direct
+    like.engine.set_farfield(args.far_field)
 
     # ---------------- device-resident timing
     theta_dev = torch.as_tensor(thetas, device=dev)
@@ -303,12 +311,22 @@ def run_gpu(args, rank, world, local):
                      "frac": achieved / fp64_peak, "traffic": prof.get("dram_bytes_per_launch"),
                      "peak_source": "DFMA dependent-chain probe measured in this run (rbv_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 entry (spec: 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
-                     "kernel": "voigt_tile_kernel", "kernel_ms": k_ms,
+                     "kernel": "voigt_tile_kernel", "kernel_ms": k_ms, "far_field": args.far_field,
                      "algorithmic_flops_per_walker_pixel": F, "tiers": tiers,
+                     "algorithm_note": "far wings of each 1024-px super-chunk are summed at 8 Chebyshev nodes and "
+                                       "interpolated (a-priori gated, |dtau| <= 1e-13): F counts THAT algorithm "
+                                       "(rbvfit_b200/roofline.py:flops_farfield); direct_equivalent applies SURVEY "
+                                       "8(d)'s per-(line,pixel) rule to the same throughput and may exceed the peak",
+                     "direct_equivalent": {"algorithmic_flops_per_walker_pixel": F_direct,
+                                           "tflops": F_direct * n_inb * total_px / (k_ms * 1e-3) / 1e12,
+                                           "tiers": tiers_direct},
                      "hbm_sanity": {"algorithmic_gbs": hbm_alg_bytes / (k_ms * 1e-3) / 1e9,
                                     "peak_gbs": peaks.get("hbm_gbs"), "peaks": peaks_kind}},
     }
     if world == 1 and not args.no_extras:
+        if args.far_field == "chebyshev":
+            line["direct_far_wings"] = direct_leg(like, theta_dev, lnp, W, total_px, args.steps, flush, F_direct,
+                                                  n_inb, fp64_peak)
         line["fp32_gated"] = fp32_gated_leg(like, theta_dev, thetas, W, total_px, args.steps, flush)
         line["mcmc"] = mcmc_leg(local, with_cpu=not args.no_cpu)
     if not args.no_cpu and world >= 1:
@@ -409,6 +427,34 @@ def run_gpu_sightlines(args, rank, world, local, n_sightlines=1024, walkers=64):
         "finite_fraction": float(np.isfinite(res).mean())}))
 
 
+def direct_leg(like, theta_dev, lnp_default, W, total_px, steps, flush, F_direct, n_inb, fp64_peak):
+    """The same batch with the far field switched off (every (line, pixel) pair evaluated on its own): the kernel
+    SURVEY.md 8(d)'s flop rule describes, timed exactly like `value`, plus its agreement with the default path."""
+    import torch
+    like.engine.set_farfield("direct")
+    try:
+        for _ in range(2):
+            out = like.lnprob_device(theta_dev)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            flush.zero_()
+            ev[k][0].record()
+            out = like.lnprob_device(theta_dev)
+            ev[k][1].record()
+        torch.cuda.synchronize()
+    finally:
+        like.engine.set_farfield("chebyshev")
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    got = out.cpu().numpy()
+    fin = np.isfinite(lnp_default)
+    dev = float(np.max(np.abs(got[fin] - lnp_default[fin]) / np.abs(lnp_default[fin]))) if fin.any() else 0.0
+    tf = F_direct * n_inb * total_px / (ms * 1e-3) / 1e12
+    return {"value": W * total_px / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "algorithmic_flops_per_walker_pixel": F_direct, "achieved_tflops": tf, "frac": tf / fp64_peak,
+            "max_rel_dev_vs_default": dev}
+
+
 def fp32_gated_leg(like, theta_dev, thetas, W, total_px, steps, flush):
     """The FP32-gated far-wing variant (north_star): kept only if it passes the tolerance check against the
     FP64 kernel on a walker sample; timed exactly like `value`."""
@@ -493,6 +539,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--far-field", default="chebyshev", choices=["chebyshev", "direct"],
+                    help="far-wing accumulation: interpolated far field (default) or every pair evaluated directly")
     ap.add_argument("--workload", default="C5a")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -67,6 +67,7 @@ class GpuLikelihood:
         self.ndim = self.lb.size
         self.total_pixels = int(sum(self.pixels))
         self.precision = "fp64"
+        self.far_field = "chebyshev"
         self.last_precision_check = None
 
     # ------------------------------------------------------------------ reference-shaped API
@@ -91,6 +92,16 @@ class GpuLikelihood:
     def lnprob_device(self, theta_t, out_t=None):
         """Device-resident variant (torch tensors in / out, asynchronous)."""
         return self.engine.lnprob_device(theta_t, out_t)
+
+    def set_far_field(self, mode: str = "chebyshev"):
+        """``"chebyshev"`` (default): the summed far wings (|x| >= 200 Doppler widths) of each 1024-pixel
+        super-chunk are evaluated at 8 Chebyshev nodes and interpolated; a line takes part only where an
+        a-priori bound keeps its interpolation error <= 1e-13 / L in optical depth.
+        ``"direct"``: every (line, pixel) pair is evaluated on its own."""
+        if mode not in ("chebyshev", "direct"):
+            raise ValueError("far field mode must be 'chebyshev' or 'direct'")
+        self.engine.set_farfield(mode)
+        self.far_field = mode
 
     def set_precision(self, precision: str = "fp64", check_thetas=None, rtol: float = 1e-9) -> bool:
         """Select the far-wing arithmetic.  ``"fp32-gated"`` moves far-wing lines whose contribution is provably

@@ -161,3 +161,61 @@ def test_sightline_batch_equals_individual_fits():
     assert len(set(np.round(ref[np.isfinite(ref)], 3))) > S     # sightlines really differ
     with pytest.raises(ValueError):
         batch.lnprob(thetas[:5])
+
+
+@pytest.mark.parametrize("workload,nw", [("C5a", 96), ("C2", 80), ("C4", 32), ("C4w", 32), ("C3", 50)])
+def test_far_field_interpolant_matches_direct_evaluation(workload, nw):
+    """Default path (Chebyshev far field per 1024-px super-chunk) against the direct evaluation of every
+    (line, pixel) pair: the a-priori gate promises |dtau| <= 1e-13 per pixel."""
+    w, models, compiled, spectra, like, thetas = _problem(workload, nw)
+    name0 = like.names[0]
+    ok = thetas[np.all((thetas >= w["lb"]) & (thetas <= w["ub"]), axis=1)][:6]
+    res = {}
+    for mode in ("direct", "chebyshev"):
+        like.set_far_field(mode)
+        res[mode] = (like.lnprob(thetas), like.engine.model_flux(0, ok))
+    (la, fa), (lb_, fb) = res["direct"], res["chebyshev"]
+    assert np.array_equal(np.isneginf(la), np.isneginf(lb_))
+    fin = np.isfinite(la)
+    assert np.max(np.abs(la[fin] - lb_[fin]) / np.abs(la[fin])) <= 1e-12
+    assert np.max(np.abs(fa - fb)) <= 2e-13
+    with pytest.raises(ValueError):
+        like.set_far_field("fmm")
+
+
+def test_far_field_stress_strong_lines_and_extreme_widths():
+    """Far-field gate under stress: damped (logN 22) and very narrow / very broad components next to weak ones, on
+    a coarse and on a fine wavelength grid; direct and interpolated paths must agree to the flux tolerance."""
+    from rbvfit_b200 import FitConfiguration
+    from rbvfit_b200.likelihood import GpuLikelihood
+    from rbvfit_b200.model import GpuVoigtModel
+    rng = np.random.default_rng(5)
+    cfg = FitConfiguration()
+    cfg.add_system(z=2.5, ion="HI", transitions=[1215.67, 1025.72, 972.54], components=2)
+    cfg.add_system(z=2.1, ion="CIV", transitions=[1548.2, 1550.77], components=2)
+    cfg.add_system(z=1.9, ion="SiIV", transitions=[1393.76, 1402.77], components=1)
+    model = GpuVoigtModel(cfg, FWHM="6.5")
+    C = 5
+    for P in (3000, 60000):
+        wave = np.linspace(3200.0, 5600.0, P)
+        rows = []
+        for _ in range(24):
+            logN = np.array([rng.uniform(19.0, 22.0), rng.uniform(12.0, 15.0), rng.uniform(12.0, 16.0),
+                             rng.uniform(12.0, 14.0), rng.uniform(12.0, 17.0)])
+            b = np.array([rng.uniform(15, 80), rng.uniform(1.0, 5.0), rng.uniform(2, 150), rng.uniform(5, 30),
+                          rng.uniform(1.0, 200.0)])
+            v = rng.uniform(-300, 300, C)
+            rows.append(np.concatenate([logN, b, v]))
+        thetas = np.array(rows)
+        lb, ub = np.full(3 * C, -1e9), np.full(3 * C, 1e9)
+        flux = 1.0 + 0.05 * rng.standard_normal(P)
+        like = GpuLikelihood({"S": dict(model=model, wave=wave, flux=flux, error=np.full(P, 0.05))}, lb, ub)
+        out = {}
+        for mode in ("direct", "chebyshev"):
+            like.set_far_field(mode)
+            out[mode] = (like.lnprob(thetas), like.engine.model_flux(0, thetas[:8]))
+        (la, fa), (lb_, fb) = out["direct"], out["chebyshev"]
+        assert np.all(np.isfinite(la))
+        assert np.max(np.abs(fa - fb)) <= 1e-12, P
+        assert np.max(np.abs(la - lb_) / np.abs(la)) <= 1e-11, P
+        like.close()
