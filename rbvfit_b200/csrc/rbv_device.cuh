@@ -32,7 +32,10 @@ namespace rbv {
 #ifndef RBV_MIN_CTAS
 #define RBV_MIN_CTAS 2
 #endif
-constexpr int kThreads = 256;
+#ifndef RBV_THREADS
+#define RBV_THREADS 256
+#endif
+constexpr int kThreads = RBV_THREADS;
 constexpr int kPixPerThread = RBV_PPT;
 constexpr int kPass = kThreads * kPixPerThread;  // pixels per phase-1 pass
 constexpr int kWarpPix = 32 * kPixPerThread;     // pixels covered by one warp per pass ("chunk")

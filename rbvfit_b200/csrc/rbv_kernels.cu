@@ -44,7 +44,8 @@ struct InstDev {
   const double2* ublk;     // [ceil(P / 256)] (min, max) of 1/wave over aligned 256-pixel blocks
   const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
   double sum_log_inv_sigma2;   // sum_p log_inv_sigma2[p] (theta-independent part of lnlike), fixed order
-  int vec16;                   // flux and inv_sigma2 are 16-byte aligned (vector loads in phase 2)
+  const double2* obs_w;        // (flux, inv_sigma2) pairs re-ordered per 256-pixel block so that phase 2 loads them
+                               // coalesced: element (lane, r) = pixel 256 J + 8 lane + r sits at 256 J + 32 r + lane
   int P, K, Kpad, L, C, method;
   int R;                   // register blocking of the LSF stage (context-wide)
   int line_base;           // first row of this instrument in the per-walker line-constant block
@@ -617,27 +618,19 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       }
       c = c_next;
     }
-    // observed spectrum of a group of R outputs: 16-byte loads (the R doubles of a thread are contiguous);
-    // the first group's loads are issued BEFORE the barrier so that their latency overlaps the wait
+    // observed spectrum of a group of R outputs from the block-transposed (flux, inv_sigma2) copy: lane-contiguous
+    // 16-byte loads (tiles start on 256-pixel boundaries); the first group's loads are issued BEFORE the barrier
+    // so that their latency overlaps the wait
+    static_assert(R == 8, "the packed observed-spectrum layout assumes 8 outputs per lane");
     const int n_groups = (n_out + R - 1) >> LOGR;
     double obs[R], wgt[R];
     auto load_group = [&](int g) {
-      const int pg = p0 + (g << LOGR);
-      if (I.vec16 && pg + R <= I.P) {
+      const double2* src = I.obs_w + ((size_t)(p0 >> 8) + (g >> 5)) * 256 + lane;
 #pragma unroll
-        for (int r = 0; r < R; r += 2) {
-          const double2 o = __ldg(reinterpret_cast<const double2*>(I.flux + pg + r));
-          const double2 v = __ldg(reinterpret_cast<const double2*>(I.inv_sigma2 + pg + r));
-          obs[r] = o.x; obs[r + 1] = o.y;
-          wgt[r] = v.x; wgt[r + 1] = v.y;
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int p = min(pg + r, I.P - 1);
-          obs[r] = __ldg(I.flux + p);
-          wgt[r] = __ldg(I.inv_sigma2 + p);
-        }
+      for (int r = 0; r < R; ++r) {
+        const double2 v = __ldg(src + 32 * r);
+        obs[r] = v.x;
+        wgt[r] = v.y;
       }
     };
     if (MODE == 0 && tid < n_groups) load_group(tid);
@@ -756,6 +749,15 @@ __global__ void __launch_bounds__(256) block_range_kernel(const double* __restri
     }
     out[blockIdx.x] = make_double2(lo, hi);
   }
+}
+
+// (flux, inv_sigma2) -> block-transposed pairs (InstDev::obs_w); pixels beyond the spectrum are zero-filled
+__global__ void __launch_bounds__(256) pack_observed_kernel(const double* __restrict__ flux,
+                                                            const double* __restrict__ inv_sigma2,
+                                                            double2* __restrict__ out, int n) {
+  const int t = threadIdx.x, lane = t & 31, r = t >> 5;
+  const int p = blockIdx.x * 256 + 8 * lane + r;
+  out[(size_t)blockIdx.x * 256 + t] = (p < n) ? make_double2(flux[p], inv_sigma2[p]) : make_double2(0.0, 0.0);
 }
 
 // sum_p v[p] in a fixed order (one CTA; set-up only)
@@ -971,7 +973,7 @@ static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, si
     int need = (I.P + I.K - 1 + kPass - 1) / kPass;
     n_pass = std::max(1, std::min(n_pass, need));
     TileGeom g;
-    g.tile = n_pass * kPass - (I.K - 1);
+    g.tile = (n_pass * kPass - (I.K - 1)) & ~255;   // tiles start on the 256-pixel blocks of InstDev::obs_w
     g.ext_alloc = n_pass * kPass + 2 * I.R;
     g.n_super = (n_pass * kPass + kSuperPix - 1) / kSuperPix;
     g.first_tile = total;
@@ -987,7 +989,7 @@ static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, si
 // Picks the largest tile scale that still gives every SM several CTAs and fits two CTAs per SM.
 static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t* smem_out,
                            size_t n_inst_used = (size_t)-1) {
-  const long long want = 4LL * 2 * ctx->sm_count;   // >= 4 waves at 2 CTAs / SM
+  const long long want = 4LL * RBV_MIN_CTAS * ctx->sm_count;   // >= 4 waves of resident CTAs
   int total = 0;
   for (int scale = 4; scale >= 1; scale >>= 1) {
     size_t smem = 0;
@@ -1059,7 +1061,6 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
   I.flux = sp->flux;
   I.inv_sigma2 = sp->inv_sigma2;
   I.log_inv_sigma2 = sp->log_inv_sigma2;
-  I.vec16 = (((uintptr_t)sp->flux | (uintptr_t)sp->inv_sigma2) & 15) == 0;
 
   // LSF taps as the reference applies them; "no kernel" = the single tap 1.0
   hi.taps.assign(sp->n_taps > 0 ? sp->n_taps : 1, 1.0);
@@ -1093,6 +1094,15 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
   RBV_CUDA(cudaDeviceSynchronize());
   I.ublk = d_blk;
   ctx->launches += 2;
+  if (I.flux && I.inv_sigma2) {
+    double2* d_ow;
+    RBV_CUDA(cudaMalloc((void**)&d_ow, (size_t)n_blk * 256 * sizeof(double2)));
+    hi.owned.push_back(d_ow);
+    pack_observed_kernel<<<n_blk, 256>>>(I.flux, I.inv_sigma2, d_ow, I.P);
+    RBV_CUDA(cudaGetLastError());
+    I.obs_w = d_ow;
+    ctx->launches++;
+  }
   if (I.log_inv_sigma2) {
     double* d_sum;
     RBV_CUDA(cudaMalloc((void**)&d_sum, sizeof(double)));
