@@ -1,10 +1,13 @@
 // rbvfit_b200 -- fused Voigt forward model + likelihood kernels for sm_100a, and their C ABI.
 //
 // One CTA = one (walker, pixel tile).  Per CTA:
-//   prep    theta row -> per-line constants in shared memory (A, B, a^2, kappa-scaled series
-//           coefficients; _evaluate_compiled_model :192-200 and _vectorized_voigt_tau :142-150)
-//   phase 1 tau_p = sum_l coef_l H(a_l, x_lp) for the tile's pixels + LSF halo, flux = exp(-tau) into
-//           shared memory (edge pixels replicated = ndimage 'nearest' / astropy 'extend')
+//   prep    (prep_kernel, once per walker) theta row -> per-line constants (A, B, a^2, kappa-scaled series
+//           coefficients; _evaluate_compiled_model :192-200 and _vectorized_voigt_tau :142-150) + prior flag
+//   phase 0 per 1024-pixel super-chunk: tier of every line from the chunk's range of 1/lambda, and the far-field
+//           record: the summed far wings at 8 Chebyshev nodes -> 8 polynomial coefficients
+//   phase 1 tau_p = far-field polynomial + sum over the remaining lines coef_l H(a_l, x_lp) for the tile's pixels
+//           + LSF halo, flux = exp(-tau) into shared memory (edge pixels replicated = ndimage 'nearest' /
+//           astropy 'extend')
 //   phase 2 LSF convolution from shared memory with R outputs per thread (register-blocked sliding
 //           window), then either the chi^2 partial of vfit.lnlike (vfit_mcmc.py:309-311) reduced with
 //           warp shuffles, or the model flux written out
@@ -13,8 +16,9 @@
 //           (vfit.lnprior :291-295, lnprob :348-353).
 //
 // Data layout in HBM (all float64): per instrument 1/wave, flux, inv_sigma2, log_inv_sigma2 [P] shared by
-// every walker (L2-resident); theta [W, ndim] row-major; lnprob [W]; workspace = tile partials
-// [W, n_tiles] + tickets [W].  No per-line optical depth is ever materialised.
+// every walker (L2-resident) + derived block tables; theta [W, ndim] row-major; lnprob [W]; workspace = tickets,
+// prior flags, tile partials [W, n_tiles], line constants [W, L, 22].  No per-line optical depth is ever
+// materialised.
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -137,3 +137,26 @@ def test_roofline_flops_rule():
     F, tiers = rf.flops_per_walker_pixel(m, w["theta_true"], w["instruments"]["COS"]["wave"], 23)
     assert abs(sum(tiers.values()) - 1) < 1e-12
     assert 150 < F < 398            # ~280 for C1, upper bound 80 L + 2 K + 32 = 398
+
+
+def test_roofline_farfield_rule():
+    """Algorithmic flops of the far-field algorithm (rbvfit_b200/roofline.py): never more than the direct rule, equal
+    to it when no line qualifies (C1: every pixel is within 200 Doppler widths of the doublet), ~5x less at C5a's
+    structure (C2 grid here to keep the CPU suite fast)."""
+    from rbvfit_b200 import roofline as rf, workloads as wl
+    from oracle import voigt_oracle as vo
+    out = {}
+    for name in ("C1", "C2", "C4"):
+        w = wl.get_workload(name)
+        cfg = vo.OracleConfig()
+        for (z, ion, trans, comps) in w["systems"]:
+            cfg.add_system(z, ion, trans, comps)
+        m = vo.lower(cfg)
+        wave = list(w["instruments"].values())[0]["wave"]
+        Fd, _ = rf.flops_per_walker_pixel(m, w["theta_true"], wave, 23)
+        Ff, t = rf.flops_farfield(m, w["theta_true"], wave, 23)
+        assert abs(sum(t.values()) - 1) < 1e-12
+        out[name] = (Fd, Ff, t)
+    assert out["C1"][0] == out["C1"][1] and out["C1"][2]["farfield"] == 0.0
+    assert out["C2"][1] < 0.4 * out["C2"][0] and out["C2"][2]["farfield"] > 0.75
+    assert out["C4"][1] < out["C4"][0] and 0.5 < out["C4"][2]["farfield"] < 0.9     # the DLA's wings stay direct
