@@ -127,6 +127,25 @@ int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int n_walke
                           double* theta_dev, double* lnprob_dev, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* Device-resident affine-invariant ensemble sampler (stretch move).  Replaces the sampling loop
+ * emcee.EnsembleSampler(nwalkers, ndim, self.lnprob).run_mcmc(guesses, no_of_steps), vfit_mcmc.py:408-423, 536-540
+ * (emcee >= 3.0.0 is not vendored in the reference; its RedBlueMove + StretchMove is restated from the published
+ * algorithm).  Proposal, likelihood and accept/reject of every half-step run on the device with no host round trip;
+ * random numbers come from Philox4x32-10 keyed by `seed` with counter (first_step + s, walker, purpose), so a run
+ * continued with first_step = steps already done reproduces one long run.
+ *   coords      DEVICE [n_walkers, ndim]  current ensemble, updated in place
+ *   lnprob      DEVICE [n_walkers]        its log-probabilities (from rbv_lnprob_batch), updated in place
+ *   chain       DEVICE [n_steps, n_walkers, ndim] or NULL; lnprob_chain DEVICE [n_steps, n_walkers] or NULL
+ *   n_accepted  DEVICE int[n_walkers], accumulated;  flag DEVICE int, bit 0 set if a proposal's lnprob was NaN
+ *   workspace   DEVICE, rbv_stretch_workspace_bytes(); use_graph != 0 captures one step in a CUDA graph and
+ *               replays it (needs a non-default stream; the call then returns after the run has finished),
+ *               otherwise the launches are only enqueued (asynchronous). */
+int rbv_stretch_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
+int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                    unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                    int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                    void* stream);
+
 /* Model flux for a batch of walkers on instrument `inst`; CompiledVoigtModel.model_flux,
  * voigt_model.py:295-311 (convolve != 0) or VoigtModel.evaluate(return_unconvolved=True), :509-558.
  *   out_flux DEVICE [n_walkers, n_pixels] row-major doubles.  Asynchronous. */

@@ -31,6 +31,7 @@
 
 #include "../../include/rbvfit_b200.h"
 #include "rbv_device.cuh"
+#include "rbv_sampler.cuh"
 
 namespace rbv {
 
@@ -1263,6 +1264,116 @@ int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, doub
   if (rc != RBV_OK) return rc;
   RBV_CUDA(cudaMemcpyAsync(lnprob_host, lnprob_dev, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st));
   RBV_CUDA(cudaStreamSynchronize(st));
+  return RBV_OK;
+}
+
+// ------------------------------------------------------------------------------------------ device-resident sampler
+struct StretchLayout {
+  size_t prop, lnp_prop, factors, ctr, lnprob_ws, total;
+};
+static StretchLayout stretch_layout(const RbvContext* ctx, int W) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t h = (size_t)(W + 1) / 2;
+  StretchLayout lay;
+  lay.prop = 0;
+  lay.lnp_prop = up(h * std::max(ctx->ndim, 1) * sizeof(double));
+  lay.factors = lay.lnp_prop + up(h * sizeof(double));
+  lay.ctr = lay.factors + up(h * sizeof(double));
+  lay.lnprob_ws = lay.ctr + 256;
+  lay.total = lay.lnprob_ws + workspace_layout(ctx, (int)h, false).total;
+  return lay;
+}
+
+int rbv_stretch_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes) {
+  if (!ctx || !bytes || n_walkers < 2) return fail(RBV_EINVAL, "rbv_stretch_workspace_bytes: bad argument");
+  *bytes = stretch_layout(ctx, n_walkers).total;
+  return RBV_OK;
+}
+
+int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                    unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                    int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                    void* stream) {
+  if (!ctx || !coords || !lnprob || !n_accepted || !flag)
+    return fail(RBV_EINVAL, "rbv_stretch_run: null argument");
+  if (n_walkers < 2) return fail(RBV_EINVAL, "rbv_stretch_run: need at least two walkers");
+  if (n_steps < 0 || !(a > 1.0)) return fail(RBV_EINVAL, "rbv_stretch_run: n_steps < 0 or stretch scale a <= 1");
+  if (ctx->inst.empty() || ctx->ndim == 0) return fail(RBV_ESTATE, "rbv_stretch_run: context not set up");
+  if (n_steps == 0) return RBV_OK;
+  const StretchLayout lay = stretch_layout(ctx, n_walkers);
+  if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, "rbv_stretch_run: workspace too small");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  StretchParams P;
+  P.coords = coords;
+  P.lnp = lnprob;
+  P.prop = (double*)(ws + lay.prop);
+  P.lnp_prop = (double*)(ws + lay.lnp_prop);
+  P.factors = (double*)(ws + lay.factors);
+  P.chain = chain;
+  P.lnp_chain = lnprob_chain;
+  P.n_accepted = n_accepted;
+  P.flag = flag;
+  P.step_ctr = (unsigned long long*)(ws + lay.ctr);
+  P.ticket = (unsigned int*)(ws + lay.ctr + 64);
+  P.first_step = first_step;
+  P.seed = seed;
+  P.a = a;
+  P.W = n_walkers;
+  P.ndim = ctx->ndim;
+  RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
+  const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
+  const int h = (n_walkers + 1) / 2;
+  const int rec_blocks = (int)std::min<size_t>(((size_t)n_walkers * ctx->ndim + 255) / 256, (size_t)ctx->sm_count);
+
+  auto one_step = [&]() -> int {
+    for (int split = 0; split < 2; ++split) {
+      const int nS = split == 0 ? h : n_walkers - h;
+      stretch_propose_kernel<<<(nS + 127) / 128, 128, 0, st>>>(P, split);
+      int rc = launch_lnprob(ctx, P.prop, nS, 0, P.lnp_prop, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
+                             "rbv_stretch_run");
+      if (rc != RBV_OK) return rc;
+      stretch_accept_kernel<<<(nS + 127) / 128, 128, 0, st>>>(P, split);
+      ctx->launches += 2;
+    }
+    stretch_record_kernel<<<rec_blocks, 256, 0, st>>>(P);
+    ctx->launches++;
+    RBV_CUDA(cudaGetLastError());
+    return RBV_OK;
+  };
+
+  if (use_graph && st != nullptr && n_steps >= 4) {
+    // one step captured once, replayed n_steps times (the step index lives in device memory)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const long long launches_before = ctx->launches;
+    RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = one_step();
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != RBV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    const long long per_step = ctx->launches - launches_before;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    for (int s = 0; s < n_steps && e == cudaSuccess; ++s) e = cudaGraphLaunch(exec, st);
+    ctx->launches = launches_before + per_step * n_steps;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("rbv_stretch_run (graph): ") + cudaGetErrorString(e));
+    return RBV_OK;
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    int rc = one_step();
+    if (rc != RBV_OK) return rc;
+  }
   return RBV_OK;
 }
 

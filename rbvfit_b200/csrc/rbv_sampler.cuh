@@ -1,0 +1,160 @@
+// rbvfit_b200 -- device-resident affine-invariant ensemble sampler (stretch move), sm_100a.
+//
+// The reference runs emcee.EnsembleSampler(nwalkers, ndim, vfit.lnprob).run_mcmc(...) (vfit_mcmc.py:408-423,
+// 536-540).  emcee is a third-party dependency that is not vendored in the reference; its algorithm is restated
+// from the published description (Goodman & Weare 2010; Foreman-Mackey et al. 2013, emcee 3 RedBlueMove +
+// StretchMove), exactly as rbvfit_b200/sampler.py does on the host:
+//
+//   per step: split the walkers at random into two halves; for each half S with complement C
+//       z_k   = ((a - 1) u_k + 1)^2 / a,  u_k ~ U(0,1)
+//       Y_k   = C_j(k) - (C_j(k) - S_k) z_k,             j(k) uniform over the complement
+//       ln q  = (ndim - 1) ln z_k + lnp(Y_k) - lnp(S_k);  accept when ln U < ln q
+//
+// Here the whole loop lives on the device: three small kernels around the likelihood launch per half-step, no host
+// round trip, every random number from a counter-based generator (Philox4x32-10 keyed by the seed, counter =
+// (step, walker, split, purpose)) so that a run is reproducible whatever the launch geometry.  The random split of
+// emcee (shuffle of 0/1 labels) becomes a random affine permutation pos -> (a pos + b) mod W, gcd(a, W) = 1, whose
+// first half is S; like emcee's it is drawn independently of the walker positions, which is all detailed balance
+// needs.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rbv {
+
+struct StretchParams {
+  double* coords;        // [W, ndim] current ensemble (in/out)
+  double* lnp;           // [W]       its log-probabilities (in/out)
+  double* prop;          // [ceil(W/2), ndim] proposals of the active half
+  double* lnp_prop;      // [ceil(W/2)]
+  double* factors;       // [ceil(W/2)] (ndim - 1) ln z
+  double* chain;         // [n_steps, W, ndim] or NULL
+  double* lnp_chain;     // [n_steps, W] or NULL
+  int* n_accepted;       // [W] accumulates
+  int* flag;             // bit 0: a proposal's lnprob was NaN
+  unsigned long long* step_ctr;   // [0] steps done in this run (device counter, advanced by the record kernel)
+  unsigned int* ticket;  // block ticket of the record kernel
+  unsigned long long first_step;  // global index of the run's first step (continues the random streams)
+  unsigned long long seed;
+  double a;
+  int W, ndim;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// uniform in (0, 1): 53 random bits, never 0 or 1
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+  const unsigned long long m = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)m + 0.5) * 1.1102230246251565e-16;
+}
+
+__device__ __forceinline__ uint4 stretch_rand(const StretchParams& P, unsigned long long step, uint32_t walker,
+                                              uint32_t purpose) {
+  return philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), walker, purpose),
+                       make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+}
+
+// the step's affine permutation of walker positions: walker(pos) = (a pos + b) mod W
+__device__ __forceinline__ void stretch_perm(const StretchParams& P, unsigned long long step, uint32_t& a, uint32_t& b) {
+  const uint4 r = stretch_rand(P, step, 0xffffffffu, 0u);
+  const uint32_t W = (uint32_t)P.W;
+  a = r.x % W;
+  b = r.y % W;
+  for (;;) {
+    uint32_t x = a, y = W;
+    while (y) {
+      const uint32_t t = x % y;
+      x = y;
+      y = t;
+    }
+    if (x == 1u || W == 1u) break;
+    a = (a + 1u) % W;
+  }
+}
+
+__device__ __forceinline__ int walker_at(uint32_t a, uint32_t b, int W, int pos) {
+  return (int)(((unsigned long long)a * (unsigned)pos + b) % (unsigned)W);
+}
+
+// sizes/offsets of the active half and its complement for split s (first half = ceil(W/2) walkers)
+__device__ __forceinline__ void split_geometry(int W, int split, int& offS, int& nS, int& offC, int& nC) {
+  const int h = (W + 1) / 2;
+  if (split == 0) { offS = 0; nS = h; offC = h; nC = W - h; }
+  else            { offS = h; nS = W - h; offC = 0; nC = h; }
+}
+
+__global__ void __launch_bounds__(128) stretch_propose_kernel(const StretchParams P, int split) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int offS, nS, offC, nC;
+  split_geometry(P.W, split, offS, nS, offC, nC);
+  if (k >= nS) return;
+  const unsigned long long step = P.first_step + *P.step_ctr;
+  uint32_t pa, pb;
+  stretch_perm(P, step, pa, pb);
+  const int i = walker_at(pa, pb, P.W, offS + k);
+  const uint4 r = stretch_rand(P, step, (uint32_t)i, 1u + (uint32_t)split);
+  const double u = u01(r.x, r.y);
+  const int j = walker_at(pa, pb, P.W, offC + (int)(r.z % (uint32_t)nC));
+  // explicitly rounded operations (no FMA contraction): the proposal is bit-identical to the numpy expression
+  const double t = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+  const double zz = __ddiv_rn(__dmul_rn(t, t), P.a);
+  P.factors[k] = (P.ndim - 1.0) * log(zz);
+  const double* s = P.coords + (size_t)i * P.ndim;
+  const double* c = P.coords + (size_t)j * P.ndim;
+  double* q = P.prop + (size_t)k * P.ndim;
+  for (int d = 0; d < P.ndim; ++d) q[d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), zz));
+}
+
+__global__ void __launch_bounds__(128) stretch_accept_kernel(const StretchParams P, int split) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int offS, nS, offC, nC;
+  split_geometry(P.W, split, offS, nS, offC, nC);
+  if (k >= nS) return;
+  const unsigned long long step = P.first_step + *P.step_ctr;
+  uint32_t pa, pb;
+  stretch_perm(P, step, pa, pb);
+  const int i = walker_at(pa, pb, P.W, offS + k);
+  const double new_lp = P.lnp_prop[k];
+  if (new_lp != new_lp) atomicOr(P.flag, 1);                 // emcee: "Probability function returned NaN"
+  const uint4 r = stretch_rand(P, step, (uint32_t)i, 3u + (uint32_t)split);
+  const double lnpdiff = P.factors[k] + new_lp - P.lnp[i];
+  if (log(u01(r.x, r.y)) < lnpdiff) {
+    const double* q = P.prop + (size_t)k * P.ndim;
+    double* s = P.coords + (size_t)i * P.ndim;
+    for (int d = 0; d < P.ndim; ++d) s[d] = q[d];
+    P.lnp[i] = new_lp;
+    P.n_accepted[i] += 1;
+  }
+}
+
+// end of a step: append the ensemble to the chain; the last block to finish advances the device step counter
+__global__ void __launch_bounds__(256) stretch_record_kernel(const StretchParams P) {
+  const unsigned long long s = *P.step_ctr;
+  const size_t n = (size_t)P.W * P.ndim;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    if (P.chain) P.chain[s * n + idx] = P.coords[idx];
+    if (P.lnp_chain && idx < (size_t)P.W) P.lnp_chain[s * P.W + idx] = P.lnp[idx];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(P.ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *P.ticket = 0u;
+      *P.step_ctr = s + 1;
+    }
+  }
+}
+
+}  // namespace rbv

@@ -192,6 +192,30 @@ class Engine:
               "rbv_lnprob_batch_sightlines")
         return out_t
 
+    def stretch_run(self, coords_t, lnp_t, n_steps: int, a: float, seed: int, first_step: int, chain_t, lnp_chain_t,
+                    n_accepted_t, flag_t, use_graph: bool = True):
+        """Device-resident stretch-move sampling (rbv_stretch_run): every tensor stays on the device; runs on the
+        current torch stream (a CUDA graph needs a non-default one)."""
+        torch = _torch()
+        W, ndim = coords_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"coords has {ndim} columns, bounds were set for ndim={self.ndim}")
+        for t, dt in ((coords_t, torch.float64), (lnp_t, torch.float64), (n_accepted_t, torch.int32),
+                      (flag_t, torch.int32)):
+            if t.dtype != dt or not t.is_contiguous() or t.device != self.tdev:
+                raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
+        nbytes = C.c_size_t(0)
+        check(self.lib.rbv_stretch_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_stretch_workspace_bytes")
+        if getattr(self, "_stretch_ws", None) is None or self._stretch_ws.numel() < nbytes.value:
+            self._stretch_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
+        check(self.lib.rbv_stretch_run(
+            self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), float(a),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_step),
+            chain_t.data_ptr() if chain_t is not None else None,
+            lnp_chain_t.data_ptr() if lnp_chain_t is not None else None,
+            n_accepted_t.data_ptr(), flag_t.data_ptr(), self._stretch_ws.data_ptr(), self._stretch_ws.numel(),
+            int(bool(use_graph)), self._stream()), "rbv_stretch_run")
+
     def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:
         """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``."""
         torch = _torch()

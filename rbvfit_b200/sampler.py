@@ -237,3 +237,77 @@ class EnsembleSampler:
 
     def get_last_sample(self):
         return self._last
+
+
+class DeviceEnsembleSampler(EnsembleSampler):
+    """Same sampler, same accessor contract, but the whole loop runs on the GPU (``rbv_stretch_run``): proposals,
+    the likelihood batch and accept/reject of every half-step are device kernels replayed from a CUDA graph, and
+    the chain is copied to the host once per ``run_mcmc`` call.  ``likelihood`` is a ``GpuLikelihood``; random
+    numbers come from a counter-based generator keyed by ``seed``, so a run is reproducible and can be continued
+    (``run_mcmc(None, n)``) without changing the stream of a single long run."""
+
+    def __init__(self, nwalkers: int, ndim: int, likelihood, a: float = 2.0, seed: Optional[int] = None,
+                 use_graph: bool = True, **_ignored):
+        if not hasattr(likelihood, "engine"):
+            raise TypeError("DeviceEnsembleSampler needs a GpuLikelihood (the log-probability must run on the device)")
+        if likelihood.ndim != ndim:
+            raise ValueError(f"likelihood has ndim={likelihood.ndim}, sampler was given ndim={ndim}")
+        self.likelihood = likelihood
+        self.use_graph = bool(use_graph)
+        self._seed = int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
+        self._stream = None
+        self._state = None
+        super().__init__(nwalkers, ndim, likelihood.lnprob, a=a, seed=seed)
+
+    def reset(self):
+        super().reset()
+        self._state = None
+
+    def run_mcmc(self, initial_state, nsteps, progress=False, skip_initial_state_check=False, **_ignored):
+        import torch
+        eng = self.likelihood.engine
+        dev = eng.tdev
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        with torch.cuda.stream(self._stream):
+            if initial_state is None:
+                if self._state is None:
+                    raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
+                coords_t, lnp_t = self._state
+            else:
+                coords = np.array(initial_state, dtype=np.float64, copy=True)
+                if coords.shape != (self.nwalkers, self.ndim):
+                    raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+                if np.any(np.isinf(coords)):
+                    raise ValueError("At least one parameter value was infinite")
+                if np.any(np.isnan(coords)):
+                    raise ValueError("At least one parameter value was NaN")
+                if not skip_initial_state_check and not walkers_independent(coords):
+                    raise ValueError("Initial state has a large condition number. Make sure that your walkers are "
+                                     "linearly independent for the best performance")
+                coords_t = torch.as_tensor(coords, device=dev)
+                lnp_t = eng.lnprob_device(coords_t)
+                self.n_logp_calls += 1
+                self.n_logp_rows += self.nwalkers
+                if bool(torch.isnan(lnp_t).any()):
+                    raise ValueError("Probability function returned NaN")
+            chain_t = torch.empty((nsteps, self.nwalkers, self.ndim), dtype=torch.float64, device=dev)
+            lps_t = torch.empty((nsteps, self.nwalkers), dtype=torch.float64, device=dev)
+            nacc_t = torch.zeros(self.nwalkers, dtype=torch.int32, device=dev)
+            flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
+            eng.stretch_run(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t, nacc_t,
+                            flag_t, use_graph=self.use_graph)
+            self._stream.synchronize()
+            if int(flag_t.item()) & 1:
+                raise ValueError("Probability function returned NaN")
+            chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
+            self._accepted += nacc_t.cpu().numpy()
+        self._state = (coords_t, lnp_t)
+        self.n_logp_calls += 2 * nsteps
+        self.n_logp_rows += self.nwalkers * nsteps
+        self._chain = np.concatenate([self._chain, chain], axis=0)
+        self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self.iteration += nsteps
+        self._last = (chain[-1].copy(), lps[-1].copy()) if nsteps else self._last
+        return self._last

@@ -18,12 +18,13 @@ from typing import Dict
 import numpy as np
 
 from .likelihood import GpuLikelihood
-from .sampler import EnsembleSampler
+from .sampler import DeviceEnsembleSampler, EnsembleSampler
 
 
 class vfit:
     def __init__(self, instrument_data: Dict, theta, lb, ub, no_of_Chain=50, no_of_steps=1000,
-                 perturbation=1e-4, sampler="emcee", skip_initial_state_check=False, device=None, seed=None):
+                 perturbation=1e-4, sampler="emcee", skip_initial_state_check=False, device=None, seed=None,
+                 device_sampler=True):
         self._validate_unified_instrument_data(instrument_data)
         self._validate_guesses(theta, lb, ub)
         self.theta = np.asarray(theta)
@@ -48,6 +49,7 @@ class vfit:
         self.nwalkers = no_of_Chain
         self._rng = np.random.default_rng(seed)
         self._seed = seed
+        self.device_sampler = bool(device_sampler)   # stretch move entirely on the GPU (rbv_stretch_run)
 
     # ------------------------------------------------------------------ validation (vfit_mcmc.py:199-229)
     def _validate_unified_instrument_data(self, instrument_data):
@@ -162,6 +164,8 @@ class vfit:
         if self.sampler_name == "zeus":
             from .slice_sampler import EnsembleSliceSampler
             sampler = EnsembleSliceSampler(self.nwalkers, self.ndim, self.lnprob, seed=self._seed)
+        elif self.device_sampler:
+            sampler = DeviceEnsembleSampler(self.nwalkers, self.ndim, self._like, seed=self._seed)
         else:
             sampler = EnsembleSampler(self.nwalkers, self.ndim, self.lnprob, seed=self._seed)
         if verbose:

@@ -160,3 +160,38 @@ def test_roofline_farfield_rule():
     assert out["C1"][0] == out["C1"][1] and out["C1"][2]["farfield"] == 0.0
     assert out["C2"][1] < 0.4 * out["C2"][0] and out["C2"][2]["farfield"] > 0.75
     assert out["C4"][1] < out["C4"][0] and 0.5 < out["C4"][2]["farfield"] < 0.9     # the DLA's wings stay direct
+
+
+def test_stretch_replay_philox_known_answers_and_gaussian_target():
+    """oracle/stretch_replay.py (numpy restatement of the device sampler): Philox4x32-10 against the Random123
+    known-answer vectors, the step permutation is a bijection with balanced halves, and the sampler -- random
+    affine split included -- recovers a correlated Gaussian."""
+    from oracle import stretch_replay as sr
+    assert sr.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert sr.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert sr.philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == \
+        (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+    for W in (2, 7, 50, 64):
+        for step in range(5):
+            a, b = sr.step_perm(12345, step, W)
+            assert sorted((a * p + b) % W for p in range(W)) == list(range(W))
+    us = [sr.u01(*sr._rand(9, s, 3, 1)[:2]) for s in range(2000)]
+    assert 0.0 < min(us) and max(us) < 1.0 and abs(np.mean(us) - 0.5) < 0.02
+    mu = np.array([1.0, -2.0, 0.5])
+    cov = np.array([[0.25, 0.3, 0.0], [0.3, 4.0, 0.5], [0.0, 0.5, 1.0]])
+    icov = np.linalg.inv(cov)
+
+    def lnp(x):
+        d = np.atleast_2d(x) - mu
+        return -0.5 * np.einsum("ni,ij,nj->n", d, icov, d)
+
+    rng = np.random.default_rng(0)
+    p0 = mu + 0.1 * rng.standard_normal((24, 3))
+    chain, lps, nacc = sr.run(lnp, p0, lnp(p0), 1500, seed=424242)
+    assert np.allclose(lps[-1], lnp(chain[-1]))
+    flat = chain[300:].reshape(-1, 3)
+    sig = np.sqrt(np.diag(cov))
+    assert np.all(np.abs(flat.mean(0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(0) / sig - 1) < 0.12)
+    assert abs(np.corrcoef(flat.T)[0, 1] - 0.3) < 0.1
+    assert 0.3 < (nacc / 1500).mean() < 0.85
