@@ -38,9 +38,8 @@ namespace rbv {
 constexpr int kThreads = RBV_THREADS;
 constexpr int kPixPerThread = RBV_PPT;
 constexpr int kPass = kThreads * kPixPerThread;  // pixels per phase-1 pass
-constexpr int kWarpPix = 32 * kPixPerThread;     // pixels covered by one warp per pass ("chunk")
-constexpr int kSuperChunks = 4;                  // chunks per super-chunk (unit of tier classification + far field)
-constexpr int kSuperPix = kSuperChunks * kWarpPix;
+constexpr int kSuperPix = 1024;                  // super-chunk: unit of tier classification + far field
+constexpr int kSmallChunkLimit = 17;             // tiles with fewer 256-px chunks than this use 64-px chunks
 
 // line-constant record (doubles)
 constexpr int LC_A = 0, LC_B = 1, LC_A2 = 2, LC_a = 3, LC_Q = 4 /* Q1..Q13 */, LC_COEF = 17,

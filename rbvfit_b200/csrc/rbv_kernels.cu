@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -224,12 +225,14 @@ __device__ __forceinline__ int4 classify_lines(int lc_off, int L, unsigned short
 // (line, chunk) and du = u - u_ref exact in FP64, both then rounded to FP32 (no cancellation left in FP32);
 // two pixels share one MUFU.RCP through 1/(d1 d2).  Error model: relative 3e-7 per
 // contribution + 6e-8 per FP32 accumulation step; the gate bounds the gated sum by 4e-6, i.e. |dtau| <= 1e-11.
+template <int PPT>
 __device__ __forceinline__ void accum_far32(int lc_off, const unsigned short* __restrict__ list32, int n32,
-                                            const double (&u)[kPixPerThread], double (&tau)[kPixPerThread]) {
+                                            const double (&u)[PPT], double (&tau)[PPT]) {
+  static_assert(PPT % 2 == 0, "pairs of pixels share one reciprocal");
   const double u_ref = __shfl_sync(0xffffffffu, u[0], 0);
-  float du[kPixPerThread], acc[kPixPerThread];
+  float du[PPT], acc[PPT];
 #pragma unroll
-  for (int j = 0; j < kPixPerThread; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     du[j] = (float)(u[j] - u_ref);
     acc[j] = 0.f;
   }
@@ -240,7 +243,7 @@ __device__ __forceinline__ void accum_far32(int lc_off, const unsigned short* __
     const float4 c = *reinterpret_cast<const float4*>(smem + off + LC_F32A);   // A, a^2, Q1, Q2
     const float q3 = reinterpret_cast<const float2*>(smem + off + LC_F32B)->x;
 #pragma unroll
-    for (int j = 0; j < kPixPerThread; j += 2) {
+    for (int j = 0; j < PPT; j += 2) {
       const float x0 = fmaf(c.x, du[j], X0), x1 = fmaf(c.x, du[j + 1], X0);
       const float d0 = fmaf(x0, x0, c.y), d1 = fmaf(x1, x1, c.y);
       float r;
@@ -251,18 +254,17 @@ __device__ __forceinline__ void accum_far32(int lc_off, const unsigned short* __
     }
   }
 #pragma unroll
-  for (int j = 0; j < kPixPerThread; ++j) tau[j] += (double)acc[j];
+  for (int j = 0; j < PPT; ++j) tau[j] += (double)acc[j];
 }
 
-template <int NQ>
-__device__ __forceinline__ void accum_asym_line(int off, const double (&u)[kPixPerThread],
-                                                double (&tau)[kPixPerThread]) {
+template <int NQ, int PPT>
+__device__ __forceinline__ void accum_asym_line(int off, const double (&u)[PPT], double (&tau)[PPT]) {
   const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2];
   double Q[NQ];
 #pragma unroll
   for (int p = 0; p < NQ; ++p) Q[p] = smem[off + LC_Q + p];
 #pragma unroll
-  for (int j = 0; j < kPixPerThread; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     const double x = fma(A, u[j], -B);
     const double rho = rcp_pos(fma(x, x, a2));
     double s = Q[NQ - 1];
@@ -288,7 +290,7 @@ constexpr int SC_COEF = 0, SC_SCALE = 8, SC_OFFSET = 9, SC_COUNTS = 10 /* 4 ints
 
 __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned short* __restrict__ listff,
                                                       int n_ff, double umin, double umax, int rec_off, int lane) {
-  static_assert(RBV_FF_M == 8 && kPixPerThread == 8, "far-field code is written for 8 nodes and 8 pixels/lane");
+  static_assert(RBV_FF_M == 8, "far-field code is written for 8 nodes");
   const double um = 0.5 * (umin + umax), uh = 0.5 * (umax - umin);
   double S[8];
   {
@@ -298,7 +300,7 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
       un[k] = fma(uh, c_ff_nodes[k], um);
       S[k] = 0.0;
     }
-    for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQFar>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
+    for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQFar, 8>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
   }
   // transpose-reduce: after the three halving steps lane holds node (lane >> 2) & 7 summed over 8 lanes
   double T4[4], T2[2], T1;
@@ -334,8 +336,8 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
   if (lane == 9) smem[rec_off + SC_OFFSET] = -um * sc;
 }
 
-__device__ __forceinline__ void farfield_eval(int rec_off, const double (&u)[kPixPerThread],
-                                              double (&tau)[kPixPerThread]) {
+template <int PPT>
+__device__ __forceinline__ void farfield_eval(int rec_off, const double (&u)[PPT], double (&tau)[PPT]) {
   double c[8];
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
@@ -345,7 +347,7 @@ __device__ __forceinline__ void farfield_eval(int rec_off, const double (&u)[kPi
   }
   const double2 so = *reinterpret_cast<const double2*>(smem + rec_off + SC_SCALE);
 #pragma unroll
-  for (int j = 0; j < kPixPerThread; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     const double t = fma(u[j], so.x, so.y);
     double p = c[7];
 #pragma unroll
@@ -375,22 +377,23 @@ __device__ __forceinline__ void prepare_super_chunk(const InstDev& I, int lc_off
   if (lane == 0) *reinterpret_cast<int4*>(smem + rec_off + SC_COUNTS) = n;
 }
 
+template <int PPT>
 __device__ __forceinline__ void tau_wofz(int lc_off, int L, const unsigned short* __restrict__ list,
                                          const unsigned short* __restrict__ list32, int rec_off,
-                                         const double (&u)[kPixPerThread], double (&tau)[kPixPerThread],
+                                         const double (&u)[PPT], double (&tau)[PPT],
                                          const double* __restrict__ core_tab) {
   const int4 n = *reinterpret_cast<const int4*>(smem + rec_off + SC_COUNTS);   // n_far, n_other, n_fp32, n_farfield
   if (n.w > 0) {
     farfield_eval(rec_off, u, tau);
   } else {
 #pragma unroll
-    for (int j = 0; j < kPixPerThread; ++j) tau[j] = 0.0;
+    for (int j = 0; j < PPT; ++j) tau[j] = 0.0;
   }
   if (n.z > 0) accum_far32(lc_off, list32, n.z, u, tau);
 
   // far lines: branch-free body, 8 FP64 instructions per (line, pixel)
 #pragma unroll 2
-  for (int k = 0; k < n.x; ++k) accum_asym_line<kNQFar>(lc_off + (int)list[k] * LC_STRIDE, u, tau);
+  for (int k = 0; k < n.x; ++k) accum_asym_line<kNQFar, PPT>(lc_off + (int)list[k] * LC_STRIDE, u, tau);
 
   // everything else (a few lines per chunk at most)
   for (int k = 0; k < n.y; ++k) {
@@ -398,21 +401,21 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, const unsigned short
     const int off = lc_off + (e & 0xfff) * LC_STRIDE;
     const int tier = e >> 12;
     if (tier == kTierMid) {
-      accum_asym_line<kNQMid>(off, u, tau);
+      accum_asym_line<kNQMid, PPT>(off, u, tau);
     } else if (tier == kTierNear) {
-      accum_asym_line<kNQNear>(off, u, tau);
+      accum_asym_line<kNQNear, PPT>(off, u, tau);
     } else {
       const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2], a = smem[off + LC_a],
                    coef = smem[off + LC_COEF];
       if (tier == kTierGeneral) {
 #pragma unroll
-        for (int j = 0; j < kPixPerThread; ++j) {   // unrolled: tau/u must stay in registers
+        for (int j = 0; j < PPT; ++j) {   // unrolled: tau/u must stay in registers
           const double x = fma(A, u[j], -B);
           tau[j] = fma(coef, general_H(x, a, fma(x, x, a2)), tau[j]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < kPixPerThread; ++j) {
+        for (int j = 0; j < PPT; ++j) {
           const double x = fma(A, u[j], -B);
           const double d = fma(x, x, a2);
           if (d < kDCore) tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
@@ -423,16 +426,16 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, const unsigned short
   }
 }
 
-__device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[kPixPerThread],
-                                         double (&tau)[kPixPerThread]) {
+template <int PPT>
+__device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[PPT], double (&tau)[PPT]) {
 #pragma unroll
-  for (int j = 0; j < kPixPerThread; ++j) tau[j] = 0.0;
+  for (int j = 0; j < PPT; ++j) tau[j] = 0.0;
   for (int l = 0; l < L; ++l) {
     const int off = lc_off + l * LC_STRIDE;
     const double A = smem[off + LC_A], B = smem[off + LC_B], eps = smem[off + LC_A2], aos = smem[off + LC_a],
                  cf = smem[off + LC_AUX], coef = smem[off + LC_COEF];
 #pragma unroll
-    for (int j = 0; j < kPixPerThread; ++j) {
+    for (int j = 0; j < PPT; ++j) {
       double x = fma(A, u[j], -B);
       tau[j] = fma(coef, tg_H(x, aos, eps, cf), tau[j]);
     }
@@ -482,9 +485,13 @@ __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
 
 // ------------------------------------------------------------------------------------------ main kernel
 // MODE 0: lnprob (chi^2 partial + ticket finalisation); MODE 1: model flux out.
-template <int LOGR, int MODE>
+// PPT = pixels per lane in phase 1: 8 for big tiles (ILP), 2 when a tile has only a few chunks per warp, so that
+// the chunks that hold line cores (several times the cost of a far-wing chunk) can be balanced over the warps.
+template <int LOGR, int MODE, int PPT>
 __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(const LaunchParams prm) {
   constexpr int R = 1 << LOGR;
+  constexpr int kWarpPix = 32 * PPT;                  // pixels per chunk
+  constexpr int kSuperChunks = kSuperPix / kWarpPix;  // chunks per super-chunk
   __shared__ double s_red[kThreads / 32];
   __shared__ int s_next;   // dynamic chunk counter of phase 1
 
@@ -574,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       }
       __syncthreads();
     }
-    // warps pull 32*kPixPerThread-pixel chunks from a CTA-wide counter: chunks that contain a line core cost
+    // warps pull 32*PPT-pixel chunks from a CTA-wide counter: chunks that contain a line core cost
     // several times a far-wing chunk, and static assignment would leave the other warps waiting at the barrier
     // (the ticket for the NEXT chunk is drawn one iteration ahead, so that its 1/lambda lines can be prefetched
     // into L1 while the current chunk is computed)
@@ -585,15 +592,15 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       int c_next = 0;
       if (lane == 0) c_next = atomicAdd(&s_next, 1);
       const int i0 = c * kWarpPix;
-      double u[kPixPerThread], tau[kPixPerThread];
+      double u[PPT], tau[PPT];
 #pragma unroll
-      for (int j = 0; j < kPixPerThread; ++j) {
+      for (int j = 0; j < PPT; ++j) {
         int i = i0 + j * 32 + lane;
         int p = min(max(p0 - h + i, 0), I.P - 1);   // edge replication
         u[j] = __ldg(I.inv_wave + p);
       }
       c_next = __shfl_sync(0xffffffffu, c_next, 0);
-      if (c_next < n_chunks && lane < kWarpPix / 16) {          // 16 doubles per 128-byte line
+      if (c_next < n_chunks && lane < (kWarpPix + 15) / 16) {   // 16 doubles per 128-byte line
         const int p = min(max(p0 - h + c_next * kWarpPix + lane * 16, 0), I.P - 1);
         asm volatile("prefetch.global.L1 [%0];" ::"l"(I.inv_wave + p));
       }
@@ -607,16 +614,16 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       // where the degree-7 Taylor polynomial is exact to 9e-20 and needs no range reduction.
       unsigned hmax = 0u;
 #pragma unroll
-      for (int j = 0; j < kPixPerThread; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]) & 0x7fffffffu);
+      for (int j = 0; j < PPT; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]) & 0x7fffffffu);
       if (__reduce_max_sync(0xffffffffu, hmax) < 0x3F900000u) {       // NaN has a larger high word: slow path
 #pragma unroll
-        for (int j = 0; j < kPixPerThread; ++j) {
+        for (int j = 0; j < PPT; ++j) {
           const int i = i0 + j * 32 + lane;
           if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_small(-tau[j]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < kPixPerThread; ++j) {
+        for (int j = 0; j < PPT; ++j) {
           const int i = i0 + j * 32 + lane;
           if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_flux(-tau[j]);
         }
@@ -846,6 +853,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
 using namespace rbv;
 
 static thread_local std::string g_last_error;
+static int g_force_ppt = 0;   // tuning hook (RBVFIT_B200_PPT=2|8)
 
 static int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -916,6 +924,7 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaSetDevice(device));
   RbvContext* ctx = new RbvContext();
   ctx->device = device;
+  if (const char* e = getenv("RBVFIT_B200_PPT")) g_force_ppt = atoi(e);
   cudaDeviceProp prop;
   RBV_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
@@ -926,8 +935,10 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(upload(&ctx->d_core_tab, RBV_CORE_TABLE_HOST, (size_t)RBV_CORE_TABLE_LEN));
   const int max_dyn = (int)prop.sharedMemPerBlockOptin - 2048;
   ctx->max_dyn_smem = max_dyn;
-  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   *out = ctx;
   return RBV_OK;
 }
@@ -989,6 +1000,15 @@ static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, si
   }
   if (smem_out) *smem_out = smem;
   return total;
+}
+
+// Chunk size of phase 1: 64-pixel chunks (2 px per lane) when the biggest tile of the launch has fewer than
+// kSmallChunkLimit 256-pixel chunks (<= 2 per warp: no room to balance line-core chunks), else 256-pixel chunks.
+static bool small_chunks(const RbvContext* ctx, const TileGeom* geom, int n) {
+  if (g_force_ppt) return g_force_ppt == 2;
+  int big = 0;
+  for (int k = 0; k < n; ++k) big = std::max(big, geom[k].ext_alloc);
+  return big < kSmallChunkLimit * 256;
 }
 
 // Picks the largest tile scale that still gives every SM several CTAs and fits two CTAs per SM.
@@ -1233,7 +1253,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   prep_kernel<<<pgrid, 128, 0, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
-  voigt_tile_kernel<3, 0><<<grid, kThreads, smem, st>>>(prm);
+  if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
+  else voigt_tile_kernel<3, 0, 8><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   return RBV_OK;
@@ -1403,7 +1424,8 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   size_t smem = smem_bytes_for(I, prm.geom[inst], ndim);
   dim3 grid((unsigned)W, (unsigned)prm.geom[inst].n_tiles);
   cudaStream_t st = (cudaStream_t)stream;
-  voigt_tile_kernel<3, 1><<<grid, kThreads, smem, st>>>(prm);
+  if (small_chunks(ctx, prm.geom + inst, 1)) voigt_tile_kernel<3, 1, 2><<<grid, kThreads, smem, st>>>(prm);
+  else voigt_tile_kernel<3, 1, 8><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   return RBV_OK;
