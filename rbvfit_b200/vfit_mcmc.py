@@ -217,6 +217,28 @@ class vfit:
             print("⚠️  Warning: Could not calculate auto-correlation time")
         print("=" * 60)
 
+    def chi_squared(self, theta=None, instrument_name=None):
+        """Reduced chi-squared per instrument (and 'combined' for several) at ``theta`` (default: best_theta, else
+        the current guess) -- the computation of UnifiedResults.chi_squared (core/unified_results.py:305-369):
+        chi2 = sum(((flux - model) / error)**2), dof = max(n_data - n_params, 1); the model comes from the GPU."""
+        if theta is None:
+            theta = self.best_theta if self.best_theta is not None else self.theta
+        theta = np.asarray(theta, dtype=np.float64)
+        if instrument_name is not None and instrument_name not in self.instrument_data:
+            raise ValueError(f"Instrument '{instrument_name}' not found. Available: {list(self.instrument_data)}")
+        names = [instrument_name] if instrument_name is not None else list(self.instrument_data)
+        results, total_chi2, total_n = {}, 0.0, 0
+        for name in names:
+            d = self.instrument_data[name]
+            model = d["model"](theta, d["wave"])
+            chi2 = float(np.sum(((d["flux"] - model) / d["error"]) ** 2))
+            results[name] = chi2 / max(len(d["wave"]) - len(theta), 1)
+            total_chi2 += chi2
+            total_n += len(d["wave"])
+        if instrument_name is None and len(names) > 1:
+            results["combined"] = total_chi2 / max(total_n - len(theta), 1)
+        return results
+
     def get_samples(self, flat=True, burn_in=0.5):
         if not self.mcmc_flag:
             raise RuntimeError("MCMC has not been run")

@@ -158,3 +158,33 @@ def test_device_sampler_matches_numpy_replay():
         assert np.allclose(dev.get_chain(), chain, rtol=0, atol=1e-9)
         assert np.max(np.abs(dev.get_log_prob() - lps) / np.abs(lps)) <= 1e-9
         assert np.array_equal(np.rint(dev.acceptance_fraction * 60).astype(int), nacc)
+
+
+def test_curve_of_growth_grid_and_chi_squared_match_oracle():
+    """Other callers of model_flux: the COG grid as one batch (compute_cog.py:23-184) and the
+    reduced chi-squared of UnifiedResults.chi_squared (unified_results.py:305-369), against the CPU oracle."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200.cog import compute_cog
+    Nlist, blist = np.linspace(12.0, 20.0, 9), [5.0, 20.0, 60.0]
+    cog = compute_cog(1215.67, Nlist, blist)
+    assert cog.Wlist.shape == (9, 3) and str(np.atleast_1d(cog.st["name"])[0]).startswith("HI")
+    ocfg = vo.OracleConfig()
+    ocfg.add_system(0.0, "HI", [cog.st["wave"]], 1)
+    om = vo.lower(ocfg, FWHM=None)
+    wave = np.linspace(cog.st["wave"] - 5.0, cog.st["wave"] + 5.0, 1000)
+    for i in (0, 4, 8):
+        for j in range(3):
+            flx = vo.model_flux(om, np.array([Nlist[i], blist[j], 0.0]), wave)
+            ref = np.sum(np.diff(wave) * ((1 - flx)[1:] + (1 - flx)[:-1]) / 2.0)
+            assert abs(cog.Wlist[i, j] - ref) <= 1e-9 * max(1.0, ref)
+    assert np.all(np.diff(cog.Wlist, axis=0) > 0)                       # W grows with N on every b track
+    w, fitter, comp, theta0 = _c1_fitter()
+    got = fitter.chi_squared(w["theta_true"])
+    d = fitter.instrument_data["COS"]
+    m = vo.model_flux(comp["COS"]["model"], w["theta_true"], d["wave"]) if "model" in comp.get("COS", {}) else None
+    if m is not None:
+        ref = float(np.sum(((d["flux"] - m) / d["error"]) ** 2)) / (len(d["wave"]) - 6)
+        assert abs(got["COS"] - ref) <= 1e-9 * ref
+    assert 0.8 < got["COS"] < 1.25                                       # noise realisation at the truth
+    with pytest.raises(ValueError):
+        fitter.chi_squared(instrument_name="HIRES")
