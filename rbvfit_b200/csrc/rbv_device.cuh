@@ -39,6 +39,7 @@ constexpr int kThreads = RBV_THREADS;
 constexpr int kPixPerThread = RBV_PPT;
 constexpr int kPass = kThreads * kPixPerThread;  // pixels per phase-1 pass
 constexpr int kSuperPix = 1024;                  // super-chunk: unit of tier classification + far field
+constexpr int kWantWaves = 1;                    // biggest tiles that still fill every CTA slot of the GPU once
 constexpr int kSmallChunkLimit = 17;             // tiles with fewer 256-px chunks than this use 64-px chunks
 
 // line-constant record (doubles)

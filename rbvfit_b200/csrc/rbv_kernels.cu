@@ -32,7 +32,7 @@
 
 #include "../../include/rbvfit_b200.h"
 #include "rbv_device.cuh"
-#include "rbv_sampler.cuh"
+#include "rbv_sampler.cuh"   // StretchParams + Philox streams (embedded in LaunchParams for the fused sampler step)
 
 namespace rbv {
 
@@ -86,6 +86,10 @@ struct LaunchParams {
   int precision;
   int farfield;          // 1 = far wings of a chunk through the Chebyshev far-field interpolant (section 4c)
   int wps;               // sightline mode: walkers per sightline (walker w belongs to instrument w / wps); 0 = off
+  // device-resident sampler (rbv_stretch_run): when sampler_split >= 0 the prep kernel first builds the stretch
+  // proposal of row w, and the CTA that finalises lnprob[w] also applies accept/reject and records the chain
+  int sampler_split;
+  StretchParams sp;
 };
 
 __device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
@@ -447,10 +451,7 @@ __device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[PP
 // walker instead of once per tile (pow, five divisions and the 13 series coefficients are ~400 dependent
 // FP64 instructions -- as long as a tile's whole phase 1 when done by 33 threads of every CTA).
 // Thread 0 of each walker also evaluates the uniform prior (vfit.lnprior, vfit_mcmc.py:291-295).
-__global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
-  const int w = blockIdx.x;
-  const int g = blockIdx.y * blockDim.x + threadIdx.x;
-  const double* th = prm.theta + (size_t)w * prm.ndim;
+__device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w, int g, const double* __restrict__ th) {
   if (g == 0) {
     int bad = 0;
     for (int i = 0; i < prm.ndim; ++i) {
@@ -481,6 +482,56 @@ __global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
   double2* dst = reinterpret_cast<double2*>(prm.lc + ((size_t)w * prm.n_lines_total + g) * LC_STRIDE);
 #pragma unroll
   for (int i = 0; i < LC_STRIDE / 2; ++i) dst[i] = make_double2(lc[2 * i], lc[2 * i + 1]);
+}
+
+__global__ void __launch_bounds__(128) prep_kernel(const LaunchParams prm) {
+  const int w = blockIdx.x;
+  prep_walker_lines(prm, w, blockIdx.y * blockDim.x + threadIdx.x, prm.theta + (size_t)w * prm.ndim);
+}
+
+// Sampler variant: row w of the batch is the stretch proposal of the w-th walker of the active half, built here
+// (every block of the walker rebuilds it in shared memory; block y = 0 also writes it to prm.theta for the accept
+// step) and then lowered to line constants exactly as above.
+__global__ void __launch_bounds__(128) prep_propose_kernel(const LaunchParams prm) {
+  extern __shared__ double s_row[];           // [ndim]
+  __shared__ int s_ij[2];
+  __shared__ double s_zz;
+  const StretchParams& P = prm.sp;
+  const int k = blockIdx.x, split = prm.sampler_split;
+  if (threadIdx.x == 0) {
+    int offS, nS, offC, nC;
+    split_geometry(P.W, split, offS, nS, offC, nC);
+    const unsigned long long step = P.first_step + *P.step_ctr;
+    uint32_t pa, pb;
+    stretch_perm(P, step, pa, pb);
+    const int i = walker_at(pa, pb, P.W, offS + k);
+    const uint4 r = stretch_rand(P, step, (uint32_t)i, 1u + (uint32_t)split);
+    const double u = u01(r.x, r.y);
+    const int j = walker_at(pa, pb, P.W, offC + (int)(r.z % (uint32_t)nC));
+    // explicitly rounded operations (no FMA contraction): the proposal is bit-identical to the numpy expression
+    const double t = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+    const double zz = __ddiv_rn(__dmul_rn(t, t), P.a);
+    s_ij[0] = i;
+    s_ij[1] = j;
+    s_zz = zz;
+    if (blockIdx.y == 0) {
+      P.factors[k] = (P.ndim - 1.0) * log(zz);
+      P.walker_of[k] = i;
+    }
+  }
+  __syncthreads();
+  {
+    const double* s = P.coords + (size_t)s_ij[0] * P.ndim;
+    const double* c = P.coords + (size_t)s_ij[1] * P.ndim;
+    const double zz = s_zz;
+    for (int d = threadIdx.x; d < P.ndim; d += blockDim.x) {
+      const double q = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), zz));
+      s_row[d] = q;
+      if (blockIdx.y == 0) P.prop[(size_t)k * P.ndim + d] = q;
+    }
+  }
+  __syncthreads();
+  prep_walker_lines(prm, k, blockIdx.y * blockDim.x + threadIdx.x, s_row);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -726,6 +777,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         }
       }
       prm.lnprob[w] = total;
+      if (prm.sampler_split >= 0) stretch_accept_record(prm.sp, prm.sampler_split, w, total);
     }
   }
 }
@@ -854,6 +906,7 @@ using namespace rbv;
 
 static thread_local std::string g_last_error;
 static int g_force_ppt = 0;   // tuning hook (RBVFIT_B200_PPT=2|8)
+static int g_force_level = -1;   // tuning hook (RBVFIT_B200_GEOM=0..5)
 
 static int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -925,6 +978,7 @@ int rbv_create(int device, RbvContext** out) {
   RbvContext* ctx = new RbvContext();
   ctx->device = device;
   if (const char* e = getenv("RBVFIT_B200_PPT")) g_force_ppt = atoi(e);
+  if (const char* e = getenv("RBVFIT_B200_GEOM")) g_force_level = atoi(e);
   cudaDeviceProp prop;
   RBV_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
@@ -976,22 +1030,33 @@ int rbv_set_farfield(RbvContext* ctx, int mode) {
 // Tile geometry of every instrument for one launch.  ``scale`` multiplies the base tile (1, 2, 4, ...):
 // big tiles amortise the per-CTA preamble and halo and make the dynamic chunk scheduling effective, small
 // tiles keep the grid full when there are few walkers.  Returns the total tile count and the dynamic smem.
-static int compute_geometry(const RbvContext* ctx, int scale, TileGeom* geom, size_t* smem_out,
+// Tile geometry in units of 256 flux slots: level 0..kGeomLevels-1 -> 2, 3, 4, 8, 16, 32 units for an LSF with a
+// short halo (tile = units * 256 - (K - 1), rounded down to whole 256-pixel blocks); wide LSFs start from the
+// size that keeps the halo below ~8 % of the slots.  Small tiles = many CTAs per walker (latency of small
+// batches), big tiles = less halo and per-CTA preamble (throughput of big batches).
+constexpr int kGeomLevels = 6;
+static const int kGeomUnits[kGeomLevels] = {2, 3, 4, 8, 16, 32};
+
+static int compute_geometry(const RbvContext* ctx, int level, TileGeom* geom, size_t* smem_out,
                             size_t n_inst_used = (size_t)-1) {
   int total = 0;
   size_t smem = 0;
   int ndim = ctx->ndim;
   for (size_t k = 0; k < std::min(ctx->inst.size(), n_inst_used); ++k) {
     const InstDev& I = ctx->inst[k].dev;
-    int n_pass = 1;
-    if (I.K - 1 > 64) n_pass = (int)std::ceil((I.K - 1) / (0.08 * kPass));   // halo overhead <= ~8 %
-    n_pass = std::min(n_pass, 8) * scale;
-    int need = (I.P + I.K - 1 + kPass - 1) / kPass;
-    n_pass = std::max(1, std::min(n_pass, need));
+    int units = kGeomUnits[level];
+    if (I.K - 1 > 20) {                                     // halo <= ~8 % of the slots, at least one whole block out
+      const int min_units = std::max((int)std::ceil((I.K - 1) / (0.08 * 256)), (I.K - 1 + 255) / 256 + 1);
+      if (units < 8) units = std::max(units, std::min(min_units, 8 * 8));
+      else units = std::max(units, std::min(min_units, 8 * 8) * (units / 8));
+      units = std::min(units, 8 * 32);
+    }
+    const int need = (I.P + I.K - 1 + 255) / 256;           // no bigger than the spectrum
+    units = std::max(std::min(units, need), (I.K - 1 + 255) / 256 + 1);
     TileGeom g;
-    g.tile = (n_pass * kPass - (I.K - 1)) & ~255;   // tiles start on the 256-pixel blocks of InstDev::obs_w
-    g.ext_alloc = n_pass * kPass + 2 * I.R;
-    g.n_super = (n_pass * kPass + kSuperPix - 1) / kSuperPix;
+    g.tile = (units * 256 - (I.K - 1)) & ~255;              // tiles start on the 256-pixel blocks of InstDev::obs_w
+    g.ext_alloc = units * 256 + 2 * I.R;
+    g.n_super = (units * 256 + kSuperPix - 1) / kSuperPix;
     g.first_tile = total;
     g.n_tiles = (I.P + g.tile - 1) / g.tile;
     total += g.n_tiles;
@@ -1011,16 +1076,18 @@ static bool small_chunks(const RbvContext* ctx, const TileGeom* geom, int n) {
   return big < kSmallChunkLimit * 256;
 }
 
-// Picks the largest tile scale that still gives every SM several CTAs and fits two CTAs per SM.
+// Picks the largest tiles that still give every SM several CTAs (and fit RBV_MIN_CTAS CTAs per SM); a batch too
+// small for that gets the smallest tiles, i.e. the most CTAs per walker.
 static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t* smem_out,
                            size_t n_inst_used = (size_t)-1) {
-  const long long want = 4LL * RBV_MIN_CTAS * ctx->sm_count;   // >= 4 waves of resident CTAs
+  const long long want = (long long)kWantWaves * RBV_MIN_CTAS * ctx->sm_count;
   int total = 0;
-  for (int scale = 4; scale >= 1; scale >>= 1) {
+  for (int level = kGeomLevels - 1; level >= 0; --level) {
+    if (g_force_level >= 0) level = g_force_level;
     size_t smem = 0;
-    total = compute_geometry(ctx, scale, geom, &smem, n_inst_used);
-    bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, (227 * 1024) / RBV_MIN_CTAS - 2048);   // RBV_MIN_CTAS CTAs per SM
-    if (scale == 1 || (fits && (long long)W * total >= want)) {
+    total = compute_geometry(ctx, level, geom, &smem, n_inst_used);
+    bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, (227 * 1024) / RBV_MIN_CTAS - 2048);
+    if (level == 0 || g_force_level >= 0 || (fits && (long long)W * total >= want)) {
       if (smem_out) *smem_out = smem;
       return total;
     }
@@ -1049,7 +1116,7 @@ static int rebuild_tables(RbvContext* ctx) {
   TileGeom geom[kMaxInst];
   // smallest tiles = most tiles: sizes the workspace (joint fits use <= 16 instruments; larger contexts are
   // sightline batches, which size their workspace from one instrument)
-  ctx->n_tiles = compute_geometry(ctx, 1, geom, nullptr, kMaxInst);
+  ctx->n_tiles = compute_geometry(ctx, 0, geom, nullptr, kMaxInst);
   ctx->n_lines_total = 0;
   for (auto& hi : ctx->inst) ctx->n_lines_total += hi.dev.L;
   std::vector<InstDev> flat;
@@ -1177,7 +1244,7 @@ static WorkspaceLayout workspace_layout_raw(int W, int tiles_per_walker, int lin
 static WorkspaceLayout workspace_layout(const RbvContext* ctx, int W, bool sightlines) {
   if (!sightlines) return workspace_layout_raw(W, ctx->n_tiles, ctx->n_lines_total);
   TileGeom g[1];
-  int tiles = compute_geometry(ctx, 1, g, nullptr, 1);
+  int tiles = compute_geometry(ctx, 0, g, nullptr, 1);
   return workspace_layout_raw(W, tiles, ctx->inst.empty() ? 1 : ctx->inst[0].dev.L);
 }
 
@@ -1195,7 +1262,8 @@ int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t*
 }
 
 static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, double* lnprob, void* workspace,
-                         size_t workspace_bytes, void* stream, const char* who) {
+                         size_t workspace_bytes, void* stream, const char* who,
+                         const StretchParams* sampler = nullptr, int sampler_split = -1) {
   if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, std::string(who) + ": null argument");
   if (W < 0) return fail(RBV_EINVAL, std::string(who) + ": negative n_walkers");
   if (W == 0) return RBV_OK;
@@ -1241,6 +1309,11 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   prm.precision = ctx->precision;
   prm.farfield = ctx->farfield;
   prm.wps = wps;
+  prm.sampler_split = -1;
+  if (sampler) {
+    prm.sampler_split = sampler_split;
+    prm.sp = *sampler;
+  }
   cudaStream_t st = (cudaStream_t)stream;
 
   // ONE launch covers every instrument: grid = (walkers, tiles per walker); the tile size is chosen per launch
@@ -1250,7 +1323,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
   dim3 pgrid((unsigned)W, (unsigned)((prm.n_lines_total + 127) / 128));
-  prep_kernel<<<pgrid, 128, 0, st>>>(prm);
+  if (sampler) prep_propose_kernel<<<pgrid, 128, (size_t)prm.ndim * sizeof(double), st>>>(prm);
+  else prep_kernel<<<pgrid, 128, 0, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
@@ -1290,7 +1364,7 @@ int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, doub
 
 // ------------------------------------------------------------------------------------------ device-resident sampler
 struct StretchLayout {
-  size_t prop, lnp_prop, factors, ctr, lnprob_ws, total;
+  size_t prop, lnp_prop, factors, walker_of, ctr, lnprob_ws, total;
 };
 static StretchLayout stretch_layout(const RbvContext* ctx, int W) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1299,7 +1373,8 @@ static StretchLayout stretch_layout(const RbvContext* ctx, int W) {
   lay.prop = 0;
   lay.lnp_prop = up(h * std::max(ctx->ndim, 1) * sizeof(double));
   lay.factors = lay.lnp_prop + up(h * sizeof(double));
-  lay.ctr = lay.factors + up(h * sizeof(double));
+  lay.walker_of = lay.factors + up(h * sizeof(double));
+  lay.ctr = lay.walker_of + up(h * sizeof(int));
   lay.lnprob_ws = lay.ctr + 256;
   lay.total = lay.lnprob_ws + workspace_layout(ctx, (int)h, false).total;
   return lay;
@@ -1332,6 +1407,7 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
   P.prop = (double*)(ws + lay.prop);
   P.lnp_prop = (double*)(ws + lay.lnp_prop);
   P.factors = (double*)(ws + lay.factors);
+  P.walker_of = (int*)(ws + lay.walker_of);
   P.chain = chain;
   P.lnp_chain = lnprob_chain;
   P.n_accepted = n_accepted;
@@ -1346,21 +1422,16 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
   RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
   const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
   const int h = (n_walkers + 1) / 2;
-  const int rec_blocks = (int)std::min<size_t>(((size_t)n_walkers * ctx->ndim + 255) / 256, (size_t)ctx->sm_count);
 
+  // one step = two half-steps of two launches each: prep_propose_kernel (proposal + line constants) and the tile
+  // kernel, whose per-walker finalisation also applies accept/reject and appends the walker's row to the chain
   auto one_step = [&]() -> int {
     for (int split = 0; split < 2; ++split) {
       const int nS = split == 0 ? h : n_walkers - h;
-      stretch_propose_kernel<<<(nS + 127) / 128, 128, 0, st>>>(P, split);
       int rc = launch_lnprob(ctx, P.prop, nS, 0, P.lnp_prop, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
-                             "rbv_stretch_run");
+                             "rbv_stretch_run", &P, split);
       if (rc != RBV_OK) return rc;
-      stretch_accept_kernel<<<(nS + 127) / 128, 128, 0, st>>>(P, split);
-      ctx->launches += 2;
     }
-    stretch_record_kernel<<<rec_blocks, 256, 0, st>>>(P);
-    ctx->launches++;
-    RBV_CUDA(cudaGetLastError());
     return RBV_OK;
   };
 
@@ -1418,8 +1489,9 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   prm.W = W;
   prm.precision = ctx->precision;
   prm.farfield = ctx->farfield;
+  prm.sampler_split = -1;
   if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "rbv_model_flux_batch: more than 16 instruments");
-  prm.n_tiles = compute_geometry(ctx, 1, prm.geom, nullptr);
+  prm.n_tiles = compute_geometry(ctx, W >= 64 ? 3 : 1, prm.geom, nullptr);   // flux mode: 2048- or 768-slot tiles
   prm.tile_base = prm.geom[inst].first_tile;
   size_t smem = smem_bytes_for(I, prm.geom[inst], ndim);
   dim3 grid((unsigned)W, (unsigned)prm.geom[inst].n_tiles);

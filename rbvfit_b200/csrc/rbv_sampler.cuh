@@ -29,12 +29,13 @@ struct StretchParams {
   double* prop;          // [ceil(W/2), ndim] proposals of the active half
   double* lnp_prop;      // [ceil(W/2)]
   double* factors;       // [ceil(W/2)] (ndim - 1) ln z
+  int* walker_of;        // [ceil(W/2)] walker index of the k-th row of the active half
   double* chain;         // [n_steps, W, ndim] or NULL
   double* lnp_chain;     // [n_steps, W] or NULL
   int* n_accepted;       // [W] accumulates
   int* flag;             // bit 0: a proposal's lnprob was NaN
   unsigned long long* step_ctr;   // [0] steps done in this run (device counter, advanced by the record kernel)
-  unsigned int* ticket;  // block ticket of the record kernel
+  unsigned int* ticket;  // walkers of the current half-step whose accept/record is done
   unsigned long long first_step;  // global index of the run's first step (continues the random streams)
   unsigned long long seed;
   double a;
@@ -94,66 +95,35 @@ __device__ __forceinline__ void split_geometry(int W, int split, int& offS, int&
   else            { offS = h; nS = W - h; offC = 0; nC = h; }
 }
 
-__global__ void __launch_bounds__(128) stretch_propose_kernel(const StretchParams P, int split) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// Accept / reject for row k of the active half once its lnprob is known, by the thread that finalised it (last CTA
+// of the walker in the tile kernel).  The walker's row of the chain is written here too: after its own half-step a
+// walker does not change again within the step.  The last walker of the second half advances the step counter.
+__device__ __forceinline__ void stretch_accept_record(const StretchParams& P, int split, int k, double new_lp) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
-  if (k >= nS) return;
-  const unsigned long long step = P.first_step + *P.step_ctr;
-  uint32_t pa, pb;
-  stretch_perm(P, step, pa, pb);
-  const int i = walker_at(pa, pb, P.W, offS + k);
-  const uint4 r = stretch_rand(P, step, (uint32_t)i, 1u + (uint32_t)split);
-  const double u = u01(r.x, r.y);
-  const int j = walker_at(pa, pb, P.W, offC + (int)(r.z % (uint32_t)nC));
-  // explicitly rounded operations (no FMA contraction): the proposal is bit-identical to the numpy expression
-  const double t = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-  const double zz = __ddiv_rn(__dmul_rn(t, t), P.a);
-  P.factors[k] = (P.ndim - 1.0) * log(zz);
-  const double* s = P.coords + (size_t)i * P.ndim;
-  const double* c = P.coords + (size_t)j * P.ndim;
-  double* q = P.prop + (size_t)k * P.ndim;
-  for (int d = 0; d < P.ndim; ++d) q[d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), zz));
-}
-
-__global__ void __launch_bounds__(128) stretch_accept_kernel(const StretchParams P, int split) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  int offS, nS, offC, nC;
-  split_geometry(P.W, split, offS, nS, offC, nC);
-  if (k >= nS) return;
-  const unsigned long long step = P.first_step + *P.step_ctr;
-  uint32_t pa, pb;
-  stretch_perm(P, step, pa, pb);
-  const int i = walker_at(pa, pb, P.W, offS + k);
-  const double new_lp = P.lnp_prop[k];
+  const unsigned long long s = *P.step_ctr, step = P.first_step + s;
+  const int i = P.walker_of[k];
   if (new_lp != new_lp) atomicOr(P.flag, 1);                 // emcee: "Probability function returned NaN"
   const uint4 r = stretch_rand(P, step, (uint32_t)i, 3u + (uint32_t)split);
   const double lnpdiff = P.factors[k] + new_lp - P.lnp[i];
+  double* x = P.coords + (size_t)i * P.ndim;
+  double lp = P.lnp[i];
   if (log(u01(r.x, r.y)) < lnpdiff) {
     const double* q = P.prop + (size_t)k * P.ndim;
-    double* s = P.coords + (size_t)i * P.ndim;
-    for (int d = 0; d < P.ndim; ++d) s[d] = q[d];
-    P.lnp[i] = new_lp;
+    for (int d = 0; d < P.ndim; ++d) x[d] = q[d];
+    P.lnp[i] = lp = new_lp;
     P.n_accepted[i] += 1;
   }
-}
-
-// end of a step: append the ensemble to the chain; the last block to finish advances the device step counter
-__global__ void __launch_bounds__(256) stretch_record_kernel(const StretchParams P) {
-  const unsigned long long s = *P.step_ctr;
-  const size_t n = (size_t)P.W * P.ndim;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    if (P.chain) P.chain[s * n + idx] = P.coords[idx];
-    if (P.lnp_chain && idx < (size_t)P.W) P.lnp_chain[s * P.W + idx] = P.lnp[idx];
+  if (P.chain) {
+    double* row = P.chain + (s * P.W + i) * (size_t)P.ndim;
+    for (int d = 0; d < P.ndim; ++d) row[d] = x[d];
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (P.lnp_chain) P.lnp_chain[s * P.W + i] = lp;
+  __threadfence();
+  if (atomicAdd(P.ticket, 1u) == (unsigned)nS - 1u) {        // last walker of this half-step
+    *P.ticket = 0u;
+    if (split == 1) *P.step_ctr = s + 1;
     __threadfence();
-    const unsigned int t = atomicAdd(P.ticket, 1u);
-    if (t == gridDim.x - 1) {
-      *P.ticket = 0u;
-      *P.step_ctr = s + 1;
-    }
   }
 }
 

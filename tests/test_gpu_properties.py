@@ -157,7 +157,14 @@ def test_sightline_batch_equals_individual_fits():
     ref = np.array([singles[s].lnprob(thetas[s]) for s in range(S)])
     assert got.shape == (S, Ws)
     assert np.isneginf(ref).sum() >= S
-    assert np.array_equal(got, ref, equal_nan=True)          # same kernel, same tiles: bit-identical
+    # 16-walker calls use smaller tiles than the 384-walker batch (geometry follows the batch size): same values up
+    # to the order of the tile sums ...
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-12
+    # ... and bit-identical when the single-sightline call has the batch's size (same kernel, same tiles)
+    same = np.array([singles[s].lnprob(np.tile(thetas[s], (S, 1)))[:Ws] for s in range(0, S, 5)])
+    assert np.array_equal(got[0:S:5], same, equal_nan=True)
     assert len(set(np.round(ref[np.isfinite(ref)], 3))) > S     # sightlines really differ
     with pytest.raises(ValueError):
         batch.lnprob(thetas[:5])
