@@ -904,6 +904,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
 // =============================================================================================== host / C ABI
 using namespace rbv;
 
+constexpr int kGeomLevels = 6;   // tile sizes, see compute_geometry
 static thread_local std::string g_last_error;
 static int g_force_ppt = 0;   // tuning hook (RBVFIT_B200_PPT=2|8)
 static int g_force_level = -1;   // tuning hook (RBVFIT_B200_GEOM=0..5)
@@ -977,8 +978,12 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaSetDevice(device));
   RbvContext* ctx = new RbvContext();
   ctx->device = device;
-  if (const char* e = getenv("RBVFIT_B200_PPT")) g_force_ppt = atoi(e);
-  if (const char* e = getenv("RBVFIT_B200_GEOM")) g_force_level = atoi(e);
+  {   // tuning / test hooks, re-read whenever a context is created
+    const char* e = getenv("RBVFIT_B200_PPT");
+    g_force_ppt = e ? atoi(e) : 0;
+    e = getenv("RBVFIT_B200_GEOM");
+    g_force_level = e ? std::min(std::max(atoi(e), 0), kGeomLevels - 1) : -1;
+  }
   cudaDeviceProp prop;
   RBV_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
@@ -1034,7 +1039,6 @@ int rbv_set_farfield(RbvContext* ctx, int mode) {
 // short halo (tile = units * 256 - (K - 1), rounded down to whole 256-pixel blocks); wide LSFs start from the
 // size that keeps the halo below ~8 % of the slots.  Small tiles = many CTAs per walker (latency of small
 // batches), big tiles = less halo and per-CTA preamble (throughput of big batches).
-constexpr int kGeomLevels = 6;
 static const int kGeomUnits[kGeomLevels] = {2, 3, 4, 8, 16, 32};
 
 static int compute_geometry(const RbvContext* ctx, int level, TileGeom* geom, size_t* smem_out,

@@ -1,0 +1,131 @@
+"""GPU edge cases against the CPU oracle (same seeded inputs, sizes the oracle finishes in seconds): ragged and tiny
+spectra, LSF wider than the spectrum, many lines, unsorted wavelength grids, single walkers, every tile geometry and
+both chunk sizes.  Tolerances are the north-star ones (flux 1e-10, lnprob 1e-9 relative)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FLUX_TOL = 1e-10
+LNPROB_RTOL = 1e-9
+
+
+def _models(systems, FWHM="6.5", taps=None):
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import FitConfiguration
+    from rbvfit_b200.model import GpuVoigtModel
+    cfg, ocfg = FitConfiguration(), vo.OracleConfig()
+    for (z, ion, trans, comps) in systems:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+        ocfg.add_system(z, ion, trans, comps)
+    return GpuVoigtModel(cfg, FWHM=FWHM, lsf_taps=taps), vo.lower(ocfg, FWHM=FWHM, custom_taps=taps)
+
+
+def _check(model, omodel, wave, thetas, lb, ub, rng, error_dtype=np.float64):
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200.likelihood import GpuLikelihood
+    wave = np.asarray(wave, dtype=np.float64)
+    flux = 1.0 + 0.05 * rng.standard_normal(wave.size)
+    error = np.full(wave.size, 0.05, dtype=error_dtype)
+    like = GpuLikelihood({"S": dict(model=model, wave=wave, flux=flux, error=error)}, lb, ub)
+    comp = vo.compile_instruments({"S": dict(model=omodel, wave=wave, flux=flux, error=error)})
+    got = like.lnprob(thetas)
+    ref = vo.lnprob_batch(comp, np.atleast_2d(thetas), lb, ub)
+    got = np.atleast_1d(got)
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    if fin.any():
+        assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= LNPROB_RTOL
+    th0 = np.atleast_2d(thetas)[int(np.flatnonzero(fin)[0])] if fin.any() else np.atleast_2d(thetas)[0]
+    gf = model.compile().model_flux(th0, wave)
+    assert np.max(np.abs(gf - vo.model_flux(omodel, th0, wave))) <= FLUX_TOL
+    like.close()
+    return got
+
+
+MGII = [(0.348, "MgII", [2796.3, 2803.5], 2)]
+TH = np.array([14.2, 14.5, 40.0, 30.0, -25.0, 35.0])
+LB, UB = TH - np.array([2, 2, 38, 28, 50, 50.0]), TH + np.array([2, 2, 40, 40, 50, 50.0])
+
+
+@pytest.mark.parametrize("P", [1, 2, 7, 22, 23, 255, 256, 257, 1791, 1793, 2049, 4100])
+def test_ragged_and_tiny_spectra(P):
+    """Spectra shorter than the 23-tap LSF, one pixel, and sizes around the tile / block boundaries."""
+    rng = np.random.default_rng(100 + P)
+    model, om = _models(MGII)
+    wave = np.linspace(3762.0, 3786.0, P) if P > 1 else np.array([3769.5])
+    thetas = np.clip(TH + rng.standard_normal((9, 6)) * [0.05, 0.05, 1, 1, 2, 2], LB, UB)
+    thetas[3, 0] = UB[0] + 1.0                                           # one row outside the prior box
+    _check(model, om, wave, thetas, LB, UB, rng)
+
+
+def test_lsf_wider_than_spectrum_and_widest_supported():
+    from rbvfit_b200 import lsf
+    rng = np.random.default_rng(7)
+    taps = lsf.cos_like_taps(321)
+    model, om = _models(MGII, FWHM=None, taps=taps)
+    thetas = np.clip(TH + rng.standard_normal((5, 6)) * [0.05, 0.05, 1, 1, 2, 2], LB, UB)
+    for P in (40, 320, 321, 700):
+        _check(model, om, np.linspace(3762.0, 3786.0, P), thetas, LB, UB, rng)
+    wide = np.exp(-0.5 * (np.arange(-1500, 1501) / 400.0) ** 2)
+    model, om = _models(MGII, FWHM=None, taps=wide / wide.sum())
+    _check(model, om, np.linspace(3740.0, 3800.0, 5000), thetas[:3], LB, UB, rng)
+
+
+def test_unsorted_and_descending_wavelength_grids():
+    """The kernel takes the range of 1/lambda from block min/max tables: no monotonicity is assumed.  (The LSF acts
+    on pixel order, as in the reference, so the oracle sees the same arrays.)"""
+    rng = np.random.default_rng(11)
+    model, om = _models(MGII)
+    thetas = np.clip(TH + rng.standard_normal((6, 6)) * [0.05, 0.05, 1, 1, 2, 2], LB, UB)
+    wave = np.linspace(3755.0, 3795.0, 3000)
+    _check(model, om, wave[::-1].copy(), thetas, LB, UB, rng)
+    _check(model, om, rng.permutation(wave), thetas, LB, UB, rng)
+
+
+def test_many_lines_many_components():
+    """L = 96 lines over 32 tied components (the per-warp line lists and classification run several rounds)."""
+    rng = np.random.default_rng(13)
+    systems = []
+    for k, z in enumerate(np.linspace(1.9, 2.9, 8)):
+        systems.append((float(z), "CIV", [1548.2, 1550.77], 2))
+        systems.append((float(z), "HI", [1215.67, 1025.72, 972.54, 949.74], 2))
+    model, om = _models(systems)
+    C = om.total_components
+    assert om.n_lines == 96 and C == 32
+    n, b, v = rng.uniform(12.5, 14.5, C), rng.uniform(8, 45, C), rng.uniform(-120, 120, C)
+    th = np.concatenate([n, b, v])
+    lb, ub = th - np.concatenate([np.full(C, 2.0), np.full(C, 6.0), np.full(C, 50.0)]), th + 50.0
+    thetas = th + rng.standard_normal((7, 3 * C)) * np.concatenate([np.full(C, 0.05), np.full(C, 1.0), np.full(C, 2.0)])
+    _check(model, om, np.linspace(3400.0, 6100.0, 9000), thetas, lb, ub, rng)
+
+
+def test_single_walker_scalar_and_float32_errors():
+    rng = np.random.default_rng(17)
+    model, om = _models(MGII)
+    wave = np.linspace(3755.0, 3795.0, 2048)
+    got = _check(model, om, wave, TH, LB, UB, rng, error_dtype=np.float32)       # (ndim,) -> scalar
+    assert got.shape == (1,)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("ppt", [2, 8])
+def test_every_tile_geometry_and_chunk_size(level, ppt):
+    """RBVFIT_B200_GEOM / RBVFIT_B200_PPT pin the tile size and the phase-1 chunk size (read when a context is
+    created): every combination must give the oracle's numbers on a spectrum with several tiles."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import workloads as wl
+    rng = np.random.default_rng(19)
+    w = wl.get_workload("C2")
+    model, om = _models(w["systems"])
+    wave = np.linspace(3300.0, 5700.0, 6000)
+    thetas = wl.make_ensemble(w, 12)
+    os.environ["RBVFIT_B200_GEOM"], os.environ["RBVFIT_B200_PPT"] = str(level), str(ppt)
+    try:
+        _check(model, om, wave, thetas, w["lb"], w["ub"], rng)
+    finally:
+        del os.environ["RBVFIT_B200_GEOM"], os.environ["RBVFIT_B200_PPT"]
+        from rbvfit_b200.engine import Engine
+        Engine(0).close()                      # a context created without the variables resets the hooks
