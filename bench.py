@@ -309,6 +309,7 @@ def run_gpu(args, rank, world, local):
         "gpu_launches": int(launches),       # prep_kernel + voigt_tile_kernel per step
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": prof.get("dram_bytes_per_launch"),
+                     "traffic_capture": None if not prof else f"{prof.get('report')}: {prof.get('note')}",
                      "peak_source": "DFMA dependent-chain probe measured in this run (rbv_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 entry (spec: 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
                      "kernel": "voigt_tile_kernel", "kernel_ms": k_ms, "far_field": args.far_field,

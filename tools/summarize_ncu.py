@@ -112,7 +112,8 @@ def main():
         fh.write("\n".join(lines) + "\n")
     if "--latest" in sys.argv:
         with open(os.path.join(os.path.dirname(out) or ".", "latest_ncu_summary.json"), "w") as fh:
-            json.dump({"report": summ["report"], "dram_bytes_per_launch": summ["dram_bytes_per_launch"],
+            note = sys.argv[sys.argv.index("--note") + 1] if "--note" in sys.argv else None
+            json.dump({"report": summ["report"], "note": note, "dram_bytes_per_launch": summ["dram_bytes_per_launch"],
                        "duration_ms": summ["duration_ms"],
                        "fp64_pipe_pct": metrics.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
                                                     {}).get("value")}, fh, indent=1)
