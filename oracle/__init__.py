@@ -11,6 +11,8 @@ Nothing in ``rbvfit_b200/`` may import this package.  Only ``tests/``,
                     has no ``/root/reference``).
 * ``make_golden``   runs the real reference through ``refshim`` and writes the committed
                     fixtures under ``tests/golden/``.
+* ``stretch_replay`` numpy restatement of the device-resident stretch-move sampler
+                    (``rbv_stretch_run``), Philox random streams included.
 
 Parity status: the reference ships no golden vectors or value-asserting tests for this path
 (SURVEY.md section 4), so the oracle is pinned against outputs of the reference code itself,

@@ -136,6 +136,57 @@ class vfit:
                              bounds=list(zip(lb, ub)))
         return result.x
 
+    # ------------------------------------------------------------------ quick fit (vfit_mcmc.py:362-406)
+    def _chi2_batch(self, thetas):
+        """chi^2 summed over instruments for every row (quick_fit_interface.py:30-51), without the prior:
+        chi^2 = -2 lnlike + sum_px log_inv_sigma2, the second term being constant.  One device batch."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        const = sum(float(np.sum(np.asarray(d["log_inv_sigma2"], dtype=np.float64)))
+                    for d in self.instrument_data.values())
+        ll = np.atleast_1d(self.lnlike(thetas))
+        chi2 = -2.0 * ll + const
+        return np.where(np.isfinite(chi2), chi2, 1e10)            # the reference returns 1e10 when evaluation fails
+
+    def fit_quick(self, verbose=True):
+        """Deterministic chi^2 fit (L-BFGS-B, maxfun 5000) with finite-difference 1-sigma errors -- same
+        objective, optimiser, step rule and fallbacks as core/quick_fit_interface.py:10-128; the objective, its
+        gradient probes and the 2 ndim + 1 curvature probes are device batches."""
+        import scipy.optimize as op
+        self.mcmc_flag = False
+        lb, ub = self.lb.astype(float), self.ub.astype(float)
+        h = 1e-8
+        theta0 = np.asarray(self.theta, dtype=np.float64)
+
+        def fun_and_grad(x):
+            x = np.asarray(x, dtype=np.float64)
+            steps = np.full(self.ndim, h)
+            steps[x + h > ub] = -h
+            vals = self._chi2_batch(np.vstack([x, x[None, :] + np.diag(steps)]))
+            return vals[0], (vals[1:] - vals[0]) / steps
+
+        try:
+            result = op.minimize(fun_and_grad, theta0, jac=True, bounds=list(zip(lb, ub)), method="L-BFGS-B",
+                                 options={"maxfun": 5000})
+            best = result.x
+            if not result.success:
+                warnings.warn(f"Optimization may not have converged: {result.message}")
+            # _estimate_parameter_errors (:93-128): central second difference, chi2 + 1 criterion
+            delta = np.maximum(np.maximum(np.abs(best) * 0.01, np.abs(theta0) * 0.01), 1e-6)
+            probes = np.vstack([best, best[None, :] + np.diag(delta), best[None, :] - np.diag(delta)])
+            c = self._chi2_batch(probes)
+            d2 = (c[1:self.ndim + 1] - 2.0 * c[0] + c[self.ndim + 1:]) / delta ** 2
+            with np.errstate(divide="ignore", invalid="ignore"):
+                err = np.where(d2 > 0, np.sqrt(1.0 / d2), np.abs(best - theta0))
+        except Exception as e:   # pragma: no cover - mirrors the reference's fallback
+            warnings.warn(f"Minimize fitting failed: {e}")
+            best, err = theta0.copy(), np.zeros_like(theta0)
+        if verbose:
+            print("Quick fit completed")
+            if np.any(np.isnan(err)):
+                print("WARNING: Some uncertainties are NaN")
+        self.theta_best, self.theta_best_error = best, err
+        return best, err
+
     # ------------------------------------------------------------------ walkers (vfit_mcmc.py:442-466)
     def _initialize_walkers(self, popt):
         """Same distribution and bounds clipping as the reference; validity is checked for all walkers in one

@@ -188,3 +188,21 @@ def test_curve_of_growth_grid_and_chi_squared_match_oracle():
     assert 0.8 < got["COS"] < 1.25                                       # noise realisation at the truth
     with pytest.raises(ValueError):
         fitter.chi_squared(instrument_name="HIRES")
+
+
+def test_fit_quick_recovers_truth_with_sane_errors():
+    """vfit.fit_quick (quick_fit_interface.py:10-128) through device batches: the chi^2 objective equals the
+    oracle's, the optimum sits near the truth the spectrum was drawn from, errors are finite and bracket it."""
+    from oracle import voigt_oracle as vo
+    w, fitter, comp, theta0 = _c1_fitter()
+    d = comp["COS"]
+    probe = np.vstack([w["theta_true"], theta0])
+    ref = np.array([np.sum(((d["flux"] - vo.model_flux(d["model"], th, d["wave"])) / d["error"]) ** 2) for th in probe])
+    assert np.max(np.abs(fitter._chi2_batch(probe) - ref) / ref) <= 1e-9
+    best, err = fitter.fit_quick(verbose=False)
+    assert best.shape == (6,) and err.shape == (6,) and np.all(np.isfinite(err)) and np.all(err > 0)
+    assert np.all(best >= w["lb"]) and np.all(best <= w["ub"])
+    assert fitter._chi2_batch(best)[0] <= fitter._chi2_batch(w["theta_true"])[0] + 1e-6
+    # (the diagonal-curvature errors ignore the N1-N2 / v1-v2 degeneracy of the blended doublet, as in the reference)
+    assert np.all(np.abs(best - w["theta_true"]) < np.array([0.5, 0.5, 5.0, 5.0, 10.0, 10.0]))
+    assert fitter.mcmc_flag is False and np.array_equal(fitter.theta_best, best)
