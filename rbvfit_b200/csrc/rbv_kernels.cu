@@ -89,6 +89,7 @@ struct LaunchParams {
   // device-resident sampler (rbv_stretch_run): when sampler_split >= 0 the prep kernel first builds the stretch
   // proposal of row w, and the CTA that finalises lnprob[w] also applies accept/reject and records the chain
   int sampler_split;
+  int separate_finalize; // 1 = lnprob is formed by finalize_kernel (big grids), 0 = by the walker's last CTA
   StretchParams sp;
 };
 
@@ -534,6 +535,26 @@ __global__ void __launch_bounds__(128) prep_propose_kernel(const LaunchParams pr
   prep_walker_lines(prm, k, blockIdx.y * blockDim.x + threadIdx.x, s_row);
 }
 
+// Sum of a walker's tile partials in fixed order -> lnprob (and, for the device-resident sampler, accept/reject).
+__device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, int inst_id, int oob) {
+  double total;
+  if (oob) {
+    total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
+  } else {
+    total = 0.0;
+    const volatile double* pp = prm.partials + (size_t)w * prm.n_tiles;
+    const int n_sum = (prm.wps > 0) ? 1 : prm.n_inst;   // a sightline walker sees one instrument only
+    for (int k = 0; k < n_sum; ++k) {
+      double s = 0.0;
+      for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
+      const int ki = (prm.wps > 0) ? inst_id : k;
+      total += -0.5 * (s - prm.inst[ki].sum_log_inv_sigma2);      // vfit_mcmc.py:309-313
+    }
+  }
+  prm.lnprob[w] = total;
+  if (prm.sampler_split >= 0) stretch_accept_record(prm.sp, prm.sampler_split, w, total);
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 // MODE 0: lnprob (chi^2 partial + ticket finalisation); MODE 1: model flux out.
 // PPT = pixels per lane in phase 1: 8 for big tiles (ILP), 2 when a tile has only a few chunks per warp, so that
@@ -758,28 +779,23 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 #pragma unroll
       for (int k = 0; k < kThreads / 32; ++k) s += s_red[k];
       prm.partials[(size_t)w * prm.n_tiles + tile_id] = s;
+      if (prm.separate_finalize) return;       // big grids: finalize_kernel adds the partials (no tail in this CTA)
       // release our partial / acquire the others' with ONE acq_rel ticket atomic; the walker's last CTA finalises
       unsigned int prev;
       asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(prm.tickets + w) : "memory");
       if (prev != (unsigned int)(prm.n_tiles - 1)) return;
-      double total;
-      if (oob) {
-        total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
-      } else {
-        total = 0.0;
-        const volatile double* pp = prm.partials + (size_t)w * prm.n_tiles;
-        const int n_sum = (prm.wps > 0) ? 1 : prm.n_inst;   // a sightline walker sees one instrument only
-        for (int k = 0; k < n_sum; ++k) {
-          double s = 0.0;
-          for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
-          const int ki = (prm.wps > 0) ? inst_id : k;
-          total += -0.5 * (s - prm.inst[ki].sum_log_inv_sigma2);      // vfit_mcmc.py:309-313
-        }
-      }
-      prm.lnprob[w] = total;
-      if (prm.sampler_split >= 0) stretch_accept_record(prm.sp, prm.sampler_split, w, total);
+      finalize_walker(prm, w, inst_id, oob);
     }
   }
+}
+
+// lnprob of every walker from its tile partials, as a separate launch.  Used for big grids: the in-kernel
+// finalisation keeps one thread of every CTA (and with it the CTA's registers and shared memory) alive for the
+// round trip of the ticket atomic -- about 15 % of a CTA's lifetime at C5a.
+__global__ void __launch_bounds__(128) finalize_kernel(const LaunchParams prm) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= prm.W) return;
+  finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w]);
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
@@ -908,6 +924,7 @@ constexpr int kGeomLevels = 6;   // tile sizes, see compute_geometry
 static thread_local std::string g_last_error;
 static int g_force_ppt = 0;   // tuning hook (RBVFIT_B200_PPT=2|8)
 static int g_force_level = -1;   // tuning hook (RBVFIT_B200_GEOM=0..5)
+static int g_force_finalize = -1;   // tuning hook (RBVFIT_B200_FINALIZE=0|1)
 
 static int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -981,6 +998,8 @@ int rbv_create(int device, RbvContext** out) {
   {   // tuning / test hooks, re-read whenever a context is created
     const char* e = getenv("RBVFIT_B200_PPT");
     g_force_ppt = e ? atoi(e) : 0;
+    e = getenv("RBVFIT_B200_FINALIZE");
+    g_force_finalize = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_GEOM");
     g_force_level = e ? std::min(std::max(atoi(e), 0), kGeomLevels - 1) : -1;
   }
@@ -1331,10 +1350,19 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   else prep_kernel<<<pgrid, 128, 0, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
+  // the walker's last CTA finalises in-kernel when the grid is small (one launch less on the latency path); big
+  // grids use a separate tiny launch instead, so that no CTA waits for the ticket round trip
+  prm.separate_finalize = (long long)W * prm.n_tiles >= 8LL * RBV_MIN_CTAS * ctx->sm_count;
+  if (g_force_finalize >= 0) prm.separate_finalize = g_force_finalize;
   if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
   else voigt_tile_kernel<3, 0, 8><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
+  if (prm.separate_finalize) {
+    finalize_kernel<<<(W + 127) / 128, 128, 0, st>>>(prm);
+    RBV_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
   return RBV_OK;
 }
 
