@@ -90,7 +90,9 @@ struct LaunchParams {
   // proposal of row w, and the CTA that finalises lnprob[w] also applies accept/reject and records the chain
   int sampler_split;
   int separate_finalize; // 1 = lnprob is formed by finalize_kernel (big grids), 0 = by the walker's last CTA
+  int inst_in_params;    // 1 = inst_v holds the instruments (joint fits: no global round trip in the CTA prologue)
   StretchParams sp;
+  InstDev inst_v[kMaxInst];
 };
 
 __device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
@@ -467,10 +469,11 @@ __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w
   if (prm.wps > 0) {
     k = w / prm.wps;                       // sightline mode: the walker's own instrument, all L lines
   } else {
-    while (k + 1 < prm.n_inst && g >= prm.inst[k + 1].line_base) ++k;
-    l = g - prm.inst[k].line_base;
+    const InstDev* tab = prm.inst_in_params ? prm.inst_v : prm.inst;
+    while (k + 1 < prm.n_inst && g >= tab[k + 1].line_base) ++k;
+    l = g - tab[k].line_base;
   }
-  const InstDev& I = prm.inst[k];
+  const InstDev& I = prm.inst_in_params ? prm.inst_v[k] : prm.inst[k];
   __align__(16) double lc[LC_STRIDE];
   if (I.method == RBV_VOIGT_FAST) {
     prep_line_fast(I, l, th, lc);
@@ -548,7 +551,8 @@ __device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, 
       double s = 0.0;
       for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
       const int ki = (prm.wps > 0) ? inst_id : k;
-      total += -0.5 * (s - prm.inst[ki].sum_log_inv_sigma2);      // vfit_mcmc.py:309-313
+      const double slog = prm.inst_in_params ? prm.inst_v[ki].sum_log_inv_sigma2 : prm.inst[ki].sum_log_inv_sigma2;
+      total += -0.5 * (s - slog);                                   // vfit_mcmc.py:309-313
     }
   }
   prm.lnprob[w] = total;
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     while (inst_id + 1 < prm.n_inst && tile_id >= prm.geom[inst_id + 1].first_tile) ++inst_id;
   }
   const TileGeom G = prm.geom[prm.wps > 0 ? 0 : inst_id];
-  const InstDev I = prm.inst[inst_id];
+  const InstDev I = prm.inst_in_params ? prm.inst_v[inst_id] : prm.inst[inst_id];
   const int ndim = prm.ndim;
   if (tid == 0) s_next = 0;
 
@@ -602,15 +606,16 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   int oob = 0;
   const bool fast = (I.method == RBV_VOIGT_FAST);
   if (MODE == 0) {
-    // ---- per-line constants and the prior flag were computed once per walker by prep_kernel
-    oob = prm.oob[w];
-    if (!oob) {
+    // ---- per-line constants and the prior flag were computed once per walker by prep_kernel; the copy does not
+    // wait for the flag (an out-of-bounds row's constants are finite or NaN, never read)
+    {
       const double2* src =
           reinterpret_cast<const double2*>(
               prm.lc + ((size_t)w * prm.n_lines_total + (prm.wps > 0 ? 0 : I.line_base)) * LC_STRIDE);
       double2* dst = reinterpret_cast<double2*>(s_lc);
       for (int i = tid; i < I.L * (LC_STRIDE / 2); i += kThreads) dst[i] = src[i];
     }
+    oob = prm.oob[w];
     __syncthreads();
   } else {
     // ---- flux mode: the CTA prepares its own constants (no workspace in this entry point)
@@ -1352,6 +1357,9 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   ctx->launches++;
   // the walker's last CTA finalises in-kernel when the grid is small (one launch less on the latency path); big
   // grids use a separate tiny launch instead, so that no CTA waits for the ticket round trip
+  prm.inst_in_params = !sl && ctx->inst.size() <= (size_t)kMaxInst;
+  if (prm.inst_in_params)
+    for (size_t k = 0; k < ctx->inst.size(); ++k) prm.inst_v[k] = ctx->inst[k].dev;
   prm.separate_finalize = (long long)W * prm.n_tiles >= 8LL * RBV_MIN_CTAS * ctx->sm_count;
   if (g_force_finalize >= 0) prm.separate_finalize = g_force_finalize;
   if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
@@ -1523,6 +1531,8 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   prm.farfield = ctx->farfield;
   prm.sampler_split = -1;
   if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "rbv_model_flux_batch: more than 16 instruments");
+  prm.inst_in_params = 1;
+  for (size_t k = 0; k < ctx->inst.size(); ++k) prm.inst_v[k] = ctx->inst[k].dev;
   prm.n_tiles = compute_geometry(ctx, W >= 64 ? 3 : 1, prm.geom, nullptr);   // flux mode: 2048- or 768-slot tiles
   prm.tile_base = prm.geom[inst].first_tile;
   size_t smem = smem_bytes_for(I, prm.geom[inst], ndim);
