@@ -65,6 +65,9 @@ typedef struct RbvLineTable {
  * error's dtype) and then promoted to double.  flux/inv_sigma2/log_inv_sigma2 may be NULL for an instrument
  * that is only used with rbv_model_flux_batch().
  * inv_wave is a DEVICE scratch array of n_pixels doubles that the library fills with 1/wave.
+ * The spectrum is read ONCE, by rbv_add_instrument: the library derives its own tables from it (1/wave, the range
+ * of 1/wave per 256-pixel block, a block-transposed copy of (flux, inv_sigma2) for coalesced loads, the sum of
+ * log_inv_sigma2) -- changing the arrays afterwards has no effect; build a new context for new data.
  * taps is a HOST array of n_taps (odd) LSF taps exactly as the reference would apply them
  * (Gaussian1DKernel.array for ndimage.convolve1d(mode='nearest'), voigt_model.py:222-224, or the
  * CustomKernel array for astropy convolve(boundary='extend'), :225-230); NULL / 0 = no convolution.
