@@ -38,7 +38,7 @@ extern "C" {
 #define RBV_PRECISION_FP32_GATED 1 /* FP32 far-wing arithmetic, used only when the gate passes */
 
 #define RBV_FARFIELD_DIRECT 0    /* every (line, pixel) pair evaluated on its own                          */
-#define RBV_FARFIELD_CHEBYSHEV 1 /* default: summed far wings of a 256-pixel chunk interpolated from 8 nodes, */
+#define RBV_FARFIELD_CHEBYSHEV 1 /* default: summed far wings of a 1024-pixel super-chunk interpolated from 8 nodes, */
                                  /* used per (line, chunk) only when an a-priori bound keeps |dtau| <= 1e-13  */
 
 typedef struct RbvContext RbvContext;
@@ -91,7 +91,8 @@ void rbv_destroy(RbvContext* ctx);
 /* Select the arithmetic of the far-wing tier (default RBV_PRECISION_FP64). */
 int rbv_set_precision(RbvContext* ctx, int precision);
 
-/* Select how far line wings (|x| >= 200 Doppler widths) are accumulated (default RBV_FARFIELD_CHEBYSHEV). */
+/* Select how far line wings (lines >= 24 Doppler widths away from a 1024-pixel super-chunk) are accumulated
+ * (default RBV_FARFIELD_CHEBYSHEV). */
 int rbv_set_farfield(RbvContext* ctx, int mode);
 
 /* Append an instrument (model + spectrum).  *out_index receives its index (0, 1, ...).

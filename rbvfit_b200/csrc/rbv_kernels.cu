@@ -167,8 +167,9 @@ constexpr double kFFEps = 1e-13;
 // then evaluates their SUM at RBV_FF_M Chebyshev nodes and interpolates it.  A-priori error bound of the
 // degree-(m-1) Chebyshev interpolant of kappa/x^2 on [xm, xm + 2 hw] (m-th derivative (m+1)!/x^(m+2)):
 //     |err| <= 2 (m+1) kappa (hw / (2 xm))^m / xm^2;
-// the gate uses 8 (m+1) (4x margin covers the a^2 and rho^2, rho^3 corrections, all <= 1e-4 relative at
-// |z|^2 >= 4e4, a <= 1) and runs in FP32 with every rounding pushed to the conservative side.
+// the gate uses 8 (m+1): the 4x margin covers the a^2 and rho^2, rho^3, ... corrections, whose m-th derivatives
+// add <= 6 % at the smallest admitted distance (|z|^2 >= 576, a <= 1: the mid and far tiers, evaluated at the
+// nodes with the 6-term series); it runs in FP32 with every rounding pushed to the conservative side.
 __device__ __forceinline__ int4 classify_lines(int lc_off, int L, unsigned short* __restrict__ list,
                                                unsigned short* __restrict__ list32,
                                                unsigned short* __restrict__ listff, double gate32, float ff_eps,
@@ -193,7 +194,7 @@ __device__ __forceinline__ int4 classify_lines(int lc_off, int L, unsigned short
              : (hmin >= kHiNear) ? kTierMid
              : (hmin >= kHiCore) ? kTierNear
                                  : kTierCore;
-      if (ff_eps > 0.f && tier == kTierFar) {
+      if (ff_eps > 0.f && (tier == kTierFar || tier == kTierMid)) {   // |z|^2 >= 576: the 6-term series is exact
         const float xm = fminf(fabsf((float)x1), fabsf((float)x2)) * 0.99999f;     // rounded towards the line
         const float hw = (float)(0.5 * fabs(A) * du) * 1.00001f;
         const float r = __fdividef(hw, 2.f * xm) * 1.00001f;
@@ -307,7 +308,7 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
       un[k] = fma(uh, c_ff_nodes[k], um);
       S[k] = 0.0;
     }
-    for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQFar, 8>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
+    for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQMid, 8>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
   }
   // transpose-reduce: after the three halving steps lane holds node (lane >> 2) & 7 summed over 8 lanes
   double T4[4], T2[2], T1;

@@ -94,7 +94,7 @@ class GpuLikelihood:
         return self.engine.lnprob_device(theta_t, out_t)
 
     def set_far_field(self, mode: str = "chebyshev"):
-        """``"chebyshev"`` (default): the summed far wings (|x| >= 200 Doppler widths) of each 1024-pixel
+        """``"chebyshev"`` (default): the summed far wings (lines >= 24 Doppler widths away) of each 1024-pixel
         super-chunk are evaluated at 8 Chebyshev nodes and interpolated; a line takes part only where an
         a-priori bound keeps its interpolation error <= 1e-13 / L in optical depth.
         ``"direct"``: every (line, pixel) pair is evaluated on its own."""

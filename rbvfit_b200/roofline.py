@@ -13,11 +13,12 @@ wings of a 1024-pixel super-chunk are summed at 8 Chebyshev nodes and interpolat
 algorithmic work of THAT algorithm (the honest numerator for its roofline); the rule above is kept as the
 "direct-evaluation equivalent":
 
-    per super-chunk : 8 nodes x n_ff lines x 21 (one far-tier evaluation each) + 2 x 64 (node values -> coefficients)
+    per super-chunk : 8 nodes x n_ff lines x c (one series evaluation each: 21 at |x| >= 100, 40 below)
+                      + 2 x 64 (node values -> coefficients)
     per pixel       : 16 if the super-chunk has a far field (t by one FMA + degree-7 Horner), else 0
                       + sum over the lines NOT in the far field of c(x_lp)           (same tiers as above)
                       + 2 K + 32
-    line l is in the far field of a super-chunk when min |z|^2 >= 4e4 over it and
+    line l is in the far field of a super-chunk when min |z|^2 >= 576 over it (6-term series valid) and
         72 |kappa_l| (hw / (2 xm))^8 / xm^2 <= 1e-13 / L,   kappa = N f K a / sqrt(pi),  xm = min |x|, hw = half width in x
 """
 from __future__ import annotations
@@ -92,11 +93,12 @@ def flops_farfield(data, theta, wave, n_taps):
         hw = 0.5 * np.abs(x2 - x1)
         with np.errstate(divide="ignore", invalid="ignore"):
             bound = 72.0 * np.abs(kappa) * (hw / (2 * xm)) ** FF_NODES / xm ** 2
-        ff = (~crosses) & (xm * xm + a * a >= 4e4) & (a < 1.0) & (bound <= FF_EPS / L)
+        ff = (~crosses) & (xm * xm + a * a >= 576.0) & (a < 1.0) & (bound <= FF_EPS / L)
         n_ff = int(ff.sum())
         npx = len(uc)
         if n_ff:
-            flops += FF_NODES * n_ff * C_FAR + 2.0 * FF_NODES * FF_NODES + 16.0 * npx
+            node_cost = np.where(xm[ff] >= 100.0, C_FAR, C_MID).sum()
+            flops += FF_NODES * node_cost + 2.0 * FF_NODES * FF_NODES + 16.0 * npx
             n_ffp += n_ff * npx
         d = np.flatnonzero(~ff)
         if len(d):
