@@ -26,9 +26,6 @@
 
 namespace rbv {
 
-#ifndef RBV_PPT
-#define RBV_PPT 8
-#endif
 #ifndef RBV_MIN_CTAS
 #define RBV_MIN_CTAS 2
 #endif
@@ -36,8 +33,7 @@ namespace rbv {
 #define RBV_THREADS 256
 #endif
 constexpr int kThreads = RBV_THREADS;
-constexpr int kPixPerThread = RBV_PPT;
-constexpr int kPass = kThreads * kPixPerThread;  // pixels per phase-1 pass
+constexpr int kMaxHalo = 8192;                   // K - 1 <= kMaxHalo (tiles have at most 256 * 256 flux slots)
 constexpr int kSuperPix = 1024;                  // super-chunk: unit of tier classification + far field
 constexpr int kWantWaves = 1;                    // biggest tiles that still fill every CTA slot of the GPU once
 constexpr int kSmallChunkLimit = 17;             // tiles with fewer 256-px chunks than this use 64-px chunks

@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   if (tid == 0) s_next = 0;
 
   const int lc_off = (ndim + 1) & ~1;                  // smem layout (doubles): theta | line consts | taps |
-  const int taps_off = lc_off + I.L * LC_STRIDE;       //   flux tile | per-warp line lists (u16)
+  const int taps_off = lc_off + I.L * LC_STRIDE;       //   flux tile | super-chunk records | line lists (u16)
   const int flux_off = taps_off + I.Kpad;
   const int rec_off = flux_off + ((smem_pos(G.ext_alloc, LOGR) + 1) & ~1);              // super-chunk records
   const int list_off = rec_off + G.n_super * SC_STRIDE;
@@ -1057,9 +1057,7 @@ int rbv_set_farfield(RbvContext* ctx, int mode) {
   return RBV_OK;
 }
 
-// Tile geometry of every instrument for one launch.  ``scale`` multiplies the base tile (1, 2, 4, ...):
-// big tiles amortise the per-CTA preamble and halo and make the dynamic chunk scheduling effective, small
-// tiles keep the grid full when there are few walkers.  Returns the total tile count and the dynamic smem.
+// Tile geometry of every instrument for one launch; returns the total tile count and the dynamic smem.
 // Tile geometry in units of 256 flux slots: level 0..kGeomLevels-1 -> 2, 3, 4, 8, 16, 32 units for an LSF with a
 // short halo (tile = units * 256 - (K - 1), rounded down to whole 256-pixel blocks); wide LSFs start from the
 // size that keeps the halo below ~8 % of the slots.  Small tiles = many CTAs per walker (latency of small
@@ -1193,7 +1191,7 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
       for (double& t : hi.taps) t /= s;
     }
   }
-  if ((int)hi.taps.size() - 1 > 4 * kPass) return fail(RBV_EINVAL, "rbv_add_instrument: LSF too wide (max 4097 taps)");
+  if ((int)hi.taps.size() - 1 > kMaxHalo) return fail(RBV_EINVAL, "rbv_add_instrument: LSF too wide (max 8193 taps)");
 
   double *d_l0, *d_g, *d_f, *d_z;
   int* d_c;

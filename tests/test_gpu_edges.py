@@ -72,6 +72,14 @@ def test_lsf_wider_than_spectrum_and_widest_supported():
     wide = np.exp(-0.5 * (np.arange(-1500, 1501) / 400.0) ** 2)
     model, om = _models(MGII, FWHM=None, taps=wide / wide.sum())
     _check(model, om, np.linspace(3740.0, 3800.0, 5000), thetas[:3], LB, UB, rng)
+    widest = np.exp(-0.5 * (np.arange(-4096, 4097) / 900.0) ** 2)              # 8193 taps: the documented maximum
+    model, om = _models(MGII, FWHM=None, taps=widest / widest.sum())
+    _check(model, om, np.linspace(3740.0, 3800.0, 20000), thetas[:2], LB, UB, rng)
+    from rbvfit_b200._lib import RbvError
+    too_wide = np.ones(8195) / 8195.0
+    model, om = _models(MGII, FWHM=None, taps=too_wide)
+    with pytest.raises(RbvError):
+        model.compile().model_flux(TH, np.linspace(3740.0, 3800.0, 9000))
 
 
 def test_unsorted_and_descending_wavelength_grids():
