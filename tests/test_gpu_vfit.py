@@ -206,3 +206,30 @@ def test_fit_quick_recovers_truth_with_sane_errors():
     # (the diagonal-curvature errors ignore the N1-N2 / v1-v2 degeneracy of the blended doublet, as in the reference)
     assert np.all(np.abs(best - w["theta_true"]) < np.array([0.5, 0.5, 5.0, 5.0, 10.0, 10.0]))
     assert fitter.mcmc_flag is False and np.array_equal(fitter.theta_best, best)
+
+
+def test_device_sampler_with_separate_finalisation_launch():
+    """Big grids form lnprob (and the sampler's accept/reject) in finalize_kernel instead of the walker's last CTA;
+    RBVFIT_B200_FINALIZE=1 forces that path on a small problem: same chain as the numpy replay, bit-identical
+    lnprob to the in-kernel path."""
+    import os
+    from oracle import stretch_replay as sr
+    from rbvfit_b200.sampler import DeviceEnsembleSampler
+    w, fitter0, comp, theta0 = _c1_fitter()
+    rng = np.random.default_rng(9)
+    p0 = np.clip(w["theta_true"] + 1e-3 * rng.standard_normal((18, 6)), w["lb"], w["ub"])
+    ref = fitter0._like.lnprob(p0)
+    os.environ["RBVFIT_B200_FINALIZE"] = "1"
+    try:
+        w, fitter, comp, theta0 = _c1_fitter()            # new context: reads the hook
+        like = fitter._like
+        assert np.array_equal(like.lnprob(p0), ref)
+        dev = DeviceEnsembleSampler(18, 6, like, seed=31)
+        dev.run_mcmc(p0, 40)
+        chain, lps, nacc = sr.run(like.lnprob, p0, like.lnprob(p0), 40, dev._seed)
+        assert np.allclose(dev.get_chain(), chain, rtol=0, atol=1e-9)
+        assert np.array_equal(np.rint(dev.acceptance_fraction * 40).astype(int), nacc)
+    finally:
+        del os.environ["RBVFIT_B200_FINALIZE"]
+        from rbvfit_b200.engine import Engine
+        Engine(0).close()
