@@ -540,24 +540,31 @@ __global__ void __launch_bounds__(128) prep_propose_kernel(const LaunchParams pr
 }
 
 // Sum of a walker's tile partials in fixed order -> lnprob (and, for the device-resident sampler, accept/reject).
-__device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, int inst_id, int oob) {
+// Called by a whole warp: the partials are loaded lane-parallel and added by lane 0 in tile order (the same
+// order whatever path or geometry calls it), the sampler step uses all lanes.
+__device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, int inst_id, int oob, int lane) {
   double total;
   if (oob) {
     total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
   } else {
     total = 0.0;
-    const volatile double* pp = prm.partials + (size_t)w * prm.n_tiles;
+    const double* pp = prm.partials + (size_t)w * prm.n_tiles;
     const int n_sum = (prm.wps > 0) ? 1 : prm.n_inst;   // a sightline walker sees one instrument only
     for (int k = 0; k < n_sum; ++k) {
       double s = 0.0;
-      for (int t = 0; t < prm.geom[k].n_tiles; ++t) s += pp[prm.geom[k].first_tile + t];
+      const int first = prm.geom[k].first_tile, n = prm.geom[k].n_tiles;
+      for (int t0 = 0; t0 < n; t0 += 32) {
+        const double v = (t0 + lane < n) ? __ldcg(pp + first + t0 + lane) : 0.0;     // L2: written by other CTAs
+        const int m = min(32, n - t0);
+        for (int t = 0; t < m; ++t) s += __shfl_sync(0xffffffffu, v, t);
+      }
       const int ki = (prm.wps > 0) ? inst_id : k;
       const double slog = prm.inst_in_params ? prm.inst_v[ki].sum_log_inv_sigma2 : prm.inst[ki].sum_log_inv_sigma2;
       total += -0.5 * (s - slog);                                   // vfit_mcmc.py:309-313
     }
   }
-  prm.lnprob[w] = total;
-  if (prm.sampler_split >= 0) stretch_accept_record(prm.sp, prm.sampler_split, w, total);
+  if (lane == 0) prm.lnprob[w] = total;
+  if (prm.sampler_split >= 0) stretch_accept_record(prm.sp, prm.sampler_split, w, total, lane);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -780,17 +787,22 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     part = warp_sum(part);
     if (lane == 0) s_red[warp] = part;
     __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
+    if (warp == 0) {
+      unsigned int prev = 0u;
+      if (lane == 0) {
+        double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < kThreads / 32; ++k) s += s_red[k];
-      prm.partials[(size_t)w * prm.n_tiles + tile_id] = s;
-      if (prm.separate_finalize) return;       // big grids: finalize_kernel adds the partials (no tail in this CTA)
-      // release our partial / acquire the others' with ONE acq_rel ticket atomic; the walker's last CTA finalises
-      unsigned int prev;
-      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(prm.tickets + w) : "memory");
+        for (int k = 0; k < kThreads / 32; ++k) s += s_red[k];
+        prm.partials[(size_t)w * prm.n_tiles + tile_id] = s;
+        // big grids: finalize_kernel adds the partials (no tail in this CTA); otherwise release our partial /
+        // acquire the others' with ONE acq_rel ticket atomic: the walker's last CTA finalises
+        if (!prm.separate_finalize)
+          asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(prm.tickets + w) : "memory");
+      }
+      if (prm.separate_finalize) return;
+      prev = __shfl_sync(0xffffffffu, prev, 0);
       if (prev != (unsigned int)(prm.n_tiles - 1)) return;
-      finalize_walker(prm, w, inst_id, oob);
+      finalize_walker(prm, w, inst_id, oob, lane);
     }
   }
 }
@@ -799,9 +811,9 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 // finalisation keeps one thread of every CTA (and with it the CTA's registers and shared memory) alive for the
 // round trip of the ticket atomic -- about 15 % of a CTA's lifetime at C5a.
 __global__ void __launch_bounds__(128) finalize_kernel(const LaunchParams prm) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // one warp per walker
   if (w >= prm.W) return;
-  finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w]);
+  finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
@@ -1366,7 +1378,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   if (prm.separate_finalize) {
-    finalize_kernel<<<(W + 127) / 128, 128, 0, st>>>(prm);
+    finalize_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
     RBV_CUDA(cudaGetLastError());
     ctx->launches++;
   }

@@ -95,35 +95,43 @@ __device__ __forceinline__ void split_geometry(int W, int split, int& offS, int&
   else            { offS = h; nS = W - h; offC = 0; nC = h; }
 }
 
-// Accept / reject for row k of the active half once its lnprob is known, by the thread that finalised it (last CTA
-// of the walker in the tile kernel).  The walker's row of the chain is written here too: after its own half-step a
-// walker does not change again within the step.  The last walker of the second half advances the step counter.
-__device__ __forceinline__ void stretch_accept_record(const StretchParams& P, int split, int k, double new_lp) {
+// Accept / reject for row k of the active half once its lnprob is known, by the WARP that finalised it (last CTA of
+// the walker in the tile kernel, or finalize_kernel).  Every lane takes the same decision; the lanes copy the
+// parameter columns in parallel (a single thread would pay one L2 round trip per column: proposal -> walker ->
+// chain row).  The walker's row of the chain is written here too: after its own half-step a walker does not change
+// again within the step.  The last walker of the second half advances the step counter.
+__device__ __forceinline__ void stretch_accept_record(const StretchParams& P, int split, int k, double new_lp,
+                                                      int lane) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   const unsigned long long s = *P.step_ctr, step = P.first_step + s;
   const int i = P.walker_of[k];
-  if (new_lp != new_lp) atomicOr(P.flag, 1);                 // emcee: "Probability function returned NaN"
   const uint4 r = stretch_rand(P, step, (uint32_t)i, 3u + (uint32_t)split);
-  const double lnpdiff = P.factors[k] + new_lp - P.lnp[i];
-  double* x = P.coords + (size_t)i * P.ndim;
-  double lp = P.lnp[i];
-  if (log(u01(r.x, r.y)) < lnpdiff) {
-    const double* q = P.prop + (size_t)k * P.ndim;
-    for (int d = 0; d < P.ndim; ++d) x[d] = q[d];
-    P.lnp[i] = lp = new_lp;
-    P.n_accepted[i] += 1;
+  const double old_lp = P.lnp[i];
+  const double lnpdiff = P.factors[k] + new_lp - old_lp;
+  const bool accept = log(u01(r.x, r.y)) < lnpdiff;
+  const double* __restrict__ src = accept ? P.prop + (size_t)k * P.ndim : P.coords + (size_t)i * P.ndim;
+  double* __restrict__ x = P.coords + (size_t)i * P.ndim;
+  double* __restrict__ row = P.chain ? P.chain + (s * P.W + i) * (size_t)P.ndim : nullptr;
+  for (int d = lane; d < P.ndim; d += 32) {
+    const double v = src[d];
+    if (accept) x[d] = v;
+    if (row) row[d] = v;
   }
-  if (P.chain) {
-    double* row = P.chain + (s * P.W + i) * (size_t)P.ndim;
-    for (int d = 0; d < P.ndim; ++d) row[d] = x[d];
-  }
-  if (P.lnp_chain) P.lnp_chain[s * P.W + i] = lp;
-  __threadfence();
-  if (atomicAdd(P.ticket, 1u) == (unsigned)nS - 1u) {        // last walker of this half-step
-    *P.ticket = 0u;
-    if (split == 1) *P.step_ctr = s + 1;
+  __syncwarp();
+  if (lane == 0) {
+    if (new_lp != new_lp) atomicOr(P.flag, 1);               // emcee: "Probability function returned NaN"
+    if (accept) {
+      P.lnp[i] = new_lp;
+      P.n_accepted[i] += 1;
+    }
+    if (P.lnp_chain) P.lnp_chain[s * P.W + i] = accept ? new_lp : old_lp;
     __threadfence();
+    if (atomicAdd(P.ticket, 1u) == (unsigned)nS - 1u) {      // last walker of this half-step
+      *P.ticket = 0u;
+      if (split == 1) *P.step_ctr = s + 1;
+      __threadfence();
+    }
   }
 }
 
