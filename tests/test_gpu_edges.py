@@ -137,3 +137,30 @@ def test_every_tile_geometry_and_chunk_size(level, ppt):
         del os.environ["RBVFIT_B200_GEOM"], os.environ["RBVFIT_B200_PPT"]
         from rbvfit_b200.engine import Engine
         Engine(0).close()                      # a context created without the variables resets the hooks
+
+
+def test_joint_fit_with_different_line_lists_per_instrument():
+    """Joint fit where the instruments see different transitions of the same ion (different L, same theta layout),
+    different pixel counts and different LSFs: summed lnprob against the oracle."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200.likelihood import GpuLikelihood
+    rng = np.random.default_rng(23)
+    m_a, o_a = _models([(0.348, "MgII", [2796.3], 2)], FWHM="6.5")
+    m_b, o_b = _models([(0.348, "MgII", [2796.3, 2803.5], 2)], FWHM="3.0")
+    assert o_a.n_lines == 2 and o_b.n_lines == 4
+    wa, wb = np.linspace(3760.0, 3776.0, 700), np.linspace(3755.0, 3795.0, 5000)
+    data = {}
+    for name, (gm, om, wave) in {"A": (m_a, o_a, wa), "B": (m_b, o_b, wb)}.items():
+        flux = vo.model_flux(om, TH, wave) + 0.05 * rng.standard_normal(wave.size)
+        data[name] = dict(g=gm, o=om, wave=wave, flux=flux, error=np.full(wave.size, 0.05))
+    like = GpuLikelihood({n: dict(model=d["g"], wave=d["wave"], flux=d["flux"], error=d["error"])
+                          for n, d in data.items()}, LB, UB)
+    comp = vo.compile_instruments({n: dict(model=d["o"], wave=d["wave"], flux=d["flux"], error=d["error"])
+                                   for n, d in data.items()})
+    thetas = np.clip(TH + rng.standard_normal((11, 6)) * [0.05, 0.05, 1, 1, 2, 2], LB, UB)
+    thetas[5, 2] = LB[2] - 1.0
+    got, ref = like.lnprob(thetas), vo.lnprob_batch(comp, thetas, LB, UB)
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.isneginf(ref).sum() == 1
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= LNPROB_RTOL
+    like.close()
