@@ -330,6 +330,7 @@ def run_gpu(args, rank, world, local):
                                                   n_inb, fp64_peak)
         line["fp32_gated"] = fp32_gated_leg(like, theta_dev, thetas, W, total_px, args.steps, flush)
         line["mcmc"] = mcmc_leg(local, with_cpu=not args.no_cpu)
+        line["mcmc"]["large_ensemble"] = mcmc_large_leg(like, w, thetas, total_px)
     if not args.no_cpu and world >= 1:
         r = cpu_arm(args.workload, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -478,6 +479,25 @@ def fp32_gated_leg(like, theta_dev, thetas, W, total_px, steps, flush):
         out.update(value=W * total_px / (ms * 1e-3), unit=UNIT, ms_per_step=ms)
     like.set_precision("fp64")
     return out
+
+
+def mcmc_large_leg(like, w, thetas, total_px, nsteps=12):
+    """MCMC steps/s at the bench workload's own scale (C5a: ~8000 walkers x 100 000 px): the device-resident stretch
+    move on the in-bounds rows of the bench ensemble; one step = every walker updated once = one full ensemble
+    evaluation."""
+    import torch
+    from rbvfit_b200.sampler import DeviceEnsembleSampler
+    ok = thetas[np.all((thetas >= w["lb"]) & (thetas <= w["ub"]), axis=1)]
+    W = len(ok) - (len(ok) % 2)
+    smp = DeviceEnsembleSampler(W, like.ndim, like, seed=4)
+    smp.run_mcmc(ok[:W], 2, skip_initial_state_check=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    smp.run_mcmc(None, nsteps)
+    dt = time.perf_counter() - t0
+    return {"walkers": int(W), "pixels": int(total_px), "steps": nsteps, "steps_per_sec": nsteps / dt,
+            "walker_pixel_per_sec": nsteps * W * total_px / dt, "acceptance": float(smp.acceptance_fraction.mean()),
+            "note": "includes the D2H copy of the chain (W x ndim x 8 B per step)"}
 
 
 def mcmc_leg(device, with_cpu=True, nsteps=300, cpu_steps=12):
