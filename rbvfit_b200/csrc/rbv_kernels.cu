@@ -97,6 +97,15 @@ struct LaunchParams {
 
 __device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
 
+// ticket = (*counter)++ on a shared-memory counter: one ATOMS instruction (atomicAdd on the generic address costs
+// an address-space check and a dozen instructions per draw)
+__device__ __forceinline__ int smem_ticket(int* counter) {
+  int t;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;"
+               : "=r"(t) : "r"((unsigned)__cvta_generic_to_shared(counter)) : "memory");
+  return t;
+}
+
 // ------------------------------------------------------------------------------------------ prep
 // per-line constants for the wofz method
 __device__ __forceinline__ void prep_line_wofz(const InstDev& I, int l, const double* __restrict__ th,
@@ -671,18 +680,24 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     // (the ticket for the NEXT chunk is drawn one iteration ahead, so that its 1/lambda lines can be prefetched
     // into L1 while the current chunk is computed)
     int c = 0;
-    if (lane == 0) c = atomicAdd(&s_next, 1);
+    if (lane == 0) c = smem_ticket(&s_next);
     c = __shfl_sync(0xffffffffu, c, 0);
     while (c < n_chunks) {
       int c_next = 0;
-      if (lane == 0) c_next = atomicAdd(&s_next, 1);
+      if (lane == 0) c_next = smem_ticket(&s_next);
       const int i0 = c * kWarpPix;
       double u[PPT], tau[PPT];
+      const int pc = p0 - h + i0;                     // first pixel of the chunk
+      if (pc >= 0 && pc + kWarpPix <= I.P) {          // interior chunk: base pointer + compile-time offsets
+        const double* up = I.inv_wave + pc + lane;
 #pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        int i = i0 + j * 32 + lane;
-        int p = min(max(p0 - h + i, 0), I.P - 1);   // edge replication
-        u[j] = __ldg(I.inv_wave + p);
+        for (int j = 0; j < PPT; ++j) u[j] = __ldg(up + j * 32);
+      } else {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const int p = min(max(pc + j * 32 + lane, 0), I.P - 1);   // edge replication
+          u[j] = __ldg(I.inv_wave + p);
+        }
       }
       c_next = __shfl_sync(0xffffffffu, c_next, 0);
       if (c_next < n_chunks && lane < (kWarpPix + 15) / 16) {   // 16 doubles per 128-byte line
@@ -700,18 +715,23 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       unsigned hmax = 0u;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]) & 0x7fffffffu);
-      if (__reduce_max_sync(0xffffffffu, hmax) < 0x3F900000u) {       // NaN has a larger high word: slow path
+      // slot(i0 + 32 j + lane) = slot(i0) + (R + 1) * (32 / R) * j + lane + lane / R   (i0 and 32 are multiples of R)
+      static_assert(32 % (1 << LOGR) == 0, "chunk rows must be whole groups of R");
+      double* fo = s_flux + smem_pos(i0, LOGR) + lane + (lane >> LOGR);
+      constexpr int kRow = (R + 1) * (32 / R);
+      const bool small = __reduce_max_sync(0xffffffffu, hmax) < 0x3F900000u;   // NaN has a larger high word
+      if (i0 + kWarpPix <= ext) {               // full chunk: no per-pixel predicate
+        if (small) {
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-          const int i = i0 + j * 32 + lane;
-          if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_small(-tau[j]);
+          for (int j = 0; j < PPT; ++j) fo[j * kRow] = exp_small(-tau[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) fo[j * kRow] = exp_flux(-tau[j]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-          const int i = i0 + j * 32 + lane;
-          if (i < ext) s_flux[smem_pos(i, LOGR)] = exp_flux(-tau[j]);
-        }
+        for (int j = 0; j < PPT; ++j)
+          if (i0 + j * 32 + lane < ext) fo[j * kRow] = small ? exp_small(-tau[j]) : exp_flux(-tau[j]);
       }
       c = c_next;
     }
@@ -765,12 +785,21 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       }
       const int pbase = p0 + e0;
       if (MODE == 0) {
+        // vfit_mcmc.py:310; the log_inv_sigma2 term is summed once per instrument at set-up
+        // (InstDev::sum_log_inv_sigma2).  Same order of additions in both branches.
+        if (e0 + R <= n_out) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (e0 + r < n_out) {
+          for (int r = 0; r < R; ++r) {
             const double resid = obs[r] - acc[r];
-            part = fma(resid * resid, wgt[r], part);   // vfit_mcmc.py:310; the log_inv_sigma2 term is summed once
-                                                       // per instrument at set-up (InstDev::sum_log_inv_sigma2)
+            part = fma(resid * resid, wgt[r], part);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (e0 + r < n_out) {
+              const double resid = obs[r] - acc[r];
+              part = fma(resid * resid, wgt[r], part);
+            }
           }
         }
       } else {
