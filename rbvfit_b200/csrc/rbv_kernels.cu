@@ -353,6 +353,22 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
   if (lane == 9) smem[rec_off + SC_OFFSET] = -um * sc;
 }
 
+// same series from precomputed |z|^2
+template <int NQ, int PPT>
+__device__ __forceinline__ void accum_asym_from_d(int off, const double (&d)[PPT], double (&tau)[PPT]) {
+  double Q[NQ];
+#pragma unroll
+  for (int p = 0; p < NQ; ++p) Q[p] = smem[off + LC_Q + p];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const double rho = rcp_pos(d[j]);
+    double s = Q[NQ - 1];
+#pragma unroll
+    for (int p = NQ - 2; p >= 0; --p) s = fma(s, rho, Q[p]);
+    tau[j] = fma(s, rho, tau[j]);
+  }
+}
+
 template <int PPT>
 __device__ __forceinline__ void farfield_eval(int rec_off, const double (&u)[PPT], double (&tau)[PPT]) {
   double c[8];
@@ -431,12 +447,38 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, const unsigned short
           tau[j] = fma(coef, general_H(x, a, fma(x, x, a2)), tau[j]);
         }
       } else {
+        if (PPT == 2) {
+          // small tiles (64-pixel chunks): the tier was taken over the whole super-chunk, refine it for this chunk
+          // from the pixels themselves -- a super-chunk that holds a line core is mostly wing.  (Measured: +4 %
+          // on the sightline workload; with 8 pixels per lane the extra warp reduction costs more than it saves.)
+          double x[PPT], d[PPT];
+          int hmin = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-          const double x = fma(A, u[j], -B);
-          const double d = fma(x, x, a2);
-          if (d < kDCore) tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
-          else tau[j] += asym_series<kNQNear>(smem + off + LC_Q, d);
+          for (int j = 0; j < PPT; ++j) {
+            x[j] = fma(A, u[j], -B);
+            d[j] = fma(x[j], x[j], a2);
+            hmin = min(hmin, __double2hiint(d[j]));
+          }
+          hmin = __reduce_min_sync(0xffffffffu, hmin);
+          if (hmin >= kHiNear) {
+            accum_asym_from_d<kNQMid, PPT>(off, d, tau);
+          } else if (hmin >= kHiCore) {
+            accum_asym_from_d<kNQNear, PPT>(off, d, tau);
+          } else {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              if (d[j] < kDCore) tau[j] = fma(coef, core_H(x[j], a, a2, core_tab), tau[j]);
+              else tau[j] += asym_series<kNQNear>(smem + off + LC_Q, d[j]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) {
+            const double x = fma(A, u[j], -B);
+            const double d = fma(x, x, a2);
+            if (d < kDCore) tau[j] = fma(coef, core_H(x, a, a2, core_tab), tau[j]);
+            else tau[j] += asym_series<kNQNear>(smem + off + LC_Q, d);
+          }
         }
       }
     }
