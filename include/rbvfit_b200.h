@@ -150,6 +150,25 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
                     int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
                     void* stream);
 
+/* Multi-GPU form of the same sampler (one process per GPU, ensemble state replicated on every rank): a half-step
+ * is split around the caller's all-gather of the proposals' lnprob (NCCL over NVLink, 8 B per walker).
+ *   rbv_stretch_propose_eval: builds ALL n_S proposals of half `split` of step `step` (identical on every rank:
+ *       counter-based random streams) and evaluates rows [row_lo, row_hi) -> lnprob_rows[row_lo .. row_hi)
+ *       (DEVICE [n_S], n_S = ceil(W/2) for split 0, floor(W/2) for split 1).
+ *   rbv_stretch_accept: with lnprob_rows complete (all-gathered), applies accept/reject to every walker of the
+ *       half, updates coords / lnprob / n_accepted in place and writes the walkers' rows of this step into
+ *       chain_row [W, ndim] / lnprob_chain_row [W] (DEVICE, may be NULL).
+ * Both use the rbv_stretch_workspace_bytes() workspace (it carries the proposals between the two calls) and are
+ * asynchronous.  The walker layout of a step is the same as in rbv_stretch_run, so a run is reproducible across
+ * GPU counts. */
+int rbv_stretch_propose_eval(RbvContext* ctx, const double* coords, int n_walkers, double a, unsigned long long seed,
+                             unsigned long long step, int split, int row_lo, int row_hi, double* lnprob_rows,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, double a,
+                       unsigned long long seed, unsigned long long step, int split, const double* lnprob_rows,
+                       double* chain_row, double* lnprob_chain_row, int* n_accepted, int* flag, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Model flux for a batch of walkers on instrument `inst`; CompiledVoigtModel.model_flux,
  * voigt_model.py:295-311 (convolve != 0) or VoigtModel.evaluate(return_unconvolved=True), :509-558.
  *   out_flux DEVICE [n_walkers, n_pixels] row-major doubles.  Asynchronous. */

@@ -555,18 +555,9 @@ __global__ void __launch_bounds__(128) prep_propose_kernel(const LaunchParams pr
   const StretchParams& P = prm.sp;
   const int k = blockIdx.x, split = prm.sampler_split;
   if (threadIdx.x == 0) {
-    int offS, nS, offC, nC;
-    split_geometry(P.W, split, offS, nS, offC, nC);
-    const unsigned long long step = P.first_step + *P.step_ctr;
-    uint32_t pa, pb;
-    stretch_perm(P, step, pa, pb);
-    const int i = walker_at(pa, pb, P.W, offS + k);
-    const uint4 r = stretch_rand(P, step, (uint32_t)i, 1u + (uint32_t)split);
-    const double u = u01(r.x, r.y);
-    const int j = walker_at(pa, pb, P.W, offC + (int)(r.z % (uint32_t)nC));
-    // explicitly rounded operations (no FMA contraction): the proposal is bit-identical to the numpy expression
-    const double t = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
-    const double zz = __ddiv_rn(__dmul_rn(t, t), P.a);
+    int i, j;
+    double zz;
+    stretch_propose_row(P, split, k, i, j, zz);
     s_ij[0] = i;
     s_ij[1] = j;
     s_zz = zz;
@@ -1588,6 +1579,81 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
     int rc = one_step();
     if (rc != RBV_OK) return rc;
   }
+  return RBV_OK;
+}
+
+// ---- multi-GPU form of the sampler: half-step = propose_eval | caller's all-gather of lnprob | accept ----------
+static int stretch_params(RbvContext* ctx, int n_walkers, void* workspace, size_t workspace_bytes, const char* who,
+                          StretchParams* P, StretchLayout* lay_out) {
+  if (!ctx) return fail(RBV_EINVAL, std::string(who) + ": null context");
+  if (n_walkers < 2) return fail(RBV_EINVAL, std::string(who) + ": need at least two walkers");
+  if (ctx->inst.empty() || ctx->ndim == 0) return fail(RBV_ESTATE, std::string(who) + ": context not set up");
+  const StretchLayout lay = stretch_layout(ctx, n_walkers);
+  if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, std::string(who) + ": workspace too small");
+  char* ws = (char*)workspace;
+  memset(P, 0, sizeof(*P));
+  P->prop = (double*)(ws + lay.prop);
+  P->lnp_prop = (double*)(ws + lay.lnp_prop);
+  P->factors = (double*)(ws + lay.factors);
+  P->walker_of = (int*)(ws + lay.walker_of);
+  P->step_ctr = nullptr;      // host-driven steps
+  P->ticket = nullptr;
+  P->W = n_walkers;
+  P->ndim = ctx->ndim;
+  *lay_out = lay;
+  return RBV_OK;
+}
+
+int rbv_stretch_propose_eval(RbvContext* ctx, const double* coords, int n_walkers, double a, unsigned long long seed,
+                             unsigned long long step, int split, int row_lo, int row_hi, double* lnprob_rows,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  StretchParams P;
+  StretchLayout lay;
+  int rc = stretch_params(ctx, n_walkers, workspace, workspace_bytes, "rbv_stretch_propose_eval", &P, &lay);
+  if (rc != RBV_OK) return rc;
+  const int h = (n_walkers + 1) / 2, nS = split == 0 ? h : n_walkers - h;
+  if (!coords || !lnprob_rows || (split != 0 && split != 1) || row_lo < 0 || row_hi < row_lo || row_hi > nS || !(a > 1.0))
+    return fail(RBV_EINVAL, "rbv_stretch_propose_eval: bad argument");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  P.coords = const_cast<double*>(coords);
+  P.first_step = step;
+  P.seed = seed;
+  P.a = a;
+  stretch_propose_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
+  RBV_CUDA(cudaGetLastError());
+  ctx->launches++;
+  if (row_hi == row_lo) return RBV_OK;
+  return launch_lnprob(ctx, P.prop + (size_t)row_lo * ctx->ndim, row_hi - row_lo, 0, lnprob_rows + row_lo,
+                       (char*)workspace + lay.lnprob_ws, workspace_bytes - lay.lnprob_ws, stream,
+                       "rbv_stretch_propose_eval");
+}
+
+int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, double a,
+                       unsigned long long seed, unsigned long long step, int split, const double* lnprob_rows,
+                       double* chain_row, double* lnprob_chain_row, int* n_accepted, int* flag, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  StretchParams P;
+  StretchLayout lay;
+  int rc = stretch_params(ctx, n_walkers, workspace, workspace_bytes, "rbv_stretch_accept", &P, &lay);
+  if (rc != RBV_OK) return rc;
+  if (!coords || !lnprob || !lnprob_rows || !n_accepted || !flag || (split != 0 && split != 1))
+    return fail(RBV_EINVAL, "rbv_stretch_accept: bad argument");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  const int h = (n_walkers + 1) / 2, nS = split == 0 ? h : n_walkers - h;
+  P.coords = coords;
+  P.lnp = lnprob;
+  P.lnp_prop = const_cast<double*>(lnprob_rows);
+  P.chain = chain_row;
+  P.lnp_chain = lnprob_chain_row;
+  P.n_accepted = n_accepted;
+  P.flag = flag;
+  P.first_step = step;
+  P.seed = seed;
+  P.a = a;
+  stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, (cudaStream_t)stream>>>(P, split);
+  RBV_CUDA(cudaGetLastError());
+  ctx->launches++;
   return RBV_OK;
 }
 

@@ -34,7 +34,8 @@ struct StretchParams {
   double* lnp_chain;     // [n_steps, W] or NULL
   int* n_accepted;       // [W] accumulates
   int* flag;             // bit 0: a proposal's lnprob was NaN
-  unsigned long long* step_ctr;   // [0] steps done in this run (device counter, advanced by the record kernel)
+  unsigned long long* step_ctr;   // [0] steps done in this run (device counter, advanced by the last accept of a step);
+                                  // NULL = the host drives the steps (multi-GPU form): step = first_step, chain row 0
   unsigned int* ticket;  // walkers of the current half-step whose accept/record is done
   unsigned long long first_step;  // global index of the run's first step (continues the random streams)
   unsigned long long seed;
@@ -104,7 +105,7 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
                                                       int lane) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
-  const unsigned long long s = *P.step_ctr, step = P.first_step + s;
+  const unsigned long long s = P.step_ctr ? *P.step_ctr : 0ull, step = P.first_step + s;
   const int i = P.walker_of[k];
   const uint4 r = stretch_rand(P, step, (uint32_t)i, 3u + (uint32_t)split);
   const double old_lp = P.lnp[i];
@@ -126,6 +127,7 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
       P.n_accepted[i] += 1;
     }
     if (P.lnp_chain) P.lnp_chain[s * P.W + i] = accept ? new_lp : old_lp;
+    if (!P.step_ctr) return;                                 // host-driven steps: no device counters
     __threadfence();
     if (atomicAdd(P.ticket, 1u) == (unsigned)nS - 1u) {      // last walker of this half-step
       *P.ticket = 0u;
@@ -133,6 +135,53 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
       __threadfence();
     }
   }
+}
+
+// ---- multi-GPU form: the half-step is split around the caller's all-gather of lnprob -------------------------
+// Every rank builds ALL proposals of the active half (the state is replicated and the random streams are counter
+// based, so the rows are identical on every rank), evaluates only its own rows, and after the all-gather applies
+// the same accept/reject to every walker.
+__device__ __forceinline__ void stretch_propose_row(const StretchParams& P, int split, int k, int& i_out,
+                                                    int& j_out, double& zz_out) {
+  int offS, nS, offC, nC;
+  split_geometry(P.W, split, offS, nS, offC, nC);
+  const unsigned long long step = P.first_step + (P.step_ctr ? *P.step_ctr : 0ull);
+  uint32_t pa, pb;
+  stretch_perm(P, step, pa, pb);
+  const int i = walker_at(pa, pb, P.W, offS + k);
+  const uint4 r = stretch_rand(P, step, (uint32_t)i, 1u + (uint32_t)split);
+  const double u = u01(r.x, r.y);
+  // explicitly rounded operations (no FMA contraction): the proposal is bit-identical to the numpy expression
+  const double t = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
+  i_out = i;
+  j_out = walker_at(pa, pb, P.W, offC + (int)(r.z % (uint32_t)nC));
+  zz_out = __ddiv_rn(__dmul_rn(t, t), P.a);
+}
+
+__global__ void __launch_bounds__(128) stretch_propose_kernel(const StretchParams P, int split) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp per row
+  int offS, nS, offC, nC;
+  split_geometry(P.W, split, offS, nS, offC, nC);
+  if (k >= nS) return;
+  int i, j;
+  double zz;
+  stretch_propose_row(P, split, k, i, j, zz);
+  if (lane == 0) {
+    P.factors[k] = (P.ndim - 1.0) * log(zz);
+    P.walker_of[k] = i;
+  }
+  const double* s = P.coords + (size_t)i * P.ndim;
+  const double* c = P.coords + (size_t)j * P.ndim;
+  for (int d = lane; d < P.ndim; d += 32)
+    P.prop[(size_t)k * P.ndim + d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), zz));
+}
+
+__global__ void __launch_bounds__(128) stretch_accept_kernel(const StretchParams P, int split) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp per row
+  int offS, nS, offC, nC;
+  split_geometry(P.W, split, offS, nS, offC, nC);
+  if (k >= nS) return;
+  stretch_accept_record(P, split, k, P.lnp_prop[k], lane);
 }
 
 }  // namespace rbv

@@ -216,6 +216,36 @@ class Engine:
             n_accepted_t.data_ptr(), flag_t.data_ptr(), self._stretch_ws.data_ptr(), self._stretch_ws.numel(),
             int(bool(use_graph)), self._stream()), "rbv_stretch_run")
 
+    def _stretch_workspace(self, W: int):
+        torch = _torch()
+        nbytes = C.c_size_t(0)
+        check(self.lib.rbv_stretch_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_stretch_workspace_bytes")
+        if getattr(self, "_stretch_ws", None) is None or self._stretch_ws.numel() < nbytes.value:
+            self._stretch_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
+        return self._stretch_ws
+
+    def stretch_propose_eval(self, coords_t, a: float, seed: int, step: int, split: int, row_lo: int, row_hi: int,
+                             lnp_rows_t):
+        """Multi-GPU half-step, first part (rbv_stretch_propose_eval): all proposals of the half, lnprob of rows
+        [row_lo, row_hi) into ``lnp_rows_t``; asynchronous on the current stream."""
+        ws = self._stretch_workspace(coords_t.shape[0])
+        check(self.lib.rbv_stretch_propose_eval(self._h, coords_t.data_ptr(), coords_t.shape[0], float(a),
+                                                int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), int(split), int(row_lo),
+                                                int(row_hi), lnp_rows_t.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                self._stream()), "rbv_stretch_propose_eval")
+
+    def stretch_accept(self, coords_t, lnp_t, a: float, seed: int, step: int, split: int, lnp_rows_t, chain_row_t,
+                       lnp_chain_row_t, n_accepted_t, flag_t):
+        """Multi-GPU half-step, second part (rbv_stretch_accept), after the all-gather of ``lnp_rows_t``."""
+        ws = self._stretch_workspace(coords_t.shape[0])
+        check(self.lib.rbv_stretch_accept(self._h, coords_t.data_ptr(), lnp_t.data_ptr(), coords_t.shape[0], float(a),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), int(split),
+                                          lnp_rows_t.data_ptr(),
+                                          chain_row_t.data_ptr() if chain_row_t is not None else None,
+                                          lnp_chain_row_t.data_ptr() if lnp_chain_row_t is not None else None,
+                                          n_accepted_t.data_ptr(), flag_t.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          self._stream()), "rbv_stretch_accept")
+
     def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:
         """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``."""
         torch = _torch()
