@@ -47,6 +47,7 @@ class Engine:
         self._theta_pin = self._lnp_pin = None
         self._ws_bytes = 0
         self._ws_sightlines = False
+        self._stretch_ws = None               # workspace of the device-resident sampler
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -206,7 +207,7 @@ class Engine:
                 raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
         nbytes = C.c_size_t(0)
         check(self.lib.rbv_stretch_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_stretch_workspace_bytes")
-        if getattr(self, "_stretch_ws", None) is None or self._stretch_ws.numel() < nbytes.value:
+        if self._stretch_ws is None or self._stretch_ws.numel() < nbytes.value:
             self._stretch_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
         check(self.lib.rbv_stretch_run(
             self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), float(a),
@@ -220,7 +221,7 @@ class Engine:
         torch = _torch()
         nbytes = C.c_size_t(0)
         check(self.lib.rbv_stretch_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_stretch_workspace_bytes")
-        if getattr(self, "_stretch_ws", None) is None or self._stretch_ws.numel() < nbytes.value:
+        if self._stretch_ws is None or self._stretch_ws.numel() < nbytes.value:
             self._stretch_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
         return self._stretch_ws
 

@@ -44,8 +44,13 @@ def main():
     w, models, like, thetas, spectra = bench.build_problem("C5a", local)
     ok = thetas[np.all((thetas >= w["lb"]) & (thetas <= w["ub"]), axis=1)]
     W = len(ok) - (len(ok) % 2)
+    ref = DeviceEnsembleSampler(W, like.ndim, like, seed=7)          # fused path (finalize_kernel at this size)
+    ref.run_mcmc(ok[:W], 2, skip_initial_state_check=True)
     dsm = DistributedDeviceSampler(W, like.ndim, like, part, seed=7)
     dsm.run_mcmc(ok[:W], 2, skip_initial_state_check=True)
+    d = np.max(np.abs(dsm.get_chain() - ref.get_chain()))
+    print(f"[rank {rank}/{world}] C5a W={W}: max |chain - single-GPU chain| after 2 steps = {d:.3e}", flush=True)
+    assert d <= 1e-9 and np.array_equal(dsm.acceptance_fraction, ref.acceptance_fraction)
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
