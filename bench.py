@@ -246,7 +246,7 @@ def run_gpu(args, rank, world, local):
         ev[k][0].record()
         if hi > lo:
             kev[k][0].record()
-            local_out = like.lnprob_device(theta_dev[lo:hi])          # the tile kernel (1 launch)
+            local_out = like.lnprob_device(theta_dev[lo:hi])          # prep + tile + finalize kernels
             kev[k][1].record()
         else:
             local_out = theta_dev.new_empty(0)
@@ -306,7 +306,7 @@ def run_gpu(args, rank, world, local):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8)},
-        "gpu_launches": int(launches),       # prep_kernel + voigt_tile_kernel per step
+        "gpu_launches": int(launches),       # prep_kernel + voigt_tile_kernel + finalize_kernel per step
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "traffic": prof.get("dram_bytes_per_launch"),
                      "traffic_capture": None if not prof else f"{prof.get('report')}: {prof.get('note')}",
