@@ -744,10 +744,10 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
                  rec_off + sc * SC_STRIDE, u, tau, prm.core_tab);
       }
       // flux = exp(-tau), voigt_model.py:217.  Away from line cores every pixel of the chunk has |tau| < 2^-6,
-      // where the degree-7 Taylor polynomial is exact to 9e-20 and needs no range reduction.
+      // where the degree-6 Taylor polynomial is exact to 4.5e-17 (under half an ulp) and needs no range reduction.
       unsigned hmax = 0u;
 #pragma unroll
-      for (int j = 0; j < PPT; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]) & 0x7fffffffu);
+      for (int j = 0; j < PPT; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]));   // negative or NaN: huge
       // slot(i0 + 32 j + lane) = slot(i0) + (R + 1) * (32 / R) * j + lane + lane / R   (i0 and 32 are multiples of R)
       static_assert(32 % (1 << LOGR) == 0, "chunk rows must be whole groups of R");
       double* fo = s_flux + smem_pos(i0, LOGR) + lane + (lane >> LOGR);
