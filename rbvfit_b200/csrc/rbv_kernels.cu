@@ -800,8 +800,11 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       int fw = flux_off + (R + 1) * g;
 #pragma unroll
       for (int q = 0; q < R - 1; ++q) win[q] = smem[fw + q];
+      const int n_blocks = I.Kpad >> LOGR;              // >= 1: Kpad is a positive multiple of R
+      __builtin_assume(n_blocks >= 1);
 #pragma unroll 3
-      for (int m0 = 0; m0 < I.Kpad; m0 += R, fw += R + 1) {
+      for (int blk = 0; blk < n_blocks; ++blk, fw += R + 1) {
+        const int m0 = blk << LOGR;
         win[R - 1] = smem[fw + R - 1];
 #pragma unroll
         for (int q = 1; q < R; ++q) win[R - 1 + q] = smem[fw + R + q];
