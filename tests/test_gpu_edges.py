@@ -164,3 +164,71 @@ def test_joint_fit_with_different_line_lists_per_instrument():
     fin = np.isfinite(ref)
     assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= LNPROB_RTOL
     like.close()
+
+
+def test_no_writes_outside_caller_buffers():
+    """Canary check through the raw C ABI: lnprob, workspace (exactly rbv_workspace_bytes), model flux, sampler state
+    and chain buffers sit inside larger allocations filled with a sentinel; nothing outside the documented extents
+    may change.  (compute-sanitizer is not available on the GPU pool.)"""
+    import ctypes as C
+    import torch
+    from rbvfit_b200 import workloads as wl
+    from rbvfit_b200._lib import check
+    from rbvfit_b200.likelihood import GpuLikelihood
+    rng = np.random.default_rng(29)
+    w = wl.get_workload("C2")
+    model, om = _models(w["systems"])
+    wave = np.linspace(3300.0, 5700.0, 5003)
+    flux = 1.0 + 0.05 * rng.standard_normal(wave.size)
+    like = GpuLikelihood({"S": dict(model=model, wave=wave, flux=flux, error=np.full(wave.size, 0.05))}, w["lb"], w["ub"])
+    eng, lib = like.engine, like.engine.lib
+    SENT, PAD = -12345.678, 4096
+    for W in (1, 7, 130):
+        thetas = wl.make_ensemble(w, max(W, 4))[:W]
+        th = torch.as_tensor(thetas, device="cuda")
+        nbytes = C.c_size_t(0)
+        check(lib.rbv_workspace_bytes(eng._h, W, C.byref(nbytes)))
+        nws = (int(nbytes.value) + 7) // 8
+        big_ws = torch.full((nws + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+        big_out = torch.full((W + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+        check(lib.rbv_lnprob_batch(eng._h, th.data_ptr(), W, big_out[PAD:].data_ptr(), big_ws[PAD:].data_ptr(),
+                                   int(nbytes.value), None), "rbv_lnprob_batch")
+        torch.cuda.synchronize()
+        assert torch.all(big_out[:PAD] == SENT) and torch.all(big_out[PAD + W:] == SENT)
+        assert torch.all(big_ws[:PAD] == SENT) and torch.all(big_ws[PAD + nws:] == SENT)
+        assert np.array_equal(big_out[PAD:PAD + W].cpu().numpy(), like.lnprob(thetas), equal_nan=True)
+        P = wave.size
+        big_flux = torch.full((W * P + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+        check(lib.rbv_model_flux_batch(eng._h, 0, th.data_ptr(), W, 1, big_flux[PAD:].data_ptr(), None))
+        torch.cuda.synchronize()
+        assert torch.all(big_flux[:PAD] == SENT) and torch.all(big_flux[PAD + W * P:] == SENT)
+        assert torch.all(torch.isfinite(big_flux[PAD:PAD + W * P]))
+    # sampler: coords / lnprob / chain / counters with canaries
+    W, nd, nsteps = 22, like.ndim, 6
+    ok = wl.make_ensemble(w, 60)
+    ok = ok[np.all((ok >= w["lb"]) & (ok <= w["ub"]), axis=1)][:W]
+    bufs = {}
+    for name, n in (("coords", W * nd), ("lnp", W), ("chain", nsteps * W * nd), ("lps", nsteps * W)):
+        bufs[name] = torch.full((n + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+    bufs["coords"][PAD:PAD + W * nd] = torch.as_tensor(ok.ravel(), device="cuda")
+    bufs["lnp"][PAD:PAD + W] = torch.as_tensor(like.lnprob(ok), device="cuda")
+    nacc = torch.full((W + 2 * PAD,), -7, dtype=torch.int32, device="cuda")
+    nacc[PAD:PAD + W] = 0
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.rbv_stretch_workspace_bytes(eng._h, W, C.byref(nbytes)))
+    nws = (int(nbytes.value) + 7) // 8
+    big_ws = torch.full((nws + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    check(lib.rbv_stretch_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), W, nsteps, 2.0,
+                              99, 0, bufs["chain"][PAD:].data_ptr(), bufs["lps"][PAD:].data_ptr(),
+                              nacc[PAD:].data_ptr(), flag.data_ptr(), big_ws[PAD:].data_ptr(), int(nbytes.value), 1,
+                              st.cuda_stream), "rbv_stretch_run")
+    torch.cuda.synchronize()
+    for name, n in (("coords", W * nd), ("lnp", W), ("chain", nsteps * W * nd), ("lps", nsteps * W)):
+        b = bufs[name]
+        assert torch.all(b[:PAD] == SENT) and torch.all(b[PAD + n:] == SENT), name
+        assert torch.all(torch.isfinite(b[PAD:PAD + n])) and not torch.any(b[PAD:PAD + n] == SENT), name
+    assert torch.all(nacc[:PAD] == -7) and torch.all(nacc[PAD + W:] == -7) and int(nacc[PAD:PAD + W].sum()) > 0
+    assert torch.all(big_ws[:PAD] == SENT) and torch.all(big_ws[PAD + nws:] == SENT)
+    like.close()
