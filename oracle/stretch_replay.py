@@ -55,39 +55,55 @@ def step_perm(seed, step, W):
     return a, b
 
 
+def split_geometry(W, split):
+    h = (W + 1) // 2
+    return (0, h, h, W - h) if split == 0 else (h, W - h, 0, h)
+
+
+def propose_half(coords, seed, step, split, a_scale=2.0):
+    """Proposals of half `split` of step `step`: (walker index per row, proposals [nS, ndim], (ndim-1) ln z)."""
+    W, ndim = coords.shape
+    pa, pb = step_perm(seed, step, W)
+    walker = [(pa * pos + pb) % W for pos in range(W)]
+    offS, nS, offC, nC = split_geometry(W, split)
+    idx = np.array([walker[offS + k] for k in range(nS)])
+    q = np.empty((nS, ndim))
+    fac = np.empty(nS)
+    for k, i in enumerate(idx):
+        r = _rand(seed, step, i, 1 + split)
+        u = u01(r[0], r[1])
+        j = walker[offC + r[2] % nC]
+        t = (a_scale - 1.0) * u + 1.0
+        zz = t * t / a_scale
+        fac[k] = (ndim - 1.0) * np.log(zz)
+        q[k] = coords[j] - (coords[j] - coords[i]) * zz
+    return idx, q, fac
+
+
+def accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new):
+    """Accept / reject in place; same draws as rbv_stretch_accept."""
+    for k, i in enumerate(idx):
+        r = _rand(seed, step, i, 3 + split)
+        with np.errstate(invalid="ignore"):
+            if np.log(u01(r[0], r[1])) < fac[k] + new[k] - lnp[i]:
+                coords[i] = q[k]
+                lnp[i] = new[k]
+                nacc[i] += 1
+
+
 def run(lnprob_fn, coords, lnp, nsteps, seed, a_scale=2.0, first_step=0):
     """Returns (chain [nsteps, W, ndim], lnp_chain [nsteps, W], n_accepted [W]); ``lnprob_fn`` maps (n, ndim) -> (n,)."""
     coords = np.array(coords, dtype=np.float64, copy=True)
     lnp = np.array(lnp, dtype=np.float64, copy=True)
     W, ndim = coords.shape
-    h = (W + 1) // 2
     chain = np.empty((nsteps, W, ndim))
     lps = np.empty((nsteps, W))
     nacc = np.zeros(W, dtype=np.int64)
     for s in range(nsteps):
         step = first_step + s
-        pa, pb = step_perm(seed, step, W)
-        walker = [(pa * pos + pb) % W for pos in range(W)]
         for split in (0, 1):
-            offS, nS, offC, nC = (0, h, h, W - h) if split == 0 else (h, W - h, 0, h)
-            idx = np.array([walker[offS + k] for k in range(nS)])
-            q = np.empty((nS, ndim))
-            fac = np.empty(nS)
-            for k, i in enumerate(idx):
-                r = _rand(seed, step, i, 1 + split)
-                u = u01(r[0], r[1])
-                j = walker[offC + r[2] % nC]
-                t = (a_scale - 1.0) * u + 1.0
-                zz = t * t / a_scale
-                fac[k] = (ndim - 1.0) * np.log(zz)
-                q[k] = coords[j] - (coords[j] - coords[i]) * zz
+            idx, q, fac = propose_half(coords, seed, step, split, a_scale)
             new = np.asarray(lnprob_fn(q), dtype=np.float64)
-            for k, i in enumerate(idx):
-                r = _rand(seed, step, i, 3 + split)
-                with np.errstate(invalid="ignore"):
-                    if np.log(u01(r[0], r[1])) < fac[k] + new[k] - lnp[i]:
-                        coords[i] = q[k]
-                        lnp[i] = new[k]
-                        nacc[i] += 1
+            accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new)
         chain[s], lps[s] = coords, lnp
     return chain, lps, nacc

@@ -67,3 +67,88 @@ def test_partition_rows_cover_everything():
                 lo, hi = WalkerPartition(r, world).rows(W)
                 got.extend(range(lo, hi))
             assert got == list(range(W))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DistributedDeviceSampler over gloo: the engine is replaced by a CPU stub that restates rbv_stretch_propose_eval /
+# rbv_stretch_accept with oracle/stretch_replay.py (host logic under test: row partition of the half-steps, the
+# in-place all-gather with padding, replicated state; NOT a CPU fallback of the product)
+MU = np.array([1.0, -2.0, 0.5])
+SIG = np.array([0.5, 2.0, 1.0])
+
+
+def _gauss(x):
+    return -0.5 * np.sum(((np.atleast_2d(x) - MU) / SIG) ** 2, axis=1)
+
+
+class _StubEngine:
+    def __init__(self):
+        self.tdev = torch.device("cpu")
+        self.rows_evaluated = 0
+
+    def lnprob_device(self, theta_t):
+        return torch.as_tensor(_gauss(theta_t.numpy()))
+
+    def stretch_propose_eval(self, coords_t, a, seed, step, split, lo, hi, rows_t):
+        from oracle import stretch_replay as sr
+        self._half = sr.propose_half(coords_t.numpy(), seed, step, split, a)
+        rows_t[lo:hi] = torch.as_tensor(_gauss(self._half[1][lo:hi]))
+        self.rows_evaluated += hi - lo
+
+    def stretch_accept(self, coords_t, lnp_t, a, seed, step, split, rows_t, chain_row_t, lps_row_t, nacc_t, flag_t):
+        from oracle import stretch_replay as sr
+        idx, q, fac = self._half
+        nacc = nacc_t.numpy()
+        sr.accept_half(coords_t.numpy(), lnp_t.numpy(), nacc, seed, step, split, idx, q, fac,
+                       rows_t.numpy()[: len(idx)])
+        for i in idx:
+            chain_row_t[i] = coords_t[i]
+            lps_row_t[i] = lnp_t[i]
+
+
+class _StubLikelihood:
+    ndim = 3
+
+    def __init__(self):
+        self.engine = _StubEngine()
+
+    def lnprob(self, theta):
+        return _gauss(theta)
+
+
+def _sampler_worker(rank, world, port, W, nsteps, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.cuda
+    torch.cuda.synchronize = lambda *a, **k: None            # no device in this test
+    from rbvfit_b200 import dist as rdist
+    from rbvfit_b200.sampler import DistributedDeviceSampler
+    r, w, _ = rdist.init_from_env("gloo")
+    like = _StubLikelihood()
+    smp = DistributedDeviceSampler(W, 3, like, rdist.WalkerPartition(r, w), seed=77)
+    p0 = MU + 0.1 * np.random.default_rng(5).standard_normal((W, 3))
+    smp.run_mcmc(p0, nsteps - 4)
+    smp.run_mcmc(None, 4)
+    ret[rank] = (smp.get_chain().copy(), smp.get_log_prob().copy(), smp.acceptance_fraction.copy(), smp._seed,
+                 like.engine.rows_evaluated)
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("W", [12, 11])
+def test_distributed_device_sampler_gloo(W):
+    from oracle import stretch_replay as sr
+    world, nsteps = 2, 14
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sampler_worker, args=(world, port, W, nsteps, ret), nprocs=world, join=True)
+    p0 = MU + 0.1 * np.random.default_rng(5).standard_normal((W, 3))
+    chain, lps, nacc = sr.run(_gauss, p0, _gauss(p0), nsteps, ret[0][3])
+    for r in range(world):
+        c, l, af, seed, rows = ret[r]
+        assert np.array_equal(c, chain) and np.array_equal(l, lps)          # every rank: the single-process chain
+        assert np.array_equal(np.rint(af * nsteps).astype(int), nacc)
+    assert ret[0][4] + ret[1][4] == nsteps * W                              # each proposal evaluated exactly once
+    assert ret[0][4] > 0 and ret[1][4] > 0
