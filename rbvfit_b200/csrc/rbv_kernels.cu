@@ -407,6 +407,7 @@ __device__ __forceinline__ void prepare_super_chunk(const InstDev& I, int lc_off
   const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
   const int4 n = classify_lines(lc_off, I.L, list, list32, listff, gate32, ff_eps, umin, umax, lane);
   if (n.w > 0) farfield_coefficients(lc_off, listff, n.w, umin, umax, rec_off, lane);
+  else if (lane < SC_COUNTS) smem[rec_off + lane] = 0.0;          // zero polynomial, t = 0
   if (lane == 0) *reinterpret_cast<int4*>(smem + rec_off + SC_COUNTS) = n;
 }
 
@@ -416,7 +417,9 @@ __device__ __forceinline__ void tau_wofz(int lc_off, int L, const unsigned short
                                          const double (&u)[PPT], double (&tau)[PPT],
                                          const double* __restrict__ core_tab) {
   const int4 n = *reinterpret_cast<const int4*>(smem + rec_off + SC_COUNTS);   // n_far, n_other, n_fp32, n_farfield
-  if (n.w > 0) {
+  // big tiles: the record always holds a polynomial (all-zero coefficients when no line qualified), so tau needs
+  // no separate zeroing and no branch; small tiles often have no far field at all and keep the test
+  if (PPT == 8 || n.w > 0) {
     farfield_eval(rec_off, u, tau);
   } else {
 #pragma unroll
@@ -710,8 +713,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     }
     // warps pull 32*PPT-pixel chunks from a CTA-wide counter: chunks that contain a line core cost
     // several times a far-wing chunk, and static assignment would leave the other warps waiting at the barrier
-    // (the ticket for the NEXT chunk is drawn one iteration ahead, so that its 1/lambda lines can be prefetched
-    // into L1 while the current chunk is computed)
+    // (the ticket for the NEXT chunk is drawn one iteration ahead: the shared-memory atomic's latency overlaps the
+    // current chunk)
     int c = 0;
     if (lane == 0) c = smem_ticket(&s_next);
     c = __shfl_sync(0xffffffffu, c, 0);
@@ -733,10 +736,6 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         }
       }
       c_next = __shfl_sync(0xffffffffu, c_next, 0);
-      if (c_next < n_chunks && lane < (kWarpPix + 15) / 16) {   // 16 doubles per 128-byte line
-        const int p = min(max(p0 - h + c_next * kWarpPix + lane * 16, 0), I.P - 1);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(I.inv_wave + p));
-      }
       if (fast) tau_fast(lc_off, I.L, u, tau);
       else {
         const int sc = c / kSuperChunks;
