@@ -347,7 +347,7 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
   double c = 0.0;                                   // lane j < 8: c_j = sum_k MINV[j][k] S_k
 #pragma unroll
   for (int k = 0; k < 8; ++k) c = fma(c_ff_minv[(lane & 7) * 8 + k], __shfl_sync(0xffffffffu, T1, 4 * k), c);
-  const double sc = 1.0 / uh;
+  const double sc = rcp_pos(uh);                      // uh > 0 (umax carries an all-ones low word)
   if (lane < 8) smem[rec_off + SC_COEF + lane] = c;
   if (lane == 8) smem[rec_off + SC_SCALE] = sc;
   if (lane == 9) smem[rec_off + SC_OFFSET] = -um * sc;
