@@ -306,7 +306,8 @@ __device__ __forceinline__ void accum_asym_line(int off, const double (&u)[PPT],
 constexpr int SC_COEF = 0, SC_SCALE = 8, SC_OFFSET = 9, SC_COUNTS = 10 /* 4 ints */, SC_STRIDE = 12;
 
 __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned short* __restrict__ listff,
-                                                      int n_ff, double umin, double umax, int rec_off, int lane) {
+                                                      int n_ff, double umin, double umax, int rec_off,
+                                                      int scratch_off, int lane) {
   static_assert(RBV_FF_M == 8, "far-field code is written for 8 nodes");
   const double um = 0.5 * (umin + umax), uh = 0.5 * (umax - umin);
   double S[8];
@@ -319,31 +320,22 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
     }
     for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQMid, 8>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
   }
-  // transpose-reduce: after the three halving steps lane holds node (lane >> 2) & 7 summed over 8 lanes
-  double T4[4], T2[2], T1;
+  // transpose-reduce through shared memory (the flux tile is still unused in phase 0): lane writes its 8 node
+  // values, then lane (k = lane >> 2, q = lane & 3) adds the values of lanes 8q .. 8q+7 for node k in lane order and
+  // two shuffle-adds finish the sum -- fixed order, 8 STS + 8 LDS + 10 adds instead of a 3-level select/shuffle tree
+  double T1 = 0.0;
   {
-    const bool hi = lane & 16;
+    const int base = scratch_off;                   // [8 nodes][33] doubles of this warp
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double send = hi ? S[i] : S[i + 4], keep = hi ? S[i + 4] : S[i];
-      T4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
+    for (int k = 0; k < 8; ++k) smem[base + k * 33 + lane] = S[k];
+    __syncwarp();
+    const int rd = base + (lane >> 2) * 33 + (lane & 3) * 8;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const double send = hi ? T4[i] : T4[i + 2], keep = hi ? T4[i + 2] : T4[i];
-      T2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
+    for (int i = 0; i < 8; ++i) T1 += smem[rd + i];
+    T1 += __shfl_xor_sync(0xffffffffu, T1, 1);
+    T1 += __shfl_xor_sync(0xffffffffu, T1, 2);     // every lane: S_k of node k = lane >> 2
+    __syncwarp();
   }
-  {
-    const bool hi = lane & 4;
-    const double send = hi ? T2[0] : T2[1], keep = hi ? T2[1] : T2[0];
-    T1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  T1 += __shfl_xor_sync(0xffffffffu, T1, 2);
-  T1 += __shfl_xor_sync(0xffffffffu, T1, 1);       // every lane: S_k of node k = lane >> 2
   double c = 0.0;                                   // lane j < 8: c_j = sum_k MINV[j][k] S_k
 #pragma unroll
   for (int k = 0; k < 8; ++k) c = fma(c_ff_minv[(lane & 7) * 8 + k], __shfl_sync(0xffffffffu, T1, 4 * k), c);
@@ -395,7 +387,7 @@ __device__ __forceinline__ void prepare_super_chunk(const InstDev& I, int lc_off
                                                     unsigned short* __restrict__ list,
                                                     unsigned short* __restrict__ list32,
                                                     unsigned short* __restrict__ listff, double gate32,
-                                                    float ff_eps, int plo, int phi, int lane) {
+                                                    float ff_eps, int plo, int phi, int scratch_off, int lane) {
   int hlo = 0x7fffffff, hhi = 0;
   for (int b = (plo >> 8) + lane; b <= (phi >> 8); b += 32) {
     const double2 mm = I.ublk[b];
@@ -406,7 +398,7 @@ __device__ __forceinline__ void prepare_super_chunk(const InstDev& I, int lc_off
   hhi = __reduce_max_sync(0xffffffffu, hhi);
   const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
   const int4 n = classify_lines(lc_off, I.L, list, list32, listff, gate32, ff_eps, umin, umax, lane);
-  if (n.w > 0) farfield_coefficients(lc_off, listff, n.w, umin, umax, rec_off, lane);
+  if (n.w > 0) farfield_coefficients(lc_off, listff, n.w, umin, umax, rec_off, scratch_off, lane);
   else if (lane < SC_COUNTS) smem[rec_off + lane] = 0.0;          // zero polynomial, t = 0
   if (lane == 0) *reinterpret_cast<int4*>(smem + rec_off + SC_COUNTS) = n;
 }
@@ -707,7 +699,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
         const int plo = min(max(p0 - h + sc * kSuperPix, 0), I.P - 1);
         const int phi = min(max(p0 - h + min((sc + 1) * kSuperPix, ext) - 1, 0), I.P - 1);
         prepare_super_chunk(I, lc_off, rec_off + sc * SC_STRIDE, s_lists + sc * 2 * list_stride,
-                            s_lists + (sc * 2 + 1) * list_stride, s_listff, gate32, ff_eps, plo, phi, lane);
+                            s_lists + (sc * 2 + 1) * list_stride, s_listff, gate32, ff_eps, plo, phi,
+                            flux_off + min(warp, n_sc - 1) * (8 * 33), lane);   // scratch: the idle flux tile
       }
       __syncthreads();
     }
