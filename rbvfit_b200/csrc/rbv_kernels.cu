@@ -298,7 +298,7 @@ __device__ __forceinline__ void accum_asym_line(int off, const double (&u)[PPT],
 //   phase 0, once per super-chunk (one warp):
 //   1. lane = line: evaluate the line at the RBV_FF_M Chebyshev nodes of [umin, umax] (same 8-FMA body as the
 //      direct far tier, ILP 8 over the nodes);
-//   2. transpose-reduce over the lanes (9 shuffle-adds) -> node sums S_k;
+//   2. transpose-reduce over the lanes (through shared memory, fixed order) -> node sums S_k;
 //   3. lanes 0..7: monomial coefficients c_j = sum_k MINV[j][k] S_k (constant matrix, generated in 60-digit
 //      arithmetic) -> the super-chunk's record in shared memory, with the affine map u -> t in [-1, 1];
 //   phase 1, every pixel: t = u * scale + offset (one FMA), tau = Horner_7(t): 8 FMAs whatever the number of lines.
