@@ -331,6 +331,7 @@ def run_gpu(args, rank, world, local):
         line["fp32_gated"] = fp32_gated_leg(like, theta_dev, thetas, W, total_px, args.steps, flush)
         line["mcmc"] = mcmc_leg(local, with_cpu=not args.no_cpu)
         line["mcmc"]["large_ensemble"] = mcmc_large_leg(like, w, thetas, total_px)
+        line["mcmc"]["zeus"] = mcmc_zeus_leg(local, with_cpu=not args.no_cpu)
     if not args.no_cpu and world >= 1:
         r = cpu_arm(args.workload, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -498,6 +499,60 @@ def mcmc_large_leg(like, w, thetas, total_px, nsteps=12):
     return {"walkers": int(W), "pixels": int(total_px), "steps": nsteps, "steps_per_sec": nsteps / dt,
             "walker_pixel_per_sec": nsteps * W * total_px / dt, "acceptance": float(smp.acceptance_fraction.mean()),
             "note": "includes the D2H copy of the chain (W x ndim x 8 B per step)"}
+
+
+def mcmc_zeus_leg(device, with_cpu=True, nsteps=200, cpu_steps=2):
+    """MCMC steps/s of the configuration BASELINE.json pairs with the zeus sampler: C2 (3 redshifts x CIV + SiIV + HI
+    Lyman series, 33 lines, 36 parameters, 20 000 px, 80 walkers), ensemble slice sampling.  Device-resident loop
+    (rbv_slice_run, what vfit.runmcmc(sampler='zeus') uses) vs the host-driven sampler on GPU batches vs the same
+    host-driven sampler on the CPU oracle under a fork pool.  One step = every walker moved once (~6 likelihood
+    evaluations per walker)."""
+    from rbvfit_b200.slice_sampler import DeviceEnsembleSliceSampler, EnsembleSliceSampler
+    w, _models, like, thetas, spectra = build_problem("C2", device)
+    ok = thetas[np.all((thetas >= w["lb"]) & (thetas <= w["ub"]), axis=1)]
+    W = 2 * like.ndim + 8
+    rng = np.random.default_rng(5)
+    p0 = np.clip(w["theta_true"] + 1e-3 * rng.standard_normal((W, like.ndim)), w["lb"] + 1e-10, w["ub"] - 1e-10)
+    p0[:min(W, len(ok)) // 2] = ok[:min(W, len(ok)) // 2]          # half of the bench ensemble's own rows
+    dev = DeviceEnsembleSliceSampler(W, like.ndim, like, seed=3)
+    dev.run_mcmc(p0, 40)                                           # mu adapts here
+    calls0, batches0, rates = dev.ncall, dev.nbatches, []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        dev.run_mcmc(None, nsteps)
+        rates.append(nsteps / (time.perf_counter() - t0))
+    total_px = sum(len(s["wave"]) for s in spectra.values())
+    evals = (dev.ncall - calls0) / (3.0 * nsteps)
+    host = EnsembleSliceSampler(W, like.ndim, like.lnprob, seed=3)
+    host.run_mcmc(p0, 40)
+    hb0 = host.nbatches
+    t0 = time.perf_counter()
+    host.run_mcmc(None, nsteps // 2)
+    host_sps = (nsteps // 2) / (time.perf_counter() - t0)
+    out = {"workload": f"C2 ({W} walkers x {total_px} px, L=33, ndim={like.ndim}, ensemble slice sampling)",
+           "steps_per_sec": sorted(rates)[1], "steps_per_sec_runs": rates,
+           "lnprob_rows_per_step": evals, "walker_pixel_per_sec": sorted(rates)[1] * evals * total_px,
+           "batches_per_step": (dev.nbatches - batches0) / (3.0 * nsteps), "mu": dev.mu,
+           "sampler": "device-resident (rbv_slice_run), chain D2H included; median of 3 runs",
+           "host_driven_steps_per_sec": host_sps,
+           "host_driven_batches_per_step": (host.nbatches - hb0) / float(nsteps // 2)}
+    if with_cpu:
+        from oracle import voigt_oracle as vo
+        _w, ocomp, _t = oracle_problem("C2")
+        cores = len(os.sched_getaffinity(0))
+        pool = vo.make_pool(ocomp, w["lb"], w["ub"], processes=cores)
+        try:
+            cpu = EnsembleSliceSampler(W, like.ndim, lambda th: vo.lnprob_pool(ocomp, th, w["lb"], w["ub"], pool=pool),
+                                       seed=3, mu=host.mu, tune=False)
+            cpu.run_mcmc(p0, 1)
+            t0 = time.perf_counter()
+            cpu.run_mcmc(None, cpu_steps)
+            out["cpu_pool_steps_per_sec"] = cpu_steps / (time.perf_counter() - t0)
+            out["cpu_cores"] = cores
+        finally:
+            pool.close()
+            pool.join()
+    return out
 
 
 def mcmc_leg(device, with_cpu=True, nsteps=300, cpu_steps=12):

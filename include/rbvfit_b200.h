@@ -169,6 +169,41 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
                        double* chain_row, double* lnprob_chain_row, int* n_accepted, int* flag, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Device-resident ensemble slice sampler (differential move).  Replaces the sampling loop
+ * zeus.EnsembleSampler(nwalkers, ndim, self.lnprob).run_mcmc(guesses, no_of_steps), vfit_mcmc.py:425-440, 536-540
+ * (zeus-mcmc >= 2.3.0 is not vendored in the reference; Karamanis & Beutler 2021, Algorithms 2-3 with zeus's defaults,
+ * is restated).  Every walker of the active half is a small state machine (widen L, widen R, shrink, finished) kept in
+ * the workspace; one iteration = candidate kernel -> the lnprob launch over the half (finished rows masked) -> update
+ * kernel, so a half-step costs as many device batches as the longest chain of evaluations any one walker needs.
+ * Between iterations the host only reads back a 24-byte counter block (one iteration behind the device, so the GPU
+ * never waits for it) to learn when the half-step is complete; ensemble, directions, brackets and the chain never
+ * leave the device.  Random numbers: the Philox streams of rbv_stretch_run (purposes 8.., see rbv_slice.cuh), so a
+ * run continued with first_step = steps already done reproduces one long run.
+ *   coords, lnprob   DEVICE [n_walkers, ndim] / [n_walkers], updated in place (n_walkers >= 4)
+ *   tuning           HOST, in/out: scale mu and its adaptation state (zeus: tune, tolerance 0.05, patience 5,
+ *                    maxsteps 10000, maxiter 10000); the totals of this run are written to the n_* fields
+ *   chain            DEVICE [n_steps, n_walkers, ndim] or NULL; lnprob_chain DEVICE [n_steps, n_walkers] or NULL
+ *   mu_history       HOST [n_steps] or NULL: mu after each step
+ *   flag             DEVICE int, bit 0 set if a candidate's lnprob was NaN
+ *   workspace        DEVICE, rbv_slice_workspace_bytes().  The call returns after the run has finished. */
+typedef struct RbvSliceTuning {
+  double mu;        /* length scale of the directions 2 mu (C_j - C_l)                                  */
+  double tolerance; /* tuning stops counting a step as good when |n_exp / (n_exp + n_con) - 1/2| >= tolerance */
+  int tune;         /* != 0 while mu is still adapted (cleared after more than `patience` good steps)   */
+  int good;         /* good steps so far                                                                 */
+  int patience;
+  int maxsteps;     /* stepping-out budget per walker and step, shared between the two sides             */
+  int maxiter;      /* iterations per half-step before RBV_ESTATE is returned                            */
+  int reserved;
+  unsigned long long n_expansions, n_contractions; /* out */
+  unsigned long long n_calls;                      /* out: lnprob rows evaluated                        */
+  unsigned long long n_batches;                    /* out: lnprob launches                               */
+} RbvSliceTuning;
+int rbv_slice_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
+int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, RbvSliceTuning* tuning,
+                  unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                  double* mu_history, int* flag, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Model flux for a batch of walkers on instrument `inst`; CompiledVoigtModel.model_flux,
  * voigt_model.py:295-311 (convolve != 0) or VoigtModel.evaluate(return_unconvolved=True), :509-558.
  *   out_flux DEVICE [n_walkers, n_pixels] row-major doubles.  Asynchronous. */

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the device-resident ensemble slice sampler
+(rbvfit_b200/csrc/rbv_slice.cuh, C ABI rbv_slice_run), random streams included.
+
+The algorithm is zeus's ensemble slice sampling with the differential move (Karamanis & Beutler 2021, Algorithms
+2-3; zeus 2.x defaults), the sampler the reference builds in vfit_mcmc.py:425-440 when sampler='zeus'; zeus-mcmc
+itself is not vendored in the reference and not installed here.  What is specific to the device version and
+restated here bit for bit:
+
+  * the Philox4x32-10 streams and the step's split of ``stretch_replay`` (counter = step, walker, purpose);
+  * half s, walker i: partners j != l of the complement and the stepping-out budget J from purpose 8 + s
+    (x -> j, y -> l, (z, w) -> J = floor(maxsteps u)); slice level lnp + ln u and left edge -u' from purpose 10 + s
+    ((x, y) -> u, (z, w) -> u'); the shrink draw of iteration ``it`` from purpose 16 + 2 it + s;
+  * lockstep iterations: every unfinished walker of the half advances by ONE evaluation per iteration (phase 0
+    widens L, 1 widens R, 2 shrinks), so ``lnprob_fn`` sees one batch per iteration;
+  * candidate = X + s * direction, direction = (2 mu) * (C_j - C_l), t = L + u (R - L): separate multiply and add;
+  * mu <- mu * (2 n_exp / (n_exp + n_con)) after every step while tuning (n_exp at least 1).
+
+Driving this replica with the GPU's lnprob must reproduce the device chain exactly (tests/test_gpu_vfit.py); driving
+it with an analytic Gaussian checks the algorithm itself on the CPU (tests/test_host_logic.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .stretch_replay import _rand, split_geometry, step_perm, u01
+
+
+def run(lnprob_fn, coords, lnp, nsteps, seed, mu=1.0, tune=True, tolerance=0.05, patience=5, maxsteps=10000,
+        maxiter=10000, first_step=0, good=0):
+    """Returns a dict: chain [nsteps, W, ndim], lnp_chain [nsteps, W], mus [nsteps], mu, tune, good, nexp, ncon,
+    ncall, nbatches.  ``lnprob_fn`` maps (n, ndim) -> (n,) and is called once per iteration with the candidates of
+    the walkers that are still unfinished."""
+    X = np.array(coords, dtype=np.float64, copy=True)
+    Z = np.array(lnp, dtype=np.float64, copy=True)
+    W, ndim = X.shape
+    chain = np.empty((nsteps, W, ndim))
+    lps = np.empty((nsteps, W))
+    mus = np.empty(nsteps)
+    tot_exp = tot_con = ncall = nbatches = 0
+    for s in range(nsteps):
+        step = first_step + s
+        pa, pb = step_perm(seed, step, W)
+        walker = [(pa * pos + pb) % W for pos in range(W)]
+        nexp = ncon = 0
+        for split in (0, 1):
+            offS, nS, offC, nC = split_geometry(W, split)
+            idx = np.array([walker[offS + k] for k in range(nS)])
+            direction = np.empty((nS, ndim))
+            z0, lo, hi = np.empty(nS), np.empty(nS), np.empty(nS)
+            jb, kb = np.empty(nS, dtype=np.int64), np.empty(nS, dtype=np.int64)
+            for k, i in enumerate(idx):
+                r = _rand(seed, step, i, 8 + split)
+                j = r[0] % nC
+                l = (j + 1 + r[1] % (nC - 1)) % nC
+                direction[k] = (2.0 * mu) * (X[walker[offC + j]] - X[walker[offC + l]])
+                J = int(np.floor(maxsteps * u01(r[2], r[3])))
+                q = _rand(seed, step, i, 10 + split)
+                z0[k] = Z[i] + np.log(u01(q[0], q[1]))
+                lo[k] = -u01(q[2], q[3])
+                hi[k] = lo[k] + 1.0
+                jb[k], kb[k] = J, maxsteps - 1 - J
+            phase = np.zeros(nS, dtype=np.int64)
+            tcur = np.zeros(nS)
+            it = 0
+            while np.any(phase != 3):
+                if it > maxiter:
+                    raise RuntimeError("Number of contractions exceeded maximum limit!")
+                act = np.flatnonzero(phase != 3)
+                cand = np.empty((len(act), ndim))
+                for n, k in enumerate(act):
+                    i = idx[k]
+                    if phase[k] == 0:
+                        sk = lo[k]
+                    elif phase[k] == 1:
+                        sk = hi[k]
+                    else:
+                        r = _rand(seed, step, i, 16 + 2 * it + split)
+                        sk = lo[k] + u01(r[0], r[1]) * (hi[k] - lo[k])
+                        tcur[k] = sk
+                    cand[n] = X[i] + sk * direction[k]
+                zs = np.asarray(lnprob_fn(cand), dtype=np.float64)
+                ncall += len(act)
+                nbatches += 1
+                if np.any(np.isnan(zs)):
+                    raise ValueError("Probability function returned NaN")
+                for n, k in enumerate(act):
+                    inside = zs[n] >= z0[k]
+                    if phase[k] == 2 and inside:
+                        X[idx[k]] = cand[n]
+                        Z[idx[k]] = zs[n]
+                        phase[k] = 3
+                    elif phase[k] == 0:
+                        if inside and jb[k] >= 1:
+                            lo[k] -= 1.0
+                            jb[k] -= 1
+                            nexp += 1
+                        else:
+                            phase[k] = 1
+                    elif phase[k] == 1:
+                        if inside and kb[k] >= 1:
+                            hi[k] += 1.0
+                            kb[k] -= 1
+                            nexp += 1
+                        else:
+                            phase[k] = 2
+                    else:
+                        if tcur[k] < 0.0:
+                            lo[k] = tcur[k]
+                        else:
+                            hi[k] = tcur[k]
+                        ncon += 1
+                it += 1
+        chain[s], lps[s] = X, Z
+        tot_exp += nexp
+        tot_con += ncon
+        if tune:
+            ne = max(nexp, 1)
+            mu = mu * (2.0 * ne / (ne + ncon))
+            if abs(ne / (ne + ncon) - 0.5) < tolerance:
+                good += 1
+            if good > patience:
+                tune = False
+        mus[s] = mu
+    return dict(chain=chain, lnp_chain=lps, mus=mus, mu=mu, tune=tune, good=good, nexp=tot_exp, ncon=tot_con,
+                ncall=ncall, nbatches=nbatches)

@@ -26,6 +26,13 @@ class RbvSpectrum(C.Structure):
                 ("taps", C.POINTER(C.c_double)), ("n_taps", C.c_int), ("normalize_taps", C.c_int)]
 
 
+class RbvSliceTuning(C.Structure):
+    _fields_ = [("mu", C.c_double), ("tolerance", C.c_double), ("tune", C.c_int), ("good", C.c_int),
+                ("patience", C.c_int), ("maxsteps", C.c_int), ("maxiter", C.c_int), ("reserved", C.c_int),
+                ("n_expansions", C.c_ulonglong), ("n_contractions", C.c_ulonglong), ("n_calls", C.c_ulonglong),
+                ("n_batches", C.c_ulonglong)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "rbv_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -52,6 +59,10 @@ EXPORTS = {
     "rbv_stretch_accept": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_ulonglong,
                                      C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rbv_slice_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "rbv_slice_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(RbvSliceTuning),
+                                C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rbv_model_flux_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p]),
     "rbv_num_instruments": (C.c_int, [C.c_void_p]),

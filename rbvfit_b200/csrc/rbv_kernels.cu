@@ -33,6 +33,7 @@
 #include "../../include/rbvfit_b200.h"
 #include "rbv_device.cuh"
 #include "rbv_sampler.cuh"   // StretchParams + Philox streams (embedded in LaunchParams for the fused sampler step)
+#include "rbv_slice.cuh"     // device-resident ensemble slice sampler (kernels around the lnprob launch)
 
 namespace rbv {
 
@@ -79,6 +80,8 @@ struct LaunchParams {
   double* partials;      // [W, n_tiles]
   unsigned int* tickets; // [W]
   int* oob;              // [W] 1 = row violates the prior bounds (written by prep_kernel)
+  const int* row_skip;   // [W] or NULL: rows with a non-zero entry are not evaluated at all (their lnprob is -inf);
+                         // the slice sampler masks the walkers that have finished their half-step this way
   double* lc;            // [W, n_lines_total, LC_STRIDE] per-walker line constants (written by prep_kernel)
   double* out_flux;      // flux mode: [W, P]
   int ndim, n_tiles, n_inst, W, n_lines_total;
@@ -502,8 +505,9 @@ __device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[PP
 // FP64 instructions -- as long as a tile's whole phase 1 when done by 33 threads of every CTA).
 // Thread 0 of each walker also evaluates the uniform prior (vfit.lnprior, vfit_mcmc.py:291-295).
 __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w, int g, const double* __restrict__ th) {
+  const bool skipped = prm.row_skip != nullptr && prm.row_skip[w] != 0;
   if (g == 0) {
-    int bad = 0;
+    int bad = skipped;
     for (int i = 0; i < prm.ndim; ++i) {
       double t = th[i];
       bad |= (t < prm.lb[i]) || (t > prm.ub[i]);
@@ -511,7 +515,7 @@ __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w
     prm.oob[w] = bad;
     prm.tickets[w] = 0u;   // the workspace layout depends on W: never trust ticket state from an earlier call
   }
-  if (g >= prm.n_lines_total) return;
+  if (g >= prm.n_lines_total || skipped) return;
   int k = 0, l = g;
   if (prm.wps > 0) {
     k = w / prm.wps;                       // sightline mode: the walker's own instrument, all L lines
@@ -1036,6 +1040,9 @@ struct RbvContext {
   double* d_ub = nullptr;
   double* d_core_tab = nullptr;
   size_t max_smem_lnprob[2] = {0, 0};  // per LOGR in {2,3}
+  // rbv_slice_run: pinned landing slots + events for the per-iteration read-back of the counters
+  SliceCounters* h_poll = nullptr;     // [2], page-locked
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
 };
 
 template <typename T>
@@ -1070,6 +1077,10 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaSetDevice(device));
   RbvContext* ctx = new RbvContext();
   ctx->device = device;
+  struct Guard {   // a failed set-up must not leak the half-built context
+    RbvContext* c;
+    ~Guard() { if (c) rbv_destroy(c); }
+  } guard{ctx};
   {   // tuning / test hooks, re-read whenever a context is created
     const char* e = getenv("RBVFIT_B200_PPT");
     g_force_ppt = e ? atoi(e) : 0;
@@ -1092,6 +1103,9 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaMallocHost((void**)&ctx->h_poll, 2 * sizeof(SliceCounters)));
+  for (int k = 0; k < 2; ++k) RBV_CUDA(cudaEventCreateWithFlags(&ctx->poll_ev[k], cudaEventDisableTiming));
+  guard.c = nullptr;
   *out = ctx;
   return RBV_OK;
 }
@@ -1107,6 +1121,9 @@ void rbv_destroy(RbvContext* ctx) {
   cudaFree(ctx->d_lb);
   cudaFree(ctx->d_ub);
   cudaFree(ctx->d_core_tab);
+  if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+  for (int k = 0; k < 2; ++k)
+    if (ctx->poll_ev[k]) cudaEventDestroy(ctx->poll_ev[k]);
   delete ctx;
 }
 
@@ -1359,7 +1376,8 @@ int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t*
 
 static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, double* lnprob, void* workspace,
                          size_t workspace_bytes, void* stream, const char* who,
-                         const StretchParams* sampler = nullptr, int sampler_split = -1) {
+                         const StretchParams* sampler = nullptr, int sampler_split = -1,
+                         const int* row_skip = nullptr) {
   if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, std::string(who) + ": null argument");
   if (W < 0) return fail(RBV_EINVAL, std::string(who) + ": negative n_walkers");
   if (W == 0) return RBV_OK;
@@ -1396,6 +1414,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   prm.lnprob = lnprob;
   prm.tickets = (unsigned int*)((char*)workspace + lay.tickets);
   prm.oob = (int*)((char*)workspace + lay.oob);
+  prm.row_skip = row_skip;
   prm.partials = (double*)((char*)workspace + lay.partials);
   prm.lc = (double*)((char*)workspace + lay.lc);
   prm.n_lines_total = sl ? ctx->inst[0].dev.L : ctx->n_lines_total;
@@ -1649,6 +1668,147 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
   stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, (cudaStream_t)stream>>>(P, split);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
+  return RBV_OK;
+}
+
+// ---- device-resident ensemble slice sampler (zeus's differential move), rbv_slice.cuh ------------------------
+struct SliceLayout {
+  size_t cand, lnp_cand, dir, z0, lo, hi, tcur, jbudget, kbudget, phase, skip, walker_of, ctr, lnprob_ws, total;
+};
+static SliceLayout slice_layout(const RbvContext* ctx, int W) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t h = (size_t)(W + 1) / 2, row = h * std::max(ctx->ndim, 1) * sizeof(double);
+  SliceLayout lay;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += up(bytes); return at; };
+  lay.cand = take(row);
+  lay.lnp_cand = take(h * sizeof(double));
+  lay.dir = take(row);
+  lay.z0 = take(h * sizeof(double));
+  lay.lo = take(h * sizeof(double));
+  lay.hi = take(h * sizeof(double));
+  lay.tcur = take(h * sizeof(double));
+  lay.jbudget = take(h * sizeof(int));
+  lay.kbudget = take(h * sizeof(int));
+  lay.phase = take(h * sizeof(int));
+  lay.skip = take(h * sizeof(int));
+  lay.walker_of = take(h * sizeof(int));
+  lay.ctr = take(sizeof(SliceCounters));
+  lay.lnprob_ws = o;
+  lay.total = o + workspace_layout(ctx, (int)h, false).total;
+  return lay;
+}
+
+int rbv_slice_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes) {
+  if (!ctx || !bytes || n_walkers < 4) return fail(RBV_EINVAL, "rbv_slice_workspace_bytes: bad argument");
+  *bytes = slice_layout(ctx, n_walkers).total;
+  return RBV_OK;
+}
+
+int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, RbvSliceTuning* tuning,
+                  unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                  double* mu_history, int* flag, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ctx || !coords || !lnprob || !tuning || !flag) return fail(RBV_EINVAL, "rbv_slice_run: null argument");
+  if (n_walkers < 4) return fail(RBV_EINVAL, "rbv_slice_run: need at least four walkers (two per complement)");
+  if (n_steps < 0 || !(tuning->mu > 0.0) || tuning->maxsteps < 1 || tuning->maxiter < 1)
+    return fail(RBV_EINVAL, "rbv_slice_run: n_steps < 0, mu <= 0, maxsteps < 1 or maxiter < 1");
+  if (ctx->inst.empty() || ctx->ndim == 0) return fail(RBV_ESTATE, "rbv_slice_run: context not set up");
+  if (n_steps == 0) return RBV_OK;
+  const SliceLayout lay = slice_layout(ctx, n_walkers);
+  if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, "rbv_slice_run: workspace too small");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  SliceParams P;
+  P.coords = coords;
+  P.lnp = lnprob;
+  P.cand = (double*)(ws + lay.cand);
+  P.lnp_cand = (double*)(ws + lay.lnp_cand);
+  P.dir = (double*)(ws + lay.dir);
+  P.z0 = (double*)(ws + lay.z0);
+  P.lo = (double*)(ws + lay.lo);
+  P.hi = (double*)(ws + lay.hi);
+  P.tcur = (double*)(ws + lay.tcur);
+  P.jbudget = (int*)(ws + lay.jbudget);
+  P.kbudget = (int*)(ws + lay.kbudget);
+  P.phase = (int*)(ws + lay.phase);
+  P.skip = (int*)(ws + lay.skip);
+  P.walker_of = (int*)(ws + lay.walker_of);
+  P.flag = flag;
+  P.ctr = (SliceCounters*)(ws + lay.ctr);
+  P.seed = seed;
+  P.mu = tuning->mu;
+  P.W = n_walkers;
+  P.ndim = ctx->ndim;
+  P.maxsteps = tuning->maxsteps;
+  RBV_CUDA(cudaMemsetAsync(P.ctr, 0, sizeof(SliceCounters), st));
+  const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
+  const int h = (n_walkers + 1) / 2;
+  unsigned long long total_exp = 0, total_con = 0, batches = 0, calls = 0;
+
+  for (int s = 0; s < n_steps; ++s) {
+    const unsigned long long step = first_step + (unsigned long long)s;
+    unsigned int nexp = 0, ncon = 0;
+    for (int split = 0; split < 2; ++split) {
+      const int nS = split == 0 ? h : n_walkers - h;
+      const unsigned rows_grid = (unsigned)((nS + 3) / 4);
+      slice_begin_kernel<<<rows_grid, 128, 0, st>>>(P, step, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+      // Iterations are enqueued one ahead of the read-back: while the host waits for the counters of iteration
+      // it - 1 the device already runs iteration it.  When it - 1 left nothing to do, iteration it found every row
+      // masked and changed nothing.
+      bool done = false;
+      for (int it = 0; !done; ++it) {
+        if (it > tuning->maxiter) {
+          cudaStreamSynchronize(st);
+          return fail(RBV_ESTATE, "rbv_slice_run: number of contractions exceeded the maximum (maxiter)");
+        }
+        slice_candidate_kernel<<<rows_grid, 128, 0, st>>>(P, step, split, it);
+        RBV_CUDA(cudaGetLastError());
+        ctx->launches++;
+        int rc = launch_lnprob(ctx, P.cand, nS, 0, P.lnp_cand, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
+                               "rbv_slice_run", nullptr, -1, P.skip);
+        if (rc != RBV_OK) return rc;
+        slice_update_kernel<<<rows_grid, 128, 0, st>>>(P, split);
+        RBV_CUDA(cudaGetLastError());
+        ctx->launches++;
+        ++batches;
+        RBV_CUDA(cudaMemcpyAsync(&ctx->h_poll[it & 1], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost, st));
+        RBV_CUDA(cudaEventRecord(ctx->poll_ev[it & 1], st));
+        if (it >= 2) {      // no walker can finish in fewer than three evaluations (L, R, one draw)
+          RBV_CUDA(cudaEventSynchronize(ctx->poll_ev[(it - 1) & 1]));
+          const SliceCounters& c = ctx->h_poll[(it - 1) & 1];
+          if (c.remaining == 0u) {
+            done = true;
+            nexp = c.nexp;
+            ncon = c.ncon;
+            calls = c.ncall;
+          }
+        }
+      }
+    }
+    slice_record_kernel<<<(unsigned)((n_walkers + 3) / 4), 128, 0, st>>>(
+        P, chain ? chain + (size_t)s * n_walkers * ctx->ndim : nullptr,
+        lnprob_chain ? lnprob_chain + (size_t)s * n_walkers : nullptr);
+    RBV_CUDA(cudaGetLastError());
+    ctx->launches++;
+    total_exp += nexp;
+    total_con += ncon;
+    if (tuning->tune) {     // zeus: stochastic approximation of mu towards an expansion fraction of 1/2
+      const double ne = (double)std::max(nexp, 1u), tot = ne + (double)ncon;
+      P.mu = P.mu * (2.0 * ne / tot);
+      if (std::fabs(ne / tot - 0.5) < tuning->tolerance) tuning->good += 1;
+      if (tuning->good > tuning->patience) tuning->tune = 0;
+    }
+    if (mu_history) mu_history[s] = P.mu;
+  }
+  RBV_CUDA(cudaStreamSynchronize(st));
+  tuning->mu = P.mu;
+  tuning->n_expansions = total_exp;
+  tuning->n_contractions = total_con;
+  tuning->n_calls = calls;
+  tuning->n_batches = batches;
   return RBV_OK;
 }
 

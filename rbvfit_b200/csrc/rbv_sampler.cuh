@@ -61,16 +61,23 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
   return ((double)m + 0.5) * 1.1102230246251565e-16;
 }
 
-__device__ __forceinline__ uint4 stretch_rand(const StretchParams& P, unsigned long long step, uint32_t walker,
+// the sampler's random stream: counter = (step lo, step hi, walker, purpose), key = seed
+__device__ __forceinline__ uint4 sampler_rand(unsigned long long seed, unsigned long long step, uint32_t walker,
                                               uint32_t purpose) {
   return philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), walker, purpose),
-                       make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint4 stretch_rand(const StretchParams& P, unsigned long long step, uint32_t walker,
+                                              uint32_t purpose) {
+  return sampler_rand(P.seed, step, walker, purpose);
 }
 
 // the step's affine permutation of walker positions: walker(pos) = (a pos + b) mod W
-__device__ __forceinline__ void stretch_perm(const StretchParams& P, unsigned long long step, uint32_t& a, uint32_t& b) {
-  const uint4 r = stretch_rand(P, step, 0xffffffffu, 0u);
-  const uint32_t W = (uint32_t)P.W;
+__device__ __forceinline__ void sampler_perm(unsigned long long seed, int n_walkers, unsigned long long step,
+                                             uint32_t& a, uint32_t& b) {
+  const uint4 r = sampler_rand(seed, step, 0xffffffffu, 0u);
+  const uint32_t W = (uint32_t)n_walkers;
   a = r.x % W;
   b = r.y % W;
   for (;;) {
@@ -83,6 +90,10 @@ __device__ __forceinline__ void stretch_perm(const StretchParams& P, unsigned lo
     if (x == 1u || W == 1u) break;
     a = (a + 1u) % W;
   }
+}
+
+__device__ __forceinline__ void stretch_perm(const StretchParams& P, unsigned long long step, uint32_t& a, uint32_t& b) {
+  sampler_perm(P.seed, P.W, step, a, b);
 }
 
 __device__ __forceinline__ int walker_at(uint32_t a, uint32_t b, int W, int pos) {

@@ -48,6 +48,7 @@ class Engine:
         self._ws_bytes = 0
         self._ws_sightlines = False
         self._stretch_ws = None               # workspace of the device-resident sampler
+        self._slice_ws = None                 # workspace of the device-resident slice sampler
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -246,6 +247,31 @@ class Engine:
                                           lnp_chain_row_t.data_ptr() if lnp_chain_row_t is not None else None,
                                           n_accepted_t.data_ptr(), flag_t.data_ptr(), ws.data_ptr(), ws.numel(),
                                           self._stream()), "rbv_stretch_accept")
+
+    def slice_run(self, coords_t, lnp_t, n_steps: int, tuning, seed: int, first_step: int, chain_t, lnp_chain_t,
+                  flag_t) -> np.ndarray:
+        """Device-resident ensemble slice sampling (rbv_slice_run) on the current torch stream; ``tuning`` is an
+        ``RbvSliceTuning`` updated in place.  Returns mu after each step; the call returns when the run is done."""
+        torch = _torch()
+        W, ndim = coords_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"coords has {ndim} columns, bounds were set for ndim={self.ndim}")
+        for t, dt in ((coords_t, torch.float64), (lnp_t, torch.float64), (flag_t, torch.int32)):
+            if t.dtype != dt or not t.is_contiguous() or t.device != self.tdev:
+                raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
+        nbytes = C.c_size_t(0)
+        check(self.lib.rbv_slice_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_slice_workspace_bytes")
+        if self._slice_ws is None or self._slice_ws.numel() < nbytes.value:
+            self._slice_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
+        mus = np.empty(max(int(n_steps), 1), dtype=np.float64)
+        check(self.lib.rbv_slice_run(
+            self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), C.byref(tuning),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_step),
+            chain_t.data_ptr() if chain_t is not None else None,
+            lnp_chain_t.data_ptr() if lnp_chain_t is not None else None,
+            _dptr(mus), flag_t.data_ptr(), self._slice_ws.data_ptr(), self._slice_ws.numel(), self._stream()),
+            "rbv_slice_run")
+        return mus[:int(n_steps)]
 
     def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:
         """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``."""

@@ -15,7 +15,9 @@ defaults: DifferentialMove, mu = 1 tuned by stochastic approximation, tolerance 
 
 Every lnp evaluation inside the two loops is ONE device batch over the walkers that are still active in
 that loop (``vectorize=True`` contract) -- the long tail of small batches is latency-bound on the GPU
-(SURVEY.md section 7.3), which is why the stretch move remains the default.
+(SURVEY.md section 7.3).  ``DeviceEnsembleSliceSampler`` keeps the whole loop on the device instead
+(``rbv_slice_run``): the walkers of a half advance in lockstep through their own widen / shrink state machines, one
+masked device batch per iteration, and only a 24-byte counter block is read back between iterations.
 """
 from __future__ import annotations
 
@@ -192,4 +194,87 @@ class EnsembleSliceSampler:
         return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
 
     def get_last_sample(self):
+        return self._last
+
+
+class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
+    """Same move, same accessor contract, but the whole loop runs on the GPU (``rbv_slice_run``, C ABI): directions,
+    slice levels, brackets and the per-walker widen / shrink state machines live in device memory, every iteration
+    is one masked likelihood batch over the active half, and the chain is copied to the host once per ``run_mcmc``
+    call.  ``likelihood`` is a ``GpuLikelihood``; random numbers come from the counter-based Philox streams of the
+    device stretch move, so a run is reproducible and can be continued (``run_mcmc(None, n)``) without changing
+    the stream of one long run (``oracle/slice_replay.py`` restates it in numpy for the tests)."""
+
+    def __init__(self, nwalkers: int, ndim: int, likelihood, mu: float = 1.0, tune: bool = True,
+                 tolerance: float = 0.05, patience: int = 5, maxsteps: int = 10000, maxiter: int = 10000,
+                 seed: Optional[int] = None, **_ignored):
+        if not hasattr(likelihood, "engine"):
+            raise TypeError("DeviceEnsembleSliceSampler needs a GpuLikelihood (the log-probability must run on "
+                            "the device)")
+        if likelihood.ndim != ndim:
+            raise ValueError(f"likelihood has ndim={likelihood.ndim}, sampler was given ndim={ndim}")
+        self.likelihood = likelihood
+        self._seed = int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
+        self._stream = None
+        self._state = None
+        self.good = 0
+        super().__init__(nwalkers, ndim, likelihood.lnprob, mu=mu, tune=tune, tolerance=tolerance,
+                         patience=patience, maxsteps=maxsteps, maxiter=maxiter, seed=seed)
+
+    def reset(self):
+        super().reset()
+        self._state = None
+        self.nexp = self.ncon = 0
+
+    def run_mcmc(self, start, nsteps, progress=False, **_ignored):
+        import torch
+        from ._lib import RbvSliceTuning
+        eng = self.likelihood.engine
+        dev = eng.tdev
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        with torch.cuda.stream(self._stream):
+            if start is None:
+                if self._state is None:
+                    raise ValueError("Cannot have `start=None` if run_mcmc has never been called.")
+                coords_t, lnp_t = self._state
+            else:
+                X = np.array(start, dtype=np.float64, copy=True)
+                if X.shape != (self.nwalkers, self.ndim):
+                    raise ValueError("Incompatible input dimensions! Please provide array of shape (nwalkers, ndim)")
+                coords_t = torch.as_tensor(X, device=dev)
+                lnp_t = eng.lnprob_device(coords_t)
+                self.ncall += self.nwalkers
+                self.nbatches += 1
+                if not bool(torch.isfinite(lnp_t).all()):
+                    raise ValueError("Invalid walker initial positions! Initialise walkers from positions of "
+                                     "finite log probability.")
+            chain_t = torch.empty((nsteps, self.nwalkers, self.ndim), dtype=torch.float64, device=dev)
+            lps_t = torch.empty((nsteps, self.nwalkers), dtype=torch.float64, device=dev)
+            flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
+            tuning = RbvSliceTuning(mu=self.mu, tolerance=self.tolerance, tune=int(self.tune), good=int(self.good),
+                                    patience=self.patience, maxsteps=self.maxsteps, maxiter=self.maxiter)
+            mus = eng.slice_run(coords_t, lnp_t, nsteps, tuning, self._seed, self.iteration, chain_t, lps_t, flag_t)
+            self._stream.synchronize()
+            if int(flag_t.item()) & 1:
+                raise ValueError("Probability function returned NaN")
+            was_tuning = self.tune
+            self.mu, self.tune, self.good = float(tuning.mu), bool(tuning.tune), int(tuning.good)
+            if was_tuning:
+                self.mus.extend(float(m) for m in mus)
+            self.ncall += int(tuning.n_calls)
+            self.nbatches += int(tuning.n_batches)
+            self.nexp += int(tuning.n_expansions)
+            self.ncon += int(tuning.n_contractions)
+            self._state = (coords_t, lnp_t)
+            chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
+        if len(self._chain) == 0:
+            self._chain, self._log_prob = chain, lps
+        else:
+            self._chain = np.concatenate([self._chain, chain], axis=0)
+            self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self.iteration += nsteps
+        if nsteps:
+            self._last = (chain[-1].copy(), lps[-1].copy())
         return self._last

@@ -49,7 +49,7 @@ class vfit:
         self.nwalkers = no_of_Chain
         self._rng = np.random.default_rng(seed)
         self._seed = seed
-        self.device_sampler = bool(device_sampler)   # stretch move entirely on the GPU (rbv_stretch_run)
+        self.device_sampler = bool(device_sampler)   # sampling loop entirely on the GPU (rbv_stretch_run / rbv_slice_run)
 
     # ------------------------------------------------------------------ validation (vfit_mcmc.py:199-229)
     def _validate_unified_instrument_data(self, instrument_data):
@@ -213,8 +213,11 @@ class vfit:
                 print("✓ Starting guess optimized")
         guesses = self._initialize_walkers(self.theta)
         if self.sampler_name == "zeus":
-            from .slice_sampler import EnsembleSliceSampler
-            sampler = EnsembleSliceSampler(self.nwalkers, self.ndim, self.lnprob, seed=self._seed)
+            from .slice_sampler import DeviceEnsembleSliceSampler, EnsembleSliceSampler
+            if self.device_sampler:
+                sampler = DeviceEnsembleSliceSampler(self.nwalkers, self.ndim, self._like, seed=self._seed)
+            else:
+                sampler = EnsembleSliceSampler(self.nwalkers, self.ndim, self.lnprob, seed=self._seed)
         elif self.device_sampler:
             sampler = DeviceEnsembleSampler(self.nwalkers, self.ndim, self._like, seed=self._seed)
         else:

@@ -265,3 +265,75 @@ def test_distributed_device_sampler_single_rank_and_multi_gpu():
                               os.path.join(root, "tools", "check_dist_sampler.py")],
                              capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_device_slice_sampler_matches_numpy_replay():
+    """rbv_slice_run against its numpy restatement (oracle/slice_replay.py: same Philox streams, same lockstep
+    state machines, same mu adaptation) driven by the GPU lnprob: identical candidates, identical decisions, the
+    same counters.  The device launches exactly one speculative batch per half-step on top of the replay's."""
+    from oracle import slice_replay as sl
+    from rbvfit_b200.slice_sampler import DeviceEnsembleSliceSampler
+    w, fitter, comp, theta0 = _c1_fitter()
+    like = fitter._like
+    rng = np.random.default_rng(8)
+    for W, nsteps in ((12, 40), (16, 25)):
+        p0 = np.clip(w["theta_true"] + 1e-3 * rng.standard_normal((W, 6)), w["lb"], w["ub"])
+        dev = DeviceEnsembleSliceSampler(W, 6, like, seed=77)
+        dev.run_mcmc(p0, nsteps)
+        ref = sl.run(like.lnprob, p0, like.lnprob(p0), nsteps, dev._seed)
+        assert np.allclose(dev.get_chain(), ref["chain"], rtol=0, atol=1e-9)
+        assert np.max(np.abs(dev.get_log_prob() - ref["lnp_chain"]) / np.abs(ref["lnp_chain"])) <= 1e-9
+        assert (dev.nexp, dev.ncon) == (ref["nexp"], ref["ncon"])
+        assert dev.ncall == W + ref["ncall"] and dev.nbatches == 1 + ref["nbatches"] + 2 * nsteps
+        assert dev.mu == ref["mu"] and dev.tune == ref["tune"] and np.array_equal(dev.mus, ref["mus"][:len(dev.mus)])
+
+
+def test_device_slice_sampler_bookkeeping_continuation_and_posterior():
+    """rbv_slice_run: the recorded lnprob of every stored position equals the likelihood recomputed for it, walkers
+    stay inside the prior box (out-of-bounds candidates are -inf, i.e. outside every slice), every walker moves
+    every step, run(30) + run(None, 20) equals run(50), and through vfit(sampler='zeus') the posterior brackets the
+    truth with zeus's accessor contract."""
+    from rbvfit_b200.slice_sampler import DeviceEnsembleSliceSampler, EnsembleSliceSampler
+    w, fitter, comp, theta0 = _c1_fitter()
+    like = fitter._like
+    rng = np.random.default_rng(3)
+    p0 = np.clip(w["theta_true"] + 1e-3 * rng.standard_normal((14, 6)), w["lb"], w["ub"])
+    a = DeviceEnsembleSliceSampler(14, 6, like, seed=5)
+    a.run_mcmc(p0, 50)
+    chain, lps = a.get_chain(), a.get_log_prob()
+    assert chain.shape == (50, 14, 6) and lps.shape == (50, 14)
+    for step in (0, 17, 49):
+        assert np.array_equal(like.lnprob(chain[step]), lps[step])
+    assert np.all(chain >= w["lb"]) and np.all(chain <= w["ub"]) and np.all(np.isfinite(lps))
+    assert np.all(np.any(chain[1:] != chain[:-1], axis=2)) and a.acceptance_fraction.min() > 0.95
+    b = DeviceEnsembleSliceSampler(14, 6, like, seed=5)
+    b.run_mcmc(p0, 30)
+    b.run_mcmc(None, 20)
+    assert np.array_equal(b.get_chain(), chain) and np.array_equal(b.get_log_prob(), lps)
+    assert (b.mu, b.ncall, b.nexp, b.ncon) == (a.mu, a.ncall, a.nexp, a.ncon)
+    c = DeviceEnsembleSliceSampler(14, 6, like, seed=6)
+    c.run_mcmc(p0, 10)
+    assert not np.array_equal(c.get_chain(), chain[:10])
+    assert a.efficiency > 0.05 and a.get_last_sample()[0].shape == (14, 6)
+    with pytest.raises(ValueError):
+        DeviceEnsembleSliceSampler(5, 6, like)                    # zeus: >= 2 * ndim walkers, an even number
+    with pytest.raises(TypeError):
+        DeviceEnsembleSliceSampler(14, 6, fitter.lnprob)
+    bad = p0.copy()
+    bad[0, 0] = w["ub"][0] + 1.0
+    with pytest.raises(ValueError):
+        DeviceEnsembleSliceSampler(14, 6, like, seed=1).run_mcmc(bad, 3)
+    # through the fitter
+    w2, f2, _, _ = _c1_fitter(nwalkers=24, nsteps=250, seed=13, sampler="zeus")
+    f2.runmcmc(optimize=True, verbose=False, progress=False)
+    s = f2.sampler
+    assert isinstance(s, DeviceEnsembleSliceSampler) and s.get_chain().shape == (250, 24, 6)
+    assert f2.samples.shape == (150 * 24, 6)
+    lo, hi = np.percentile(f2.samples, [0.5, 99.5], axis=0)
+    assert np.all(lo < w2["theta_true"]) and np.all(w2["theta_true"] < hi)
+    tau = s.get_autocorr_time(quiet=True)
+    assert tau.shape == (6,) and np.all(np.isfinite(tau))
+    w3, f3, _, _ = _c1_fitter(nwalkers=24, nsteps=110, seed=13, sampler="zeus")     # burn-in of 100 steps is fixed
+    f3.device_sampler = False
+    f3.runmcmc(optimize=False, verbose=False, progress=False)
+    assert type(f3.sampler) is EnsembleSliceSampler and f3.sampler.get_chain().shape == (110, 24, 6)

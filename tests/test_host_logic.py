@@ -195,3 +195,40 @@ def test_stretch_replay_philox_known_answers_and_gaussian_target():
     assert np.all(np.abs(flat.std(0) / sig - 1) < 0.12)
     assert abs(np.corrcoef(flat.T)[0, 1] - 0.3) < 0.1
     assert 0.3 < (nacc / 1500).mean() < 0.85
+
+
+def test_slice_replay_recovers_gaussian_and_tunes_mu():
+    """oracle/slice_replay.py (numpy restatement of rbv_slice_run: lockstep widen / shrink state machines, Philox
+    streams): it recovers a correlated Gaussian, every stored lnprob belongs to its stored position, mu settles
+    (expansions ~ contractions), a continued run equals one long run, and every half-step needs at least three
+    batches (L, R, one draw)."""
+    from oracle import slice_replay as sl
+    mu = np.array([1.0, -2.0, 0.5])
+    cov = np.array([[0.25, 0.3, 0.0], [0.3, 4.0, 0.5], [0.0, 0.5, 1.0]])
+    icov = np.linalg.inv(cov)
+
+    def lnp(x):
+        d = np.atleast_2d(x) - mu
+        return -0.5 * np.einsum("ni,ij,nj->n", d, icov, d)
+
+    rng = np.random.default_rng(1)
+    p0 = mu + 0.1 * rng.standard_normal((12, 3))
+    out = sl.run(lnp, p0, lnp(p0), 700, seed=20260, mu=1.0)
+    chain, lps = out["chain"], out["lnp_chain"]
+    assert np.allclose(lps, lnp(chain.reshape(-1, 3)).reshape(lps.shape))
+    assert np.all(np.any(chain[1:] != chain[:-1], axis=2))            # a slice move always moves
+    flat = chain[150:].reshape(-1, 3)
+    sig = np.sqrt(np.diag(cov))
+    assert np.all(np.abs(flat.mean(0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(0) / sig - 1) < 0.12)
+    assert abs(np.corrcoef(flat.T)[0, 1] - 0.3) < 0.1
+    assert not out["tune"] and out["good"] == 6 and 0.2 < out["mu"] < 5.0
+    assert out["nbatches"] >= 2 * 3 * 700 and out["ncall"] >= 3 * 12 * 700
+    # continuation: 300 + 400 steps with the carried tuning state == 700 steps
+    a = sl.run(lnp, p0, lnp(p0), 300, seed=20260, mu=1.0)
+    b = sl.run(lnp, a["chain"][-1], a["lnp_chain"][-1], 400, seed=20260, mu=a["mu"], tune=a["tune"], good=a["good"],
+               first_step=300)
+    assert np.array_equal(np.concatenate([a["chain"], b["chain"]]), chain)
+    # a tiny stepping-out budget still samples correctly (the bracket just cannot widen)
+    c = sl.run(lnp, p0, lnp(p0), 50, seed=3, mu=0.01, maxsteps=1, tune=False)
+    assert c["nexp"] == 0 and np.all(np.isfinite(c["lnp_chain"]))
