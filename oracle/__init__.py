@@ -13,6 +13,8 @@ Nothing in ``rbvfit_b200/`` may import this package.  Only ``tests/``,
                     fixtures under ``tests/golden/``.
 * ``stretch_replay`` numpy restatement of the device-resident stretch-move sampler
                     (``rbv_stretch_run``), Philox random streams included.
+* ``slice_replay``  numpy restatement of the device-resident ensemble slice sampler
+                    (``rbv_slice_run``), same random streams.
 
 Parity status: the reference ships no golden vectors or value-asserting tests for this path
 (SURVEY.md section 4), so the oracle is pinned against outputs of the reference code itself,
