@@ -172,9 +172,10 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
 /* Device-resident ensemble slice sampler (differential move).  Replaces the sampling loop
  * zeus.EnsembleSampler(nwalkers, ndim, self.lnprob).run_mcmc(guesses, no_of_steps), vfit_mcmc.py:425-440, 536-540
  * (zeus-mcmc >= 2.3.0 is not vendored in the reference; Karamanis & Beutler 2021, Algorithms 2-3 with zeus's defaults,
- * is restated).  Every walker of the active half is a small state machine (widen L, widen R, shrink, finished) kept in
- * the workspace; one iteration = candidate kernel -> the lnprob launch over the half (finished rows masked) -> update
- * kernel, so a half-step costs as many device batches as the longest chain of evaluations any one walker needs.
+ * is restated).  Every walker of the active half is a small state machine (widening, shrinking, finished) kept in
+ * the workspace; one iteration = candidate kernel -> the lnprob launch over the half (masked rows skipped) -> update
+ * kernel.  Both ends of a widening bracket are evaluated in the same iteration (two rows per walker), so a half-step
+ * costs as many device batches as the longest chain max(n_L, n_R) + 1 + n_shrink any one walker needs.
  * Between iterations the host only reads back a 24-byte counter block (one iteration behind the device, so the GPU
  * never waits for it) to learn when the half-step is complete; ensemble, directions, brackets and the chain never
  * leave the device.  Random numbers: the Philox streams of rbv_stretch_run (purposes 8.., see rbv_slice.cuh), so a

@@ -10,8 +10,9 @@ restated here bit for bit:
   * half s, walker i: partners j != l of the complement and the stepping-out budget J from purpose 8 + s
     (x -> j, y -> l, (z, w) -> J = floor(maxsteps u)); slice level lnp + ln u and left edge -u' from purpose 10 + s
     ((x, y) -> u, (z, w) -> u'); the shrink draw of iteration ``it`` from purpose 16 + 2 it + s;
-  * lockstep iterations: every unfinished walker of the half advances by ONE evaluation per iteration (phase 0
-    widens L, 1 widens R, 2 shrinks), so ``lnprob_fn`` sees one batch per iteration;
+  * lockstep iterations: every unfinished walker of the half advances by one step of its state machine per
+    iteration -- while it widens, BOTH open ends of its bracket are evaluated (independent budgets J and K), then
+    one shrink draw per iteration -- so ``lnprob_fn`` sees one batch per iteration;
   * candidate = X + s * direction, direction = (2 mu) * (C_j - C_l), t = L + u (R - L): separate multiply and add;
   * mu <- mu * (2 n_exp / (n_exp + n_con)) after every step while tuning (n_exp at least 1).
 
@@ -23,6 +24,8 @@ from __future__ import annotations
 import numpy as np
 
 from .stretch_replay import _rand, split_geometry, step_perm, u01
+
+LEFT, RIGHT, SHRINK, DONE = 1, 2, 4, 8          # walker state (rbv_slice.cuh: kSlice*)
 
 
 def run(lnprob_fn, coords, lnp, nsteps, seed, mu=1.0, tune=True, tolerance=0.05, patience=5, maxsteps=10000,
@@ -59,56 +62,62 @@ def run(lnprob_fn, coords, lnp, nsteps, seed, mu=1.0, tune=True, tolerance=0.05,
                 lo[k] = -u01(q[2], q[3])
                 hi[k] = lo[k] + 1.0
                 jb[k], kb[k] = J, maxsteps - 1 - J
-            phase = np.zeros(nS, dtype=np.int64)
+            state = np.full(nS, LEFT | RIGHT, dtype=np.int64)
             tcur = np.zeros(nS)
             it = 0
-            while np.any(phase != 3):
+            while np.any(state != DONE):
                 if it > maxiter:
                     raise RuntimeError("Number of contractions exceeded maximum limit!")
-                act = np.flatnonzero(phase != 3)
-                cand = np.empty((len(act), ndim))
-                for n, k in enumerate(act):
+                rows = []                                    # (walker row k, which end / draw)
+                cand = []
+                for k in np.flatnonzero(state != DONE):
                     i = idx[k]
-                    if phase[k] == 0:
-                        sk = lo[k]
-                    elif phase[k] == 1:
-                        sk = hi[k]
-                    else:
+                    if state[k] == SHRINK:
                         r = _rand(seed, step, i, 16 + 2 * it + split)
-                        sk = lo[k] + u01(r[0], r[1]) * (hi[k] - lo[k])
-                        tcur[k] = sk
-                    cand[n] = X[i] + sk * direction[k]
+                        tcur[k] = lo[k] + u01(r[0], r[1]) * (hi[k] - lo[k])
+                        rows.append((k, SHRINK))
+                        cand.append(X[i] + tcur[k] * direction[k])
+                        continue
+                    if state[k] & LEFT:
+                        rows.append((k, LEFT))
+                        cand.append(X[i] + lo[k] * direction[k])
+                    if state[k] & RIGHT:
+                        rows.append((k, RIGHT))
+                        cand.append(X[i] + hi[k] * direction[k])
+                cand = np.array(cand)
                 zs = np.asarray(lnprob_fn(cand), dtype=np.float64)
-                ncall += len(act)
+                ncall += len(rows)
                 nbatches += 1
                 if np.any(np.isnan(zs)):
                     raise ValueError("Probability function returned NaN")
-                for n, k in enumerate(act):
+                for n, (k, what) in enumerate(rows):
                     inside = zs[n] >= z0[k]
-                    if phase[k] == 2 and inside:
-                        X[idx[k]] = cand[n]
-                        Z[idx[k]] = zs[n]
-                        phase[k] = 3
-                    elif phase[k] == 0:
+                    if what == SHRINK:
+                        if inside:
+                            X[idx[k]] = cand[n]
+                            Z[idx[k]] = zs[n]
+                            state[k] = DONE
+                        else:
+                            if tcur[k] < 0.0:
+                                lo[k] = tcur[k]
+                            else:
+                                hi[k] = tcur[k]
+                            ncon += 1
+                    elif what == LEFT:
                         if inside and jb[k] >= 1:
                             lo[k] -= 1.0
                             jb[k] -= 1
                             nexp += 1
                         else:
-                            phase[k] = 1
-                    elif phase[k] == 1:
+                            state[k] &= ~LEFT
+                    else:
                         if inside and kb[k] >= 1:
                             hi[k] += 1.0
                             kb[k] -= 1
                             nexp += 1
                         else:
-                            phase[k] = 2
-                    else:
-                        if tcur[k] < 0.0:
-                            lo[k] = tcur[k]
-                        else:
-                            hi[k] = tcur[k]
-                        ncon += 1
+                            state[k] &= ~RIGHT
+                state[state == 0] = SHRINK                  # both ends closed: shrink from the next iteration on
                 it += 1
         chain[s], lps[s] = X, Z
         tot_exp += nexp

@@ -1681,8 +1681,8 @@ static SliceLayout slice_layout(const RbvContext* ctx, int W) {
   SliceLayout lay;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += up(bytes); return at; };
-  lay.cand = take(row);
-  lay.lnp_cand = take(h * sizeof(double));
+  lay.cand = take(2 * row);                       // two rows per walker while it widens its bracket
+  lay.lnp_cand = take(2 * h * sizeof(double));
   lay.dir = take(row);
   lay.z0 = take(h * sizeof(double));
   lay.lo = take(h * sizeof(double));
@@ -1691,11 +1691,11 @@ static SliceLayout slice_layout(const RbvContext* ctx, int W) {
   lay.jbudget = take(h * sizeof(int));
   lay.kbudget = take(h * sizeof(int));
   lay.phase = take(h * sizeof(int));
-  lay.skip = take(h * sizeof(int));
+  lay.skip = take(2 * h * sizeof(int));
   lay.walker_of = take(h * sizeof(int));
   lay.ctr = take(sizeof(SliceCounters));
   lay.lnprob_ws = o;
-  lay.total = o + workspace_layout(ctx, (int)h, false).total;
+  lay.total = o + workspace_layout(ctx, (int)(2 * h), false).total;
   return lay;
 }
 
@@ -1757,8 +1757,9 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
       ctx->launches++;
       // Iterations are enqueued one ahead of the read-back: while the host waits for the counters of iteration
       // it - 1 the device already runs iteration it.  When it - 1 left nothing to do, iteration it found every row
-      // masked and changed nothing.
-      bool done = false;
+      // masked and changed nothing.  The batch has 2 n_S rows (both bracket ends) until the counters show that no
+      // walker widens any more -- the count never grows within a half-step, so acting on it one iteration late is safe.
+      bool done = false, widening = true;
       for (int it = 0; !done; ++it) {
         if (it > tuning->maxiter) {
           cudaStreamSynchronize(st);
@@ -1767,8 +1768,8 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
         slice_candidate_kernel<<<rows_grid, 128, 0, st>>>(P, step, split, it);
         RBV_CUDA(cudaGetLastError());
         ctx->launches++;
-        int rc = launch_lnprob(ctx, P.cand, nS, 0, P.lnp_cand, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
-                               "rbv_slice_run", nullptr, -1, P.skip);
+        int rc = launch_lnprob(ctx, P.cand, widening ? 2 * nS : nS, 0, P.lnp_cand, ws + lay.lnprob_ws, lnprob_ws_bytes,
+                               stream, "rbv_slice_run", nullptr, -1, P.skip);
         if (rc != RBV_OK) return rc;
         slice_update_kernel<<<rows_grid, 128, 0, st>>>(P, split);
         RBV_CUDA(cudaGetLastError());
@@ -1776,9 +1777,10 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
         ++batches;
         RBV_CUDA(cudaMemcpyAsync(&ctx->h_poll[it & 1], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost, st));
         RBV_CUDA(cudaEventRecord(ctx->poll_ev[it & 1], st));
-        if (it >= 2) {      // no walker can finish in fewer than three evaluations (L, R, one draw)
+        if (it >= 1) {
           RBV_CUDA(cudaEventSynchronize(ctx->poll_ev[(it - 1) & 1]));
           const SliceCounters& c = ctx->h_poll[(it - 1) & 1];
+          if (c.widening == 0u) widening = false;
           if (c.remaining == 0u) {
             done = true;
             nexp = c.nexp;

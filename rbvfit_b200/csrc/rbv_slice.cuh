@@ -13,15 +13,18 @@
 //       shrinking:    t ~ U(L, R); accept X_k + t eta_k when lnp >= y_k, else L = t (t < 0) or R = t
 //   after the step: mu <- mu * 2 n_exp / (n_exp + n_con) while tuning is on (done by the host part of rbv_slice_run)
 //
-// Here every walker of the half is a small state machine (phase 0 = widening L, 1 = widening R, 2 = shrinking,
-// 3 = finished) and one ITERATION advances every unfinished walker by one likelihood evaluation:
-//   slice_candidate_kernel  ->  the lnprob launch over the half (finished rows are skipped through row_skip)
+// Here every walker of the half is a small state machine (widening: either end of the bracket still open;
+// shrinking; finished) and one ITERATION advances every unfinished walker by one step of it:
+//   slice_candidate_kernel  ->  the lnprob launch over the half (masked rows are skipped through row_skip)
 //                           ->  slice_update_kernel
-// so the number of device batches per half-step is the longest chain of evaluations any single walker needs (the
-// host sampler needs the sum of the three loops' longest chains).  Random numbers come from the same counter-based
-// Philox streams as the stretch move: purpose 8 + split (partners, budget), 10 + split (slice level, bracket),
-// 16 + 2 it + split (the shrink draw of iteration it).  All floating-point steps that decide the chain are written
-// with explicitly rounded operations so that oracle/slice_replay.py reproduces them bit for bit in numpy.
+// While a walker widens, BOTH ends of its bracket are evaluated in the same iteration (row k = X + L eta, row
+// n_S + k = X + R eta; the two sides have independent budgets, so this is zeus's left-then-right loop run
+// concurrently); while it shrinks only row k is live.  The number of device batches per half-step is therefore the
+// longest chain  max(n_L, n_R) + 1 + n_shrink  over the walkers, where the host sampler pays the sum of the longest
+// chains of its three loops.  Random numbers come from the same counter-based Philox streams as the stretch move:
+// purpose 8 + split (partners, budget), 10 + split (slice level, bracket), 16 + 2 it + split (the shrink draw of
+// iteration it).  All floating-point steps that decide the chain are written with explicitly rounded operations so
+// that oracle/slice_replay.py reproduces them bit for bit in numpy.
 #pragma once
 
 #include "rbv_sampler.cuh"
@@ -29,17 +32,20 @@
 namespace rbv {
 
 struct SliceCounters {          // device, read back by the host after every iteration
-  unsigned int remaining;       // rows of the half-step that are not finished after the last update
+  unsigned int remaining;       // walkers of the half-step that are not finished after the last update
   unsigned int nexp, ncon;      // expansions / contractions of the current step
-  unsigned int pad;
+  unsigned int widening;        // walkers that still widen their bracket (while > 0 the batch has 2 n_S rows)
   unsigned long long ncall;     // likelihood rows evaluated in this run
 };
+
+// walker state: bit 0 = left end still open, bit 1 = right end still open (widening while either is set)
+constexpr int kSliceLeft = 1, kSliceRight = 2, kSliceShrink = 4, kSliceDone = 8;
 
 struct SliceParams {
   double* coords;        // [W, ndim] current ensemble (in/out)
   double* lnp;           // [W]       its log-probabilities (in/out)
-  double* cand;          // [h, ndim] candidates of the active half, h = ceil(W/2)
-  double* lnp_cand;      // [h]
+  double* cand;          // [2 h, ndim] candidates of the active half, h = ceil(W/2): row k and row n_S + k
+  double* lnp_cand;      // [2 h]
   double* dir;           // [h, ndim] directions
   double* z0;            // [h] slice levels
   double* lo;            // [h] bracket
@@ -47,8 +53,8 @@ struct SliceParams {
   double* tcur;          // [h] the shrink draw that produced the current candidate
   int* jbudget;          // [h] expansions left on the left / right side
   int* kbudget;          // [h]
-  int* phase;            // [h]
-  int* skip;             // [h] row_skip of the lnprob launch (1 = finished)
+  int* phase;            // [h] kSlice* state
+  int* skip;             // [2 h] row_skip of the lnprob launch (1 = no candidate in this row)
   int* walker_of;        // [h] walker index of row k
   int* flag;             // bit 0: a candidate's lnprob was NaN
   SliceCounters* ctr;
@@ -86,85 +92,110 @@ __global__ void __launch_bounds__(128) slice_begin_kernel(const SliceParams P, u
     P.hi[k] = __dadd_rn(left, 1.0);
     P.jbudget[k] = J;
     P.kbudget[k] = P.maxsteps - 1 - J;
-    P.phase[k] = 0;
+    P.phase[k] = kSliceLeft | kSliceRight;
     P.walker_of[k] = i;
   }
 }
 
-// One candidate per unfinished walker: X_k + s eta_k with s = L (phase 0), R (phase 1) or a draw from (L, R).
+// Candidates of iteration `it`: widening walkers put X + L eta into row k and X + R eta into row n_S + k (open ends
+// only), shrinking walkers X + t eta with t drawn from (L, R) into row k; every other row is masked.
 __global__ void __launch_bounds__(128) slice_candidate_kernel(const SliceParams P, unsigned long long step, int split,
                                                               int it) {
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   if (k >= nS) return;
-  if (k == 0 && lane == 0) P.ctr->remaining = 0u;     // every block of this iteration's update kernel runs later
-  const int ph = P.phase[k];
-  if (lane == 0) P.skip[k] = (ph == 3);
-  if (ph == 3) return;
-  const int i = P.walker_of[k];
-  double s;
-  if (ph == 0) {
-    s = P.lo[k];
-  } else if (ph == 1) {
-    s = P.hi[k];
-  } else {
-    const uint4 r = sampler_rand(P.seed, step, (uint32_t)i, 16u + 2u * (uint32_t)it + (uint32_t)split);
-    const double L = P.lo[k], R = P.hi[k];
-    s = __dadd_rn(L, __dmul_rn(u01(r.x, r.y), __dsub_rn(R, L)));
-    if (lane == 0) P.tcur[k] = s;
+  if (k == 0 && lane == 0) {      // every block of this iteration's update kernel runs later
+    P.ctr->remaining = 0u;
+    P.ctr->widening = 0u;
   }
+  const int ph = P.phase[k];
+  const bool rowA = (ph & (kSliceLeft | kSliceShrink)) != 0, rowB = (ph & kSliceRight) != 0;
+  if (lane == 0) {
+    P.skip[k] = !rowA;
+    P.skip[nS + k] = !rowB;
+  }
+  if (!rowA && !rowB) return;
+  const int i = P.walker_of[k];
   const double* x = P.coords + (size_t)i * P.ndim;
   const double* e = P.dir + (size_t)k * P.ndim;
-  for (int d = lane; d < P.ndim; d += 32) P.cand[(size_t)k * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s, e[d]));
+  if (rowA) {
+    double s = P.lo[k];
+    if (ph & kSliceShrink) {
+      const uint4 r = sampler_rand(P.seed, step, (uint32_t)i, 16u + 2u * (uint32_t)it + (uint32_t)split);
+      s = __dadd_rn(s, __dmul_rn(u01(r.x, r.y), __dsub_rn(P.hi[k], s)));
+      if (lane == 0) P.tcur[k] = s;
+    }
+    for (int d = lane; d < P.ndim; d += 32) P.cand[(size_t)k * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s, e[d]));
+  }
+  if (rowB) {
+    const double s = P.hi[k];
+    for (int d = lane; d < P.ndim; d += 32) P.cand[(size_t)(nS + k) * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s, e[d]));
+  }
 }
 
-// Advance every unfinished walker's state machine with the lnprob of its candidate.
+// Advance every unfinished walker's state machine with the lnprob of its candidate(s).
 __global__ void __launch_bounds__(128) slice_update_kernel(const SliceParams P, int split) {
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   if (k >= nS) return;
   int ph = P.phase[k];
-  if (ph == 3) return;
-  const double zs = P.lnp_cand[k], z0 = P.z0[k];
-  const bool inside = zs >= z0;                        // NaN: outside (and flagged)
-  if (ph == 2 && inside) {                             // accepted: the candidate becomes the walker
-    const int i = P.walker_of[k];
-    for (int d = lane; d < P.ndim; d += 32) P.coords[(size_t)i * P.ndim + d] = P.cand[(size_t)k * P.ndim + d];
-    if (lane == 0) P.lnp[i] = zs;
-    ph = 3;
-  } else if (lane == 0) {
-    if (ph == 0) {
-      const int b = P.jbudget[k];
-      if (inside && b >= 1) {
-        P.lo[k] = __dsub_rn(P.lo[k], 1.0);
-        P.jbudget[k] = b - 1;
-        atomicAdd(&P.ctr->nexp, 1u);
-      } else {
-        ph = 1;
-      }
-    } else if (ph == 1) {
-      const int b = P.kbudget[k];
-      if (inside && b >= 1) {
-        P.hi[k] = __dadd_rn(P.hi[k], 1.0);
-        P.kbudget[k] = b - 1;
-        atomicAdd(&P.ctr->nexp, 1u);
-      } else {
-        ph = 2;
-      }
-    } else {
+  if (ph & kSliceDone) return;
+  const double z0 = P.z0[k];
+  if (ph & kSliceShrink) {
+    const double zs = P.lnp_cand[k];
+    if (zs >= z0) {                                    // accepted: the candidate becomes the walker
+      const int i = P.walker_of[k];
+      for (int d = lane; d < P.ndim; d += 32) P.coords[(size_t)i * P.ndim + d] = P.cand[(size_t)k * P.ndim + d];
+      if (lane == 0) P.lnp[i] = zs;
+      ph = kSliceDone;
+    } else if (lane == 0) {                            // NaN: outside (and flagged)
       const double t = P.tcur[k];
       if (t < 0.0) P.lo[k] = t;
       else P.hi[k] = t;
       atomicAdd(&P.ctr->ncon, 1u);
     }
+    if (lane == 0) {
+      if (zs != zs) atomicOr(P.flag, 1);               // zeus / emcee: "Probability function returned NaN"
+      atomicAdd(&P.ctr->ncall, 1ull);
+    }
+  } else if (lane == 0) {
+    unsigned int widened = 0u, evaluated = 0u;
+    if (ph & kSliceLeft) {
+      const double zs = P.lnp_cand[k];
+      const int b = P.jbudget[k];
+      if (zs != zs) atomicOr(P.flag, 1);
+      if (zs >= z0 && b >= 1) {
+        P.lo[k] = __dsub_rn(P.lo[k], 1.0);
+        P.jbudget[k] = b - 1;
+        ++widened;
+      } else {
+        ph &= ~kSliceLeft;
+      }
+      ++evaluated;
+    }
+    if (ph & kSliceRight) {
+      const double zs = P.lnp_cand[nS + k];
+      const int b = P.kbudget[k];
+      if (zs != zs) atomicOr(P.flag, 1);
+      if (zs >= z0 && b >= 1) {
+        P.hi[k] = __dadd_rn(P.hi[k], 1.0);
+        P.kbudget[k] = b - 1;
+        ++widened;
+      } else {
+        ph &= ~kSliceRight;
+      }
+      ++evaluated;
+    }
+    if (widened) atomicAdd(&P.ctr->nexp, widened);
+    atomicAdd(&P.ctr->ncall, (unsigned long long)evaluated);
+    if (ph == 0) ph = kSliceShrink;
+    else atomicAdd(&P.ctr->widening, 1u);
   }
   if (lane == 0) {
-    if (zs != zs) atomicOr(P.flag, 1);                 // zeus / emcee: "Probability function returned NaN"
     P.phase[k] = ph;
-    if (ph != 3) atomicAdd(&P.ctr->remaining, 1u);
-    atomicAdd(&P.ctr->ncall, 1ull);
+    if (!(ph & kSliceDone)) atomicAdd(&P.ctr->remaining, 1u);
   }
 }
 
