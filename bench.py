@@ -414,12 +414,33 @@ def run_gpu_sightlines(args, rank, world, local, n_sightlines=1024, walkers=64):
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
     e2e_ms = float(e2e_s.item()) * 1e3 / args.steps
+    # MCMC in survey mode: one stretch-move ensemble per sightline, all in lockstep on the device
+    # (rbv_stretch_run_sightlines); every rank samples its own sightlines, no collective
+    from rbvfit_b200.sampler import SightlineEnsembleSampler
+    p0 = thetas.copy()
+    bad = ~np.all((p0 >= batch.lb) & (p0 <= batch.ub), axis=2)
+    p0[bad] = np.clip(p0[bad], batch.lb + 1e-9, batch.ub - 1e-9)
+    smp = SightlineEnsembleSampler(Ws, ndim, batch, seed=6)
+    smp.run_mcmc(p0, 3, skip_initial_state_check=True)
+    mc_steps = 20
+    barrier()
+    t0 = time.perf_counter()
+    smp.run_mcmc(None, mc_steps)
+    mc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(mc_s, op=torch.distributed.ReduceOp.MAX)
+    mc_sps = mc_steps / float(mc_s.item())
+    mcmc = {"sampler": "device-resident stretch move, one ensemble per sightline in lockstep "
+                       "(rbv_stretch_run_sightlines), chain D2H included",
+            "steps_per_sec": mc_sps, "sightline_steps_per_sec": mc_sps * n_sightlines,
+            "walker_pixel_per_sec": mc_sps * n_sightlines * Ws * P,
+            "acceptance": float(smp.acceptance_fraction.mean())}
     if rank != 0:
         return
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mcmc": mcmc,
         "config": {"workload": "C5b", "sightlines": n_sightlines, "walkers_per_sightline": Ws, "pixels": P,
                    "lines": 4, "lsf_taps": 23, "partition": f"sightlines/{world}",
                    "l2": "flushed between timed steps (256 MiB memset, untimed)"},
@@ -631,6 +652,7 @@ def main():
     ap.add_argument("--far-field", default="chebyshev", choices=["chebyshev", "direct"],
                     help="far-wing accumulation: interpolated far field (default) or every pair evaluated directly")
     ap.add_argument("--workload", default="C5a")
+    ap.add_argument("--sightlines", type=int, default=1024, help="number of sightlines of workload C5b")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32-gated and MCMC legs")
@@ -651,7 +673,7 @@ def main():
     rank, world, local = rdist.init_from_env("nccl" if world_env > 1 else None)
     try:
         if args.workload == "C5b":
-            run_gpu_sightlines(args, rank, world, local)
+            run_gpu_sightlines(args, rank, world, local, n_sightlines=args.sightlines)
         else:
             run_gpu(args, rank, world, local)
     finally:

@@ -169,6 +169,22 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
                        double* chain_row, double* lnprob_chain_row, int* n_accepted, int* flag, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Survey mode of the same sampler: the context holds S sightlines (see rbv_lnprob_batch_sightlines) and every
+ * sightline has its OWN ensemble of walkers_per_sightline walkers -- what the reference does as S separate
+ * vfit(...).runmcmc() calls, one after the other (vfit_mcmc.py:492-561).  The S ensembles advance in lockstep: a
+ * half-step is stretch_propose_kernel over all S * n_S rows -> ONE sightline lnprob launch -> stretch_accept_kernel,
+ * with no host round trip; ensembles never mix (partners come from the same sightline's complementary half).
+ * Random streams: those of rbv_stretch_run with the walker counter offset by sightline * walkers_per_sightline, so
+ * sightline 0 of a survey run reproduces the single-ensemble run with the same seed.
+ *   coords      DEVICE [S, walkers_per_sightline, ndim], updated in place;  lnprob DEVICE [S, walkers_per_sightline]
+ *   chain       DEVICE [n_steps, S, walkers_per_sightline, ndim] or NULL; lnprob_chain [n_steps, S, wps] or NULL
+ *   n_accepted  DEVICE int[S, walkers_per_sightline], accumulated;  flag as in rbv_stretch_run.  Asynchronous. */
+int rbv_stretch_workspace_bytes_sightlines(const RbvContext* ctx, int walkers_per_sightline, size_t* bytes);
+int rbv_stretch_run_sightlines(RbvContext* ctx, double* coords, double* lnprob, int walkers_per_sightline, int n_steps,
+                               double a, unsigned long long seed, unsigned long long first_step, double* chain,
+                               double* lnprob_chain, int* n_accepted, int* flag, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Device-resident ensemble slice sampler (differential move).  Replaces the sampling loop
  * zeus.EnsembleSampler(nwalkers, ndim, self.lnprob).run_mcmc(guesses, no_of_steps), vfit_mcmc.py:425-440, 536-540
  * (zeus-mcmc >= 2.3.0 is not vendored in the reference; Karamanis & Beutler 2021, Algorithms 2-3 with zeus's defaults,

@@ -9,7 +9,9 @@ What is specific to the device version and restated here bit for bit:
   * uniform (0,1) doubles from the top 53 bits of (x, y): (m + 0.5) * 2^-53;
   * the step's split: positions 0..W-1 -> walkers (a pos + b) mod W with (a, b) from purpose 0 / walker 0xffffffff,
     a advanced until gcd(a, W) = 1; the first ceil(W/2) positions are half 0;
-  * half s: u and the partner index from purpose 1 + s (x, y -> u; z -> partner), the accept draw from purpose 3 + s.
+  * half s: u and the partner index from purpose 1 + s (x, y -> u; z -> partner), the accept draw from purpose 3 + s;
+  * survey mode (rbv_stretch_run_sightlines): ensemble e of W walkers uses the same streams with the walker counter
+    offset by e W (``walker_offset``); the step's split is shared by all ensembles.
 
 Driving this replica with the GPU's lnprob must reproduce the device chain exactly (tests/test_gpu_vfit.py); driving
 it with an analytic Gaussian checks the algorithm itself on the CPU (tests/test_host_logic.py).
@@ -60,8 +62,10 @@ def split_geometry(W, split):
     return (0, h, h, W - h) if split == 0 else (h, W - h, 0, h)
 
 
-def propose_half(coords, seed, step, split, a_scale=2.0):
-    """Proposals of half `split` of step `step`: (walker index per row, proposals [nS, ndim], (ndim-1) ln z)."""
+def propose_half(coords, seed, step, split, a_scale=2.0, walker_offset=0):
+    """Proposals of half `split` of step `step`: (walker index per row, proposals [nS, ndim], (ndim-1) ln z).
+    ``walker_offset`` = e * W for ensemble e of a survey run (rbv_stretch_run_sightlines): the random streams are
+    those of a single ensemble with the walker counter shifted."""
     W, ndim = coords.shape
     pa, pb = step_perm(seed, step, W)
     walker = [(pa * pos + pb) % W for pos in range(W)]
@@ -70,7 +74,7 @@ def propose_half(coords, seed, step, split, a_scale=2.0):
     q = np.empty((nS, ndim))
     fac = np.empty(nS)
     for k, i in enumerate(idx):
-        r = _rand(seed, step, i, 1 + split)
+        r = _rand(seed, step, walker_offset + i, 1 + split)
         u = u01(r[0], r[1])
         j = walker[offC + r[2] % nC]
         t = (a_scale - 1.0) * u + 1.0
@@ -80,10 +84,10 @@ def propose_half(coords, seed, step, split, a_scale=2.0):
     return idx, q, fac
 
 
-def accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new):
+def accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new, walker_offset=0):
     """Accept / reject in place; same draws as rbv_stretch_accept."""
     for k, i in enumerate(idx):
-        r = _rand(seed, step, i, 3 + split)
+        r = _rand(seed, step, walker_offset + i, 3 + split)
         with np.errstate(invalid="ignore"):
             if np.log(u01(r[0], r[1])) < fac[k] + new[k] - lnp[i]:
                 coords[i] = q[k]
@@ -91,7 +95,7 @@ def accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new):
                 nacc[i] += 1
 
 
-def run(lnprob_fn, coords, lnp, nsteps, seed, a_scale=2.0, first_step=0):
+def run(lnprob_fn, coords, lnp, nsteps, seed, a_scale=2.0, first_step=0, walker_offset=0):
     """Returns (chain [nsteps, W, ndim], lnp_chain [nsteps, W], n_accepted [W]); ``lnprob_fn`` maps (n, ndim) -> (n,)."""
     coords = np.array(coords, dtype=np.float64, copy=True)
     lnp = np.array(lnp, dtype=np.float64, copy=True)
@@ -102,8 +106,8 @@ def run(lnprob_fn, coords, lnp, nsteps, seed, a_scale=2.0, first_step=0):
     for s in range(nsteps):
         step = first_step + s
         for split in (0, 1):
-            idx, q, fac = propose_half(coords, seed, step, split, a_scale)
+            idx, q, fac = propose_half(coords, seed, step, split, a_scale, walker_offset)
             new = np.asarray(lnprob_fn(q), dtype=np.float64)
-            accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new)
+            accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new, walker_offset)
         chain[s], lps[s] = coords, lnp
     return chain, lps, nacc

@@ -1546,6 +1546,7 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
   P.a = a;
   P.W = n_walkers;
   P.ndim = ctx->ndim;
+  P.S = 1;
   RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
   const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
   const int h = (n_walkers + 1) / 2;
@@ -1614,6 +1615,7 @@ static int stretch_params(RbvContext* ctx, int n_walkers, void* workspace, size_
   P->ticket = nullptr;
   P->W = n_walkers;
   P->ndim = ctx->ndim;
+  P->S = 1;
   *lay_out = lay;
   return RBV_OK;
 }
@@ -1668,6 +1670,90 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
   stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, (cudaStream_t)stream>>>(P, split);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
+  return RBV_OK;
+}
+
+// ---- survey mode: one stretch-move ensemble per sightline, all advancing in lockstep -------------------------
+static StretchLayout stretch_layout_sightlines(const RbvContext* ctx, int W) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t rows = (size_t)((W + 1) / 2) * std::max<size_t>(ctx->inst.size(), 1);
+  StretchLayout lay;
+  lay.prop = 0;
+  lay.lnp_prop = up(rows * std::max(ctx->ndim, 1) * sizeof(double));
+  lay.factors = lay.lnp_prop + up(rows * sizeof(double));
+  lay.walker_of = lay.factors + up(rows * sizeof(double));
+  lay.ctr = lay.walker_of + up(rows * sizeof(int));
+  lay.lnprob_ws = lay.ctr + 256;
+  lay.total = lay.lnprob_ws + workspace_layout(ctx, (int)rows, true).total;
+  return lay;
+}
+
+int rbv_stretch_workspace_bytes_sightlines(const RbvContext* ctx, int walkers_per_sightline, size_t* bytes) {
+  if (!ctx || !bytes || walkers_per_sightline < 2 || ctx->inst.empty())
+    return fail(RBV_EINVAL, "rbv_stretch_workspace_bytes_sightlines: bad argument");
+  if ((long long)((walkers_per_sightline + 1) / 2) * (long long)ctx->inst.size() > 0x7fffffffLL)
+    return fail(RBV_EINVAL, "rbv_stretch_workspace_bytes_sightlines: too many rows");
+  *bytes = stretch_layout_sightlines(ctx, walkers_per_sightline).total;
+  return RBV_OK;
+}
+
+int rbv_stretch_run_sightlines(RbvContext* ctx, double* coords, double* lnprob, int walkers_per_sightline, int n_steps,
+                               double a, unsigned long long seed, unsigned long long first_step, double* chain,
+                               double* lnprob_chain, int* n_accepted, int* flag, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!ctx || !coords || !lnprob || !n_accepted || !flag)
+    return fail(RBV_EINVAL, "rbv_stretch_run_sightlines: null argument");
+  const int W = walkers_per_sightline;
+  if (W < 2) return fail(RBV_EINVAL, "rbv_stretch_run_sightlines: need at least two walkers per sightline");
+  if (n_steps < 0 || !(a > 1.0))
+    return fail(RBV_EINVAL, "rbv_stretch_run_sightlines: n_steps < 0 or stretch scale a <= 1");
+  if (ctx->inst.empty() || ctx->ndim == 0) return fail(RBV_ESTATE, "rbv_stretch_run_sightlines: context not set up");
+  const long long S = (long long)ctx->inst.size();
+  if (S * W > 0x7fffffffLL) return fail(RBV_EINVAL, "rbv_stretch_run_sightlines: too many walkers");
+  if (n_steps == 0) return RBV_OK;
+  const StretchLayout lay = stretch_layout_sightlines(ctx, W);
+  if (!workspace || workspace_bytes < lay.total)
+    return fail(RBV_ENOMEM, "rbv_stretch_run_sightlines: workspace too small");
+  RBV_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  StretchParams P;
+  memset(&P, 0, sizeof(P));
+  P.coords = coords;
+  P.lnp = lnprob;
+  P.prop = (double*)(ws + lay.prop);
+  P.lnp_prop = (double*)(ws + lay.lnp_prop);
+  P.factors = (double*)(ws + lay.factors);
+  P.walker_of = (int*)(ws + lay.walker_of);
+  P.n_accepted = n_accepted;
+  P.flag = flag;
+  P.step_ctr = nullptr;       // the step index is a launch argument: chain / lnp_chain point at the step's own rows
+  P.ticket = nullptr;
+  P.seed = seed;
+  P.a = a;
+  P.W = W;
+  P.ndim = ctx->ndim;
+  P.S = (int)S;
+  const int h = (W + 1) / 2;
+  const size_t step_rows = (size_t)S * W;
+  for (int s = 0; s < n_steps; ++s) {
+    P.first_step = first_step + (unsigned long long)s;
+    P.chain = chain ? chain + (size_t)s * step_rows * ctx->ndim : nullptr;
+    P.lnp_chain = lnprob_chain ? lnprob_chain + (size_t)s * step_rows : nullptr;
+    for (int split = 0; split < 2; ++split) {
+      const int nS = split == 0 ? h : W - h;
+      const int rows = (int)S * nS;
+      stretch_propose_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(P, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+      int rc = launch_lnprob(ctx, P.prop, rows, nS, P.lnp_prop, ws + lay.lnprob_ws, workspace_bytes - lay.lnprob_ws,
+                             stream, "rbv_stretch_run_sightlines");
+      if (rc != RBV_OK) return rc;
+      stretch_accept_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(P, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+  }
   return RBV_OK;
 }
 

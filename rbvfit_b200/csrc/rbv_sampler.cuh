@@ -41,6 +41,10 @@ struct StretchParams {
   unsigned long long seed;
   double a;
   int W, ndim;
+  int S;                 // independent ensembles of W walkers each that advance in lockstep (survey mode: one per
+                         // sightline, rbv_stretch_run_sightlines); 1 everywhere else.  Ensemble e owns walkers
+                         // e W .. e W + W - 1 of coords / lnp / n_accepted and rows e n_S .. of the half-step buffers;
+                         // its random streams are those of a single ensemble with the walker counter offset by e W
 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -113,18 +117,18 @@ __device__ __forceinline__ void split_geometry(int W, int split, int& offS, int&
 // chain row).  The walker's row of the chain is written here too: after its own half-step a walker does not change
 // again within the step.  The last walker of the second half advances the step counter.
 __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, int split, int k, double new_lp,
-                                                      int lane) {
+                                                      int lane, int e = 0) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   const unsigned long long s = P.step_ctr ? *P.step_ctr : 0ull, step = P.first_step + s;
-  const int i = P.walker_of[k];
+  const int i = e * P.W + P.walker_of[k];              // k: row of the half-step buffers, i: global walker
   const uint4 r = stretch_rand(P, step, (uint32_t)i, 3u + (uint32_t)split);
   const double old_lp = P.lnp[i];
   const double lnpdiff = P.factors[k] + new_lp - old_lp;
   const bool accept = log(u01(r.x, r.y)) < lnpdiff;
   const double* __restrict__ src = accept ? P.prop + (size_t)k * P.ndim : P.coords + (size_t)i * P.ndim;
   double* __restrict__ x = P.coords + (size_t)i * P.ndim;
-  double* __restrict__ row = P.chain ? P.chain + (s * P.W + i) * (size_t)P.ndim : nullptr;
+  double* __restrict__ row = P.chain ? P.chain + (s * P.S * P.W + i) * (size_t)P.ndim : nullptr;
   for (int d = lane; d < P.ndim; d += 32) {
     const double v = src[d];
     if (accept) x[d] = v;
@@ -137,7 +141,7 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
       P.lnp[i] = new_lp;
       P.n_accepted[i] += 1;
     }
-    if (P.lnp_chain) P.lnp_chain[s * P.W + i] = accept ? new_lp : old_lp;
+    if (P.lnp_chain) P.lnp_chain[s * P.S * P.W + i] = accept ? new_lp : old_lp;
     if (!P.step_ctr) return;                                 // host-driven steps: no device counters
     __threadfence();
     if (atomicAdd(P.ticket, 1u) == (unsigned)nS - 1u) {      // last walker of this half-step
@@ -153,14 +157,14 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
 // based, so the rows are identical on every rank), evaluates only its own rows, and after the all-gather applies
 // the same accept/reject to every walker.
 __device__ __forceinline__ void stretch_propose_row(const StretchParams& P, int split, int k, int& i_out,
-                                                    int& j_out, double& zz_out) {
+                                                    int& j_out, double& zz_out, int e = 0) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   const unsigned long long step = P.first_step + (P.step_ctr ? *P.step_ctr : 0ull);
   uint32_t pa, pb;
   stretch_perm(P, step, pa, pb);
   const int i = walker_at(pa, pb, P.W, offS + k);
-  const uint4 r = stretch_rand(P, step, (uint32_t)i, 1u + (uint32_t)split);
+  const uint4 r = stretch_rand(P, step, (uint32_t)(e * P.W + i), 1u + (uint32_t)split);
   const double u = u01(r.x, r.y);
   // explicitly rounded operations (no FMA contraction): the proposal is bit-identical to the numpy expression
   const double t = __dadd_rn(__dmul_rn(P.a - 1.0, u), 1.0);
@@ -170,29 +174,30 @@ __device__ __forceinline__ void stretch_propose_row(const StretchParams& P, int 
 }
 
 __global__ void __launch_bounds__(128) stretch_propose_kernel(const StretchParams P, int split) {
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp per row
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp per row
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
-  if (k >= nS) return;
+  if (r >= P.S * nS) return;
+  const int e = r / nS, k = r - e * nS;                // ensemble, row within its half
   int i, j;
   double zz;
-  stretch_propose_row(P, split, k, i, j, zz);
+  stretch_propose_row(P, split, k, i, j, zz, e);
   if (lane == 0) {
-    P.factors[k] = (P.ndim - 1.0) * log(zz);
-    P.walker_of[k] = i;
+    P.factors[r] = (P.ndim - 1.0) * log(zz);
+    P.walker_of[r] = i;
   }
-  const double* s = P.coords + (size_t)i * P.ndim;
-  const double* c = P.coords + (size_t)j * P.ndim;
+  const double* s = P.coords + ((size_t)e * P.W + i) * P.ndim;
+  const double* c = P.coords + ((size_t)e * P.W + j) * P.ndim;
   for (int d = lane; d < P.ndim; d += 32)
-    P.prop[(size_t)k * P.ndim + d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), zz));
+    P.prop[(size_t)r * P.ndim + d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), zz));
 }
 
 __global__ void __launch_bounds__(128) stretch_accept_kernel(const StretchParams P, int split) {
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp per row
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp per row
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
-  if (k >= nS) return;
-  stretch_accept_record(P, split, k, P.lnp_prop[k], lane);
+  if (r >= P.S * nS) return;
+  stretch_accept_record(P, split, r, P.lnp_prop[r], lane, r / nS);
 }
 
 }  // namespace rbv

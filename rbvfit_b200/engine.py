@@ -248,6 +248,31 @@ class Engine:
                                           n_accepted_t.data_ptr(), flag_t.data_ptr(), ws.data_ptr(), ws.numel(),
                                           self._stream()), "rbv_stretch_accept")
 
+    def stretch_run_sightlines(self, coords_t, lnp_t, n_steps: int, a: float, seed: int, first_step: int, chain_t,
+                               lnp_chain_t, n_accepted_t, flag_t):
+        """Survey-mode stretch move (rbv_stretch_run_sightlines): ``coords_t`` [S, W, ndim], one ensemble per
+        sightline of this context, all advancing in lockstep on the current torch stream; asynchronous."""
+        torch = _torch()
+        S, W, ndim = coords_t.shape
+        if ndim != self.ndim or S != len(self.pixels):
+            raise ValueError(f"coords must be [{len(self.pixels)}, walkers_per_sightline, {self.ndim}]")
+        for t, dt in ((coords_t, torch.float64), (lnp_t, torch.float64), (n_accepted_t, torch.int32),
+                      (flag_t, torch.int32)):
+            if t.dtype != dt or not t.is_contiguous() or t.device != self.tdev:
+                raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
+        nbytes = C.c_size_t(0)
+        check(self.lib.rbv_stretch_workspace_bytes_sightlines(self._h, W, C.byref(nbytes)),
+              "rbv_stretch_workspace_bytes_sightlines")
+        if self._stretch_ws is None or self._stretch_ws.numel() < nbytes.value:
+            self._stretch_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
+        check(self.lib.rbv_stretch_run_sightlines(
+            self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), float(a),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_step),
+            chain_t.data_ptr() if chain_t is not None else None,
+            lnp_chain_t.data_ptr() if lnp_chain_t is not None else None,
+            n_accepted_t.data_ptr(), flag_t.data_ptr(), self._stretch_ws.data_ptr(), self._stretch_ws.numel(),
+            self._stream()), "rbv_stretch_run_sightlines")
+
     def slice_run(self, coords_t, lnp_t, n_steps: int, tuning, seed: int, first_step: int, chain_t, lnp_chain_t,
                   flag_t) -> np.ndarray:
         """Device-resident ensemble slice sampling (rbv_slice_run) on the current torch stream; ``tuning`` is an

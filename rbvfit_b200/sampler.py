@@ -392,3 +392,157 @@ class DistributedDeviceSampler(DeviceEnsembleSampler):
         self.n_logp_calls += 2 * nsteps
         self.n_logp_rows += W * nsteps
         return self._append(chain_t, lps_t, nacc_t)
+
+
+class _SightlineView:
+    """One sightline of a ``SightlineEnsembleSampler`` behind emcee's accessor contract (what ``vfit`` /
+    ``UnifiedResults`` read from ``fitter.sampler``, core/unified_results.py:163-299)."""
+
+    def __init__(self, parent, index: int):
+        self._p, self._s = parent, int(index)
+        self.nwalkers, self.ndim = parent.nwalkers, parent.ndim
+
+    @property
+    def iteration(self):
+        return self._p.iteration
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self._p.get_chain(discard=discard, thin=thin, flat=flat, sightline=self._s)
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        return self._p.get_log_prob(discard=discard, thin=thin, flat=flat, sightline=self._s)
+
+    @property
+    def chain(self):
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def flatchain(self):
+        return self.get_chain(flat=True)
+
+    @property
+    def lnprobability(self):
+        return self.get_log_prob().T
+
+    @property
+    def acceptance_fraction(self):
+        return self._p.acceptance_fraction[self._s]
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
+
+
+class SightlineEnsembleSampler:
+    """Survey mode (BASELINE.json config 5): one stretch-move ensemble PER SIGHTLINE of a ``SightlineBatch``, all S
+    ensembles advancing in lockstep on the device (``rbv_stretch_run_sightlines``) -- the reference would run S
+    separate ``vfit(...).runmcmc()`` calls one after the other (vfit_mcmc.py:492-561).  Per half-step: one proposal
+    kernel over all S * W/2 rows, ONE sightline likelihood launch, one accept kernel; no host round trip, the chain
+    is copied to the host once per ``run_mcmc`` call.  Ensembles never mix.  Sightline 0 reproduces the chain of a
+    ``DeviceEnsembleSampler`` with the same seed on that sightline alone (same random streams).  Sightlines shard
+    across GPUs with no collective: every rank runs this sampler over its own ``SightlineBatch``.
+
+    ``sightline(s)`` returns a per-sightline object with emcee's accessors (``get_chain(discard, thin, flat)``,
+    ``acceptance_fraction``, ``get_autocorr_time`` ...)."""
+
+    def __init__(self, nwalkers: int, ndim: int, batch, a: float = 2.0, seed: Optional[int] = None):
+        if not hasattr(batch, "engine") or not hasattr(batch, "n_sightlines"):
+            raise TypeError("SightlineEnsembleSampler needs a SightlineBatch")
+        if batch.ndim != ndim:
+            raise ValueError(f"the sightline batch has ndim={batch.ndim}, sampler was given ndim={ndim}")
+        if nwalkers < 2:
+            raise ValueError("need at least two walkers per sightline")
+        self.batch = batch
+        self.n_sightlines = int(batch.n_sightlines)
+        self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
+        self._seed = int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
+        self._stream = None
+        self.reset()
+
+    def reset(self):
+        S, W, nd = self.n_sightlines, self.nwalkers, self.ndim
+        self._chain = np.empty((0, S, W, nd))
+        self._log_prob = np.empty((0, S, W))
+        self._accepted = np.zeros((S, W))
+        self.iteration = 0
+        self._state = None
+        self._last = None
+
+    def run_mcmc(self, initial_state, nsteps, progress=False, skip_initial_state_check=False, **_ignored):
+        import torch
+        eng = self.batch.engine
+        dev = eng.tdev
+        S, W, nd = self.n_sightlines, self.nwalkers, self.ndim
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        with torch.cuda.stream(self._stream):
+            if initial_state is None:
+                if self._state is None:
+                    raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
+                coords_t, lnp_t = self._state
+            else:
+                coords = np.array(initial_state, dtype=np.float64, copy=True)
+                if coords.shape != (S, W, nd):
+                    raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+                if not np.all(np.isfinite(coords)):
+                    raise ValueError("At least one parameter value was infinite or NaN")
+                if not skip_initial_state_check and not all(walkers_independent(c) for c in coords):
+                    raise ValueError("Initial state has a large condition number. Make sure that your walkers are "
+                                     "linearly independent for the best performance")
+                coords_t = torch.as_tensor(coords, device=dev)
+                lnp_t = eng.lnprob_sightlines_device(coords_t.view(S * W, nd), W).view(S, W)
+                if bool(torch.isnan(lnp_t).any()):
+                    raise ValueError("Probability function returned NaN")
+            chain_t = torch.empty((nsteps, S, W, nd), dtype=torch.float64, device=dev)
+            lps_t = torch.empty((nsteps, S, W), dtype=torch.float64, device=dev)
+            nacc_t = torch.zeros((S, W), dtype=torch.int32, device=dev)
+            flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
+            eng.stretch_run_sightlines(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t,
+                                       nacc_t, flag_t)
+            self._stream.synchronize()
+            if int(flag_t.item()) & 1:
+                raise ValueError("Probability function returned NaN")
+            self._state = (coords_t, lnp_t)
+            chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
+            self._accepted += nacc_t.cpu().numpy()
+        if len(self._chain) == 0:
+            self._chain, self._log_prob = chain, lps
+        else:
+            self._chain = np.concatenate([self._chain, chain], axis=0)
+            self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self.iteration += nsteps
+        if nsteps:
+            self._last = (chain[-1].copy(), lps[-1].copy())
+        return self._last
+
+    def _get(self, arr, discard, thin, flat, sightline):
+        v = arr[discard + thin - 1:: thin]
+        if sightline is not None:
+            v = v[:, int(sightline)]
+            if flat:
+                return v.reshape((-1,) + v.shape[2:])
+            return v
+        if flat:                                  # [S, steps * W, ...]: flat per sightline, never across sightlines
+            v = np.swapaxes(v, 0, 1)
+            return v.reshape((v.shape[0], -1) + v.shape[3:])
+        return v
+
+    def get_chain(self, discard=0, thin=1, flat=False, sightline=None):
+        """[steps, S, W, ndim]; ``sightline=s`` -> [steps, W, ndim]; ``flat`` merges steps and walkers of a sightline."""
+        return self._get(self._chain, discard, thin, flat, sightline)
+
+    def get_log_prob(self, discard=0, thin=1, flat=False, sightline=None):
+        return self._get(self._log_prob, discard, thin, flat, sightline)
+
+    @property
+    def acceptance_fraction(self):
+        """[S, W]"""
+        return self._accepted / max(self.iteration, 1)
+
+    def sightline(self, index: int) -> _SightlineView:
+        if not 0 <= int(index) < self.n_sightlines:
+            raise IndexError(index)
+        return _SightlineView(self, index)
+
+    def get_last_sample(self):
+        return self._last

@@ -231,4 +231,38 @@ def test_no_writes_outside_caller_buffers():
         assert torch.all(torch.isfinite(b[PAD:PAD + n])) and not torch.any(b[PAD:PAD + n] == SENT), name
     assert torch.all(nacc[:PAD] == -7) and torch.all(nacc[PAD + W:] == -7) and int(nacc[PAD:PAD + W].sum()) > 0
     assert torch.all(big_ws[:PAD] == SENT) and torch.all(big_ws[PAD + nws:] == SENT)
+    # slice sampler (odd ensemble: halves of 12 and 11 walkers, two candidate rows per walker)
+    from rbvfit_b200._lib import RbvSliceTuning
+    W = 23
+    ok = wl.make_ensemble(w, 60)
+    ok = ok[np.all((ok >= w["lb"]) & (ok <= w["ub"]), axis=1)][:W]
+    for name, n in (("coords", W * nd), ("lnp", W), ("chain", nsteps * W * nd), ("lps", nsteps * W)):
+        bufs[name] = torch.full((n + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+    bufs["coords"][PAD:PAD + W * nd] = torch.as_tensor(ok.ravel(), device="cuda")
+    bufs["lnp"][PAD:PAD + W] = torch.as_tensor(like.lnprob(ok), device="cuda")
+    check(lib.rbv_slice_workspace_bytes(eng._h, W, C.byref(nbytes)))
+    nws = (int(nbytes.value) + 7) // 8
+    big_ws = torch.full((nws + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+    tuning = RbvSliceTuning(mu=1.0, tolerance=0.05, tune=1, good=0, patience=5, maxsteps=10000, maxiter=10000)
+    mus = np.full(nsteps + 2, SENT)
+    torch.cuda.synchronize()
+    check(lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), W, nsteps,
+                            C.byref(tuning), 99, 0, bufs["chain"][PAD:].data_ptr(), bufs["lps"][PAD:].data_ptr(),
+                            mus[1:].ctypes.data_as(C.POINTER(C.c_double)), flag.data_ptr(), big_ws[PAD:].data_ptr(),
+                            int(nbytes.value), st.cuda_stream), "rbv_slice_run")
+    torch.cuda.synchronize()
+    for name, n in (("coords", W * nd), ("lnp", W), ("chain", nsteps * W * nd), ("lps", nsteps * W)):
+        b = bufs[name]
+        assert torch.all(b[:PAD] == SENT) and torch.all(b[PAD + n:] == SENT), name
+        assert torch.all(torch.isfinite(b[PAD:PAD + n])) and not torch.any(b[PAD:PAD + n] == SENT), name
+    assert torch.all(big_ws[:PAD] == SENT) and torch.all(big_ws[PAD + nws:] == SENT)
+    assert mus[0] == SENT and mus[-1] == SENT and np.all(mus[1:-1] > 0) and int(flag.item()) == 0
+    assert tuning.n_calls >= 3 * W * nsteps and tuning.n_batches >= 2 * 3 * nsteps and tuning.mu == mus[-2]
+    # argument checks of the entry point
+    assert lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), 3, nsteps,
+                             C.byref(tuning), 99, 0, None, None, None, flag.data_ptr(), big_ws[PAD:].data_ptr(),
+                             int(nbytes.value), st.cuda_stream) == 1                       # RBV_EINVAL: W < 4
+    assert lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), W, nsteps,
+                             C.byref(tuning), 99, 0, None, None, None, flag.data_ptr(), big_ws[PAD:].data_ptr(),
+                             int(nbytes.value) - 256, st.cuda_stream) == 3                 # RBV_ENOMEM
     like.close()

@@ -337,3 +337,67 @@ def test_device_slice_sampler_bookkeeping_continuation_and_posterior():
     f3.device_sampler = False
     f3.runmcmc(optimize=False, verbose=False, progress=False)
     assert type(f3.sampler) is EnsembleSliceSampler and f3.sampler.get_chain().shape == (110, 24, 6)
+
+
+def test_sightline_sampler_equals_independent_replays():
+    """rbv_stretch_run_sightlines (survey mode: one ensemble per sightline, lockstep on the device): every
+    sightline's chain equals the numpy replay of ITS ensemble driven by its own single-sightline GPU likelihood
+    (ensembles never mix, random streams offset per sightline), sightline 0 equals the single-ensemble device sampler,
+    bookkeeping and continuation hold, and the per-sightline view has emcee's accessors."""
+    from oracle import stretch_replay as sr
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.likelihood import GpuLikelihood, SightlineBatch
+    from rbvfit_b200.model import GpuVoigtModel
+    from rbvfit_b200.sampler import DeviceEnsembleSampler, SightlineEnsembleSampler
+    S, nsteps = 5, 40
+    sight, singles = [], []
+    w0 = wl.c5b_sightline(0)
+    for s in range(S):
+        w = wl.c5b_sightline(s)
+        cfg = FitConfiguration()
+        for (z, ion, trans, comps) in w["systems"]:
+            cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+        m = GpuVoigtModel(cfg, FWHM="6.5")
+        c = m.compile()
+        sp = wl.make_spectra(w, lambda n, th, wave: c.model_flux(th, wave))["COS"]
+        sight.append(dict(model=m, **sp))
+        singles.append(GpuLikelihood({"COS": dict(model=m, **sp)}, w["lb"], w["ub"]))
+    batch = SightlineBatch(sight, w0["lb"], w0["ub"])
+    nd = batch.ndim
+    rng = np.random.default_rng(12)
+    for W in (14, 9):                                    # even and odd ensembles
+        p0 = np.clip(w0["theta_true"] + 1e-3 * rng.standard_normal((S, W, nd)), w0["lb"], w0["ub"])
+        smp = SightlineEnsembleSampler(W, nd, batch, seed=31)
+        smp.run_mcmc(p0, nsteps)
+        chain, lps = smp.get_chain(), smp.get_log_prob()
+        assert chain.shape == (nsteps, S, W, nd) and lps.shape == (nsteps, S, W)
+        assert smp.get_chain(flat=True, discard=10).shape == (S, (nsteps - 10) * W, nd)
+        assert np.all(chain >= w0["lb"]) and np.all(chain <= w0["ub"]) and np.all(np.isfinite(lps))
+        got = batch.lnprob(chain[-1])
+        assert np.max(np.abs(got - lps[-1]) / np.abs(got)) <= 1e-12
+        for e in range(S):
+            like = singles[e]
+            ref_chain, ref_lps, nacc = sr.run(like.lnprob, p0[e], like.lnprob(p0[e]), nsteps, smp._seed,
+                                              walker_offset=e * W)
+            assert np.allclose(chain[:, e], ref_chain, rtol=0, atol=1e-9), e
+            assert np.max(np.abs(lps[:, e] - ref_lps) / np.abs(ref_lps)) <= 1e-9
+            assert np.array_equal(np.rint(smp.acceptance_fraction[e] * nsteps).astype(int), nacc)
+        assert 0.15 < smp.acceptance_fraction.mean() < 0.9
+        one = DeviceEnsembleSampler(W, nd, singles[0], seed=31)
+        one.run_mcmc(p0[0], nsteps)
+        assert np.allclose(one.get_chain(), chain[:, 0], rtol=0, atol=1e-9)
+        view = smp.sightline(2)
+        assert view.get_chain(discard=5, flat=True).shape == ((nsteps - 5) * W, nd)
+        assert np.array_equal(view.get_chain(), chain[:, 2]) and view.acceptance_fraction.shape == (W,)
+        assert view.chain.shape == (W, nsteps, nd) and view.get_autocorr_time(quiet=True).shape == (nd,)
+        cont = SightlineEnsembleSampler(W, nd, batch, seed=31)
+        cont.run_mcmc(p0, 25)
+        cont.run_mcmc(None, nsteps - 25)
+        assert np.array_equal(cont.get_chain(), chain) and np.array_equal(cont.acceptance_fraction,
+                                                                          smp.acceptance_fraction)
+    with pytest.raises(ValueError):
+        SightlineEnsembleSampler(14, nd, batch).run_mcmc(p0[:2], 3)
+    with pytest.raises(TypeError):
+        SightlineEnsembleSampler(14, nd, singles[0])
+    with pytest.raises(IndexError):
+        smp.sightline(S)
