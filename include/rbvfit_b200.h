@@ -192,15 +192,20 @@ int rbv_stretch_run_sightlines(RbvContext* ctx, double* coords, double* lnprob, 
  * the workspace; one iteration = candidate kernel -> the lnprob launch over the half (masked rows skipped) -> update
  * kernel.  Both ends of a widening bracket are evaluated in the same iteration (two rows per walker), so a half-step
  * costs as many device batches as the longest chain max(n_L, n_R) + 1 + n_shrink any one walker needs.
- * Between iterations the host only reads back a 24-byte counter block (one iteration behind the device, so the GPU
- * never waits for it) to learn when the half-step is complete; ensemble, directions, brackets and the chain never
- * leave the device.  Random numbers: the Philox streams of rbv_stretch_run (purposes 8.., see rbv_slice.cuh), so a
- * run continued with first_step = steps already done reproduces one long run.
+ * The loop state (step, iteration, unfinished walkers, mu and its adaptation) lives in device memory.  use_graph != 0
+ * (needs a non-default stream): the iteration is the body of a CUDA-graph WHILE node whose condition the update kernel
+ * sets, so a half-step is ONE graph launch and the whole run is enqueued without a host synchronisation.
+ * use_graph == 0: the host enqueues iterations one ahead of an asynchronous read-back of the counters (the device
+ * never waits; one fully masked batch per half-step is the price).  Both modes produce the same chain.
+ * Ensemble, directions, brackets and the chain never leave the device.  Random numbers: the Philox streams of
+ * rbv_stretch_run (purposes 8.., see rbv_slice.cuh), so a run continued with first_step = steps already done
+ * reproduces one long run.
  *   coords, lnprob   DEVICE [n_walkers, ndim] / [n_walkers], updated in place (n_walkers >= 4)
  *   tuning           HOST, in/out: scale mu and its adaptation state (zeus: tune, tolerance 0.05, patience 5,
- *                    maxsteps 10000, maxiter 10000); the totals of this run are written to the n_* fields
+ *                    maxsteps 10000, maxiter 10000), adapted on the device after every step; the totals of this run
+ *                    are written to the n_* fields
  *   chain            DEVICE [n_steps, n_walkers, ndim] or NULL; lnprob_chain DEVICE [n_steps, n_walkers] or NULL
- *   mu_history       HOST [n_steps] or NULL: mu after each step
+ *   mu_history       DEVICE [n_steps] or NULL: mu after each step
  *   flag             DEVICE int, bit 0 set if a candidate's lnprob was NaN
  *   workspace        DEVICE, rbv_slice_workspace_bytes().  The call returns after the run has finished. */
 typedef struct RbvSliceTuning {
@@ -219,7 +224,8 @@ typedef struct RbvSliceTuning {
 int rbv_slice_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
 int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, RbvSliceTuning* tuning,
                   unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
-                  double* mu_history, int* flag, void* workspace, size_t workspace_bytes, void* stream);
+                  double* mu_history, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                  void* stream);
 
 /* Model flux for a batch of walkers on instrument `inst`; CompiledVoigtModel.model_flux,
  * voigt_model.py:295-311 (convolve != 0) or VoigtModel.evaluate(return_unconvolved=True), :509-558.

@@ -1793,7 +1793,8 @@ int rbv_slice_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* byte
 
 int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, RbvSliceTuning* tuning,
                   unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
-                  double* mu_history, int* flag, void* workspace, size_t workspace_bytes, void* stream) {
+                  double* mu_history, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                  void* stream) {
   if (!ctx || !coords || !lnprob || !tuning || !flag) return fail(RBV_EINVAL, "rbv_slice_run: null argument");
   if (n_walkers < 4) return fail(RBV_EINVAL, "rbv_slice_run: need at least four walkers (two per complement)");
   if (n_steps < 0 || !(tuning->mu > 0.0) || tuning->maxsteps < 1 || tuning->maxiter < 1)
@@ -1823,80 +1824,142 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   P.flag = flag;
   P.ctr = (SliceCounters*)(ws + lay.ctr);
   P.seed = seed;
-  P.mu = tuning->mu;
+  P.tolerance = tuning->tolerance;
   P.W = n_walkers;
   P.ndim = ctx->ndim;
   P.maxsteps = tuning->maxsteps;
-  RBV_CUDA(cudaMemsetAsync(P.ctr, 0, sizeof(SliceCounters), st));
+  P.maxiter = tuning->maxiter;
+  P.patience = tuning->patience;
+  {   // loop state: everything zero except mu and its adaptation state (the host slot is reused by the polls below)
+    SliceCounters init;
+    memset(&init, 0, sizeof(init));
+    init.mu = tuning->mu;
+    init.tune = tuning->tune != 0;
+    init.good = tuning->good;
+    ctx->h_poll[0] = init;
+    RBV_CUDA(cudaMemcpyAsync(P.ctr, &ctx->h_poll[0], sizeof(SliceCounters), cudaMemcpyHostToDevice, st));
+    RBV_CUDA(cudaStreamSynchronize(st));
+  }
   const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
   const int h = (n_walkers + 1) / 2;
-  unsigned long long total_exp = 0, total_con = 0, batches = 0, calls = 0;
+  const long long launches_before = ctx->launches;
 
-  for (int s = 0; s < n_steps; ++s) {
-    const unsigned long long step = first_step + (unsigned long long)s;
-    unsigned int nexp = 0, ncon = 0;
-    for (int split = 0; split < 2; ++split) {
+  // one iteration of half `split`: candidates -> lnprob of the 2 n_S rows (masked rows skipped) -> update
+  auto iteration = [&](int split, int rows, cudaGraphConditionalHandle loop, int use_loop) -> int {
+    const int nS = split == 0 ? h : n_walkers - h;
+    const unsigned rows_grid = (unsigned)((nS + 3) / 4);
+    slice_candidate_kernel<<<rows_grid, 128, 0, st>>>(P, split, loop, use_loop);
+    RBV_CUDA(cudaGetLastError());
+    int rc = launch_lnprob(ctx, P.cand, rows, 0, P.lnp_cand, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
+                           "rbv_slice_run", nullptr, -1, P.skip);
+    if (rc != RBV_OK) return rc;
+    slice_update_kernel<<<rows_grid, 128, 0, st>>>(P, split, loop, use_loop);
+    RBV_CUDA(cudaGetLastError());
+    return RBV_OK;
+  };
+  auto begin = [&](unsigned long long step, int split) -> int {
+    const int nS = split == 0 ? h : n_walkers - h;
+    slice_begin_kernel<<<(unsigned)((nS + 3) / 4), 128, 0, st>>>(P, step, split);
+    RBV_CUDA(cudaGetLastError());
+    return RBV_OK;
+  };
+  auto record = [&](int s) -> int {
+    slice_record_kernel<<<(unsigned)((n_walkers + 3) / 4), 128, 0, st>>>(
+        P, chain ? chain + (size_t)s * n_walkers * ctx->ndim : nullptr,
+        lnprob_chain ? lnprob_chain + (size_t)s * n_walkers : nullptr, mu_history ? mu_history + s : nullptr);
+    RBV_CUDA(cudaGetLastError());
+    return RBV_OK;
+  };
+
+  int rc = RBV_OK;
+  long long per_iteration = 0;
+  if (use_graph && st != nullptr) {
+    // Graph mode: per half a graph whose only node is a WHILE node; its body is one iteration, captured from the
+    // stream, and slice_update_kernel sets the condition.  A step = begin, graph, begin, graph, record -- five
+    // asynchronous launches whatever the number of iterations, and no host synchronisation inside the run.
+    cudaGraph_t graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int split = 0; split < 2 && rc == RBV_OK && e == cudaSuccess; ++split) {
       const int nS = split == 0 ? h : n_walkers - h;
-      const unsigned rows_grid = (unsigned)((nS + 3) / 4);
-      slice_begin_kernel<<<rows_grid, 128, 0, st>>>(P, step, split);
-      RBV_CUDA(cudaGetLastError());
-      ctx->launches++;
-      // Iterations are enqueued one ahead of the read-back: while the host waits for the counters of iteration
-      // it - 1 the device already runs iteration it.  When it - 1 left nothing to do, iteration it found every row
-      // masked and changed nothing.  The batch has 2 n_S rows (both bracket ends) until the counters show that no
-      // walker widens any more -- the count never grows within a half-step, so acting on it one iteration late is safe.
-      bool done = false, widening = true;
-      for (int it = 0; !done; ++it) {
-        if (it > tuning->maxiter) {
-          cudaStreamSynchronize(st);
-          return fail(RBV_ESTATE, "rbv_slice_run: number of contractions exceeded the maximum (maxiter)");
-        }
-        slice_candidate_kernel<<<rows_grid, 128, 0, st>>>(P, step, split, it);
-        RBV_CUDA(cudaGetLastError());
-        ctx->launches++;
-        int rc = launch_lnprob(ctx, P.cand, widening ? 2 * nS : nS, 0, P.lnp_cand, ws + lay.lnprob_ws, lnprob_ws_bytes,
-                               stream, "rbv_slice_run", nullptr, -1, P.skip);
+      e = cudaGraphCreate(&graph[split], 0);
+      if (e != cudaSuccess) break;
+      cudaGraphConditionalHandle loop;
+      e = cudaGraphConditionalHandleCreate(&loop, graph[split], 1, cudaGraphCondAssignDefault);
+      if (e != cudaSuccess) break;
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.conditional.handle = loop;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      e = cudaGraphAddNode(&node, graph[split], nullptr, 0, &np);
+      if (e != cudaSuccess) break;
+      e = cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                        cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) break;
+      const long long l0 = ctx->launches;
+      rc = iteration(split, 2 * nS, loop, 1);
+      per_iteration = ctx->launches - l0 + 2;
+      cudaGraph_t captured = nullptr;
+      e = cudaStreamEndCapture(st, &captured);
+      if (e != cudaSuccess || rc != RBV_OK) break;
+      e = cudaGraphInstantiate(&exec[split], graph[split], 0);
+    }
+    for (int s = 0; s < n_steps && rc == RBV_OK && e == cudaSuccess; ++s) {
+      for (int split = 0; split < 2 && rc == RBV_OK && e == cudaSuccess; ++split) {
+        rc = begin(first_step + (unsigned long long)s, split);
+        if (rc == RBV_OK) e = cudaGraphLaunch(exec[split], st);
+      }
+      if (rc == RBV_OK && e == cudaSuccess) rc = record(s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    for (int k = 0; k < 2; ++k) {
+      if (exec[k]) cudaGraphExecDestroy(exec[k]);
+      if (graph[k]) cudaGraphDestroy(graph[k]);
+    }
+    if (rc != RBV_OK) return rc;
+    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("rbv_slice_run (graph): ") + cudaGetErrorString(e));
+  } else {
+    // Polling mode: iterations are enqueued one ahead of the read-back of the counters -- while the host waits for
+    // those of iteration it - 1 the device already runs iteration it; when it - 1 left nothing to do, iteration it
+    // found every row masked and changed nothing.  (The batch always has 2 n_S rows, as in graph mode: masked rows
+    // cost a CTA prologue each, and the two modes then produce bit-identical chains.)
+    for (int s = 0; s < n_steps; ++s) {
+      for (int split = 0; split < 2; ++split) {
+        const int nS = split == 0 ? h : n_walkers - h;
+        rc = begin(first_step + (unsigned long long)s, split);
         if (rc != RBV_OK) return rc;
-        slice_update_kernel<<<rows_grid, 128, 0, st>>>(P, split);
-        RBV_CUDA(cudaGetLastError());
-        ctx->launches++;
-        ++batches;
-        RBV_CUDA(cudaMemcpyAsync(&ctx->h_poll[it & 1], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost, st));
-        RBV_CUDA(cudaEventRecord(ctx->poll_ev[it & 1], st));
-        if (it >= 1) {
-          RBV_CUDA(cudaEventSynchronize(ctx->poll_ev[(it - 1) & 1]));
-          const SliceCounters& c = ctx->h_poll[(it - 1) & 1];
-          if (c.widening == 0u) widening = false;
-          if (c.remaining == 0u) {
-            done = true;
-            nexp = c.nexp;
-            ncon = c.ncon;
-            calls = c.ncall;
+        bool done = false;
+        for (int it = 0; !done; ++it) {
+          const long long l0 = ctx->launches;
+          rc = iteration(split, 2 * nS, 0, 0);
+          if (rc != RBV_OK) return rc;
+          per_iteration = ctx->launches - l0 + 2;
+          RBV_CUDA(cudaMemcpyAsync(&ctx->h_poll[it & 1], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost, st));
+          RBV_CUDA(cudaEventRecord(ctx->poll_ev[it & 1], st));
+          if (it >= 1) {
+            RBV_CUDA(cudaEventSynchronize(ctx->poll_ev[(it - 1) & 1]));
+            const SliceCounters& c = ctx->h_poll[(it - 1) & 1];
+            if (c.remaining == 0u || c.error) done = true;
           }
         }
       }
+      rc = record(s);
+      if (rc != RBV_OK) return rc;
     }
-    slice_record_kernel<<<(unsigned)((n_walkers + 3) / 4), 128, 0, st>>>(
-        P, chain ? chain + (size_t)s * n_walkers * ctx->ndim : nullptr,
-        lnprob_chain ? lnprob_chain + (size_t)s * n_walkers : nullptr);
-    RBV_CUDA(cudaGetLastError());
-    ctx->launches++;
-    total_exp += nexp;
-    total_con += ncon;
-    if (tuning->tune) {     // zeus: stochastic approximation of mu towards an expansion fraction of 1/2
-      const double ne = (double)std::max(nexp, 1u), tot = ne + (double)ncon;
-      P.mu = P.mu * (2.0 * ne / tot);
-      if (std::fabs(ne / tot - 0.5) < tuning->tolerance) tuning->good += 1;
-      if (tuning->good > tuning->patience) tuning->tune = 0;
-    }
-    if (mu_history) mu_history[s] = P.mu;
+    RBV_CUDA(cudaStreamSynchronize(st));
   }
-  RBV_CUDA(cudaStreamSynchronize(st));
-  tuning->mu = P.mu;
-  tuning->n_expansions = total_exp;
-  tuning->n_contractions = total_con;
-  tuning->n_calls = calls;
-  tuning->n_batches = batches;
+  RBV_CUDA(cudaMemcpy(&ctx->h_poll[0], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost));
+  const SliceCounters& c = ctx->h_poll[0];
+  ctx->launches = launches_before + (long long)c.batches * per_iteration + 3LL * n_steps;
+  tuning->mu = c.mu;
+  tuning->tune = c.tune;
+  tuning->good = c.good;
+  tuning->n_expansions = c.total_exp;
+  tuning->n_contractions = c.total_con;
+  tuning->n_calls = c.ncall;
+  tuning->n_batches = c.batches;
+  if (c.error) return fail(RBV_ESTATE, "rbv_slice_run: number of contractions exceeded the maximum (maxiter)");
   return RBV_OK;
 }
 

@@ -274,9 +274,11 @@ class Engine:
             self._stream()), "rbv_stretch_run_sightlines")
 
     def slice_run(self, coords_t, lnp_t, n_steps: int, tuning, seed: int, first_step: int, chain_t, lnp_chain_t,
-                  flag_t) -> np.ndarray:
+                  flag_t, use_graph: bool = True) -> np.ndarray:
         """Device-resident ensemble slice sampling (rbv_slice_run) on the current torch stream; ``tuning`` is an
-        ``RbvSliceTuning`` updated in place.  Returns mu after each step; the call returns when the run is done."""
+        ``RbvSliceTuning`` updated in place.  ``use_graph``: the per-half-step loop is a CUDA-graph WHILE node (needs
+        a non-default stream), otherwise the host polls the device counters.  Returns mu after each step; the call
+        returns when the run is done."""
         torch = _torch()
         W, ndim = coords_t.shape
         if ndim != self.ndim:
@@ -288,15 +290,15 @@ class Engine:
         check(self.lib.rbv_slice_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_slice_workspace_bytes")
         if self._slice_ws is None or self._slice_ws.numel() < nbytes.value:
             self._slice_ws = torch.empty(int(nbytes.value), dtype=torch.uint8, device=self.tdev)
-        mus = np.empty(max(int(n_steps), 1), dtype=np.float64)
+        mus_t = torch.zeros(max(int(n_steps), 1), dtype=torch.float64, device=self.tdev)
         check(self.lib.rbv_slice_run(
             self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), C.byref(tuning),
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_step),
             chain_t.data_ptr() if chain_t is not None else None,
             lnp_chain_t.data_ptr() if lnp_chain_t is not None else None,
-            _dptr(mus), flag_t.data_ptr(), self._slice_ws.data_ptr(), self._slice_ws.numel(), self._stream()),
-            "rbv_slice_run")
-        return mus[:int(n_steps)]
+            mus_t.data_ptr(), flag_t.data_ptr(), self._slice_ws.data_ptr(), self._slice_ws.numel(),
+            int(bool(use_graph)), self._stream()), "rbv_slice_run")
+        return mus_t.cpu().numpy()[:int(n_steps)]
 
     def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:
         """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``."""

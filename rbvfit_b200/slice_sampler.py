@@ -199,15 +199,16 @@ class EnsembleSliceSampler:
 
 class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
     """Same move, same accessor contract, but the whole loop runs on the GPU (``rbv_slice_run``, C ABI): directions,
-    slice levels, brackets and the per-walker widen / shrink state machines live in device memory, every iteration
-    is one masked likelihood batch over the active half, and the chain is copied to the host once per ``run_mcmc``
-    call.  ``likelihood`` is a ``GpuLikelihood``; random numbers come from the counter-based Philox streams of the
+    slice levels, brackets, the per-walker widen / shrink state machines and the adaptation of mu live in device
+    memory, every iteration is one masked likelihood batch over the active half -- the body of a CUDA-graph WHILE
+    node whose condition the device sets (``use_graph=False``: the host polls a counter block instead) -- and the
+    chain is copied to the host once per ``run_mcmc`` call.  ``likelihood`` is a ``GpuLikelihood``; random numbers come from the counter-based Philox streams of the
     device stretch move, so a run is reproducible and can be continued (``run_mcmc(None, n)``) without changing
     the stream of one long run (``oracle/slice_replay.py`` restates it in numpy for the tests)."""
 
     def __init__(self, nwalkers: int, ndim: int, likelihood, mu: float = 1.0, tune: bool = True,
                  tolerance: float = 0.05, patience: int = 5, maxsteps: int = 10000, maxiter: int = 10000,
-                 seed: Optional[int] = None, **_ignored):
+                 seed: Optional[int] = None, use_graph: bool = True, **_ignored):
         if not hasattr(likelihood, "engine"):
             raise TypeError("DeviceEnsembleSliceSampler needs a GpuLikelihood (the log-probability must run on "
                             "the device)")
@@ -218,6 +219,7 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
         self._stream = None
         self._state = None
         self.good = 0
+        self.use_graph = bool(use_graph)
         super().__init__(nwalkers, ndim, likelihood.lnprob, mu=mu, tune=tune, tolerance=tolerance,
                          patience=patience, maxsteps=maxsteps, maxiter=maxiter, seed=seed)
 
@@ -255,7 +257,8 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
             flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
             tuning = RbvSliceTuning(mu=self.mu, tolerance=self.tolerance, tune=int(self.tune), good=int(self.good),
                                     patience=self.patience, maxsteps=self.maxsteps, maxiter=self.maxiter)
-            mus = eng.slice_run(coords_t, lnp_t, nsteps, tuning, self._seed, self.iteration, chain_t, lps_t, flag_t)
+            mus = eng.slice_run(coords_t, lnp_t, nsteps, tuning, self._seed, self.iteration, chain_t, lps_t, flag_t,
+                                use_graph=self.use_graph)
             self._stream.synchronize()
             if int(flag_t.item()) & 1:
                 raise ValueError("Probability function returned NaN")

@@ -244,13 +244,14 @@ def test_no_writes_outside_caller_buffers():
     nws = (int(nbytes.value) + 7) // 8
     big_ws = torch.full((nws + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
     tuning = RbvSliceTuning(mu=1.0, tolerance=0.05, tune=1, good=0, patience=5, maxsteps=10000, maxiter=10000)
-    mus = np.full(nsteps + 2, SENT)
+    mus_t = torch.full((nsteps + 2,), SENT, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
     check(lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), W, nsteps,
                             C.byref(tuning), 99, 0, bufs["chain"][PAD:].data_ptr(), bufs["lps"][PAD:].data_ptr(),
-                            mus[1:].ctypes.data_as(C.POINTER(C.c_double)), flag.data_ptr(), big_ws[PAD:].data_ptr(),
-                            int(nbytes.value), st.cuda_stream), "rbv_slice_run")
+                            mus_t[1:].data_ptr(), flag.data_ptr(), big_ws[PAD:].data_ptr(),
+                            int(nbytes.value), 1, st.cuda_stream), "rbv_slice_run")
     torch.cuda.synchronize()
+    mus = mus_t.cpu().numpy()
     for name, n in (("coords", W * nd), ("lnp", W), ("chain", nsteps * W * nd), ("lps", nsteps * W)):
         b = bufs[name]
         assert torch.all(b[:PAD] == SENT) and torch.all(b[PAD + n:] == SENT), name
@@ -261,8 +262,15 @@ def test_no_writes_outside_caller_buffers():
     # argument checks of the entry point
     assert lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), 3, nsteps,
                              C.byref(tuning), 99, 0, None, None, None, flag.data_ptr(), big_ws[PAD:].data_ptr(),
-                             int(nbytes.value), st.cuda_stream) == 1                       # RBV_EINVAL: W < 4
+                             int(nbytes.value), 1, st.cuda_stream) == 1                    # RBV_EINVAL: W < 4
     assert lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), W, nsteps,
                              C.byref(tuning), 99, 0, None, None, None, flag.data_ptr(), big_ws[PAD:].data_ptr(),
-                             int(nbytes.value) - 256, st.cuda_stream) == 3                 # RBV_ENOMEM
+                             int(nbytes.value) - 256, 1, st.cuda_stream) == 3              # RBV_ENOMEM
+    # a half-step that needs more than maxiter iterations ends the run with RBV_ESTATE in both loop modes
+    for use_graph in (1, 0):
+        short = RbvSliceTuning(mu=1.0, tolerance=0.05, tune=1, good=0, patience=5, maxsteps=10000, maxiter=1)
+        assert lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), W, 2,
+                                 C.byref(short), 99, 0, None, None, None, flag.data_ptr(), big_ws[PAD:].data_ptr(),
+                                 int(nbytes.value), use_graph, st.cuda_stream) == 4        # RBV_ESTATE
+        assert b"maxiter" in lib.rbv_last_error()
     like.close()

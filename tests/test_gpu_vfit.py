@@ -270,7 +270,8 @@ def test_distributed_device_sampler_single_rank_and_multi_gpu():
 def test_device_slice_sampler_matches_numpy_replay():
     """rbv_slice_run against its numpy restatement (oracle/slice_replay.py: same Philox streams, same lockstep
     state machines, same mu adaptation) driven by the GPU lnprob: identical candidates, identical decisions, the
-    same counters.  The device launches exactly one speculative batch per half-step on top of the replay's."""
+    same counters, in graph mode (WHILE node, device-set condition) and in host-polled mode, which launches exactly
+    one masked batch per half-step on top."""
     from oracle import slice_replay as sl
     from rbvfit_b200.slice_sampler import DeviceEnsembleSliceSampler
     w, fitter, comp, theta0 = _c1_fitter()
@@ -284,8 +285,14 @@ def test_device_slice_sampler_matches_numpy_replay():
         assert np.allclose(dev.get_chain(), ref["chain"], rtol=0, atol=1e-9)
         assert np.max(np.abs(dev.get_log_prob() - ref["lnp_chain"]) / np.abs(ref["lnp_chain"])) <= 1e-9
         assert (dev.nexp, dev.ncon) == (ref["nexp"], ref["ncon"])
-        assert dev.ncall == W + ref["ncall"] and dev.nbatches == 1 + ref["nbatches"] + 2 * nsteps
+        assert dev.ncall == W + ref["ncall"] and dev.nbatches == 1 + ref["nbatches"]
         assert dev.mu == ref["mu"] and dev.tune == ref["tune"] and np.array_equal(dev.mus, ref["mus"][:len(dev.mus)])
+        poll = DeviceEnsembleSliceSampler(W, 6, like, seed=77, use_graph=False)      # host-polled loop: same chain
+        poll.run_mcmc(p0, nsteps)
+        assert np.array_equal(poll.get_chain(), dev.get_chain()) and np.array_equal(poll.get_log_prob(),
+                                                                                    dev.get_log_prob())
+        assert (poll.mu, poll.ncall, poll.nexp, poll.ncon) == (dev.mu, dev.ncall, dev.nexp, dev.ncon)
+        assert poll.nbatches == dev.nbatches + 2 * nsteps        # one masked batch per half-step
 
 
 def test_device_slice_sampler_bookkeeping_continuation_and_posterior():
