@@ -503,17 +503,21 @@ __device__ __forceinline__ void tau_fast(int lc_off, int L, const double (&u)[PP
 // One thread per (walker, line of any instrument): theta row -> the 20-double line-constant record, once per
 // walker instead of once per tile (pow, five divisions and the 13 series coefficients are ~400 dependent
 // FP64 instructions -- as long as a tile's whole phase 1 when done by 33 threads of every CTA).
-// Thread 0 of each walker also evaluates the uniform prior (vfit.lnprior, vfit_mcmc.py:291-295).
+// The walker's first block also evaluates the uniform prior (vfit.lnprior, vfit_mcmc.py:291-295), one parameter per
+// thread + a block-wide OR (a single thread walking 36 parameters was a 3 us chain of dependent L2 round trips).
 __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w, int g, const double* __restrict__ th) {
   const bool skipped = prm.row_skip != nullptr && prm.row_skip[w] != 0;
-  if (g == 0) {
+  if (blockIdx.y == 0) {   // the walker's first block (every thread of it gets here): one parameter per thread
     int bad = skipped;
-    for (int i = 0; i < prm.ndim; ++i) {
-      double t = th[i];
+    for (int i = threadIdx.x; i < prm.ndim; i += blockDim.x) {
+      const double t = th[i];
       bad |= (t < prm.lb[i]) || (t > prm.ub[i]);
     }
-    prm.oob[w] = bad;
-    prm.tickets[w] = 0u;   // the workspace layout depends on W: never trust ticket state from an earlier call
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+      prm.oob[w] = bad;
+      prm.tickets[w] = 0u;   // the workspace layout depends on W: never trust ticket state from an earlier call
+    }
   }
   if (g >= prm.n_lines_total || skipped) return;
   int k = 0, l = g;
