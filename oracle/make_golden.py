@@ -141,6 +141,65 @@ def build_test_script_case():
           f"min flux={out['COS__ref_flux'][0].min()!r}")
 
 
+def build_tutorial_case(case_name, files, fwhms, systems, nguess, bguess, vguess, wave_scale=1.0, seed=20270):
+    """The reference's own multi-instrument tutorials on the REAL spectra that ship with it
+    (examples/rbvfit2-multi-instrument-tutorial.py:82-226 and ...-tutorial2.py:76-220): the rb_spec JSON slices
+    (`wave_slice`, `fnorm`, `enorm`; read directly, rbcodes is only a loader there), one VoigtModel per instrument
+    with its own FWHM, bounds from the reference's `mc.set_bounds` defaults, joint lnprob."""
+    FitConfiguration, VoigtModel, mc, vm = refshim.import_reference()
+    config = FitConfiguration()
+    for (z, ion, trans, comps) in systems:
+        config.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+    ex = os.path.join(refshim.REFERENCE_SRC, "rbvfit", "examples")
+    inst, models = {}, {}
+    for name, fname in files.items():
+        with open(os.path.join(ex, fname)) as fh:
+            d = json.load(fh)
+        wave = np.asarray(d["wave_slice"], dtype=np.float64) * wave_scale
+        models[name] = VoigtModel(config, FWHM=fwhms[name])
+        inst[name] = dict(model=models[name], wave=wave, flux=np.asarray(d["fnorm"], dtype=np.float64),
+                          error=np.asarray(d["enorm"], dtype=np.float64))
+    theta0 = np.concatenate([nguess, bguess, vguess]).astype(np.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        _bounds, lb, ub = mc.set_bounds(nguess, bguess, vguess)
+        fitter = mc.vfit(inst, theta0, lb, ub)
+    lb, ub = np.asarray(lb, dtype=np.float64), np.asarray(ub, dtype=np.float64)
+    C = len(nguess)
+    rng = np.random.default_rng(seed)
+    scale = np.concatenate([np.full(C, 0.1), np.full(C, 3.0), np.full(C, 5.0)])
+    outside = theta0.copy()
+    outside[2 * C] = ub[2 * C] + 1.0
+    thetas = np.vstack([theta0, np.clip(theta0 + scale * rng.standard_normal((18, 3 * C)), lb, ub), lb, ub, outside])
+    with np.errstate(all="ignore"):
+        ref_lnprob = np.array([fitter.lnprob(t) for t in thetas])
+    finite = np.flatnonzero(np.isfinite(ref_lnprob))[:N_FLUX_ROWS]
+    out = dict(
+        meta=json.dumps(dict(case=case_name, workload=case_name, voigt_method="wofz", error_dtype="float64",
+                             instruments=list(files.keys()), FWHM=fwhms,
+                             systems=[(z, ion, list(t), c) for (z, ion, t, c) in systems])),
+        thetas=thetas, lb=lb, ub=ub, ref_lnprob=ref_lnprob, flux_rows=finite)
+    for n, m in models.items():
+        comp = m.compile()
+        d = comp.data
+        out[f"{n}__lambda0"] = d.atomic_lambda0
+        out[f"{n}__gamma"] = d.atomic_gamma
+        out[f"{n}__f"] = d.atomic_f
+        out[f"{n}__zfac"] = d.z_factors
+        out[f"{n}__N_indices"] = d.N_indices
+        out[f"{n}__taps"] = np.asarray(d.kernel.array)
+        out[f"{n}__kernel_kind"] = np.array("gaussian")
+        for k in ("wave", "flux", "error"):
+            out[f"{n}__{k}"] = inst[n][k]
+        out[f"{n}__ref_flux"] = np.array([comp.model_flux(thetas[i], inst[n]["wave"]) for i in finite])
+        out[f"{n}__ref_flux_unconvolved"] = np.array(
+            [m.evaluate(thetas[i], inst[n]["wave"], return_unconvolved=True) for i in finite[:1]])
+    path = os.path.join(GOLDEN_DIR, f"{case_name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{case_name}: W={len(thetas)} finite={np.isfinite(ref_lnprob).sum()} lnprob[0]={ref_lnprob[0]!r} "
+          f"taps={[len(out[n + '__taps']) for n in models]} -> {os.path.relpath(path, ROOT)} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def build_wofz_lattice():
     """Known-answer lattice for Re w(x + i a): scipy.special.wofz (the reference's call) and
     mpmath at 40 digits.  Covers core, mid, far wings and the whole a range."""
@@ -192,6 +251,24 @@ def main():
     th[:, 2] = [0.02, 0.1, 0.5, 1.0, 1.9, 3.0]
     th[:, 3] = [3.0, 1.9, 1.0, 0.5, 0.1, 0.05]
     build_case("C1_smallb", cs, nwalkers=4, extra_thetas=th)
+    build_tutorial_cases()
+
+
+def build_tutorial_cases():
+    # examples/rbvfit2-multi-instrument-tutorial.py: OI 1302 of one absorber seen by XShooter and FIRE
+    build_tutorial_case("tutorial_oi1302",
+                        {"XShooter": "J159_7921_XShooter_OI1302.json", "FIRE": "J159_7921_FIRE_OI1302.json"},
+                        {"XShooter": "2.2", "FIRE": "4.0"},
+                        [(0.0, "OI", [1302.17], 1)], [14.4], [18.0], [200.0])
+    # examples/rbvfit2-multi-instrument-tutorial2.py: the same slices moved to the observed frame (z = 6.074762),
+    # fitted as a 4-component CIV doublet at z = 4.9484 by XShooter + FIRE + HIRES
+    build_tutorial_case("tutorial_civ3",
+                        {"XShooter": "J1030_9089_XShooter_OI1302.json", "FIRE": "J1030_9089_FIRE_OI1302.json",
+                         "HIRES": "J1030_9089_HIRES_OI_air2vac_updated.json"},
+                        {"XShooter": "2.2", "FIRE": "4.0", "HIRES": "4.285"},
+                        [(4.9484, "CIV", [1548.2, 1550.3], 4)],
+                        [13.25, 13.63, 13.12, 13.2], [23.0, 25.0, 50.0, 13.2], [-67.0, 0.0, -20.0, -20.0],
+                        wave_scale=6.074762 + 1.0)
 
 
 if __name__ == "__main__":

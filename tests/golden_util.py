@@ -8,7 +8,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 CASES = ["test_script", "C1", "C1_f32err", "C1_fast", "C1_nolsf", "C1_coslsf", "C1_smallb",
-         "C2", "C3", "C4", "C4w"]
+         "C2", "C3", "C4", "C4w", "tutorial_oi1302", "tutorial_civ3"]
 
 
 class Golden:
@@ -36,7 +36,8 @@ class Golden:
         if kind == "custom":
             return None, self.inst(name, "taps")
         if "FWHM" in self.meta:
-            return self.meta["FWHM"], None
+            f = self.meta["FWHM"]
+            return (f[name] if isinstance(f, dict) else f), None
         from rbvfit_b200 import workloads as wl
         w = wl.get_workload(self.meta["workload"])
         return w["instruments"][name]["FWHM"], None
