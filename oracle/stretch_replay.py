@@ -96,7 +96,8 @@ def accept_half(coords, lnp, nacc, seed, step, split, idx, q, fac, new, walker_o
 
 
 def run(lnprob_fn, coords, lnp, nsteps, seed, a_scale=2.0, first_step=0, walker_offset=0):
-    """Returns (chain [nsteps, W, ndim], lnp_chain [nsteps, W], n_accepted [W]); ``lnprob_fn`` maps (n, ndim) -> (n,)."""
+    """Returns (chain [nsteps, W, ndim], lnp_chain [nsteps, W], n_accepted [W]); ``lnprob_fn`` maps
+    (n, ndim) -> (n,)."""
     coords = np.array(coords, dtype=np.float64, copy=True)
     lnp = np.array(lnp, dtype=np.float64, copy=True)
     W, ndim = coords.shape

@@ -528,7 +528,8 @@ class SightlineEnsembleSampler:
         return v
 
     def get_chain(self, discard=0, thin=1, flat=False, sightline=None):
-        """[steps, S, W, ndim]; ``sightline=s`` -> [steps, W, ndim]; ``flat`` merges steps and walkers of a sightline."""
+        """[steps, S, W, ndim]; ``sightline=s`` -> [steps, W, ndim]; ``flat`` merges the steps and walkers of each
+        sightline (never across sightlines)."""
         return self._get(self._chain, discard, thin, flat, sightline)
 
     def get_log_prob(self, discard=0, thin=1, flat=False, sightline=None):

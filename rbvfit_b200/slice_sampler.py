@@ -202,9 +202,10 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
     slice levels, brackets, the per-walker widen / shrink state machines and the adaptation of mu live in device
     memory, every iteration is one masked likelihood batch over the active half -- the body of a CUDA-graph WHILE
     node whose condition the device sets (``use_graph=False``: the host polls a counter block instead) -- and the
-    chain is copied to the host once per ``run_mcmc`` call.  ``likelihood`` is a ``GpuLikelihood``; random numbers come from the counter-based Philox streams of the
-    device stretch move, so a run is reproducible and can be continued (``run_mcmc(None, n)``) without changing
-    the stream of one long run (``oracle/slice_replay.py`` restates it in numpy for the tests)."""
+    chain is copied to the host once per ``run_mcmc`` call.  ``likelihood`` is a ``GpuLikelihood``; random numbers
+    come from the counter-based Philox streams of the device stretch move, so a run is reproducible and can be
+    continued (``run_mcmc(None, n)``) without changing the stream of one long run (``oracle/slice_replay.py``
+    restates it in numpy for the tests)."""
 
     def __init__(self, nwalkers: int, ndim: int, likelihood, mu: float = 1.0, tune: bool = True,
                  tolerance: float = 0.05, patience: int = 5, maxsteps: int = 10000, maxiter: int = 10000,

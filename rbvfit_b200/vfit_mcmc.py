@@ -49,7 +49,7 @@ class vfit:
         self.nwalkers = no_of_Chain
         self._rng = np.random.default_rng(seed)
         self._seed = seed
-        self.device_sampler = bool(device_sampler)   # sampling loop entirely on the GPU (rbv_stretch_run / rbv_slice_run)
+        self.device_sampler = bool(device_sampler)   # sampling loop on the GPU (rbv_stretch_run / rbv_slice_run)
 
     # ------------------------------------------------------------------ validation (vfit_mcmc.py:199-229)
     def _validate_unified_instrument_data(self, instrument_data):

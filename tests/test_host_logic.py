@@ -232,3 +232,39 @@ def test_slice_replay_recovers_gaussian_and_tunes_mu():
     # a tiny stepping-out budget still samples correctly (the bracket just cannot widen)
     c = sl.run(lnp, p0, lnp(p0), 50, seed=3, mu=0.01, maxsteps=1, tune=False)
     assert c["nexp"] == 0 and np.all(np.isfinite(c["lnp_chain"]))
+
+
+def test_sightline_sampler_accessors_without_device():
+    """SightlineEnsembleSampler's bookkeeping (shapes of get_chain / get_log_prob with discard, thin, flat and per
+    sightline; the emcee-shaped per-sightline view) on a hand-filled chain -- no device involved."""
+    from rbvfit_b200.sampler import SightlineEnsembleSampler
+
+    class _Batch:                 # what the sampler reads from a SightlineBatch before sampling
+        engine, n_sightlines, ndim = object(), 3, 2
+
+    S, W, nd, n = 3, 4, 2, 10
+    smp = SightlineEnsembleSampler(W, nd, _Batch(), seed=1)
+    assert smp.get_chain().shape == (0, S, W, nd) and smp.acceptance_fraction.shape == (S, W)
+    chain = np.arange(n * S * W * nd, dtype=float).reshape(n, S, W, nd)
+    smp._chain, smp._log_prob = chain, chain[..., 0] * 0.5
+    smp._accepted[:] = np.arange(S * W).reshape(S, W)
+    smp.iteration = n
+    assert np.array_equal(smp.get_chain(discard=2, thin=2), chain[3::2])                  # emcee's thin convention
+    assert smp.get_chain(flat=True).shape == (S, n * W, nd)
+    assert np.array_equal(smp.get_chain(flat=True)[1], chain[:, 1].reshape(-1, nd))       # never mixes sightlines
+    assert smp.get_log_prob(flat=True, discard=4).shape == (S, (n - 4) * W)
+    assert np.array_equal(smp.get_chain(sightline=2, discard=1), chain[1:, 2])
+    v = smp.sightline(1)
+    assert (v.nwalkers, v.ndim, v.iteration) == (W, nd, n)
+    assert np.array_equal(v.get_chain(flat=True, discard=3), chain[3:, 1].reshape(-1, nd))
+    assert v.chain.shape == (W, n, nd) and v.flatchain.shape == (n * W, nd) and v.lnprobability.shape == (W, n)
+    assert np.array_equal(v.acceptance_fraction, np.arange(4, 8) / n)
+    assert v.get_autocorr_time(quiet=True).shape == (nd,)
+    with pytest.raises(IndexError):
+        smp.sightline(3)
+    with pytest.raises(ValueError):
+        SightlineEnsembleSampler(W, nd + 1, _Batch())
+    with pytest.raises(ValueError):
+        SightlineEnsembleSampler(1, nd, _Batch())
+    with pytest.raises(TypeError):
+        SightlineEnsembleSampler(W, nd, object())
