@@ -369,9 +369,8 @@ def run_gpu_sightlines(args, rank, world, local, n_sightlines=1024, walkers=64):
     import torch
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    per = (n_sightlines + world - 1) // world
-    first = min(rank * per, n_sightlines)
-    count = min(per, n_sightlines - first)
+    from rbvfit_b200.dist import SightlinePartition
+    first, count = SightlinePartition(rank, world).owned(n_sightlines)
     batch, thetas = build_sightlines(first, count, local, walkers)
     S, Ws, ndim = thetas.shape
     P = batch.pixels

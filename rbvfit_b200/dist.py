@@ -5,7 +5,7 @@ theta row, so rank r evaluates rows [r*ceil(W/G), (r+1)*ceil(W/G)) of every batc
 of the (MB-sized) spectra and line tables, and the only exchange is the all-gather of the W lnprob values
 (8 B per walker) over NCCL / NVLink.  Every rank runs the same sampler from the same seed, so ensemble
 state stays replicated and no theta ever crosses the wire.  Independent sightlines (survey mode) shard the
-same way with no collective at all until the final gather.
+same way with no collective at all until the final gather (``SightlinePartition``).
 
 ``WalkerPartition`` holds the host-side logic (row ranges, padding, gather) and works with any
 torch.distributed backend -- NCCL on the GPUs, gloo in the CPU tests, where a stub evaluator stands in for
@@ -80,6 +80,43 @@ class WalkerPartition:
         W = int(theta.shape[0]) if W is None else W
         lo, hi = self.rows(W)
         return self.gather(local_eval(theta[lo:hi]), W)
+
+
+class SightlinePartition:
+    """Survey mode ("sightline-parallel"): rank r owns a contiguous block of the S independent
+    sightlines, builds its own ``SightlineBatch`` / ``SightlineEnsembleSampler`` over them and never talks to the
+    other ranks while sampling; ``gather`` is the one collective at the very end, for per-sightline summaries
+    (posterior percentiles, acceptance fractions -- a few numbers per sightline, never the chains)."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        if not (0 <= rank < world):
+            raise ValueError("bad rank/world")
+        self.rank, self.world, self.group = rank, world, group
+
+    def block(self, n_sightlines: int) -> int:
+        return (n_sightlines + self.world - 1) // self.world
+
+    def owned(self, n_sightlines: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        """(first, count) of the sightlines of ``rank`` (default: this rank); trailing ranks may own none."""
+        r = self.rank if rank is None else rank
+        per = self.block(n_sightlines)
+        first = min(r * per, n_sightlines)
+        return first, min(per, n_sightlines - first)
+
+    def gather(self, local, n_sightlines: int):
+        """``local``: torch tensor [count, ...] of this rank's per-sightline summaries (any device); returns the
+        [n_sightlines, ...] tensor on every rank, in sightline order."""
+        import torch
+        if self.world == 1:
+            return local[:n_sightlines]
+        import torch.distributed as dist
+        per = self.block(n_sightlines)
+        tail = tuple(local.shape[1:])
+        padded = torch.full((per,) + tail, float("nan"), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+        full = torch.empty((per * self.world,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, padded.contiguous(), group=self.group)
+        return full[:n_sightlines]
 
 
 class DistributedLikelihood:

@@ -152,3 +152,39 @@ def test_distributed_device_sampler_gloo(W):
         assert np.array_equal(np.rint(af * nsteps).astype(int), nacc)
     assert ret[0][4] + ret[1][4] == nsteps * W                              # each proposal evaluated exactly once
     assert ret[0][4] > 0 and ret[1][4] > 0
+
+
+def _sightline_worker(rank, world, port, S, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from rbvfit_b200 import dist as rdist
+    r, w, _ = rdist.init_from_env("gloo")
+    part = rdist.SightlinePartition(r, w)
+    first, count = part.owned(S)
+    # stand-in for "sample my sightlines, summarise each": 3 percentiles x 2 parameters per sightline
+    ids = torch.arange(first, first + count, dtype=torch.float64)
+    local = ids[:, None, None] * 10.0 + torch.arange(6, dtype=torch.float64).reshape(3, 2)
+    full = part.gather(local, S)
+    ret[rank] = (full.numpy().copy(), (first, count))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("S", [8, 5, 1])
+def test_sightline_partition_gloo(S):
+    """Survey mode over 2 ranks: contiguous sightline blocks that cover 0..S-1 exactly once (the last rank may own
+    fewer or none), no collective until the final gather of the per-sightline summaries, which arrive in sightline
+    order on every rank."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sightline_worker, args=(world, port, S, ret), nprocs=world, join=True)
+    ref = np.arange(S, dtype=np.float64)[:, None, None] * 10.0 + np.arange(6, dtype=np.float64).reshape(3, 2)
+    covered = []
+    for r in range(world):
+        full, (first, count) = ret[r]
+        assert full.shape == (S, 3, 2) and np.array_equal(full, ref)
+        covered += list(range(first, first + count))
+    assert covered == list(range(S))
