@@ -94,6 +94,12 @@ def get_workload(name: str) -> dict:
         return _c4(True)
     if name == "C5a":
         return _c2(P=100000, nwalkers=8192, name="C5a", seed=20265)
+    if name == "C5a_L4":
+        # "also report an L = 4 model at the same W, P" -- C1's MgII doublet on C5a's grid and ensemble
+        w = _c1()
+        w.update(name="C5a_L4", seed=20267, nwalkers=8192,
+                 instruments={"SPEC": dict(wave=np.linspace(3300.0, 5700.0, 100000), FWHM="6.5", lsf=None)})
+        return w
     raise KeyError(name)
 
 

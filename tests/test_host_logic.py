@@ -160,6 +160,17 @@ def test_roofline_farfield_rule():
     assert out["C1"][0] == out["C1"][1] and out["C1"][2]["farfield"] == 0.0
     assert out["C2"][1] < 0.4 * out["C2"][0] and out["C2"][2]["farfield"] > 0.75
     assert out["C4"][1] < out["C4"][0] and 0.5 < out["C4"][2]["farfield"] < 0.9     # the DLA's wings stay direct
+    # SURVEY 8(d)'s L = 4 companion of C5a (the MgII doublet on C5a's 100 000-pixel grid, 8192 walkers)
+    w = wl.get_workload("C5a_L4")
+    cfg = vo.OracleConfig()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z, ion, trans, comps)
+    m = vo.lower(cfg)
+    wave = w["instruments"]["SPEC"]["wave"]
+    assert m.n_lines == 4 and wave.size == 100000 and wl.make_ensemble(w).shape == (8192, 6)
+    Fd, td = rf.flops_per_walker_pixel(m, w["theta_true"], wave, 23)
+    Ff, tf = rf.flops_farfield(m, w["theta_true"], wave, 23)
+    assert 160 < Fd < 170 and 95 < Ff < 110 and tf["farfield"] > 0.9 and td["far"] > 0.95
 
 
 def test_stretch_replay_philox_known_answers_and_gaussian_target():
