@@ -332,7 +332,7 @@ def run_gpu(args, rank, world, local):
         line["mcmc"] = mcmc_leg(local, with_cpu=not args.no_cpu)
         line["mcmc"]["large_ensemble"] = mcmc_large_leg(like, w, thetas, total_px)
         line["mcmc"]["zeus"] = mcmc_zeus_leg(local, with_cpu=not args.no_cpu)
-    if not args.no_cpu and world >= 1:
+    if not args.no_cpu and world == 1:      # the CPU baseline is reported at N = 1 only
         r = cpu_arm(args.workload, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
