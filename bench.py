@@ -13,6 +13,11 @@ total work per step is fixed) and every step ends with the NCCL all-gather of ln
 `e2e`    the same metric through the public API `lnprob(theta_host)` -> numpy: per step H2D of the theta rows
          from pinned memory, the kernel, the gather and the D2H of lnprob, timed by wall clock around
          synchronous calls.
+`mcmc`   (N = 1) the second half of the metric, MCMC steps/s vs the CPU reference path: C1 stretch move
+         (device-resident, host-driven, CPU serial / fork pool), the same move at C5a's own scale, and C2 with the
+         zeus-style ensemble slice move (device-resident CUDA-graph WHILE loop, host-driven, CPU fork pool).
+Other workloads: --workload C1 | C2 | C3 | C4 | C4w | C5a_L4, and C5b [--sightlines S] (survey mode: sightlines
+sharded over the ranks with no collective; its `mcmc` key is the per-sightline ensembles sampled in lockstep).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
