@@ -188,3 +188,51 @@ def test_sightline_partition_gloo(S):
         assert full.shape == (S, 3, 2) and np.array_equal(full, ref)
         covered += list(range(first, first + count))
     assert covered == list(range(S))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# zeus-style slice sampling over several ranks: the host-driven EnsembleSliceSampler with the partitioned likelihood
+# as its log-probability (every rank draws the same numpy random numbers from the shared seed, evaluates only its
+# rows of each -- ragged, often tiny -- batch and gathers lnprob)
+def _slice_worker(rank, world, port, W, nsteps, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from rbvfit_b200 import dist as rdist
+    from rbvfit_b200.slice_sampler import EnsembleSliceSampler
+    r, w, _ = rdist.init_from_env("gloo")
+    part = rdist.WalkerPartition(r, w)
+    rows = [0]
+
+    def lnprob(theta):             # what DistributedLikelihood.lnprob does, with a stub in place of the device call
+        th = torch.as_tensor(np.ascontiguousarray(theta))
+
+        def local_eval(sub):
+            rows[0] += sub.shape[0]
+            return torch.as_tensor(_gauss(sub.numpy())) if sub.shape[0] else torch.empty(0, dtype=torch.float64)
+
+        return part.evaluate(th, local_eval).numpy()
+
+    smp = EnsembleSliceSampler(W, 3, lnprob, seed=11)
+    p0 = MU + 0.1 * np.random.default_rng(6).standard_normal((W, 3))
+    smp.run_mcmc(p0, nsteps)
+    ret[rank] = (smp.get_chain().copy(), smp.get_log_prob().copy(), smp.mu, smp.ncall, rows[0])
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_slice_sampler_over_partitioned_likelihood_gloo():
+    from rbvfit_b200.slice_sampler import EnsembleSliceSampler
+    world, W, nsteps = 2, 8, 12
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_slice_worker, args=(world, port, W, nsteps, ret), nprocs=world, join=True)
+    ref = EnsembleSliceSampler(W, 3, _gauss, seed=11)
+    p0 = MU + 0.1 * np.random.default_rng(6).standard_normal((W, 3))
+    ref.run_mcmc(p0, nsteps)
+    for r in range(world):
+        chain, lps, mu, ncall, rows = ret[r]
+        assert np.array_equal(chain, ref.get_chain()) and np.array_equal(lps, ref.get_log_prob())
+        assert mu == ref.mu and ncall == ref.ncall
+    assert ret[0][4] + ret[1][4] == ref.ncall and ret[0][4] > 0 and ret[1][4] > 0     # every row evaluated once
