@@ -112,3 +112,45 @@ def test_refshim_runs_reference_live():
     m = VoigtModel(cfg, FWHM="6.5").compile()
     row = g.flux_rows[0]
     assert np.array_equal(m.model_flux(g.thetas[row], g.inst("COS", "wave")), g.inst("COS", "ref_flux")[0])
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_matches_live_reference_on_fuzz_problems(seed):
+    """Build container only: on the SAME seeded random problems tests/test_gpu_fuzz.py runs against the oracle on the
+    GPU box, the oracle agrees with the unmodified reference (FitConfiguration -> VoigtModel -> vfit.lnprob through
+    oracle/refshim.py): lowered tables identical, model flux to 1e-15, lnprob to 1e-13, same -inf rows."""
+    import contextlib
+    import io
+    from fuzz_util import draw_problem
+    from oracle import refshim
+    FitConfiguration, VoigtModel, mc, vm = refshim.import_reference()
+    systems, wave, fwhm, taps, theta, thetas, lb, ub, rng = draw_problem(1000 + seed)
+    cfg, ocfg = FitConfiguration(), vo.OracleConfig()
+    for (z, ion, trans, comps) in systems:
+        cfg.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+        ocfg.add_system(z, ion, trans, comps)
+    ref_model = VoigtModel(cfg, FWHM=fwhm)
+    if taps is not None:
+        from astropy.convolution import CustomKernel          # the shim's; injected as _setup_kernel would (:458-460)
+        ref_model.kernel = CustomKernel(taps)
+    om = vo.lower(ocfg, FWHM=fwhm, custom_taps=taps)
+    rc = ref_model.compile()
+    d = rc.data
+    assert np.array_equal(d.atomic_lambda0, om.atomic_lambda0) and np.array_equal(d.z_factors, om.z_factors)
+    assert np.array_equal(d.atomic_f, om.atomic_f) and np.array_equal(d.atomic_gamma, om.atomic_gamma)
+    assert np.array_equal(d.N_indices, om.N_indices) and np.array_equal(d.v_indices, om.v_indices)
+    truth = vo.model_flux(om, theta, wave)
+    flux = truth + 0.03 * rng.standard_normal(wave.size)
+    error = np.full(wave.size, 0.03)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = mc.vfit({"S": dict(model=ref_model, wave=wave, flux=flux, error=error)}, theta, lb, ub)
+    comp = vo.compile_instruments({"S": dict(model=om, wave=wave, flux=flux, error=error)})
+    with np.errstate(all="ignore"):
+        ref = np.array([fitter.lnprob(t) for t in thetas])
+    got = vo.lnprob_batch(comp, thetas, lb, ub)
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.isneginf(ref).sum() >= 1
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-13
+    for t in thetas[:2]:
+        assert np.max(np.abs(vo.model_flux(om, t, wave) - rc.model_flux(t, wave))) <= 1e-15
