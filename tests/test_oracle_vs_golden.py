@@ -154,3 +154,81 @@ def test_oracle_matches_live_reference_on_fuzz_problems(seed):
     assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-13
     for t in thetas[:2]:
         assert np.max(np.abs(vo.model_flux(om, t, wave) - rc.model_flux(t, wave))) <= 1e-15
+
+
+def _ref_vs_oracle(instruments, thetas, lb, ub, flux_tol=1e-15, rtol=1e-13):
+    """instruments: {name: (systems, FWHM, taps, wave, flux, error)} -> oracle vs LIVE reference (joint lnprob, flux)."""
+    import contextlib
+    import io
+    from oracle import refshim
+    FitConfiguration, VoigtModel, mc, vm = refshim.import_reference()
+    ref_inst, ora_inst, pairs = {}, {}, []
+    for name, (systems, fwhm, taps, wave, flux, error) in instruments.items():
+        cfg, ocfg = FitConfiguration(), vo.OracleConfig()
+        for (z, ion, trans, comps) in systems:
+            cfg.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+            ocfg.add_system(z, ion, trans, comps)
+        rm = VoigtModel(cfg, FWHM=fwhm)
+        if taps is not None:
+            from astropy.convolution import CustomKernel
+            rm.kernel = CustomKernel(taps)
+        om = vo.lower(ocfg, FWHM=fwhm, custom_taps=taps)
+        ref_inst[name] = dict(model=rm, wave=wave, flux=flux, error=error)
+        ora_inst[name] = dict(model=om, wave=wave, flux=flux, error=error)
+        pairs.append((rm.compile(), om, wave))
+    thetas = np.atleast_2d(thetas)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = mc.vfit(ref_inst, np.clip(thetas[0], lb, ub), lb, ub)
+    comp = vo.compile_instruments(ora_inst)
+    with np.errstate(all="ignore"):
+        ref = np.array([fitter.lnprob(t) for t in thetas])
+    got = vo.lnprob_batch(comp, thetas, lb, ub)
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.array_equal(np.isnan(got), np.isnan(ref))
+    fin = np.isfinite(ref)
+    if fin.any():
+        assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= rtol
+    for rc, om, wave in pairs:
+        assert np.max(np.abs(vo.model_flux(om, thetas[0], wave) - rc.model_flux(thetas[0], wave))) <= flux_tol
+    return ref
+
+
+@pytest.mark.reference
+def test_oracle_matches_live_reference_on_edge_cases():
+    """Build container only: the edge cases tests/test_gpu_edges.py runs against the oracle on the GPU box -- tiny and
+    ragged spectra (shorter than the LSF, one pixel), an LSF wider than the spectrum, descending and shuffled
+    wavelength grids, 96 lines over 32 components, float32 errors, a joint fit with different line lists per
+    instrument -- agree between the oracle and the unmodified reference."""
+    mgii = [(0.348, "MgII", [2796.3, 2803.5], 2)]
+    th = np.array([14.2, 14.5, 40.0, 30.0, -25.0, 35.0])
+    lb, ub = th - np.array([2, 2, 38, 28, 50, 50.0]), th + np.array([2, 2, 40, 40, 50, 50.0])
+    rng = np.random.default_rng(41)
+    thetas = np.clip(th + rng.standard_normal((5, 6)) * [0.05, 0.05, 1, 1, 2, 2], lb, ub)
+    thetas[3, 0] = ub[0] + 1.0
+
+    def spec(wave, dtype=np.float64):
+        wave = np.asarray(wave, dtype=np.float64)
+        return wave, 1.0 + 0.05 * rng.standard_normal(wave.size), np.full(wave.size, 0.05, dtype=dtype)
+
+    for P in (1, 2, 7, 22, 23, 257):
+        wave = np.linspace(3762.0, 3786.0, P) if P > 1 else np.array([3769.5])
+        ref = _ref_vs_oracle({"S": (mgii, "6.5", None) + spec(wave)}, thetas, lb, ub)
+        assert np.isneginf(ref[3]) and np.isfinite(ref[0])
+    x = np.arange(-160, 161)
+    taps = np.exp(-0.5 * (x / 25.0) ** 2) * (1 + 0.3 * (x > 0))
+    for P in (40, 321, 700):                                   # asymmetric 321-tap LSF, wider than the spectrum
+        _ref_vs_oracle({"S": (mgii, None, taps / taps.sum()) + spec(np.linspace(3762.0, 3786.0, P))}, thetas, lb, ub,
+                       flux_tol=5e-15)
+    wave = np.linspace(3755.0, 3795.0, 3000)
+    _ref_vs_oracle({"S": (mgii, "6.5", None) + spec(wave[::-1].copy())}, thetas, lb, ub)
+    _ref_vs_oracle({"S": (mgii, "6.5", None) + spec(rng.permutation(wave))}, thetas, lb, ub)
+    _ref_vs_oracle({"S": (mgii, "6.5", None) + spec(np.linspace(3755.0, 3795.0, 2048), np.float32)}, th, lb, ub)
+    systems = []
+    for z in np.linspace(1.9, 2.9, 8):
+        systems.append((float(z), "CIV", [1548.2, 1550.77], 2))
+        systems.append((float(z), "HI", [1215.67, 1025.72, 972.54, 949.74], 2))
+    C = 32
+    t96 = np.concatenate([rng.uniform(12.5, 14.5, C), rng.uniform(8, 45, C), rng.uniform(-120, 120, C)])
+    _ref_vs_oracle({"S": (systems, "6.5", None) + spec(np.linspace(3400.0, 6100.0, 9000))},
+                   t96 + 0.01 * rng.standard_normal((2, 3 * C)), t96 - 60.0, t96 + 60.0)
+    _ref_vs_oracle({"A": ([(0.348, "MgII", [2796.3], 2)], "6.5", None) + spec(np.linspace(3760.0, 3776.0, 700)),
+                    "B": (mgii, "3.0", None) + spec(np.linspace(3755.0, 3795.0, 5000))}, thetas, lb, ub)
