@@ -279,3 +279,50 @@ def test_sightline_sampler_accessors_without_device():
         SightlineEnsembleSampler(1, nd, _Batch())
     with pytest.raises(TypeError):
         SightlineEnsembleSampler(W, nd, object())
+
+
+@pytest.mark.reference
+def test_product_lowering_matches_live_reference():
+    """Build container only: the PRODUCT's host layer (rb_setline, FitConfiguration, GpuVoigtModel lowering, Gaussian
+    LSF taps, set_bounds) against the unmodified reference on the 24 fuzz problems and a sweep of line look-ups --
+    no device needed: lowering is host code."""
+    import contextlib
+    import io
+    import pickle
+    from fuzz_util import draw_problem
+    from oracle import refshim
+    from rbvfit_b200 import FitConfiguration, rb_setline
+    from rbvfit_b200.model import GpuVoigtModel
+    from rbvfit_b200.vfit_mcmc import set_bounds
+    RefConfig, RefModel, mc, vm = refshim.import_reference()
+    from rbvfit.rb_setline import rb_setline as ref_setline
+    for lam in (1215.67, 1025.7, 1302.17, 1304.5, 1548.2, 1550.3, 2796.3, 2803.5, 1393.76, 977.02, 2600.17):
+        with contextlib.redirect_stdout(io.StringIO()):
+            a, b = rb_setline(lam, "closest"), ref_setline(lam, "closest")
+        assert a["wave"] == b["wave"] and a["name"] == b["name"]
+        assert np.asarray(a["fval"]).dtype == np.asarray(b["fval"]).dtype == np.float32
+        assert a["fval"] == b["fval"] and a["gamma"] == b["gamma"]
+    for seed in range(24):
+        systems, wave, fwhm, taps, theta, thetas, lb, ub, rng = draw_problem(1000 + seed)
+        cfg, rcfg = FitConfiguration(), RefConfig()
+        for (z, ion, trans, comps) in systems:
+            cfg.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+            rcfg.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+        ours = pickle.loads(pickle.dumps(GpuVoigtModel(cfg, FWHM=fwhm, lsf_taps=taps).compile())).data
+        ref = RefModel(rcfg, FWHM=fwhm).compile().data
+        for key in ("atomic_lambda0", "atomic_gamma", "atomic_f", "z_factors", "N_indices", "b_indices", "v_indices"):
+            x, y = np.asarray(getattr(ours, key)), np.asarray(getattr(ref, key))
+            assert x.dtype == y.dtype and np.array_equal(x, y), (seed, key)
+        assert (ours.n_lines, ours.total_components) == (ref.n_lines, ref.total_components)
+        if taps is None and fwhm is not None:
+            assert np.array_equal(ours.kernel, np.asarray(ref.kernel.array))
+        # the reference's own FitConfiguration object is accepted as is (duck-typed)
+        again = GpuVoigtModel(rcfg, FWHM=fwhm, lsf_taps=taps).compile().data
+        assert np.array_equal(again.atomic_lambda0, ref.atomic_lambda0) and np.array_equal(again.N_indices,
+                                                                                           ref.N_indices)
+        C = ref.total_components
+        n, b, v = theta[:C], theta[C:2 * C], theta[2 * C:]
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, rlb, rub = mc.set_bounds(list(n), list(b), list(v))
+            _, olb, oub = set_bounds(list(n), list(b), list(v))
+        assert np.array_equal(np.asarray(olb), np.asarray(rlb)) and np.array_equal(np.asarray(oub), np.asarray(rub))
