@@ -179,11 +179,11 @@ def cpu_arm(workload: str, steps: int, warmup: int, sample_walkers=None):
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    r = cpu_arm(args.workload, steps, min(args.warmup, 1))
+    steps = max(1, args.steps)          # exactly K timed steps after W warm-up steps; a step is ~2 s of pool work
+    r = cpu_arm(args.workload, steps, max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "steps": steps, "warmup": max(0, args.warmup), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "sample": r["sample"]},
