@@ -1,3 +1,7 @@
+// Probe: does this driver / runtime run CUDA-graph conditional WHILE nodes whose condition a kernel sets
+// (cudaGraphSetConditional)?  Expected output on the B200 box: "add 0", "inst 0", "ctr 5" (the body ran five times).
+// rbv_slice_run's graph mode (rbvfit_b200/csrc/rbv_kernels.cu) is built the same way.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -o build/cond_graph_probe tools/micro/cond_graph_probe.cu
 #include <cuda_runtime.h>
 #include <cstdio>
 __global__ void body(int* ctr, cudaGraphConditionalHandle h) {
