@@ -142,24 +142,66 @@ def oracle_problem(workload: str):
     return w, comp, wl.make_ensemble(w)
 
 
+def reference_problem(workload: str):
+    """The workload built with the reference's OWN classes (FitConfiguration -> VoigtModel -> vfit), imported
+    unmodified from the staged copy (oracle/_ref, see oracle/build_ref.py) behind oracle/refshim.py."""
+    import contextlib
+    import io
+    from oracle import refshim, voigt_oracle as vo
+    from rbvfit_b200 import workloads as wl
+    FitConfiguration, VoigtModel, mc, _vm = refshim.import_reference()
+    from astropy.convolution import CustomKernel
+    w = wl.get_workload(workload)
+    config = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        config.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+    models = {}
+    for name, inst in w["instruments"].items():
+        m = VoigtModel(config, FWHM=inst["FWHM"])
+        if inst.get("lsf") == "cos_like":            # what _setup_kernel does with a linetools table (:458-460)
+            m.kernel = CustomKernel(vo.cos_like_lsf(321))
+        models[name] = m
+    compiled = {n: m.compile() for n, m in models.items()}
+    spectra = wl.make_spectra(w, lambda n, th, wave: compiled[n].model_flux(th, wave))
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = mc.vfit({n: dict(model=models[n], **spectra[n]) for n in models}, w["theta_true"], w["lb"], w["ub"])
+    return w, fitter, wl.make_ensemble(w), mc
+
+
 def cpu_arm(workload: str, steps: int, warmup: int, sample_walkers=None):
-    """Times the reference's CPU implementation of the path (oracle port; `use_pool=True` equivalent: fork
-    pool over all host cores, vfit_mcmc.py:41-45, 413) on a bounded walker sample of the workload."""
-    from oracle import voigt_oracle as vo
+    """Times the reference's CPU implementation of the path on a bounded walker sample of the workload, with every
+    host core.  With the staged reference present (`kind` "reference"): the reference's own `vfit.lnprob` mapped over
+    the rows by `mp.get_context('fork').Pool()` -- its `use_pool=True` path, vfit_mcmc.py:41-45, 408-414, which is
+    what emcee does with `pool=pool` once per half-step (the bound method is pickled with every chunk).  Otherwise
+    (`kind` "port") the oracle port under a fork pool that inherits the problem."""
+    from oracle import refshim, voigt_oracle as vo
     cores = len(os.sched_getaffinity(0))
-    w, comp, thetas = oracle_problem(workload)
-    total_px = sum(len(d["wave"]) for d in comp.values())
+    live = refshim.available()
+    if live:
+        w, fitter, thetas, mc = reference_problem(workload)
+        total_px = sum(len(d["wave"]) for d in fitter.instrument_data.values())
+        work = sum(len(d["wave"]) * d["model"].__self__.data.n_lines for d in fitter.instrument_data.values())
+    else:
+        w, comp, thetas = oracle_problem(workload)
+        total_px = sum(len(d["wave"]) for d in comp.values())
+        work = sum(len(d["wave"]) * d["model"].n_lines for d in comp.values())
     if sample_walkers is None:
         # ~140 ns per (line, pixel) wofz on one core -> aim at ~2 s of wall clock per pool call
-        per_walker = 1.4e-7 * sum(len(d["wave"]) * d["model"].n_lines for d in comp.values())
+        per_walker = 1.4e-7 * work
         sample_walkers = int(min(len(thetas), max(cores, round(cores * 2.0 / max(per_walker, 1e-4)))))
     sample = thetas[:sample_walkers]
     times = []
-    pool = vo.make_pool(comp, w["lb"], w["ub"], processes=cores)      # lives across steps, like emcee's
+    if live:
+        pool = mc.OptimizedPool(processes=cores)                          # lives across steps, like emcee's
+        rows = [row for row in sample]
+        step = lambda: list(pool.map(fitter.lnprob, rows))               # noqa: E731
+    else:
+        pool = vo.make_pool(comp, w["lb"], w["ub"], processes=cores)
+        step = lambda: vo.lnprob_pool(comp, sample, w["lb"], w["ub"], pool=pool)   # noqa: E731
     try:
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            vo.lnprob_pool(comp, sample, w["lb"], w["ub"], pool=pool)
+            step()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
@@ -168,11 +210,13 @@ def cpu_arm(workload: str, steps: int, warmup: int, sample_walkers=None):
         pool.join()
     best = min(times)
     mean = sum(times) / len(times)
+    how = ("the reference's own vfit.lnprob under mp.get_context('fork').Pool().map (unmodified rbvfit 2.4.0, "
+           "numpy + scipy.special.wofz)") if live else "oracle port: numpy + scipy.special.wofz"
     return {"value": sample_walkers * total_px / mean, "best": sample_walkers * total_px / best,
             "ms_per_step": mean * 1e3, "cores": cores, "sample_walkers": sample_walkers,
-            "total_px": total_px,
+            "total_px": total_px, "kind": "reference" if live else "port",
             "sample": f"{sample_walkers} of {len(thetas)} walkers x {total_px} px of {workload} per step, "
-                      f"fork pool over {cores} cores (oracle port: numpy + scipy.special.wofz)"}
+                      f"fork pool over {cores} cores ({how})"}
 
 
 # --------------------------------------------------------------------------------------------- arms
@@ -187,7 +231,7 @@ def run_reference(args, rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "sample": r["sample"]},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -339,7 +383,7 @@ def run_gpu(args, rank, world, local):
         line["mcmc"]["zeus"] = mcmc_zeus_leg(local, with_cpu=not args.no_cpu)
     if not args.no_cpu and world == 1:      # the CPU baseline is reported at N = 1 only
         r = cpu_arm(args.workload, steps=2, warmup=1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                 "sample": r["sample"]}
     print(json.dumps(line))
 

@@ -228,16 +228,29 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
                   void* stream);
 
 /* Model flux for a batch of walkers on instrument `inst`; CompiledVoigtModel.model_flux,
- * voigt_model.py:295-311 (convolve != 0) or VoigtModel.evaluate(return_unconvolved=True), :509-558.
- *   out_flux DEVICE [n_walkers, n_pixels] row-major doubles.  Asynchronous. */
+ * voigt_model.py:295-311 (convolve != 0: the instrument's LSF is applied, :221-230) or
+ * VoigtModel.evaluate(return_unconvolved=True), :509-558 (convolve == 0: exp(-tau) as it is, :217).
+ *   theta     DEVICE [n_walkers, ndim] row-major doubles (ndim = that of rbv_set_bounds, else 3 * n_components)
+ *   out_flux  DEVICE [n_walkers, n_pixels] row-major doubles
+ *   workspace DEVICE, rbv_flux_workspace_bytes(), or NULL / 0.  With a workspace the per-line constants are
+ *             prepared once per walker by a small launch of their own (as rbv_lnprob_batch does); without one every
+ *             CTA of the walker prepares them again (fine for a handful of rows).  Same results either way.
+ * No prior is applied (rows outside the bounds are evaluated like any other).  Asynchronous. */
+int rbv_flux_workspace_bytes(const RbvContext* ctx, int inst, int n_walkers, size_t* bytes);
 int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int n_walkers, int convolve,
-                         double* out_flux, void* stream);
+                         double* out_flux, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Introspection used by the host layer and the tests. */
 int rbv_num_instruments(const RbvContext* ctx);
 int rbv_num_tiles(const RbvContext* ctx);          /* CTAs per walker in rbv_lnprob_batch */
 int rbv_ndim(const RbvContext* ctx);
 long long rbv_launch_count(const RbvContext* ctx); /* kernels launched by this context so far */
+/* Which kernel the most recent lnprob launch of this context used: voigt_tile_kernel (one CTA per walker and pixel
+ * tile; small batches, very wide LSFs, FP32-gated precision) or voigt_stream_kernel (persistent warps streaming
+ * through (walker, pixel range) items; big batches).  -1 before the first launch. */
+#define RBV_KERNEL_TILE 0
+#define RBV_KERNEL_STREAM 1
+int rbv_last_kernel(const RbvContext* ctx);
 
 /* Device Voigt-Hjerting function on a lattice (test hook): out[i] = H(a[i], x[i]); all DEVICE arrays. */
 int rbv_voigt_h(RbvContext* ctx, const double* x, const double* a, double* out, int n, int method,
@@ -246,6 +259,10 @@ int rbv_voigt_h(RbvContext* ctx, const double* x, const double* a, double* out, 
 /* FP64 FMA throughput of the device (roofline denominator measured on the box): runs a dependent-chain
  * DFMA kernel for about `millis` ms and returns TFLOP/s (2 flops per FMA). */
 int rbv_measure_fp64_peak(RbvContext* ctx, double millis, double* tflops);
+
+/* Largest relative error of the device reciprocal (MUFU seed + one cubic step) used by the asymptotic tiers, over a
+ * sweep of 65 536 positive doubles (test hook; expected < 2^-52). */
+int rbv_selftest_rcp(RbvContext* ctx, double* max_rel_err);
 
 /* Text of the last error raised on this thread ("" if none). */
 const char* rbv_last_error(void);

@@ -200,6 +200,93 @@ def build_tutorial_case(case_name, files, fwhms, systems, nguess, bguess, vguess
           f"({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+
+def flux_pixel_subset(P, n_lines_hint=8, seed=7):
+    """Pixels at which the big fixtures keep the reference flux: every 8th pixel plus dense 1024-pixel windows
+    (seeded) -- a 100 000-pixel row costs 0.8 MB, the subset 0.2 MB."""
+    rng = np.random.default_rng(seed)
+    px = set(range(0, P, 8))
+    for start in rng.integers(0, max(P - 1024, 1), size=n_lines_hint):
+        px.update(range(int(start), min(int(start) + 1024, P)))
+    px.update(range(0, min(64, P)))
+    px.update(range(max(P - 64, 0), P))
+    return np.array(sorted(px), dtype=np.int64)
+
+
+def build_big_case(case_name, w, n_in=8, n_out=2):
+    """The headline geometry (C5a: 100 000 px, 33 lines; C5a_L4: the 4-line companion): `n_in` in-bounds and `n_out`
+    out-of-bounds rows of the workload's own 8192-walker ensemble through the REAL reference (~0.5 s per row).
+    Compact storage: the wavelength grid as its linspace arguments, the constant error as a scalar, the reference
+    flux of two rows on a pixel subset."""
+    config, models, mc = _ref_models(w)
+    assert len(models) == 1
+    (name, model), = models.items()
+    compiled = model.compile()
+    spectra = wl.make_spectra(w, lambda n, th, wave: compiled.model_flux(th, wave))
+    s = spectra[name]
+    ens = wl.make_ensemble(w)                       # the ensemble bench.py evaluates
+    inb = np.all((ens >= w["lb"]) & (ens <= w["ub"]), axis=1)
+    rows = np.concatenate([np.flatnonzero(inb)[:n_in], np.flatnonzero(~inb)[:n_out]])
+    thetas = ens[rows]
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = mc.vfit({name: dict(model=model, **s)}, w["theta_true"], w["lb"], w["ub"])
+    ref_lnprob = np.array([fitter.lnprob(t) for t in thetas])
+    px = flux_pixel_subset(s["wave"].size)
+    d = compiled.data
+    wave = s["wave"]
+    assert np.array_equal(wave, np.linspace(wave[0], wave[-1], wave.size))
+    assert np.all(s["error"] == s["error"][0])
+    out = dict(
+        meta=json.dumps(dict(case=case_name, workload=w["name"], voigt_method="wofz", error_dtype="float64",
+                             instruments=[name], ensemble_rows=[int(r) for r in rows],
+                             systems=[(z, ion, list(t), c) for (z, ion, t, c) in w["systems"]])),
+        thetas=thetas, lb=w["lb"], ub=w["ub"], ref_lnprob=ref_lnprob, flux_rows=np.array([0, 1]))
+    out.update({f"{name}__lambda0": d.atomic_lambda0, f"{name}__gamma": d.atomic_gamma, f"{name}__f": d.atomic_f,
+                f"{name}__zfac": d.z_factors, f"{name}__N_indices": d.N_indices,
+                f"{name}__taps": np.asarray(d.kernel.array), f"{name}__kernel_kind": np.array("gaussian"),
+                f"{name}__wave_linspace": np.array([wave[0], wave[-1], wave.size]),
+                f"{name}__error_const": np.array(s["error"][0]), f"{name}__flux": s["flux"],
+                f"{name}__flux_px": px,
+                f"{name}__ref_flux": np.array([compiled.model_flux(thetas[i], wave)[px] for i in (0, 1)]),
+                f"{name}__ref_flux_unconvolved": np.array(
+                    [model.evaluate(thetas[0], wave, return_unconvolved=True)[px]])})
+    path = os.path.join(GOLDEN_DIR, f"{case_name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{case_name}: rows={list(rows)} lnprob={ref_lnprob} -> {os.path.relpath(path, ROOT)} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def build_c5b_case(n_sightlines=8, walkers=16):
+    """Survey mode (C5b): `n_sightlines` independent sightlines (C1's structure at its own redshift, its own
+    spectrum = reference model(theta_true) + noise) x `walkers` rows each, every sightline through its own
+    reference vfit -- what S x vfit(...).lnprob does (vfit_mcmc.py:127-197, 348-353)."""
+    zs, waves, fluxes, errs, thetas, lnps = [], [], [], [], [], []
+    w0 = wl.c5b_sightline(0)
+    for sidx in range(n_sightlines):
+        w = wl.c5b_sightline(sidx)
+        config, models, mc = _ref_models(w)
+        model = models["COS"]
+        compiled = model.compile()
+        s = wl.make_spectra(w, lambda n, th, wave: compiled.model_flux(th, wave))["COS"]
+        th = wl.make_ensemble(w, walkers)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fitter = mc.vfit({"COS": dict(model=model, **s)}, w["theta_true"], w["lb"], w["ub"])
+        zs.append(w["systems"][0][0])
+        waves.append([s["wave"][0], s["wave"][-1], s["wave"].size])
+        assert np.array_equal(s["wave"], np.linspace(s["wave"][0], s["wave"][-1], s["wave"].size))
+        fluxes.append(s["flux"])
+        errs.append(s["error"][0])
+        thetas.append(th)
+        lnps.append([fitter.lnprob(t) for t in th])
+    path = os.path.join(GOLDEN_DIR, "C5b.npz")
+    np.savez_compressed(path, meta=json.dumps(dict(case="C5b", n_sightlines=n_sightlines, walkers=walkers)),
+                        z=np.array(zs), wave_linspace=np.array(waves), flux=np.array(fluxes),
+                        error_const=np.array(errs), thetas=np.array(thetas), ref_lnprob=np.array(lnps),
+                        lb=w0["lb"], ub=w0["ub"])
+    print(f"C5b: {n_sightlines} sightlines x {walkers} walkers, finite={np.isfinite(np.array(lnps)).sum()} -> "
+          f"{os.path.relpath(path, ROOT)} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def build_wofz_lattice():
     """Known-answer lattice for Re w(x + i a): scipy.special.wofz (the reference's call) and
     mpmath at 40 digits.  Covers core, mid, far wings and the whole a range."""
@@ -252,6 +339,13 @@ def main():
     th[:, 3] = [3.0, 1.9, 1.0, 0.5, 0.1, 0.05]
     build_case("C1_smallb", cs, nwalkers=4, extra_thetas=th)
     build_tutorial_cases()
+    build_big_cases()
+
+
+def build_big_cases():
+    build_big_case("C5a", wl.get_workload("C5a"))
+    build_big_case("C5a_L4", wl.get_workload("C5a_L4"))
+    build_c5b_case()
 
 
 def build_tutorial_cases():
@@ -272,4 +366,7 @@ def build_tutorial_cases():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        build_big_cases()         # only the headline-geometry / survey-mode fixtures
+    else:
+        main()

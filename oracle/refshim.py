@@ -13,8 +13,9 @@ numpy + scipy.  The stand-ins restate astropy >= 5.3 behaviour:
     edge replication.
   * ``astropy.io.ascii.read(file)``: whitespace table with columns col1..colN.
 
-Never importable on the GPU box (no /root/reference): only ``oracle/make_golden.py`` and the
-``reference``-marked tests use it.
+The reference is taken from /root/reference/src (build container) or, where that does not exist (the GPU box),
+from ``oracle/_ref`` -- the pip install of the unmodified reference staged by ``oracle/build_ref.py``.
+Users: ``oracle/make_golden.py``, the ``reference``-marked tests, ``bench.py --impl reference``.
 """
 from __future__ import annotations
 
@@ -25,11 +26,18 @@ import types
 
 import numpy as np
 
-REFERENCE_SRC = "/root/reference/src"
+STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_SRC = ("/root/reference/src" if os.path.isdir("/root/reference/src/rbvfit")
+                 and os.environ.get("RBVFIT_B200_REF") != "staged" else STAGED)
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "rbvfit"))
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "rbvfit", "vfit_mcmc.py"))
+
+
+def kind() -> str:
+    """Where the reference comes from: 'source tree' (/root/reference) or 'staged' (oracle/_ref)."""
+    return "staged" if REFERENCE_SRC == STAGED else "source tree"
 
 
 class _Kernel1D:
@@ -100,7 +108,7 @@ def _ascii_read(filename, **kwargs):
 def install():
     """Register the stand-ins and put the reference on sys.path.  Idempotent."""
     if not available():
-        raise RuntimeError("/root/reference is not present (GPU box?) -- refshim unusable")
+        raise RuntimeError("neither /root/reference nor oracle/_ref (python -m oracle.build_ref) is present")
     if "astropy" not in sys.modules:
         astropy = types.ModuleType("astropy")
         conv = types.ModuleType("astropy.convolution")

@@ -67,12 +67,14 @@ EXPORTS = {
     "rbv_slice_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(RbvSliceTuning),
                                 C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "rbv_flux_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "rbv_model_flux_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                       C.c_void_p]),
+                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "rbv_num_instruments": (C.c_int, [C.c_void_p]),
     "rbv_num_tiles": (C.c_int, [C.c_void_p]),
     "rbv_ndim": (C.c_int, [C.c_void_p]),
     "rbv_launch_count": (C.c_longlong, [C.c_void_p]),
+    "rbv_last_kernel": (C.c_int, [C.c_void_p]),
     "rbv_voigt_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "rbv_measure_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_double)]),
     "rbv_selftest_rcp": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

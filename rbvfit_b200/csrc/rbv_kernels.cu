@@ -509,9 +509,11 @@ __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w
   const bool skipped = prm.row_skip != nullptr && prm.row_skip[w] != 0;
   if (blockIdx.y == 0) {   // the walker's first block (every thread of it gets here): one parameter per thread
     int bad = skipped;
-    for (int i = threadIdx.x; i < prm.ndim; i += blockDim.x) {
-      const double t = th[i];
-      bad |= (t < prm.lb[i]) || (t > prm.ub[i]);
+    if (prm.lb != nullptr) {     // the flux entry point has no prior
+      for (int i = threadIdx.x; i < prm.ndim; i += blockDim.x) {
+        const double t = th[i];
+        bad |= (t < prm.lb[i]) || (t > prm.ub[i]);
+      }
     }
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
@@ -658,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
   int oob = 0;
   const bool fast = (I.method == RBV_VOIGT_FAST);
-  if (MODE == 0) {
+  if (MODE == 0 || prm.lc != nullptr) {
     // ---- per-line constants and the prior flag were computed once per walker by prep_kernel; the copy does not
     // wait for the flag (an out-of-bounds row's constants are finite or NaN, never read)
     {
@@ -668,10 +670,10 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       double2* dst = reinterpret_cast<double2*>(s_lc);
       for (int i = tid; i < I.L * (LC_STRIDE / 2); i += kThreads) dst[i] = src[i];
     }
-    oob = prm.oob[w];
+    if (MODE == 0) oob = prm.oob[w];
     __syncthreads();
   } else {
-    // ---- flux mode: the CTA prepares its own constants (no workspace in this entry point)
+    // ---- flux mode without a workspace: the CTA prepares its own constants
     const double* th_g = prm.theta + (size_t)w * ndim;
     for (int i = tid; i < ndim; i += kThreads) s_theta[i] = th_g[i];
     __syncthreads();
@@ -881,6 +883,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(const LaunchParams prm) {
   finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31);
 }
 
+}  // namespace rbv
+#include "rbv_stream.cuh"   // warp-autonomous streaming form of the lnprob kernel (big batches)
+namespace rbv {
+
 // ------------------------------------------------------------------------------------------ small kernels
 __global__ void reciprocal_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1005,9 +1011,33 @@ using namespace rbv;
 
 constexpr int kGeomLevels = 6;   // tile sizes, see compute_geometry
 static thread_local std::string g_last_error;
-static int g_force_ppt = 0;   // tuning hook (RBVFIT_B200_PPT=2|8)
-static int g_force_level = -1;   // tuning hook (RBVFIT_B200_GEOM=0..5)
-static int g_force_finalize = -1;   // tuning hook (RBVFIT_B200_FINALIZE=0|1)
+
+// Tuning / test hooks, read from the environment when a context is created and kept in that context
+struct Tuning {
+  int force_ppt = 0;        // RBVFIT_B200_PPT=2|8: pixels per lane in phase 1 of the tile kernel
+  int force_level = -1;     // RBVFIT_B200_GEOM=0..5: tile size of the tile kernel
+  int force_finalize = -1;  // RBVFIT_B200_FINALIZE=0|1: lnprob by a separate launch
+  int stream = -1;          // RBVFIT_B200_STREAM=0|1: streaming kernel never / whenever eligible (-1: by batch size)
+  int stream_segs = 0;      // RBVFIT_B200_STREAM_SEGS=n: 1024-pixel segments per work item of the streaming kernel
+  int stream_ctas = 0;      // RBVFIT_B200_STREAM_CTAS=n: CTAs per SM of the streaming kernel (0: occupancy)
+};
+
+// Every entry point runs on the context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;   // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define RBV_ON_DEVICE(ctx)                    \
+  DeviceGuard _guard((ctx)->device);          \
+  RBV_CUDA(_guard.err)
 
 static int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -1029,6 +1059,8 @@ struct HostInst {
 };
 
 struct RbvContext {
+  Tuning tune;
+  std::vector<std::pair<int, int>> stream_ctas_cache;   // (smem bytes, resident CTAs per SM) of voigt_stream_kernel
   int device = 0;
   int sm_count = 148;
   int ndim = 0;
@@ -1037,12 +1069,14 @@ struct RbvContext {
   int precision = RBV_PRECISION_FP64;
   int farfield = RBV_FARFIELD_CHEBYSHEV;
   long long launches = 0;
+  int last_kernel = -1;
   std::vector<HostInst> inst;
   InstDev* d_inst = nullptr;
   int max_dyn_smem = 0;
   double* d_lb = nullptr;
   double* d_ub = nullptr;
   double* d_core_tab = nullptr;
+  double* d_unit_taps = nullptr;        // {1, 0 x 7}: the 'no convolution' LSF of rbv_model_flux_batch(convolve = 0)
   size_t max_smem_lnprob[2] = {0, 0};  // per LOGR in {2,3}
   // rbv_slice_run: pinned landing slots + events for the per-iteration read-back of the counters
   SliceCounters* h_poll = nullptr;     // [2], page-locked
@@ -1078,20 +1112,27 @@ int rbv_create(int device, RbvContext** out) {
     return fail(RBV_ECUDA, std::string("rbv_create: no CUDA device (") + cudaGetErrorString(e) +
                                "); this library has no CPU fallback");
   if (device < 0 || device >= count) return fail(RBV_EINVAL, "rbv_create: bad device index");
-  RBV_CUDA(cudaSetDevice(device));
+  DeviceGuard _guard(device);
+  RBV_CUDA(_guard.err);
   RbvContext* ctx = new RbvContext();
   ctx->device = device;
   struct Guard {   // a failed set-up must not leak the half-built context
     RbvContext* c;
     ~Guard() { if (c) rbv_destroy(c); }
   } guard{ctx};
-  {   // tuning / test hooks, re-read whenever a context is created
+  {   // tuning / test hooks
     const char* e = getenv("RBVFIT_B200_PPT");
-    g_force_ppt = e ? atoi(e) : 0;
+    ctx->tune.force_ppt = e ? atoi(e) : 0;
     e = getenv("RBVFIT_B200_FINALIZE");
-    g_force_finalize = e ? atoi(e) : -1;
+    ctx->tune.force_finalize = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_GEOM");
-    g_force_level = e ? std::min(std::max(atoi(e), 0), kGeomLevels - 1) : -1;
+    ctx->tune.force_level = e ? std::min(std::max(atoi(e), 0), kGeomLevels - 1) : -1;
+    e = getenv("RBVFIT_B200_STREAM");
+    ctx->tune.stream = e ? atoi(e) : -1;
+    e = getenv("RBVFIT_B200_STREAM_SEGS");
+    ctx->tune.stream_segs = e ? std::max(atoi(e), 0) : 0;
+    e = getenv("RBVFIT_B200_STREAM_CTAS");
+    ctx->tune.stream_ctas = e ? std::max(atoi(e), 0) : 0;
   }
   cudaDeviceProp prop;
   RBV_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1101,12 +1142,17 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaMemcpyToSymbol(c_ff_nodes, RBV_FF_NODES_HOST, sizeof(RBV_FF_NODES_HOST)));
   RBV_CUDA(cudaMemcpyToSymbol(c_ff_minv, RBV_FF_MINV_HOST, sizeof(RBV_FF_MINV_HOST)));
   RBV_CUDA(upload(&ctx->d_core_tab, RBV_CORE_TABLE_HOST, (size_t)RBV_CORE_TABLE_LEN));
+  {
+    const double unit[8] = {1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    RBV_CUDA(upload(&ctx->d_unit_taps, unit, (size_t)8));
+  }
   const int max_dyn = (int)prop.sharedMemPerBlockOptin - 2048;
   ctx->max_dyn_smem = max_dyn;
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaMallocHost((void**)&ctx->h_poll, 2 * sizeof(SliceCounters)));
   for (int k = 0; k < 2; ++k) RBV_CUDA(cudaEventCreateWithFlags(&ctx->poll_ev[k], cudaEventDisableTiming));
   guard.c = nullptr;
@@ -1116,7 +1162,7 @@ int rbv_create(int device, RbvContext** out) {
 
 void rbv_destroy(RbvContext* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard _guard(ctx->device);
   for (auto& hi : ctx->inst) {
     for (void* p : hi.owned) cudaFree(p);
     cudaFree(hi.d_taps);
@@ -1125,6 +1171,7 @@ void rbv_destroy(RbvContext* ctx) {
   cudaFree(ctx->d_lb);
   cudaFree(ctx->d_ub);
   cudaFree(ctx->d_core_tab);
+  cudaFree(ctx->d_unit_taps);
   if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
   for (int k = 0; k < 2; ++k)
     if (ctx->poll_ev[k]) cudaEventDestroy(ctx->poll_ev[k]);
@@ -1154,6 +1201,25 @@ int rbv_set_farfield(RbvContext* ctx, int mode) {
 // batches), big tiles = less halo and per-CTA preamble (throughput of big batches).
 static const int kGeomUnits[kGeomLevels] = {2, 3, 4, 8, 16, 32};
 
+static TileGeom geometry_for(const InstDev& I, int level, int first_tile) {
+  int units = kGeomUnits[level];
+  if (I.K - 1 > 20) {                                     // halo <= ~8 % of the slots, at least one whole block out
+    const int min_units = std::max((int)std::ceil((I.K - 1) / (0.08 * 256)), (I.K - 1 + 255) / 256 + 1);
+    if (units < 8) units = std::max(units, std::min(min_units, 8 * 8));
+    else units = std::max(units, std::min(min_units, 8 * 8) * (units / 8));
+    units = std::min(units, 8 * 32);
+  }
+  const int need = (I.P + I.K - 1 + 255) / 256;           // no bigger than the spectrum
+  units = std::max(std::min(units, need), (I.K - 1 + 255) / 256 + 1);
+  TileGeom g;
+  g.tile = (units * 256 - (I.K - 1)) & ~255;              // tiles start on the 256-pixel blocks of InstDev::obs_w
+  g.ext_alloc = units * 256 + 2 * I.R;
+  g.n_super = (units * 256 + kSuperPix - 1) / kSuperPix;
+  g.first_tile = first_tile;
+  g.n_tiles = (I.P + g.tile - 1) / g.tile;
+  return g;
+}
+
 static int compute_geometry(const RbvContext* ctx, int level, TileGeom* geom, size_t* smem_out,
                             size_t n_inst_used = (size_t)-1) {
   int total = 0;
@@ -1161,21 +1227,7 @@ static int compute_geometry(const RbvContext* ctx, int level, TileGeom* geom, si
   int ndim = ctx->ndim;
   for (size_t k = 0; k < std::min(ctx->inst.size(), n_inst_used); ++k) {
     const InstDev& I = ctx->inst[k].dev;
-    int units = kGeomUnits[level];
-    if (I.K - 1 > 20) {                                     // halo <= ~8 % of the slots, at least one whole block out
-      const int min_units = std::max((int)std::ceil((I.K - 1) / (0.08 * 256)), (I.K - 1 + 255) / 256 + 1);
-      if (units < 8) units = std::max(units, std::min(min_units, 8 * 8));
-      else units = std::max(units, std::min(min_units, 8 * 8) * (units / 8));
-      units = std::min(units, 8 * 32);
-    }
-    const int need = (I.P + I.K - 1 + 255) / 256;           // no bigger than the spectrum
-    units = std::max(std::min(units, need), (I.K - 1 + 255) / 256 + 1);
-    TileGeom g;
-    g.tile = (units * 256 - (I.K - 1)) & ~255;              // tiles start on the 256-pixel blocks of InstDev::obs_w
-    g.ext_alloc = units * 256 + 2 * I.R;
-    g.n_super = (units * 256 + kSuperPix - 1) / kSuperPix;
-    g.first_tile = total;
-    g.n_tiles = (I.P + g.tile - 1) / g.tile;
+    const TileGeom g = geometry_for(I, level, total);
     total += g.n_tiles;
     geom[k] = g;
     smem = std::max(smem, smem_bytes_for(I, g, ndim ? ndim : 3 * I.C));
@@ -1187,7 +1239,7 @@ static int compute_geometry(const RbvContext* ctx, int level, TileGeom* geom, si
 // Chunk size of phase 1: 64-pixel chunks (2 px per lane) when the biggest tile of the launch has fewer than
 // kSmallChunkLimit 256-pixel chunks (<= 2 per warp: no room to balance line-core chunks), else 256-pixel chunks.
 static bool small_chunks(const RbvContext* ctx, const TileGeom* geom, int n) {
-  if (g_force_ppt) return g_force_ppt == 2;
+  if (ctx->tune.force_ppt) return ctx->tune.force_ppt == 2;
   int big = 0;
   for (int k = 0; k < n; ++k) big = std::max(big, geom[k].ext_alloc);
   return big < kSmallChunkLimit * 256;
@@ -1200,15 +1252,76 @@ static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t*
   const long long want = (long long)kWantWaves * RBV_MIN_CTAS * ctx->sm_count;
   int total = 0;
   for (int level = kGeomLevels - 1; level >= 0; --level) {
-    if (g_force_level >= 0) level = g_force_level;
+    if (ctx->tune.force_level >= 0) level = ctx->tune.force_level;
     size_t smem = 0;
     total = compute_geometry(ctx, level, geom, &smem, n_inst_used);
     bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, (227 * 1024) / RBV_MIN_CTAS - 2048);
-    if (level == 0 || g_force_level >= 0 || (fits && (long long)W * total >= want)) {
+    if (level == 0 || ctx->tune.force_level >= 0 || (fits && (long long)W * total >= want)) {
       if (smem_out) *smem_out = smem;
       return total;
     }
   }
+  return total;
+}
+
+// ---- streaming kernel (rbv_stream.cuh): work items = (walker, range of whole 1024-pixel segments of one instrument)
+constexpr int kStreamMaxHalo = 1024;    // K - 1 beyond this stays on the tile kernel (flux buffer per warp)
+constexpr int kStreamWarps = kThreads / 32;
+
+// Shared memory per warp (doubles) for the instruments of a launch; 0 = not eligible.
+static int stream_warp_doubles(const RbvContext* ctx, size_t n_inst_used) {
+  int need = 0;
+  for (size_t k = 0; k < std::min(ctx->inst.size(), n_inst_used); ++k) {
+    const InstDev& I = ctx->inst[k].dev;
+    if (I.K - 1 > kStreamMaxHalo) return 0;
+    need = std::max(need, stream_smem_layout(I.L, I.K, I.Kpad).total);
+  }
+  return need;
+}
+
+// Ranges per instrument for a batch of W walkers; returns the number of ranges (0 = use the tile kernel).
+static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_doubles, int* ctas_per_sm,
+                           size_t n_inst_used) {
+  if (ctx->tune.stream == 0 || ctx->precision != RBV_PRECISION_FP64) return 0;
+  const int wd = stream_warp_doubles(ctx, n_inst_used);
+  const size_t smem = (size_t)wd * kStreamWarps * sizeof(double);
+  if (wd == 0 || smem > (size_t)ctx->max_dyn_smem) return 0;
+  int ctas = -1;
+  for (auto& e : ctx->stream_ctas_cache)
+    if (e.first == (int)smem) ctas = e.second;
+  if (ctas < 0) {   // first use of this size (rebuild_tables warms the cache: no query while a stream is capturing)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, voigt_stream_kernel<3>, kThreads, smem) != cudaSuccess)
+      ctas = 0;
+    ctx->stream_ctas_cache.emplace_back((int)smem, ctas);
+  }
+  if (ctas <= 0) return 0;
+  if (ctx->tune.stream_ctas > 0) ctas = std::min(ctas, ctx->tune.stream_ctas);
+  const long long warps = (long long)ctas * kStreamWarps * ctx->sm_count;
+  const size_t n_used = std::min(ctx->inst.size(), n_inst_used);
+  TileGeom g0[kMaxInst];
+  compute_geometry(ctx, 0, g0, nullptr, n_used);     // the workspace holds one partial per level-0 tile
+  long long segs = 0;
+  for (size_t k = 0; k < n_used; ++k) segs += (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix;
+  // enough items to keep every resident warp busy several times over, else the tile kernel's small tiles win
+  if (ctx->tune.stream < 0 && (long long)W * segs < 6 * warps) return 0;
+  int seg = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
+                                      : (int)std::min<long long>(8, std::max<long long>(1, (long long)W * segs / (48 * warps)));
+  int total = 0;
+  for (size_t k = 0; k < n_used; ++k) {
+    const InstDev& I = ctx->inst[k].dev;
+    const int min_seg = (g0[k].tile + kSuperPix - 1) / kSuperPix;   // never more ranges than level-0 tiles
+    TileGeom g;
+    g.tile = std::max(seg, min_seg) * kSuperPix;
+    g.ext_alloc = 0;
+    g.n_super = 0;
+    g.first_tile = total;
+    g.n_tiles = (I.P + g.tile - 1) / g.tile;
+    total += g.n_tiles;
+    geom[k] = g;
+  }
+  if ((long long)W * total >= 0x7fffffffLL) return 0;
+  *warp_doubles = wd;
+  *ctas_per_sm = ctas;
   return total;
 }
 
@@ -1241,6 +1354,12 @@ static int rebuild_tables(RbvContext* ctx) {
   cudaFree(ctx->d_inst);
   ctx->d_inst = nullptr;
   RBV_CUDA(upload(&ctx->d_inst, flat.data(), flat.size()));
+  {   // occupancy of the streaming kernel for a joint launch and for a sightline launch
+    TileGeom g[kMaxInst];
+    int wd = 0, nb = 0;
+    stream_geometry(ctx, 1 << 20, g, &wd, &nb, kMaxInst);
+    stream_geometry(ctx, 1 << 20, g, &wd, &nb, 1);
+  }
   return RBV_OK;
 }
 
@@ -1257,9 +1376,17 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
   for (int l = 0; l < lt->n_lines; ++l)
     if (lt->comp[l] < 0 || lt->comp[l] >= lt->n_components)
       return fail(RBV_EINVAL, "rbv_add_instrument: component index out of range");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
 
   HostInst hi;
+  struct Rollback {   // a failure half-way must not leak what was already uploaded
+    HostInst* h;
+    ~Rollback() {
+      if (!h) return;
+      for (void* p : h->owned) cudaFree(p);
+      cudaFree(h->d_taps);
+    }
+  } rollback{&hi};
   InstDev& I = hi.dev;
   memset(&I, 0, sizeof(I));
   I.P = sp->n_pixels;
@@ -1315,14 +1442,15 @@ int rbv_add_instrument(RbvContext* ctx, const RbvLineTable* lt, const RbvSpectru
   if (I.log_inv_sigma2) {
     double* d_sum;
     RBV_CUDA(cudaMalloc((void**)&d_sum, sizeof(double)));
+    hi.owned.push_back(d_sum);          // freed with the instrument (or by the rollback)
     fixed_order_sum_kernel<<<1, 256>>>(I.log_inv_sigma2, I.P, d_sum);
     RBV_CUDA(cudaGetLastError());
     RBV_CUDA(cudaMemcpy(&I.sum_log_inv_sigma2, d_sum, sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_sum);
     ctx->launches++;
   }
 
   ctx->inst.push_back(hi);
+  rollback.h = nullptr;                 // the context owns the arrays from here on (rbv_destroy frees them)
   int rc = rebuild_tables(ctx);
   if (rc != RBV_OK) return rc;
   if (out_index) *out_index = (int)ctx->inst.size() - 1;
@@ -1333,7 +1461,7 @@ int rbv_set_bounds(RbvContext* ctx, const double* lb, const double* ub, int ndim
   if (!ctx || !lb || !ub || ndim <= 0) return fail(RBV_EINVAL, "rbv_set_bounds: bad argument");
   for (auto& hi : ctx->inst)
     if (3 * hi.dev.C > ndim) return fail(RBV_EINVAL, "rbv_set_bounds: ndim smaller than 3 * n_components");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   cudaFree(ctx->d_lb);
   cudaFree(ctx->d_ub);
   ctx->d_lb = ctx->d_ub = nullptr;
@@ -1406,7 +1534,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   }
   WorkspaceLayout lay = workspace_layout(ctx, W, sl);
   if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, std::string(who) + ": workspace too small");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
 
   LaunchParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -1438,7 +1566,10 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   // ONE launch covers every instrument: grid = (walkers, tiles per walker); the tile size is chosen per launch
   // from the batch size.  Sightline mode: each walker sees only its own instrument (identical geometry).
   size_t smem = 0;
-  prm.n_tiles = choose_geometry(ctx, W, prm.geom, &smem, sl ? 1 : (size_t)-1);
+  int stream_wd = 0, stream_ctas = 0;
+  const int stream_ranges = stream_geometry(ctx, W, prm.geom, &stream_wd, &stream_ctas, sl ? 1 : (size_t)-1);
+  if (stream_ranges > 0) prm.n_tiles = stream_ranges;
+  else prm.n_tiles = choose_geometry(ctx, W, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
   dim3 pgrid((unsigned)W, (unsigned)((prm.n_lines_total + 127) / 128));
@@ -1452,9 +1583,22 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   if (prm.inst_in_params)
     for (size_t k = 0; k < ctx->inst.size(); ++k) prm.inst_v[k] = ctx->inst[k].dev;
   prm.separate_finalize = (long long)W * prm.n_tiles >= 8LL * RBV_MIN_CTAS * ctx->sm_count;
-  if (g_force_finalize >= 0) prm.separate_finalize = g_force_finalize;
-  if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
-  else voigt_tile_kernel<3, 0, 8><<<grid, kThreads, smem, st>>>(prm);
+  if (ctx->tune.force_finalize >= 0) prm.separate_finalize = ctx->tune.force_finalize;
+  if (stream_ranges > 0) {
+    // persistent warps pull (walker, range) items from a global counter; lnprob always by finalize_kernel
+    prm.separate_finalize = 1;
+    const long long items = (long long)W * stream_ranges;
+    const unsigned ctas = (unsigned)std::min<long long>((long long)stream_ctas * ctx->sm_count,
+                                                        (items + kStreamWarps - 1) / kStreamWarps);
+    voigt_stream_kernel<3><<<ctas, kThreads, (size_t)stream_wd * kStreamWarps * sizeof(double), st>>>(prm, stream_wd);
+    ctx->last_kernel = RBV_KERNEL_STREAM;
+  } else if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) {
+    voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
+    ctx->last_kernel = RBV_KERNEL_TILE;
+  } else {
+    voigt_tile_kernel<3, 0, 8><<<grid, kThreads, smem, st>>>(prm);
+    ctx->last_kernel = RBV_KERNEL_TILE;
+  }
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   if (prm.separate_finalize) {
@@ -1483,7 +1627,7 @@ int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, doub
   if (!ctx || !theta_host || !lnprob_host || !theta_dev || !lnprob_dev)
     return fail(RBV_EINVAL, "rbv_lnprob_batch_host: null argument");
   if (W <= 0) return W == 0 ? RBV_OK : fail(RBV_EINVAL, "negative n_walkers");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   RBV_CUDA(cudaMemcpyAsync(theta_dev, theta_host, (size_t)W * ctx->ndim * sizeof(double), cudaMemcpyHostToDevice, st));
   int rc = rbv_lnprob_batch(ctx, theta_dev, W, lnprob_dev, workspace, workspace_bytes, stream);
@@ -1529,7 +1673,7 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
   if (n_steps == 0) return RBV_OK;
   const StretchLayout lay = stretch_layout(ctx, n_walkers);
   if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, "rbv_stretch_run: workspace too small");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   StretchParams P;
@@ -1634,7 +1778,7 @@ int rbv_stretch_propose_eval(RbvContext* ctx, const double* coords, int n_walker
   const int h = (n_walkers + 1) / 2, nS = split == 0 ? h : n_walkers - h;
   if (!coords || !lnprob_rows || (split != 0 && split != 1) || row_lo < 0 || row_hi < row_lo || row_hi > nS || !(a > 1.0))
     return fail(RBV_EINVAL, "rbv_stretch_propose_eval: bad argument");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   P.coords = const_cast<double*>(coords);
   P.first_step = step;
@@ -1659,7 +1803,7 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
   if (rc != RBV_OK) return rc;
   if (!coords || !lnprob || !lnprob_rows || !n_accepted || !flag || (split != 0 && split != 1))
     return fail(RBV_EINVAL, "rbv_stretch_accept: bad argument");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   const int h = (n_walkers + 1) / 2, nS = split == 0 ? h : n_walkers - h;
   P.coords = coords;
   P.lnp = lnprob;
@@ -1718,7 +1862,7 @@ int rbv_stretch_run_sightlines(RbvContext* ctx, double* coords, double* lnprob, 
   const StretchLayout lay = stretch_layout_sightlines(ctx, W);
   if (!workspace || workspace_bytes < lay.total)
     return fail(RBV_ENOMEM, "rbv_stretch_run_sightlines: workspace too small");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   StretchParams P;
@@ -1807,7 +1951,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   if (n_steps == 0) return RBV_OK;
   const SliceLayout lay = slice_layout(ctx, n_walkers);
   if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, "rbv_slice_run: workspace too small");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   SliceParams P;
@@ -1967,14 +2111,33 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   return RBV_OK;
 }
 
+// The instrument as the flux entry point sees it: with its LSF, or with the single tap 1.0 (convolve = 0:
+// VoigtModel.evaluate(return_unconvolved=True) skips the kernel, voigt_model.py:221, 537-548).
+static InstDev flux_instrument(const RbvContext* ctx, int inst, int convolve) {
+  InstDev I = ctx->inst[inst].dev;
+  if (!convolve) {
+    I.K = 1;
+    I.Kpad = I.R;
+    I.taps_rev = ctx->d_unit_taps;
+  }
+  I.line_base = 0;
+  return I;
+}
+
+int rbv_flux_workspace_bytes(const RbvContext* ctx, int inst, int n_walkers, size_t* bytes) {
+  if (!ctx || !bytes || n_walkers < 0 || inst < 0 || inst >= (int)ctx->inst.size())
+    return fail(RBV_EINVAL, "rbv_flux_workspace_bytes: bad argument");
+  *bytes = workspace_layout_raw(n_walkers, 1, ctx->inst[inst].dev.L).total;
+  return RBV_OK;
+}
+
 int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, int convolve, double* out_flux,
-                         void* stream) {
+                         void* workspace, size_t workspace_bytes, void* stream) {
   if (!ctx || !theta || !out_flux) return fail(RBV_EINVAL, "rbv_model_flux_batch: null argument");
   if (inst < 0 || inst >= (int)ctx->inst.size()) return fail(RBV_EINVAL, "rbv_model_flux_batch: bad instrument index");
   if (W <= 0) return W == 0 ? RBV_OK : fail(RBV_EINVAL, "negative n_walkers");
-  if (!convolve) return fail(RBV_EINVAL, "rbv_model_flux_batch: convolve=0 needs an instrument added without taps");
-  RBV_CUDA(cudaSetDevice(ctx->device));
-  const InstDev& I = ctx->inst[inst].dev;
+  RBV_ON_DEVICE(ctx);
+  const InstDev I = flux_instrument(ctx, inst, convolve);
   int ndim = ctx->ndim ? ctx->ndim : 3 * I.C;
   LaunchParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -1983,20 +2146,42 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   prm.core_tab = ctx->d_core_tab;
   prm.out_flux = out_flux;
   prm.ndim = ndim;
-  prm.n_inst = (int)ctx->inst.size();
+  prm.n_inst = 1;                     // the launch sees this one instrument (possibly without its LSF)
   prm.W = W;
   prm.precision = ctx->precision;
   prm.farfield = ctx->farfield;
   prm.sampler_split = -1;
-  if (ctx->inst.size() > (size_t)kMaxInst) return fail(RBV_EINVAL, "rbv_model_flux_batch: more than 16 instruments");
   prm.inst_in_params = 1;
-  for (size_t k = 0; k < ctx->inst.size(); ++k) prm.inst_v[k] = ctx->inst[k].dev;
-  prm.n_tiles = compute_geometry(ctx, W >= 64 ? 3 : 1, prm.geom, nullptr);   // flux mode: 2048- or 768-slot tiles
-  prm.tile_base = prm.geom[inst].first_tile;
-  size_t smem = smem_bytes_for(I, prm.geom[inst], ndim);
-  dim3 grid((unsigned)W, (unsigned)prm.geom[inst].n_tiles);
+  prm.inst_v[0] = I;
+  prm.n_lines_total = I.L;
+  // biggest tiles that still give every CTA slot of the GPU one CTA (as choose_geometry does for lnprob)
+  const long long want = (long long)kWantWaves * RBV_MIN_CTAS * ctx->sm_count;
+  size_t smem = 0;
+  for (int level = kGeomLevels - 1; level >= 0; --level) {
+    if (ctx->tune.force_level >= 0) level = ctx->tune.force_level;
+    prm.geom[0] = geometry_for(I, level, 0);
+    smem = smem_bytes_for(I, prm.geom[0], ndim);
+    const bool fits = smem <= (size_t)std::min(ctx->max_dyn_smem, (227 * 1024) / RBV_MIN_CTAS - 2048);
+    if (level == 0 || ctx->tune.force_level >= 0 || (fits && (long long)W * prm.geom[0].n_tiles >= want)) break;
+  }
+  prm.n_tiles = prm.geom[0].n_tiles;
+  prm.tile_base = 0;
+  if (prm.n_tiles > 65535) return fail(RBV_EINVAL, "rbv_model_flux_batch: more than 65535 tiles per walker");
   cudaStream_t st = (cudaStream_t)stream;
-  if (small_chunks(ctx, prm.geom + inst, 1)) voigt_tile_kernel<3, 1, 2><<<grid, kThreads, smem, st>>>(prm);
+  if (workspace) {
+    // line constants once per walker (prep_kernel), as in the lnprob launch, instead of once per CTA
+    const WorkspaceLayout lay = workspace_layout_raw(W, 1, I.L);
+    if (workspace_bytes < lay.total) return fail(RBV_ENOMEM, "rbv_model_flux_batch: workspace too small");
+    prm.tickets = (unsigned int*)((char*)workspace + lay.tickets);
+    prm.oob = (int*)((char*)workspace + lay.oob);
+    prm.lc = (double*)((char*)workspace + lay.lc);
+    dim3 pgrid((unsigned)W, (unsigned)((I.L + 127) / 128));
+    prep_kernel<<<pgrid, 128, 0, st>>>(prm);
+    RBV_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
+  if (small_chunks(ctx, prm.geom, 1)) voigt_tile_kernel<3, 1, 2><<<grid, kThreads, smem, st>>>(prm);
   else voigt_tile_kernel<3, 1, 8><<<grid, kThreads, smem, st>>>(prm);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -2007,11 +2192,12 @@ int rbv_num_instruments(const RbvContext* ctx) { return ctx ? (int)ctx->inst.siz
 int rbv_num_tiles(const RbvContext* ctx) { return ctx ? ctx->n_tiles : 0; }
 int rbv_ndim(const RbvContext* ctx) { return ctx ? ctx->ndim : 0; }
 long long rbv_launch_count(const RbvContext* ctx) { return ctx ? ctx->launches : 0; }
+int rbv_last_kernel(const RbvContext* ctx) { return ctx ? ctx->last_kernel : -1; }
 
 int rbv_voigt_h(RbvContext* ctx, const double* x, const double* a, double* out, int n, int method, void* stream) {
   if (!ctx || !x || !a || !out || n < 0) return fail(RBV_EINVAL, "rbv_voigt_h: bad argument");
   if (n == 0) return RBV_OK;
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   voigt_h_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, a, out, n, method, ctx->d_core_tab);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -2020,7 +2206,7 @@ int rbv_voigt_h(RbvContext* ctx, const double* x, const double* a, double* out, 
 
 int rbv_measure_fp64_peak(RbvContext* ctx, double millis, double* tflops) {
   if (!ctx || !tflops) return fail(RBV_EINVAL, "rbv_measure_fp64_peak: bad argument");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   double* d_out;
   RBV_CUDA(cudaMalloc(&d_out, sizeof(double)));
   cudaEvent_t e0, e1;
@@ -2054,7 +2240,7 @@ int rbv_measure_fp64_peak(RbvContext* ctx, double millis, double* tflops) {
 // max relative error of the device reciprocal used in the asymptotic tiers (test hook)
 int rbv_selftest_rcp(RbvContext* ctx, double* max_rel_err) {
   if (!ctx || !max_rel_err) return fail(RBV_EINVAL, "rbv_selftest_rcp: bad argument");
-  RBV_CUDA(cudaSetDevice(ctx->device));
+  RBV_ON_DEVICE(ctx);
   double* d;
   RBV_CUDA(cudaMalloc(&d, sizeof(double)));
   RBV_CUDA(cudaMemset(d, 0, sizeof(double)));

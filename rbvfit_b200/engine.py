@@ -300,8 +300,9 @@ class Engine:
             int(bool(use_graph)), self._stream()), "rbv_slice_run")
         return mus_t.cpu().numpy()[:int(n_steps)]
 
-    def model_flux(self, inst: int, theta: np.ndarray) -> np.ndarray:
-        """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``."""
+    def model_flux(self, inst: int, theta: np.ndarray, convolve: bool = True) -> np.ndarray:
+        """HOST theta [W, ndim] -> HOST model flux [W, P] of instrument ``inst``; ``convolve=False`` skips the LSF
+        (``VoigtModel.evaluate(return_unconvolved=True)``)."""
         torch = _torch()
         cols = self.ndim if self.ndim else 3 * self.components[inst]
         theta = np.asarray(theta, dtype=np.float64)
@@ -310,7 +311,14 @@ class Engine:
         th = torch.as_tensor(np.ascontiguousarray(theta[:, :cols]), device=self.tdev)
         W = th.shape[0]
         out = torch.empty((W, self.pixels[inst]), dtype=torch.float64, device=self.tdev)
-        check(self.lib.rbv_model_flux_batch(self._h, inst, th.data_ptr(), W, 1, out.data_ptr(), self._stream()),
+        ws, ws_bytes = None, 0
+        if W >= 4:      # line constants once per walker instead of once per CTA
+            nbytes = C.c_size_t(0)
+            check(self.lib.rbv_flux_workspace_bytes(self._h, inst, W, C.byref(nbytes)), "rbv_flux_workspace_bytes")
+            ws = torch.empty(max(int(nbytes.value), 8), dtype=torch.uint8, device=self.tdev)
+            ws_bytes = int(nbytes.value)
+        check(self.lib.rbv_model_flux_batch(self._h, inst, th.data_ptr(), W, int(bool(convolve)), out.data_ptr(),
+                                            ws.data_ptr() if ws is not None else None, ws_bytes, self._stream()),
               "rbv_model_flux_batch")
         return out.cpu().numpy()
 
@@ -331,6 +339,11 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.rbv_launch_count(self._h))
+
+    @property
+    def last_kernel(self):
+        """'tile' / 'stream': the kernel the most recent lnprob launch used (None before the first)."""
+        return {0: "tile", 1: "stream"}.get(self.lib.rbv_last_kernel(self._h))
 
     def measure_fp64_peak(self, millis: float = 200.0) -> float:
         out = C.c_double(0.0)

@@ -49,17 +49,15 @@ class _FluxEvaluator:
         self.max_grids = max_grids
         self._engines: Dict[Any, Engine] = {}
 
-    def _engine_for(self, wave: np.ndarray, convolve: bool, data: CompiledModelData) -> Engine:
+    def _engine_for(self, wave: np.ndarray, data: CompiledModelData) -> Engine:
         wave = np.ascontiguousarray(wave, dtype=np.float64)
-        key = (wave.size, hashlib.blake2b(wave.tobytes(), digest_size=16).digest(), bool(convolve),
-               id(data))
+        key = (wave.size, hashlib.blake2b(wave.tobytes(), digest_size=16).digest(), id(data))
         eng = self._engines.get(key)
         if eng is None:
             if len(self._engines) >= self.max_grids:
                 self._engines.pop(next(iter(self._engines))).close()
             eng = Engine(self.device)
-            taps = data.kernel if convolve else None
-            eng.add_instrument(data, wave, taps=taps, normalize_taps=data.kernel_normalize)
+            eng.add_instrument(data, wave, taps=data.kernel, normalize_taps=data.kernel_normalize)
             self._engines[key] = eng
         return eng
 
@@ -70,8 +68,7 @@ class _FluxEvaluator:
         th = np.atleast_2d(theta)
         if th.shape[1] < 3 * data.total_components:
             raise IndexError(f"theta has {th.shape[1]} parameters, the model needs {3 * data.total_components}")
-        eng = self._engine_for(wave, convolve, data)
-        out = eng.model_flux(0, th)
+        out = self._engine_for(wave, data).model_flux(0, th, convolve=convolve)   # convolve=0: LSF skipped in-kernel
         return out[0] if single else out
 
     def close(self):

@@ -199,10 +199,26 @@ def test_no_writes_outside_caller_buffers():
         assert np.array_equal(big_out[PAD:PAD + W].cpu().numpy(), like.lnprob(thetas), equal_nan=True)
         P = wave.size
         big_flux = torch.full((W * P + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
-        check(lib.rbv_model_flux_batch(eng._h, 0, th.data_ptr(), W, 1, big_flux[PAD:].data_ptr(), None))
+        check(lib.rbv_model_flux_batch(eng._h, 0, th.data_ptr(), W, 1, big_flux[PAD:].data_ptr(), None, 0, None))
         torch.cuda.synchronize()
         assert torch.all(big_flux[:PAD] == SENT) and torch.all(big_flux[PAD + W * P:] == SENT)
         assert torch.all(torch.isfinite(big_flux[PAD:PAD + W * P]))
+        # the same call with a workspace (line constants once per walker): same flux, workspace extent respected
+        check(lib.rbv_flux_workspace_bytes(eng._h, 0, W, C.byref(nbytes)))
+        nfw = (int(nbytes.value) + 7) // 8
+        big_fw = torch.full((nfw + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+        big_flux2 = torch.full((W * P + 2 * PAD,), SENT, dtype=torch.float64, device="cuda")
+        for conv in (1, 0):
+            check(lib.rbv_model_flux_batch(eng._h, 0, th.data_ptr(), W, conv, big_flux2[PAD:].data_ptr(),
+                                           big_fw[PAD:].data_ptr(), int(nbytes.value), None))
+            torch.cuda.synchronize()
+            assert torch.all(big_fw[:PAD] == SENT) and torch.all(big_fw[PAD + nfw:] == SENT)
+            assert torch.all(big_flux2[:PAD] == SENT) and torch.all(big_flux2[PAD + W * P:] == SENT)
+            if conv:
+                assert torch.equal(big_flux2, big_flux)
+        # convolve = 0 in-kernel == an instrument added without taps (what the reference's evaluate() computes)
+        unc = np.array([vo.model_flux(om, t, wave, convolve=False) for t in thetas[:2]])
+        assert np.max(np.abs(big_flux2[PAD:PAD + 2 * P].cpu().numpy().reshape(2, P)[:len(unc)] - unc)) <= FLUX_TOL
     # sampler: coords / lnprob / chain / counters with canaries
     W, nd, nsteps = 22, like.ndim, 6
     ok = wl.make_ensemble(w, 60)

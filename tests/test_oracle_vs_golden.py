@@ -3,7 +3,7 @@ code (oracle/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from golden_util import CASES, Golden
+from golden_util import BIG_CASES, CASES, Golden, GoldenSightlines
 from oracle import voigt_oracle as vo
 
 
@@ -52,6 +52,41 @@ def test_lnprob_matches_reference(case):
     assert np.array_equal(np.isneginf(got), np.isneginf(ref))
     fin = np.isfinite(ref)
     assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-14
+
+
+@pytest.mark.parametrize("case", BIG_CASES)
+def test_headline_geometry_matches_reference(case):
+    """C5a / C5a_L4 (100 000 px): lowering, lnprob of the 10 fixture rows and the flux of two rows on the pixel
+    subset, oracle vs the live reference's committed outputs."""
+    g = Golden(case)
+    n = g.instruments[0]
+    m = g.oracle_models()[n]
+    assert np.array_equal(m.atomic_lambda0, g.inst(n, "lambda0")) and np.array_equal(m.atomic_f, g.inst(n, "f"))
+    assert np.array_equal(m.kernel_taps, g.inst(n, "taps"))
+    wave, px = g.inst(n, "wave"), g.inst(n, "flux_px")
+    assert wave.size == 100000 and px.size < wave.size // 4
+    for k, row in enumerate(g.flux_rows):
+        got = vo.model_flux(m, g.thetas[row], wave)
+        assert np.max(np.abs(got[px] - g.inst(n, "ref_flux")[k])) <= 1e-15
+    unc = vo.model_flux(m, g.thetas[0], wave, convolve=False)
+    assert np.max(np.abs(unc[px] - g.inst(n, "ref_flux_unconvolved")[0])) <= 1e-15
+    got = vo.lnprob_batch(g.oracle_compiled(), g.thetas, g.lb, g.ub)
+    ref = g.ref_lnprob
+    assert np.count_nonzero(np.isneginf(ref)) == 2 and np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-14
+
+
+def test_sightline_fixture_matches_reference():
+    """C5b: every sightline's oracle likelihood against that sightline's own reference vfit."""
+    g = GoldenSightlines()
+    assert g.n == 8 and g.thetas.shape[1:] == (16, 6)
+    for s in range(g.n):
+        got = vo.lnprob_batch(g.oracle_compiled(s), g.thetas[s], g.lb, g.ub)
+        ref = g.ref_lnprob[s]
+        assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+        fin = np.isfinite(ref)
+        assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-14
 
 
 def test_known_answer_test_script():

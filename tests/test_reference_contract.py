@@ -58,3 +58,48 @@ def test_reference_unified_results_accepts_our_fitter(sampler_name):
     assert r.config_metadata is not None and set(r.instrument_data) == {"COS"}
     assert np.all(np.abs(r.samples.mean(axis=0) - mu) < 0.5 * sig)
     assert r.correlation_matrix().shape == (3, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload", ["C1", "C3"])
+def test_reference_vfit_drives_gpu_model(workload):
+    """SURVEY 8(b) model plug point: the UNMODIFIED reference `vfit` (staged by oracle/build_ref.py, imported through
+    the shim) takes a `GpuVoigtModel` as `instrument_data[...]['model']` -- it sees `.config` + `.compile()` and calls
+    `compile(verbose=False).model_flux(theta, wave)` per instrument (vfit_mcmc.py:238-248), then does its own
+    chi^2 in numpy (:297-319).  Its lnprob must agree with this package's fused-device `vfit.lnprob` and with the
+    oracle on the same rows."""
+    import contextlib
+    import io
+    from oracle import refshim, voigt_oracle as vo
+    from rbvfit_b200 import FitConfiguration, lsf, workloads as wl
+    from rbvfit_b200.model import GpuVoigtModel
+    from rbvfit_b200.vfit_mcmc import vfit as gpu_vfit
+    refshim.install()
+    import rbvfit.vfit_mcmc as mc
+    w = wl.get_workload(workload)
+    cfg, ocfg = FitConfiguration(), vo.OracleConfig()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+        ocfg.add_system(z, ion, trans, comps)
+    models, omodels = {}, {}
+    for name, inst in w["instruments"].items():
+        cos = inst.get("lsf") == "cos_like"
+        models[name] = GpuVoigtModel(cfg, FWHM=inst["FWHM"], lsf_taps=lsf.cos_like_taps(321) if cos else None)
+        omodels[name] = vo.lower(ocfg, FWHM=inst["FWHM"], custom_taps=vo.cos_like_lsf(321) if cos else None)
+    spectra = wl.make_spectra(w, lambda n, th, wave: vo.model_flux(omodels[n], th, wave))
+    inst_data = {n: dict(model=models[n], **spectra[n]) for n in models}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_fitter = mc.vfit(inst_data, w["theta_true"], w["lb"], w["ub"])       # the reference's own class
+    ours = gpu_vfit(inst_data, w["theta_true"], w["lb"], w["ub"])
+    thetas = wl.make_ensemble(w, 24)
+    with np.errstate(all="ignore"):
+        ref = np.array([ref_fitter.lnprob(t) for t in thetas])
+    got = ours.lnprob(thetas)
+    ora = vo.lnprob_batch(vo.compile_instruments({n: dict(model=omodels[n], **spectra[n]) for n in omodels}),
+                          thetas, w["lb"], w["ub"])
+    assert np.isneginf(ref).any() and np.array_equal(np.isneginf(ref), np.isneginf(got))
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-9
+    assert np.max(np.abs(ora[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-9
+    # the reference's optimiser entry (vfit_mcmc.py:355-360) runs on the GPU-backed model as well
+    assert np.isfinite(ref_fitter.lnprob(w["theta_true"]))
