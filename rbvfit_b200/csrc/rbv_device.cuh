@@ -117,6 +117,28 @@ __device__ __noinline__ double asym_complex(double x, double a, double d) {
   return -kInvSqrtPi * fma(rr, Si, ri * Sr);
 }
 
+// exp(x) for the flux: Cody-Waite reduction x = k ln2 + r, |r| <= 0.347, degree-13 Taylor polynomial
+// (truncation 4e-18), scaling by an exponent-field add.  Coefficients sit in constant memory so that every
+// DFMA takes its constant as a c[][] operand (CUDA's exp() spends 23 UMOVs per call on them).
+// Results below 2^-1020 flush to 0 (np.exp would return a denormal < 1e-307: irrelevant at |dflux| <= 1e-10).
+__constant__ double c_exp[14] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                                 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+
+__device__ __forceinline__ double exp_flux(double x) {
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);   // round(x log2 e) in the low word
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = c_exp[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = fma(p, r, c_exp[i]);
+  double y = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  if (!(x >= -707.0)) y = (x != x) ? x : 0.0;     // underflow (and NaN passes through)
+  if (x > 709.0) y = CUDART_INF;
+  return y;
+}
+
 // Core evaluation of H(a,x) for |z|^2 < 64, a <= kAFast, from the g_k tables (global memory, L1-resident).
 __device__ __noinline__ double core_H_table(double x, double a, double a2, const double* __restrict__ tab) {
   double ax = fabs(x);
@@ -140,7 +162,7 @@ __device__ __noinline__ double core_H_table(double x, double a, double a2, const
 #pragma unroll
   for (int k = RBV_CORE_DEG3 - 1; k >= 0; --k) g3 = fma(g3, t, __ldg(p3 + k * RBV_CORE_NINT));
   double G = fma(fma(fma(g3, a2, g2), a2, g1), a2, g0);
-  double E = exp(fma(-x, x, a2));                 // exp(a^2 - x^2)
+  double E = exp_flux(fma(-x, x, a2));            // exp(a^2 - x^2), argument in (-64, 0.0025]
   double ax_ = a * x;
   double y = ax_ * ax_;                           // cos(2 a x) = sum_k (-4 y)^k / (2k)!
   double c = -4.0 / 14175.0;
@@ -194,28 +216,6 @@ __device__ __forceinline__ double tg_H(double x, double a_over_sqrtpi, double ep
   double Htg = G - a_over_sqrtpi * numer / denom;
   double Hcore = G * core_fac;
   return (x2 < eps) ? Hcore : Htg;
-}
-
-// exp(x) for the flux: Cody-Waite reduction x = k ln2 + r, |r| <= 0.347, degree-13 Taylor polynomial
-// (truncation 4e-18), scaling by an exponent-field add.  Coefficients sit in constant memory so that every
-// DFMA takes its constant as a c[][] operand (CUDA's exp() spends 23 UMOVs per call on them).
-// Results below 2^-1020 flush to 0 (np.exp would return a denormal < 1e-307: irrelevant at |dflux| <= 1e-10).
-__constant__ double c_exp[14] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
-                                 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
-
-__device__ __forceinline__ double exp_flux(double x) {
-  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);   // round(x log2 e) in the low word
-  const int k = __double2loint(t);
-  const double kd = t - 6755399441055744.0;
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  double p = c_exp[13];
-#pragma unroll
-  for (int i = 12; i >= 0; --i) p = fma(p, r, c_exp[i]);
-  double y = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-  if (!(x >= -707.0)) y = (x != x) ? x : 0.0;     // underflow (and NaN passes through)
-  if (x > 709.0) y = CUDART_INF;
-  return y;
 }
 
 // exp(x) for -2^-6 < x <= 0: degree-6 Taylor polynomial, truncation |x|^7/7! <= 4.5e-17 (less than half an ulp of

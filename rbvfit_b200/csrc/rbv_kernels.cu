@@ -88,6 +88,7 @@ struct LaunchParams {
   int tile_base;         // flux mode: first tile of the instrument
   int precision;
   int farfield;          // 1 = far wings of a chunk through the Chebyshev far-field interpolant (section 4c)
+  double ff_budget;      // far-field error budget in optical depth per pixel, summed over lines (kFFEps)
   int wps;               // sightline mode: walkers per sightline (walker w belongs to instrument w / wps); 0 = off
   // device-resident sampler (rbv_stretch_run): when sampler_split >= 0 the prep kernel first builds the stretch
   // proposal of row w, and the CTA that finalises lnprob[w] also applies accept/reject and records the chain
@@ -165,8 +166,9 @@ extern __shared__ double smem[];   // every hot-loop access indexes this array d
 constexpr int kTierFar = 0, kTierMid = 1, kTierNear = 2, kTierCore = 3, kTierGeneral = 4, kTierFar32 = 5,
               kTierFF = 6;
 // Far-field budget: the interpolation errors of all lines of one pixel sum to <= kFFEps in optical depth
-// (flux error <= 1e-13, three decades inside the 1e-10 parity tolerance).
-constexpr double kFFEps = 1e-13;
+// (flux error <= 1e-12, two decades inside the 1e-10 parity tolerance; the bound is conservative -- measured against
+// the direct evaluation on the C1..C5a workloads the flux differs by <= 2e-14, profiles/r02_notes.md).
+constexpr double kFFEps = 1e-12;
 
 // Classify every line once per warp chunk from the chunk's range of 1/lambda (lane l handles line l):
 // far lines go to the front of the warp's list, everything else to the back with its tier in the top bits.
@@ -655,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   unsigned short* s_listff = s_lists + (G.n_super * 2 + warp) * list_stride;
   // FP32 gate: the gated contributions of one pixel sum to <= 4e-6 (=> |dtau| <= 1e-11)
   const double gate32 = (prm.precision == RBV_PRECISION_FP32_GATED) ? 4e-6 / (double)I.L : 0.0;
-  const float ff_eps = prm.farfield ? (float)(kFFEps / (double)I.L) : 0.f;
+  const float ff_eps = prm.farfield ? (float)(prm.ff_budget / (double)I.L) : 0.f;
 
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
   int oob = 0;
@@ -1020,6 +1022,7 @@ struct Tuning {
   int stream = -1;          // RBVFIT_B200_STREAM=0|1: streaming kernel never / whenever eligible (-1: by batch size)
   int stream_segs = 0;      // RBVFIT_B200_STREAM_SEGS=n: 1024-pixel segments per work item of the streaming kernel
   int stream_ctas = 0;      // RBVFIT_B200_STREAM_CTAS=n: CTAs per SM of the streaming kernel (0: occupancy)
+  double ff_budget = kFFEps;   // RBVFIT_B200_FF_EPS=x: far-field error budget (experiments only)
 };
 
 // Every entry point runs on the context's device and leaves the caller's current device as it found it.
@@ -1133,6 +1136,8 @@ int rbv_create(int device, RbvContext** out) {
     ctx->tune.stream_segs = e ? std::max(atoi(e), 0) : 0;
     e = getenv("RBVFIT_B200_STREAM_CTAS");
     ctx->tune.stream_ctas = e ? std::max(atoi(e), 0) : 0;
+    e = getenv("RBVFIT_B200_FF_EPS");
+    if (e && atof(e) > 0.0) ctx->tune.ff_budget = atof(e);
   }
   cudaDeviceProp prop;
   RBV_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1265,8 +1270,8 @@ static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t*
 }
 
 // ---- streaming kernel (rbv_stream.cuh): work items = (walker, range of whole 1024-pixel segments of one instrument)
-constexpr int kStreamMaxHalo = 1024;    // K - 1 beyond this stays on the tile kernel (flux buffer per warp)
-constexpr int kStreamWarps = kThreads / 32;
+constexpr int kStreamMaxHalo = 64;      // wider LSFs stay on the tile kernel (its LSF loop is unrolled 3 x 8 taps)
+constexpr int kStreamWarps = kStreamThreads / 32;
 
 // Shared memory per warp (doubles) for the instruments of a launch; 0 = not eligible.
 static int stream_warp_doubles(const RbvContext* ctx, size_t n_inst_used) {
@@ -1290,7 +1295,7 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_dou
   for (auto& e : ctx->stream_ctas_cache)
     if (e.first == (int)smem) ctas = e.second;
   if (ctas < 0) {   // first use of this size (rebuild_tables warms the cache: no query while a stream is capturing)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, voigt_stream_kernel<3>, kThreads, smem) != cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, voigt_stream_kernel<3>, kStreamThreads, smem) != cudaSuccess)
       ctas = 0;
     ctx->stream_ctas_cache.emplace_back((int)smem, ctas);
   }
@@ -1302,10 +1307,12 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_dou
   compute_geometry(ctx, 0, g0, nullptr, n_used);     // the workspace holds one partial per level-0 tile
   long long segs = 0;
   for (size_t k = 0; k < n_used; ++k) segs += (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix;
-  // enough items to keep every resident warp busy several times over, else the tile kernel's small tiles win
-  if (ctx->tune.stream < 0 && (long long)W * segs < 6 * warps) return 0;
-  int seg = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
-                                      : (int)std::min<long long>(8, std::max<long long>(1, (long long)W * segs / (48 * warps)));
+  // Segments per item: long ranges amortise the item start (line constants, taps, the K-1 leading flux values
+  // evaluated line by line: about one row's worth of instructions), short ones balance the tail of the launch.
+  // The choice depends on the spectra only, never on the batch size, so a walker's lnprob is bit-identical in
+  // every batch that takes this path.
+  const int seg = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
+                                            : (int)std::min<long long>(16, std::max<long long>(4, segs / 6));
   int total = 0;
   for (size_t k = 0; k < n_used; ++k) {
     const InstDev& I = ctx->inst[k].dev;
@@ -1320,6 +1327,8 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_dou
     geom[k] = g;
   }
   if ((long long)W * total >= 0x7fffffffLL) return 0;
+  // enough items to keep every resident warp busy a few times over, else the tile kernel's small tiles win
+  if (ctx->tune.stream < 0 && (long long)W * total < 2 * warps) return 0;
   *warp_doubles = wd;
   *ctas_per_sm = ctas;
   return total;
@@ -1555,6 +1564,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   prm.W = W;
   prm.precision = ctx->precision;
   prm.farfield = ctx->farfield;
+  prm.ff_budget = ctx->tune.ff_budget;
   prm.wps = wps;
   prm.sampler_split = -1;
   if (sampler) {
@@ -1590,7 +1600,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
     const long long items = (long long)W * stream_ranges;
     const unsigned ctas = (unsigned)std::min<long long>((long long)stream_ctas * ctx->sm_count,
                                                         (items + kStreamWarps - 1) / kStreamWarps);
-    voigt_stream_kernel<3><<<ctas, kThreads, (size_t)stream_wd * kStreamWarps * sizeof(double), st>>>(prm, stream_wd);
+    voigt_stream_kernel<3><<<ctas, kStreamThreads, (size_t)stream_wd * kStreamWarps * sizeof(double), st>>>(prm, stream_wd);
     ctx->last_kernel = RBV_KERNEL_STREAM;
   } else if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) {
     voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
@@ -2150,6 +2160,7 @@ int rbv_model_flux_batch(RbvContext* ctx, int inst, const double* theta, int W, 
   prm.W = W;
   prm.precision = ctx->precision;
   prm.farfield = ctx->farfield;
+  prm.ff_budget = ctx->tune.ff_budget;
   prm.sampler_split = -1;
   prm.inst_in_params = 1;
   prm.inst_v[0] = I;

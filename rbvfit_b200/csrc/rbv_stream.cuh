@@ -26,10 +26,13 @@
 
 namespace rbv {
 
-#ifndef RBV_STREAM_LSF_UNROLL
-#define RBV_STREAM_LSF_UNROLL 1
+#ifndef RBV_STREAM_THREADS
+#define RBV_STREAM_THREADS 256
 #endif
-constexpr int kStreamLsfUnroll = RBV_STREAM_LSF_UNROLL;
+#ifndef RBV_STREAM_MIN_CTAS
+#define RBV_STREAM_MIN_CTAS 2
+#endif
+constexpr int kStreamThreads = RBV_STREAM_THREADS;
 constexpr int kStreamRow = 256;        // pixels per row (8 per lane)
 constexpr int kStreamRowsPerRecord = kSuperPix / kStreamRow;
 
@@ -47,8 +50,8 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int L, int K, int Kpad)
   s.scratch = s.flux + (((K - 1) + ((K - 1) >> 3) + 1) & ~1);  // phase-0 transpose scratch: the still empty row
   s.rec = s.flux + ((slots + 1) & ~1);
   s.lists = s.rec + SC_STRIDE;
-  const int list_stride = (L + 3) & ~3;                       // u16 entries per list, 3 lists
-  s.total = (s.lists + (3 * list_stride * 2 + 7) / 8 + 1) & ~1;
+  const int list_stride = (L + 3) & ~3;                       // u16 entries per list, 2 lists
+  s.total = (s.lists + (2 * list_stride * 2 + 7) / 8 + 1) & ~1;
   return s;
 }
 
@@ -92,23 +95,25 @@ __device__ __noinline__ double core_H_call(double x, double a, double a2, const 
 __device__ __noinline__ double general_H_call(double x, double a, double d) { return general_H(x, a, d); }
 
 // a >= 1 (unphysical damping, correctness only); by value into the call: u / tau stay in registers
-__device__ __forceinline__ void stream_general_line(int off, const double (&u)[8], double (&tau)[8]) {
+template <int PPT>
+__device__ __forceinline__ void stream_general_line(int off, const double (&u)[PPT], double (&tau)[PPT]) {
   const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2], a = smem[off + LC_a],
                coef = smem[off + LC_COEF];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     const double x = fma(A, u[j], -B);
     tau[j] = fma(coef, general_H_call(x, a, fma(x, x, a2)), tau[j]);
   }
 }
 
-__device__ __forceinline__ void stream_direct_line(int off, const double (&u)[8], double (&tau)[8],
+template <int PPT>
+__device__ __forceinline__ void stream_direct_line(int off, const double (&u)[PPT], double (&tau)[PPT],
                                                    const double* __restrict__ core_tab) {
   const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2];
-  double rho[8], s[8];
+  double rho[PPT], s[PPT];
   int hm = 0x7fffffff;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     const double x = fma(A, u[j], -B);
     s[j] = fma(x, x, a2);                                   // |z|^2
     hm = min(hm, __double2hiint(s[j]));
@@ -117,48 +122,57 @@ __device__ __forceinline__ void stream_direct_line(int off, const double (&u)[8]
   const bool has_core = hm < kHiCore;
   if (!has_core) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rho[j] = rcp_pos(s[j]);
+    for (int j = 0; j < PPT; ++j) rho[j] = rcp_pos(s[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rho[j] = (__double2hiint(s[j]) < kHiCore) ? 0.0 : rcp_pos(s[j]);
+    for (int j = 0; j < PPT; ++j) rho[j] = (__double2hiint(s[j]) < kHiCore) ? 0.0 : rcp_pos(s[j]);
   }
-  const int nq = (hm >= kHiFar) ? kNQFar : (hm >= kHiNear) ? kNQMid : kNQNear;
+  // series length from the row's smallest |z|^2: 4 coefficients from 200 Doppler widths on (one more than the far
+  // tier of the tile kernel: the coefficient pairs then line up with 16-byte loads), 6 from 24, 13 below
   const int qoff = off + LC_Q;
-  {
-    const double qtop = smem[qoff + nq - 1];
+  int p;                                                    // next coefficient pair: Q[p - 1], Q[p]
+  if (hm >= kHiNear) {
+    const int top = (hm >= kHiFar) ? 2 : 4;                 // pair (Q[top], Q[top + 1])
+    const double2 q = *reinterpret_cast<const double2*>(smem + qoff + top);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = qtop;
+    for (int j = 0; j < PPT; ++j) s[j] = fma(q.y, rho[j], q.x);
+    p = top - 1;
+  } else {
+    const double qtop = smem[qoff + kNQNear - 1];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) s[j] = qtop;
+    p = kNQNear - 2;
   }
 #pragma unroll 1
-  for (int p = nq - 2; p >= 0; --p) {
-    const double q = smem[qoff + p];
+  for (; p >= 1; p -= 2) {
+    const double2 q = *reinterpret_cast<const double2*>(smem + qoff + p - 1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = fma(s[j], rho[j], q);
+    for (int j = 0; j < PPT; ++j) s[j] = fma(fma(s[j], rho[j], q.y), rho[j], q.x);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) tau[j] = fma(s[j], rho[j], tau[j]);
+  for (int j = 0; j < PPT; ++j) tau[j] = fma(s[j], rho[j], tau[j]);
   if (has_core) {
     const double a = smem[off + LC_a], coef = smem[off + LC_COEF];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < PPT; ++j) {
       const double x = fma(A, u[j], -B);
       if (__double2hiint(fma(x, x, a2)) < kHiCore) tau[j] = fma(coef, core_H_call(x, a, a2, core_tab), tau[j]);
     }
   }
 }
 
-__device__ __forceinline__ void stream_tau_row(int lc_off, int L, const unsigned short* __restrict__ list,
-                                               int rec_off, const double (&u)[8], double (&tau)[8],
+template <int PPT>
+__device__ __forceinline__ void stream_tau_row(int lc_off, const unsigned short* __restrict__ list, int rec_off,
+                                               const double (&u)[PPT], double (&tau)[PPT],
                                                const double* __restrict__ core_tab) {
-  const int4 n = *reinterpret_cast<const int4*>(smem + rec_off + SC_COUNTS);   // n_far, n_other, -, n_farfield
+  const int n_direct = *reinterpret_cast<const int*>(smem + rec_off + SC_COUNTS);
   farfield_eval(rec_off, u, tau);       // the record always holds a polynomial (zero when no line qualified)
-  const int n_direct = n.x + n.y;
 #pragma unroll 1
   for (int k = 0; k < n_direct; ++k) {
-    const int e = (k < n.x) ? (int)list[k] : (int)list[L - 1 - (k - n.x)];
-    const int off = lc_off + (e & 0xfff) * LC_STRIDE;
-    if ((e >> 12) == kTierGeneral) stream_general_line(off, u, tau);
-    else stream_direct_line(off, u, tau, core_tab);
+    const int e = list[k];
+    const int off = lc_off + (e & 0x7fff) * LC_STRIDE;
+    if (e & 0x8000) stream_general_line<PPT>(off, u, tau);
+    else stream_direct_line<PPT>(off, u, tau, core_tab);
   }
 }
 
@@ -174,19 +188,100 @@ __device__ __noinline__ void stream_exp_store(double* fo, int step, double t0, d
   fo[7 * step] = exp_flux(-t7);
 }
 
-// phase 0 as a call (once per kStreamRowsPerRecord rows)
+// Phase 0 of the streaming kernel, once per kStreamRowsPerRecord rows (a call): range of 1/lambda of the next
+// super-chunk from the block table, then per line (lane = line) far field or direct -- the a-priori gate of
+// classify_lines, rbv_kernels.cu, without its tiers (stream_direct_line takes the series length per row) -- then
+// the far-field record.  list: directly evaluated lines (bit 15: a >= 1), listff: far-field lines.
 __device__ __noinline__ void stream_prepare(const double2* __restrict__ ublk, int L, int lc_off, int rec_off,
-                                            unsigned short* list, int list_stride, float ff_eps, int plo, int phi,
-                                            int scratch_off, int lane) {
-  InstDev I;
-  I.ublk = ublk;
-  I.L = L;
-  prepare_super_chunk(I, lc_off, rec_off, list, list + list_stride, list + 2 * list_stride, 0.0, ff_eps, plo, phi,
-                      scratch_off, lane);
+                                            unsigned short* __restrict__ list, unsigned short* __restrict__ listff,
+                                            float ff_eps, int plo, int phi, int scratch_off, int lane) {
+  int hlo = 0x7fffffff, hhi = 0;
+  for (int b = (plo >> 8) + lane; b <= (phi >> 8); b += 32) {
+    const double2 mm = ublk[b];
+    hlo = min(hlo, __double2hiint(mm.x));
+    hhi = max(hhi, __double2hiint(mm.y));
+  }
+  hlo = __reduce_min_sync(0xffffffffu, hlo);       // 1/lambda > 0: the high words order like the values
+  hhi = __reduce_max_sync(0xffffffffu, hhi);
+  const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
+  const double du = umax - umin;
+  const unsigned lt = (1u << lane) - 1u;
+  int n_dir = 0, n_ff = 0;
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const bool valid = l < L;
+    bool ff = false, general = false;
+    if (valid) {
+      const int off = lc_off + l * LC_STRIDE;
+      const double A = smem[off + LC_A], B = smem[off + LC_B], a2 = smem[off + LC_A2];
+      const double x1 = fma(A, umin, -B), x2 = fma(A, umax, -B);
+      const bool crosses = ((__double2hiint(x1) ^ __double2hiint(x2)) < 0);   // line centre inside the super-chunk
+      const int hmin = min(__double2hiint(fma(x1, x1, a2)), __double2hiint(fma(x2, x2, a2)));
+      general = __double2hiint(a2) >= 0x3ff00000;                             // a >= 1
+      if (ff_eps > 0.f && !general && !crosses && hmin >= kHiNear) {           // |z|^2 >= 576: 6-term series exact
+        const float xm = fminf(fabsf((float)x1), fabsf((float)x2)) * 0.99999f;     // rounded towards the line
+        const float hw = (float)(0.5 * fabs(A) * du) * 1.00001f;
+        const float r = __fdividef(hw, 2.f * xm) * 1.00001f;
+        const float r2 = r * r, r4 = r2 * r2;
+        const float bound = (8.f * (RBV_FF_M + 1) * 1.001f) * fabsf((float)smem[off + LC_AUX]) *
+                            __fdividef(r4 * r4, xm * xm);
+        ff = bound <= ff_eps;                      // NaN fails the comparison and stays on the direct path
+      }
+    }
+    const unsigned ff_mask = __ballot_sync(0xffffffffu, valid && ff);
+    const unsigned dir_mask = __ballot_sync(0xffffffffu, valid && !ff);
+    if (valid) {
+      if (ff) listff[n_ff + __popc(ff_mask & lt)] = (unsigned short)l;
+      else list[n_dir + __popc(dir_mask & lt)] = (unsigned short)(l | (general ? 0x8000 : 0));
+    }
+    n_ff += __popc(ff_mask);
+    n_dir += __popc(dir_mask);
+  }
+  __syncwarp();
+  if (n_ff > 0) farfield_coefficients(lc_off, listff, n_ff, umin, umax, rec_off, scratch_off, lane);
+  else if (lane < SC_COUNTS) smem[rec_off + lane] = 0.0;          // zero polynomial, t = 0
+  if (lane == 0) *reinterpret_cast<int*>(smem + rec_off + SC_COUNTS) = n_dir;
+}
+
+// LSF of the lane's 8 consecutive outputs: acc[q] = sum_m taps_rev[m] * E[8 lane + q + m] with a sliding register
+// window over the padded flux buffer (slot(8 g + j) = 9 g + j).  NB > 0: exactly NB blocks of 8 taps, fully unrolled;
+// NB = 0: n_blocks at run time.
+template <int NB>
+__device__ __forceinline__ void stream_lsf(int fw, int taps_off, int n_blocks, double (&acc)[8]) {
+  constexpr int R = 8;
+  double win[2 * R - 1];
+#pragma unroll
+  for (int q = 0; q < R; ++q) acc[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < R - 1; ++q) win[q] = smem[fw + q];
+  auto block = [&](int blk) {
+    const int m0 = blk * R;
+    win[R - 1] = smem[fw + R - 1];
+#pragma unroll
+    for (int q = 1; q < R; ++q) win[R - 1 + q] = smem[fw + R + q];
+#pragma unroll
+    for (int mm = 0; mm < R; mm += 2) {
+      const double2 tap = *reinterpret_cast<const double2*>(smem + taps_off + m0 + mm);
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q] = fma(tap.x, win[mm + q], acc[q]);
+#pragma unroll
+      for (int q = 0; q < R; ++q) acc[q] = fma(tap.y, win[mm + 1 + q], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < R - 1; ++q) win[q] = win[R + q];
+    fw += R + 1;
+  };
+  if (NB > 0) {
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk) block(blk);
+  } else {
+#pragma unroll 1
+    for (int blk = 0; blk < n_blocks; ++blk) block(blk);
+  }
 }
 
 template <int LOGR>
-__global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS)
+__global__ void __launch_bounds__(kStreamThreads, RBV_STREAM_MIN_CTAS)
 voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_doubles) {
   constexpr int R = 1 << LOGR;
   static_assert(R == 8, "the packed observed-spectrum layout assumes 8 outputs per lane");
@@ -222,7 +317,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
                 rec_off = wbase + S.rec;
       const int list_stride = (I.L + 3) & ~3;
       unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + wbase + S.lists);
-      const float ff_eps = prm.farfield ? (float)(kFFEps / (double)I.L) : 0.f;
+      const float ff_eps = prm.farfield ? (float)(prm.ff_budget / (double)I.L) : 0.f;
       const int h = I.K >> 1, halo = I.K - 1;
       const int o_lo = (slot - first_slot) * range_len, o_hi = min(o_lo + range_len, I.P);
 
@@ -236,36 +331,42 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         if (lane < 16) smem[flux_off + smem_pos(halo + kStreamRow + lane, LOGR)] = 0.0;
       }
       __syncwarp();
+      // the K-1 flux values in front of the first row (the only recomputation between neighbouring ranges), every
+      // line evaluated on its own.  (Running them through the row machinery with one pixel per lane was measured
+      // 2 % slower at C5a: the second instantiation costs registers and instruction cache in the row loop.)
       for (int i = lane; i < halo; i += 32) {
         const int p = min(max(o_lo - h + i, 0), I.P - 1);
         const double tau = tau_direct_pixel(lc_off, I.L, fast, __ldg(I.inv_wave + p), prm.core_tab);
         smem[flux_off + smem_pos(i, LOGR)] = exp_flux(-tau);
       }
-
       double part = 0.0;
       const int n_rows = (o_hi - o_lo + kStreamRow - 1) / kStreamRow;
       double* fo = smem + flux_off + smem_pos(halo + lane, LOGR);     // slot(halo + 32 j + lane) = fo[36 j]
       constexpr int kRowStep = (R + 1) * (32 / R);
+      auto load_u = [&](int pf_row, double (&u)[8]) {
+        if (pf_row + kStreamRow <= I.P) {
+          const double* up = I.inv_wave + pf_row + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = __ldg(up + j * 32);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = __ldg(I.inv_wave + min(pf_row + j * 32 + lane, I.P - 1));   // edge replication
+        }
+      };
       for (int r = 0; r < n_rows; ++r) {
         const int pf = o_lo + h + r * kStreamRow;      // first pixel of the row's new flux values
         if (!fast && (r % kStreamRowsPerRecord) == 0) {
           const int plo = min(max(pf, 0), I.P - 1);
           const int phi = min(max(pf + kSuperPix - 1, 0), I.P - 1);
-          stream_prepare(I.ublk, I.L, lc_off, rec_off, s_list, list_stride, ff_eps, plo, phi, wbase + S.scratch, lane);
+          stream_prepare(I.ublk, I.L, lc_off, rec_off, s_list, s_list + list_stride, ff_eps, plo, phi,
+                         wbase + S.scratch, lane);
           __syncwarp();
         }
         // ---- phase 1: 8 pixels per lane
         double u[8], tau[8];
-        if (pf + kStreamRow <= I.P) {
-          const double* up = I.inv_wave + pf + lane;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = __ldg(up + j * 32);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = __ldg(I.inv_wave + min(pf + j * 32 + lane, I.P - 1));   // edge replication
-        }
+        load_u(pf, u);
         if (fast) tau_fast<8>(lc_off, I.L, u, tau);
-        else stream_tau_row(lc_off, I.L, s_list, rec_off, u, tau, prm.core_tab);
+        else stream_tau_row<8>(lc_off, s_list, rec_off, u, tau, prm.core_tab);
         unsigned hmax = 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) hmax = max(hmax, (unsigned)__double2hiint(tau[j]));
@@ -289,30 +390,16 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         }
         __syncwarp();
         // ---- phase 2: M_p = sum_m taps_rev[m] * E[o + m] for the lane's outputs o = 8 lane .. 8 lane + 7
-        double acc[R], win[2 * R - 1];
-#pragma unroll
-        for (int q = 0; q < R; ++q) acc[q] = 0.0;
-        int fw = flux_off + (R + 1) * lane;
-#pragma unroll
-        for (int q = 0; q < R - 1; ++q) win[q] = smem[fw + q];
-        const int n_blocks = I.Kpad >> LOGR;
-        __builtin_assume(n_blocks >= 1);
-#pragma unroll kStreamLsfUnroll
-        for (int blk = 0; blk < n_blocks; ++blk, fw += R + 1) {
-          const int m0 = blk << LOGR;
-          win[R - 1] = smem[fw + R - 1];
-#pragma unroll
-          for (int q = 1; q < R; ++q) win[R - 1 + q] = smem[fw + R + q];
-#pragma unroll
-          for (int mm = 0; mm < R; mm += 2) {
-            const double2 tap = *reinterpret_cast<const double2*>(smem + taps_off + m0 + mm);
-#pragma unroll
-            for (int q = 0; q < R; ++q) acc[q] = fma(tap.x, win[mm + q], acc[q]);
-#pragma unroll
-            for (int q = 0; q < R; ++q) acc[q] = fma(tap.y, win[mm + 1 + q], acc[q]);
-          }
-#pragma unroll
-          for (int q = 0; q < R - 1; ++q) win[q] = win[R + q];
+        double acc[R];
+        {
+          const int fw = flux_off + (R + 1) * lane;
+          const int n_blocks = I.Kpad >> LOGR;
+          // the common LSF sizes (K <= 8, 16, 24 taps) fully unrolled: every load of the window is issued up front
+          // and the window shift is register renaming; anything longer loops over 8-tap blocks
+          if (n_blocks == 3) stream_lsf<3>(fw, taps_off, 3, acc);
+          else if (n_blocks == 2) stream_lsf<2>(fw, taps_off, 2, acc);
+          else if (n_blocks == 1) stream_lsf<1>(fw, taps_off, 1, acc);
+          else stream_lsf<0>(fw, taps_off, n_blocks, acc);
         }
         const int n_out = o_hi - o_row;     // outputs of this row (>= 256 except in the last row)
         const int e0 = lane << LOGR;

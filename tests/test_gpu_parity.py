@@ -73,10 +73,11 @@ def test_lnprob_vs_golden(case):
     fin = np.isfinite(ref)
     rel = np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])
     assert rel.max() <= LNPROB_RTOL, rel.max()
-    # scalar call returns a float equal to the batch row; second call is bit-identical (fixed-order sums)
+    # scalar call returns a float that agrees with the batch row to rounding (a one-row launch may pick another tile
+    # size, i.e. another far-field / summation partition); a second call is bit-identical (fixed-order sums)
     k = int(np.flatnonzero(fin)[0])
     s = like.lnprob(g.thetas[k])
-    assert isinstance(s, float) and s == got[k]
+    assert isinstance(s, float) and abs(s - got[k]) <= 1e-13 * abs(got[k])
     assert np.array_equal(like.lnprob(g.thetas), got, equal_nan=True)
     # walker permutation invariance
     perm = np.random.default_rng(0).permutation(len(g.thetas))
