@@ -39,6 +39,8 @@ if ROOT not in sys.path:
 
 METRIC = "walker_pixel_lnprob_evals_per_sec"
 UNIT = "walker*pixel/s"
+# BASELINE.json configs 1-4 (+ SURVEY 8d's L = 4 companion of C5a): reported next to the headline in `configs`
+CONFIG_WORKLOADS = ["C1", "C2", "C3", "C4", "C4w", "C5a_L4"]
 
 
 # --------------------------------------------------------------------------------------------- helpers
@@ -239,14 +241,21 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def run_gpu(args, rank, world, local):
+def measure_workload(workload, rank, world, local, steps, warmup, far_field="chebyshev", fp64_peak=None, flush=None):
+    """One bench line's worth of numbers for `workload` on this rank's GPU (every rank calls it; the walker batch is
+    partitioned over the ranks and the step ends with the all-gather of lnprob):
+      value  device-resident throughput (theta in HBM, CUDA events per step, L2 flushed untimed between steps,
+             max over ranks); counts all W rows, the ~1 % out-of-bounds rows included (they return -inf unevaluated)
+      e2e    host theta -> host lnprob through the public API, H2D and D2H inside the timed region
+      roofline  FP64-pipe bound, F = algorithmic flops per walker.pixel of the algorithm that runs."""
     import torch
     from rbvfit_b200 import dist as rdist
     from rbvfit_b200 import roofline as rf
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    w, models, like, thetas, spectra = build_problem(args.workload, local)
+    w, models, like, thetas, spectra = build_problem(workload, local)
     part = rdist.WalkerPartition(rank, world)
+    if world > 1:
+        like.engine.comm_init()                 # the lnprob all-gather is issued by the library (NCCL, in-stream)
     dlike = rdist.DistributedLikelihood(like, part)
     W, ndim = thetas.shape
     total_px = like.total_pixels
@@ -257,13 +266,11 @@ def run_gpu(args, rank, world, local):
         if world > 1:
             torch.distributed.barrier()
 
-    # ---------------- roofline denominators
-    fp64_peak = like.engine.measure_fp64_peak(300.0)          # TFLOP/s, DFMA chain, measured on this box
+    if fp64_peak is None:
+        fp64_peak = like.engine.measure_fp64_peak(300.0)          # TFLOP/s, DFMA chain, measured on this box
     name0 = like.names[0]
     data0 = models[name0].compile().data
     n_taps = 1 if data0.kernel is None else len(data0.kernel)
-    # algorithmic flops per walker.pixel: of the far-field algorithm the default path runs (F), and of the
-    # direct evaluation of every (line, pixel) pair by SURVEY.md 8(d)'s rule (F_direct)
     F, F_direct, tiers, tiers_direct = 0.0, 0.0, {}, {}
     for n in like.names:                                        # pixel-weighted over instruments
         d = models[n].compile().data
@@ -274,117 +281,164 @@ def run_gpu(args, rank, world, local):
         F_direct += Fd * share
         F += Ff * share
         tiers[n], tiers_direct[n] = tf, td
-    if args.far_field == "direct":
+    if far_field == "direct":
         F, tiers = F_direct, tiers_direct
-    like.engine.set_farfield(args.far_field)
+    like.engine.set_farfield(far_field)
 
-    # ---------------- device-resident timing
     theta_dev = torch.as_tensor(thetas, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    for _ in range(args.warmup):
+    if flush is None:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    for _ in range(warmup):
         out = dlike.lnprob_device(theta_dev)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     launches0 = like.engine.launch_count
     barrier()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.zero_()                                     # untimed L2 flush
         ev[k][0].record()
-        if hi > lo:
-            kev[k][0].record()
-            local_out = like.lnprob_device(theta_dev[lo:hi])          # prep + tile + finalize kernels
-            kev[k][1].record()
-        else:
-            local_out = theta_dev.new_empty(0)
-        out = part.gather(local_out, W)                   # NCCL all-gather of lnprob (N > 1)
+        out = dlike.lnprob_device(theta_dev)              # prep + lnprob kernel + finalize (+ NCCL all-gather, N > 1)
         ev[k][1].record()
     barrier()
     launches = like.engine.launch_count - launches0
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    kern_ms = [a.elapsed_time(b) for a, b in kev] if hi > lo else [0.0]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = float(total_ms.item()) / steps
     value = W * total_px / (ms_per_step * 1e-3)
     lnp = out.cpu().numpy()
+    kernel = like.engine.last_kernel
+    # the kernels alone on this rank (no collective): the roofline's denominator
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if hi > lo:
+        rows = theta_dev[lo:hi].contiguous()
+        for k in range(steps):
+            flush.zero_()
+            kev[k][0].record()
+            like.lnprob_device(rows)
+            kev[k][1].record()
+        torch.cuda.synchronize(dev)
+        k_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+    else:
+        k_ms = float("nan")
 
-    # ---------------- e2e through the public API (host buffers)
-    for _ in range(min(args.warmup, 3)):
+    # e2e through the public API (host buffers)
+    for _ in range(min(warmup, 3)):
         dlike.lnprob(thetas)
     barrier()
-    e2e_steps = args.steps
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(steps):
         res = dlike.lnprob(thetas)
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
-    e2e_ms = float(e2e_s.item()) * 1e3 / e2e_steps
+    e2e_ms = float(e2e_s.item()) * 1e3 / steps
     e2e_value = W * total_px / (e2e_ms * 1e-3)
     assert np.array_equal(np.asarray(res), lnp, equal_nan=True), "e2e and device-resident results differ"
 
-    if rank != 0:
-        return
-    # ---------------- roofline of the dominant (only) kernel on this rank
-    k_ms = sum(kern_ms) / len(kern_ms)
     n_local = hi - lo
     n_inb = int(np.count_nonzero(np.isfinite(lnp[lo:hi]) | np.isnan(lnp[lo:hi])))   # rows actually evaluated
     achieved = F * n_inb * total_px / (k_ms * 1e-3) / 1e12
+    res = {
+        "workload": workload, "value": value, "ms_per_step": ms_per_step, "kernel": kernel, "clocks": clocks,
+        "launches": int(launches), "fp64_peak": fp64_peak,
+        "config": {"workload": workload, "walkers": W, "pixels": total_px, "ndim": ndim,
+                   "lines": int(sum(models[n].compile().data.n_lines for n in like.names)), "lsf_taps": n_taps,
+                   "partition": f"walkers/{world}",
+                   "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                   "walkers_out_of_bounds": int(np.count_nonzero(np.isneginf(lnp))),
+                   "value_counts": "all walkers, the out-of-bounds rows included (they return -inf unevaluated); "
+                                   "roofline.achieved counts the evaluated rows only"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8)},
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "kernel": f"voigt_{kernel}_kernel", "kernel_ms": k_ms,
+                     "far_field": far_field, "algorithmic_flops_per_walker_pixel": F, "tiers": tiers,
+                     "direct_equivalent": {"algorithmic_flops_per_walker_pixel": F_direct,
+                                           "tflops": F_direct * n_inb * total_px / (k_ms * 1e-3) / 1e12,
+                                           "frac": F_direct * n_inb * total_px / (k_ms * 1e-3) / 1e12 / fp64_peak,
+                                           "tiers": tiers_direct},
+                     "hbm_algorithmic_gbs": (n_local * ndim * 8 + n_local * 8 + 4 * 8 * total_px) / (k_ms * 1e-3) / 1e9},
+    }
+    return res, (w, models, like, thetas, spectra, theta_dev, lnp, flush, F_direct, n_inb)
+
+
+def run_gpu(args, rank, world, local):
+    import torch
+    torch.cuda.set_device(local)
+    r, ctx = measure_workload(args.workload, rank, world, local, args.steps, args.warmup, args.far_field)
+    w, models, like, thetas, spectra, theta_dev, lnp, flush, F_direct, n_inb = ctx
+    W, total_px, fp64_peak = thetas.shape[0], like.total_pixels, r["fp64_peak"]
     peaks, peaks_kind = _peaks()
-    hbm_alg_bytes = n_local * ndim * 8 + n_local * 8 + 4 * 8 * total_px
     prof = {}
     ppath = os.path.join(ROOT, "profiles", "latest_ncu_summary.json")
     if os.path.exists(ppath):
         with open(ppath) as fh:
             prof = json.load(fh)
+    roof = dict(r["roofline"])
+    roof.update({
+        "traffic": prof.get("dram_bytes_per_launch"),
+        "traffic_capture": None if not prof else f"{prof.get('report')}: {prof.get('note')}",
+        "peak_source": "DFMA dependent-chain probe measured in this run (rbv_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has no FP64 entry (spec: 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
+        "algorithm_note": "far wings of each 1024-px super-chunk are summed at 8 Chebyshev nodes and interpolated "
+                          "(a-priori gated, |dtau| <= 1e-12): F counts THAT algorithm "
+                          "(rbvfit_b200/roofline.py:flops_farfield); direct_equivalent applies SURVEY 8(d)'s "
+                          "per-(line,pixel) rule to the same throughput and may exceed the peak",
+        "hbm_sanity": {"algorithmic_gbs": roof.pop("hbm_algorithmic_gbs"), "peak_gbs": peaks.get("hbm_gbs"),
+                       "peaks": peaks_kind}})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "walkers": W, "pixels": total_px, "ndim": ndim,
-                   "lines": int(data0.n_lines), "lsf_taps": n_taps, "partition": f"walkers/{world}",
-                   "l2": "flushed between timed steps (256 MiB memset, untimed)",
-                   "walkers_out_of_bounds": int(np.count_nonzero(np.isneginf(lnp)))},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8)},
-        "gpu_launches": int(launches),       # prep_kernel + voigt_tile_kernel + finalize_kernel per step
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak, "traffic": prof.get("dram_bytes_per_launch"),
-                     "traffic_capture": None if not prof else f"{prof.get('report')}: {prof.get('note')}",
-                     "peak_source": "DFMA dependent-chain probe measured in this run (rbv_measure_fp64_peak); "
-                                    "MEASURED_PEAKS.json has no FP64 entry (spec: 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
-                     "kernel": "voigt_tile_kernel", "kernel_ms": k_ms, "far_field": args.far_field,
-                     "algorithmic_flops_per_walker_pixel": F, "tiers": tiers,
-                     "algorithm_note": "far wings of each 1024-px super-chunk are summed at 8 Chebyshev nodes and "
-                                       "interpolated (a-priori gated, |dtau| <= 1e-13): F counts THAT algorithm "
-                                       "(rbvfit_b200/roofline.py:flops_farfield); direct_equivalent applies SURVEY "
-                                       "8(d)'s per-(line,pixel) rule to the same throughput and may exceed the peak",
-                     "direct_equivalent": {"algorithmic_flops_per_walker_pixel": F_direct,
-                                           "tflops": F_direct * n_inb * total_px / (k_ms * 1e-3) / 1e12,
-                                           "tiers": tiers_direct},
-                     "hbm_sanity": {"algorithmic_gbs": hbm_alg_bytes / (k_ms * 1e-3) / 1e9,
-                                    "peak_gbs": peaks.get("hbm_gbs"), "peaks": peaks_kind}},
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": r["config"], "clocks": r["clocks"],
+        "e2e": r["e2e"],
+        "gpu_launches": r["launches"],      # prep_kernel + lnprob kernel + finalize_kernel per step
+        "roofline": roof,
     }
-    if world == 1 and not args.no_extras:
+    extras = not args.no_extras
+    # ---- MCMC steps/s at the bench workload's own scale, on all N GPUs (every rank takes part)
+    if extras:
+        large = mcmc_large_leg(like, w, thetas, total_px, rank, world)
+    # ---- the other BASELINE configurations (parity-test sizes, milliseconds each), same measurement
+    configs = {}
+    if extras and args.workload == "C5a":
+        for name in CONFIG_WORKLOADS:
+            c, cctx = measure_workload(name, rank, world, local, max(5, args.steps // 2), 3, args.far_field,
+                                       fp64_peak=fp64_peak, flush=flush)
+            cctx[2].close()
+            configs[name] = {"value": c["value"], "unit": UNIT, "ms_per_step": c["ms_per_step"],
+                             "e2e": c["e2e"]["value"], "kernel": c["kernel"], "config": c["config"],
+                             "roofline": {k: c["roofline"][k] for k in
+                                          ("achieved", "peak", "frac", "kernel_ms",
+                                           "algorithmic_flops_per_walker_pixel")},
+                             "roofline_direct_rule": {
+                                 "algorithmic_flops_per_walker_pixel":
+                                     c["roofline"]["direct_equivalent"]["algorithmic_flops_per_walker_pixel"],
+                                 "frac": c["roofline"]["direct_equivalent"]["frac"]}}
+        configs["C5b"] = sightline_leg(args, rank, world, local, fp64_peak, flush,
+                                       steps=max(5, args.steps // 2), with_mcmc=False)
+    if rank != 0:
+        return
+    if configs:
+        line["configs"] = configs
+    if world == 1 and extras:
         if args.far_field == "chebyshev":
             line["direct_far_wings"] = direct_leg(like, theta_dev, lnp, W, total_px, args.steps, flush, F_direct,
                                                   n_inb, fp64_peak)
         line["fp32_gated"] = fp32_gated_leg(like, theta_dev, thetas, W, total_px, args.steps, flush)
         line["mcmc"] = mcmc_leg(local, with_cpu=not args.no_cpu)
-        line["mcmc"]["large_ensemble"] = mcmc_large_leg(like, w, thetas, total_px)
         line["mcmc"]["zeus"] = mcmc_zeus_leg(local, with_cpu=not args.no_cpu)
+    if extras:
+        line.setdefault("mcmc", {})["large_ensemble"] = large
     if not args.no_cpu and world == 1:      # the CPU baseline is reported at N = 1 only
-        r = cpu_arm(args.workload, steps=2, warmup=1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                                "sample": r["sample"]}
+        r2 = cpu_arm(args.workload, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": r2["value"], "unit": UNIT, "cores": r2["cores"], "kind": r2["kind"],
+                                "sample": r2["sample"]}
     print(json.dumps(line))
 
 
@@ -412,33 +466,40 @@ def build_sightlines(first, count, device, walkers=64):
     return SightlineBatch(sight, w0["lb"], w0["ub"], device=device), np.array(thetas)
 
 
-def run_gpu_sightlines(args, rank, world, local, n_sightlines=1024, walkers=64):
-    """Workload C5b: sightlines are sharded across ranks (rank r owns a contiguous block); no collective on the
-    data path -- only the final max over ranks of the elapsed time."""
+def sightline_leg(args, rank, world, local, fp64_peak=None, flush=None, steps=None, with_mcmc=True,
+                  n_sightlines=None, walkers=64):
+    """Workload C5b (survey mode): S independent sightlines (C1's structure at its own redshift, 2048 px, 64 walkers
+    each) sharded across the ranks -- rank r owns a contiguous block, no collective on the data path, only the final
+    max over ranks of the elapsed time.  Returns the result dict on every rank."""
     import torch
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    from rbvfit_b200 import roofline as rf
     from rbvfit_b200.dist import SightlinePartition
+    dev = torch.device("cuda", local)
+    n_sightlines = n_sightlines or args.sightlines
+    steps = steps or args.steps
     first, count = SightlinePartition(rank, world).owned(n_sightlines)
     batch, thetas = build_sightlines(first, count, local, walkers)
     S, Ws, ndim = thetas.shape
     P = batch.pixels
     th_dev = torch.as_tensor(thetas.reshape(S * Ws, ndim), device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    if flush is None:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    if fp64_peak is None:
+        fp64_peak = batch.engine.measure_fp64_peak(300.0)
 
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
             torch.distributed.barrier()
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         out = batch.lnprob_device(th_dev, Ws)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     l0 = batch.engine.launch_count
     barrier()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.zero_()
         ev[k][0].record()
         out = batch.lnprob_device(th_dev, Ws)
@@ -446,57 +507,93 @@ def run_gpu_sightlines(args, rank, world, local, n_sightlines=1024, walkers=64):
     barrier()
     launches = batch.engine.launch_count - l0
     clocks = sampler.stop()
-    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    local_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    total_ms = torch.tensor([local_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
-    ms = float(total_ms.item()) / args.steps
+    ms = float(total_ms.item())
     value = n_sightlines * Ws * P / (ms * 1e-3)
     # e2e: host theta -> host lnprob through SightlineBatch.lnprob
     for _ in range(2):
         batch.lnprob(thetas)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = batch.lnprob(thetas)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
-    e2e_ms = float(e2e_s.item()) * 1e3 / args.steps
-    # MCMC in survey mode: one stretch-move ensemble per sightline, all in lockstep on the device
-    # (rbv_stretch_run_sightlines); every rank samples its own sightlines, no collective
-    from rbvfit_b200.sampler import SightlineEnsembleSampler
-    p0 = thetas.copy()
-    bad = ~np.all((p0 >= batch.lb) & (p0 <= batch.ub), axis=2)
-    p0[bad] = np.clip(p0[bad], batch.lb + 1e-9, batch.ub - 1e-9)
-    smp = SightlineEnsembleSampler(Ws, ndim, batch, seed=6)
-    smp.run_mcmc(p0, 3, skip_initial_state_check=True)
-    mc_steps = 20
-    barrier()
-    t0 = time.perf_counter()
-    smp.run_mcmc(None, mc_steps)
-    mc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(mc_s, op=torch.distributed.ReduceOp.MAX)
-    mc_sps = mc_steps / float(mc_s.item())
-    mcmc = {"sampler": "device-resident stretch move, one ensemble per sightline in lockstep "
-                       "(rbv_stretch_run_sightlines), chain D2H included",
-            "steps_per_sec": mc_sps, "sightline_steps_per_sec": mc_sps * n_sightlines,
-            "walker_pixel_per_sec": mc_sps * n_sightlines * Ws * P,
-            "acceptance": float(smp.acceptance_fraction.mean())}
-    if rank != 0:
-        return
-    print(json.dumps({
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mcmc": mcmc,
+    e2e_ms = float(e2e_s.item()) * 1e3 / steps
+    # roofline of this rank's launch: F of the sightline structure (C1's lines on a 2048-px grid), evaluated rows only
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.model import GpuVoigtModel
+    w0 = wl.c5b_sightline(first)
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in w0["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    d0 = GpuVoigtModel(cfg, FWHM="6.5", device=local).compile().data
+    wave0 = w0["instruments"]["COS"]["wave"]
+    F, _t = rf.flops_farfield(d0, w0["theta_true"], wave0, 23)
+    F_direct, _t = rf.flops_per_walker_pixel(d0, w0["theta_true"], wave0, 23)
+    n_inb = int(np.count_nonzero(np.isfinite(res)))
+    achieved = F * n_inb * P / (local_ms * 1e-3) / 1e12
+    result = {
+        "value": value, "unit": UNIT, "ms_per_step": ms, "kernel": batch.engine.last_kernel, "clocks": clocks,
+        "launches": int(launches),
+        "e2e": {"value": n_sightlines * Ws * P / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(S * Ws * ndim * 8), "d2h_bytes_per_step": int(S * Ws * 8)},
         "config": {"workload": "C5b", "sightlines": n_sightlines, "walkers_per_sightline": Ws, "pixels": P,
                    "lines": 4, "lsf_taps": 23, "partition": f"sightlines/{world}",
                    "l2": "flushed between timed steps (256 MiB memset, untimed)"},
-        "clocks": clocks,
-        "e2e": {"value": n_sightlines * Ws * P / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(S * Ws * ndim * 8), "d2h_bytes_per_step": int(S * Ws * 8)},
-        "gpu_launches": int(launches),
-        "finite_fraction": float(np.isfinite(res).mean())}))
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "kernel": f"voigt_{batch.engine.last_kernel}_kernel",
+                     "kernel_ms": local_ms, "algorithmic_flops_per_walker_pixel": F,
+                     "direct_equivalent": {"algorithmic_flops_per_walker_pixel": F_direct,
+                                           "frac": F_direct * n_inb * P / (local_ms * 1e-3) / 1e12 / fp64_peak},
+                     "note": "rank 0's launch over its own sightlines; F of sightline 0 (every pixel of this workload "
+                             "lies within 45 Doppler widths of all four lines: no far field to exploit)"},
+        "finite_fraction": float(np.isfinite(res).mean())}
+    if with_mcmc:
+        # MCMC in survey mode: one stretch-move ensemble per sightline, all in lockstep on the device
+        # (rbv_stretch_run_sightlines); every rank samples its own sightlines, no collective
+        from rbvfit_b200.sampler import SightlineEnsembleSampler
+        p0 = thetas.copy()
+        bad = ~np.all((p0 >= batch.lb) & (p0 <= batch.ub), axis=2)
+        p0[bad] = np.clip(p0[bad], batch.lb + 1e-9, batch.ub - 1e-9)
+        smp = SightlineEnsembleSampler(Ws, ndim, batch, seed=6)
+        smp.run_mcmc(p0, 3, skip_initial_state_check=True)
+        mc_steps = 20
+        barrier()
+        t0 = time.perf_counter()
+        smp.run_mcmc(None, mc_steps)
+        mc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(mc_s, op=torch.distributed.ReduceOp.MAX)
+        mc_sps = mc_steps / float(mc_s.item())
+        result["mcmc"] = {"sampler": "device-resident stretch move, one ensemble per sightline in lockstep "
+                                     "(rbv_stretch_run_sightlines), chain D2H included",
+                          "steps_per_sec": mc_sps, "sightline_steps_per_sec": mc_sps * n_sightlines,
+                          "walker_pixel_per_sec": mc_sps * n_sightlines * Ws * P,
+                          "acceptance": float(smp.acceptance_fraction.mean())}
+    batch.close()
+    return result
+
+
+def run_gpu_sightlines(args, rank, world, local):
+    """`--workload C5b`: the survey-mode line on its own."""
+    import torch
+    torch.cuda.set_device(local)
+    r = sightline_leg(args, rank, world, local)
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": r["config"], "clocks": r["clocks"],
+            "e2e": r["e2e"], "gpu_launches": r["launches"], "roofline": r["roofline"],
+            "finite_fraction": r["finite_fraction"]}
+    if "mcmc" in r:
+        line["mcmc"] = r["mcmc"]
+    print(json.dumps(line))
 
 
 def direct_leg(like, theta_dev, lnp_default, W, total_px, steps, flush, F_direct, n_inb, fp64_peak):
@@ -551,27 +648,42 @@ def fp32_gated_leg(like, theta_dev, thetas, W, total_px, steps, flush):
     return out
 
 
-def mcmc_large_leg(like, w, thetas, total_px, nsteps=12):
-    """MCMC steps/s at the bench workload's own scale (C5a: ~8000 walkers x 100 000 px): the device-resident stretch
-    move on the in-bounds rows of the bench ensemble; one step = every walker updated once = one full ensemble
-    evaluation."""
+def mcmc_large_leg(like, w, thetas, total_px, rank=0, world=1, nsteps=12):
+    """MCMC steps/s at the bench workload's own scale (C5a: ~8000 walkers x 100 000 px) on all N GPUs: the
+    device-resident stretch move on the in-bounds rows of the bench ensemble; one step = every walker updated once =
+    one full ensemble evaluation.  N = 1: rbv_stretch_run (one CUDA graph per step).  N > 1: rbv_stretch_run_dist --
+    the rows of every half-step are split over the ranks and the NCCL all-gather of their lnprob sits inside the
+    captured step; the chain is the single-GPU chain bit for bit (its digest is printed for comparison across N)."""
     import torch
-    from rbvfit_b200.sampler import DeviceEnsembleSampler
+    from rbvfit_b200 import dist as rdist
+    from rbvfit_b200.sampler import DeviceEnsembleSampler, DistributedDeviceSampler
     ok = thetas[np.all((thetas >= w["lb"]) & (thetas <= w["ub"]), axis=1)]
     W = len(ok) - (len(ok) % 2)
-    smp = DeviceEnsembleSampler(W, like.ndim, like, seed=4)
-    smp.run_mcmc(ok[:W], 2, skip_initial_state_check=True)
+    if world > 1:
+        smp = DistributedDeviceSampler(W, like.ndim, like, rdist.WalkerPartition(rank, world), seed=4)
+    else:
+        smp = DeviceEnsembleSampler(W, like.ndim, like, seed=4)
+    smp.run_mcmc(ok[:W], 4, skip_initial_state_check=True)
     torch.cuda.synchronize()
     rates = []
     for _ in range(3):                 # median of three runs: one run is 0.1 s of wall clock, a host stall doubles it
+        if world > 1:
+            torch.distributed.barrier()
         t0 = time.perf_counter()
         smp.run_mcmc(None, nsteps)
-        rates.append(nsteps / (time.perf_counter() - t0))
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=like.engine.tdev)
+        if world > 1:
+            torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+        rates.append(nsteps / float(dt.item()))
     sps = sorted(rates)[1]
-    return {"walkers": int(W), "pixels": int(total_px), "steps": nsteps, "steps_per_sec": sps,
+    digest = float(np.sum(smp.get_chain()[:4] * np.arange(1, 5)[:, None, None]))
+    return {"walkers": int(W), "pixels": int(total_px), "steps": nsteps, "n_gpus": world, "steps_per_sec": sps,
             "steps_per_sec_runs": rates, "walker_pixel_per_sec": sps * W * total_px,
             "acceptance": float(smp.acceptance_fraction.mean()),
-            "note": "median of 3 runs; includes the D2H copy of the chain (W x ndim x 8 B per step)"}
+            "chain_digest_first_4_steps": repr(digest),
+            "sampler": "rbv_stretch_run (CUDA graph)" if world == 1 else
+                       "rbv_stretch_run_dist (CUDA graph incl. the in-place NCCL all-gather of lnprob per half-step)",
+            "note": "median of 3 runs, max over ranks; includes the D2H copy of the chain (W x ndim x 8 B per step)"}
 
 
 def mcmc_zeus_leg(device, with_cpu=True, nsteps=200, cpu_steps=2):
@@ -725,7 +837,7 @@ def main():
     rank, world, local = rdist.init_from_env("nccl" if world_env > 1 else None)
     try:
         if args.workload == "C5b":
-            run_gpu_sightlines(args, rank, world, local, n_sightlines=args.sightlines)
+            run_gpu_sightlines(args, rank, world, local)
         else:
             run_gpu(args, rank, world, local)
     finally:

@@ -115,6 +115,12 @@ int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);
 int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int n_walkers, double* lnprob,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The likelihood alone, vfit.lnlike, vfit_mcmc.py:297-319: same launch without the prior -- rows outside the bounds
+ * are evaluated like any other (the reference's lnlike does not look at the bounds).  Same arguments and workspace
+ * as rbv_lnprob_batch; no context state is touched, so it may be interleaved freely with rbv_lnprob_batch. */
+int rbv_lnlike_batch(RbvContext* ctx, const double* theta, int n_walkers, double* lnlike,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Survey mode: the context holds S independent sightlines (instruments with identical n_pixels, n_taps,
  * n_lines, n_components; their line tables -- e.g. redshifts -- and spectra differ) and theta holds
  * walkers_per_sightline consecutive rows per sightline: row w is evaluated against sightline w / walkers_per_sightline
@@ -168,6 +174,40 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
                        unsigned long long seed, unsigned long long step, int split, const double* lnprob_rows,
                        double* chain_row, double* lnprob_chain_row, int* n_accepted, int* flag, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* ---- the collective inside the library (multi-GPU, one process and one context per GPU) --------------------------
+ * the only exchange on the path is the all-gather of lnprob values (8 B per walker) per half-step.  The
+ * library issues it itself, with NCCL, on the caller's stream between its own kernels, so that a whole MCMC step is
+ * one CUDA graph per rank and no host code runs inside it.  libnccl is resolved at run time (the copy the process
+ * has already loaded -- PyTorch's -- else the system one); single-GPU use never touches it.
+ *   rbv_comm_unique_id  rank 0 creates the 128-byte NCCL unique id; the caller broadcasts it to every rank
+ *                       (torch.distributed.broadcast in the Python layer)
+ *   rbv_comm_init       collective over all ranks: attaches rank `rank` of `world` to this context
+ *   rbv_comm_info       rank / world of the context (0 / 1 without a communicator) and the NCCL version in use
+ * Row partition of every multi-GPU call: rank r owns rows [r c, (r + 1) c) with c = ceil(n_rows / world). */
+int rbv_comm_unique_id(unsigned char* out_id128);
+int rbv_comm_init(RbvContext* ctx, const unsigned char* id128, int rank, int world);
+int rbv_comm_info(const RbvContext* ctx, int* rank, int* world, int* nccl_version);
+
+/* rbv_lnprob_batch over all ranks of the communicator: every rank passes the SAME theta [n_walkers, ndim] (replicated
+ * ensemble), evaluates its own rows and the ranks all-gather in place; lnprob must hold world * ceil(n_walkers/world)
+ * doubles and ends up complete on every rank.  The launch geometry is chosen as for the whole batch, so each row's
+ * value is bit-identical to the single-GPU call's.  Without a communicator this is rbv_lnprob_batch. */
+int rbv_lnprob_batch_allgather(RbvContext* ctx, const double* theta, int n_walkers, double* lnprob,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* rbv_stretch_run over all ranks of the communicator (same arguments, same workspace size; coords / lnprob / chain /
+ * n_accepted are replicated on every rank and every rank must pass the same seed and initial ensemble).  A half-step
+ * = stretch_propose_kernel (all proposals, identical everywhere: counter-based random streams) -> the lnprob launch
+ * over this rank's rows -> in-place NCCL all-gather of the proposals' lnprob -> stretch_accept_kernel; with
+ * use_graph != 0 the whole step is captured once (collective included) and replayed, the step index lives in device
+ * memory.  The chain is the one rbv_stretch_run produces on one GPU with the same seed, bit for bit, for any number
+ * of ranks.  rbv_slice_run needs no separate entry point: with a communicator attached it splits the rows of every
+ * iteration over the ranks in the same way.  The call returns after the run has finished. */
+int rbv_stretch_run_dist(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                         unsigned long long seed, unsigned long long first_step, double* chain,
+                         double* lnprob_chain, int* n_accepted, int* flag, void* workspace, size_t workspace_bytes,
+                         int use_graph, void* stream);
 
 /* Survey mode of the same sampler: the context holds S sightlines (see rbv_lnprob_batch_sightlines) and every
  * sightline has its OWN ensemble of walkers_per_sightline walkers -- what the reference does as S separate

@@ -20,6 +20,7 @@
 // prior flags, tile partials [W, n_tiles], line constants [W, L, 22].  No per-line optical depth is ever
 // materialised.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -1023,6 +1024,7 @@ struct Tuning {
   int stream_segs = 0;      // RBVFIT_B200_STREAM_SEGS=n: 1024-pixel segments per work item of the streaming kernel
   int stream_ctas = 0;      // RBVFIT_B200_STREAM_CTAS=n: CTAs per SM of the streaming kernel (0: occupancy)
   double ff_budget = kFFEps;   // RBVFIT_B200_FF_EPS=x: far-field error budget (experiments only)
+  int slice_dist_graph = 0;    // RBVFIT_B200_SLICE_DIST_GRAPH=1: multi-GPU slice sampler as a CUDA-graph WHILE loop
 };
 
 // Every entry point runs on the context's device and leaves the caller's current device as it found it.
@@ -1054,6 +1056,53 @@ static int fail(int code, const std::string& msg) {
       return fail(RBV_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
   } while (0)
 
+
+// ------------------------------------------------------------------------------------------ NCCL (multi-GPU)
+// The collective of the path is one tiny all-gather of lnprob values per half-step.  It is issued from
+// inside the library, on the library's stream, so that a whole multi-GPU MCMC step is one CUDA graph per rank and no
+// Python runs between its kernels.  libnccl is resolved at run time (the copy PyTorch has already loaded, else the
+// system one): a single-GPU process never needs it and the library has no link-time dependency on it.  The handful
+// of declarations below restate NCCL's public C API (nccl.h, stable since 2.x).
+typedef struct ncclComm* RbvNcclComm;
+typedef struct { char internal[128]; } RbvNcclUniqueId;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(RbvNcclUniqueId*) = nullptr;
+  int (*CommInitRank)(RbvNcclComm*, int, RbvNcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(RbvNcclComm) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, RbvNcclComm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+};
+constexpr int kNcclFloat64 = 8;    // ncclDouble / ncclFloat64 in ncclDataType_t
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return RBV_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);     // the copy torch has loaded
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(RBV_ESTATE, std::string("NCCL not available: ") + dlerror());
+  NcclApi api;
+  api.handle = h;
+  api.GetUniqueId = (int (*)(RbvNcclUniqueId*))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(RbvNcclComm*, int, RbvNcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(RbvNcclComm))dlsym(h, "ncclCommDestroy");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, RbvNcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
+  api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  api.GetVersion = (int (*)(int*))dlsym(h, "ncclGetVersion");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString)
+    return fail(RBV_ESTATE, "NCCL library lacks a required symbol");
+  g_nccl = api;
+  return RBV_OK;
+}
+
+#define RBV_NCCL(expr)                                                                                    \
+  do {                                                                                                    \
+    int _r = (expr);                                                                                      \
+    if (_r != 0) return fail(RBV_ECUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r));           \
+  } while (0)
+
 struct HostInst {
   InstDev dev;
   std::vector<double> taps;  // LSF taps as applied by the reference (normalised if requested), length K
@@ -1073,8 +1122,11 @@ struct RbvContext {
   int farfield = RBV_FARFIELD_CHEBYSHEV;
   long long launches = 0;
   int last_kernel = -1;
+  RbvNcclComm comm = nullptr;   // rbv_comm_init: one rank per context
+  int comm_rank = 0, comm_world = 1;
   std::vector<HostInst> inst;
   InstDev* d_inst = nullptr;
+  size_t d_inst_capacity = 0;
   int max_dyn_smem = 0;
   double* d_lb = nullptr;
   double* d_ub = nullptr;
@@ -1136,6 +1188,8 @@ int rbv_create(int device, RbvContext** out) {
     ctx->tune.stream_segs = e ? std::max(atoi(e), 0) : 0;
     e = getenv("RBVFIT_B200_STREAM_CTAS");
     ctx->tune.stream_ctas = e ? std::max(atoi(e), 0) : 0;
+    e = getenv("RBVFIT_B200_SLICE_DIST_GRAPH");
+    ctx->tune.slice_dist_graph = e ? atoi(e) : 0;
     e = getenv("RBVFIT_B200_FF_EPS");
     if (e && atof(e) > 0.0) ctx->tune.ff_budget = atof(e);
   }
@@ -1172,6 +1226,7 @@ void rbv_destroy(RbvContext* ctx) {
     for (void* p : hi.owned) cudaFree(p);
     cudaFree(hi.d_taps);
   }
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   cudaFree(ctx->d_inst);
   cudaFree(ctx->d_lb);
   cudaFree(ctx->d_ub);
@@ -1312,7 +1367,7 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_dou
   // The choice depends on the spectra only, never on the batch size, so a walker's lnprob is bit-identical in
   // every batch that takes this path.
   const int seg = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
-                                            : (int)std::min<long long>(16, std::max<long long>(4, segs / 6));
+                                            : (int)std::min<long long>(16, std::max<long long>(4, segs / 12));
   int total = 0;
   for (size_t k = 0; k < n_used; ++k) {
     const InstDev& I = ctx->inst[k].dev;
@@ -1338,16 +1393,17 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_dou
 // instrument has a wide LSF) so that all instruments run in ONE launch.
 static int rebuild_tables(RbvContext* ctx) {
   const int R = 8;   // outputs per thread in the LSF stage (64 FMAs per 8 flux + 8 tap loads)
+  // only what the newest instrument changes: its taps, its line base, one more slot of the device table (a survey
+  // context holds a thousand instruments -- rebuilding everything per add would be quadratic)
   for (size_t k = 0; k < ctx->inst.size(); ++k) {
     HostInst& hi = ctx->inst[k];
     InstDev& I = hi.dev;
+    if (hi.d_taps) continue;
     I.K = (int)hi.taps.size();
     I.R = R;
     I.Kpad = (I.K + R - 1) / R * R;
     std::vector<double> rev(I.Kpad, 0.0);
     for (int m = 0; m < I.K; ++m) rev[m] = hi.taps[I.K - 1 - m];   // true convolution -> correlation
-    cudaFree(hi.d_taps);
-    hi.d_taps = nullptr;
     RBV_CUDA(upload(&hi.d_taps, rev.data(), rev.size()));
     I.taps_rev = hi.d_taps;
     I.line_base = (k == 0) ? 0 : ctx->inst[k - 1].dev.line_base + ctx->inst[k - 1].dev.L;
@@ -1358,12 +1414,21 @@ static int rebuild_tables(RbvContext* ctx) {
   ctx->n_tiles = compute_geometry(ctx, 0, geom, nullptr, kMaxInst);
   ctx->n_lines_total = 0;
   for (auto& hi : ctx->inst) ctx->n_lines_total += hi.dev.L;
-  std::vector<InstDev> flat;
-  for (auto& hi : ctx->inst) flat.push_back(hi.dev);
-  cudaFree(ctx->d_inst);
-  ctx->d_inst = nullptr;
-  RBV_CUDA(upload(&ctx->d_inst, flat.data(), flat.size()));
-  {   // occupancy of the streaming kernel for a joint launch and for a sightline launch
+  const size_t n = ctx->inst.size();
+  if (n > ctx->d_inst_capacity) {
+    const size_t cap = std::max<size_t>(16, 2 * n);
+    InstDev* grown = nullptr;
+    RBV_CUDA(cudaMalloc((void**)&grown, cap * sizeof(InstDev)));
+    std::vector<InstDev> flat;
+    for (auto& hi : ctx->inst) flat.push_back(hi.dev);
+    RBV_CUDA(cudaMemcpy(grown, flat.data(), n * sizeof(InstDev), cudaMemcpyHostToDevice));
+    cudaFree(ctx->d_inst);
+    ctx->d_inst = grown;
+    ctx->d_inst_capacity = cap;
+  } else if (n > 0) {
+    RBV_CUDA(cudaMemcpy(ctx->d_inst + (n - 1), &ctx->inst[n - 1].dev, sizeof(InstDev), cudaMemcpyHostToDevice));
+  }
+  if (n <= (size_t)kMaxInst) {   // occupancy of the streaming kernel for a joint launch and for a sightline launch
     TileGeom g[kMaxInst];
     int wd = 0, nb = 0;
     stream_geometry(ctx, 1 << 20, g, &wd, &nb, kMaxInst);
@@ -1515,10 +1580,14 @@ int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t*
   return RBV_OK;
 }
 
+// W_hint (>= W, 0 = W): the launch geometry (kernel, tile size / ranges) is chosen as for a batch of W_hint rows.
+// The multi-GPU entry points pass the size of the WHOLE batch here, so that a rank evaluating 1/N of the rows uses
+// the partition -- far-field super-chunks, order of the chi^2 additions -- the single-GPU launch uses, and every
+// row's lnprob is bit-identical whatever the number of ranks.
 static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, double* lnprob, void* workspace,
                          size_t workspace_bytes, void* stream, const char* who,
                          const StretchParams* sampler = nullptr, int sampler_split = -1,
-                         const int* row_skip = nullptr) {
+                         const int* row_skip = nullptr, int W_hint = 0, bool with_prior = true) {
   if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, std::string(who) + ": null argument");
   if (W < 0) return fail(RBV_EINVAL, std::string(who) + ": negative n_walkers");
   if (W == 0) return RBV_OK;
@@ -1549,8 +1618,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   memset(&prm, 0, sizeof(prm));
   prm.inst = ctx->d_inst;
   prm.theta = theta;
-  prm.lb = ctx->d_lb;
-  prm.ub = ctx->d_ub;
+  prm.lb = with_prior ? ctx->d_lb : nullptr;      // no bounds: prep_kernel flags no row (vfit.lnlike, :297-319)
+  prm.ub = with_prior ? ctx->d_ub : nullptr;
   prm.core_tab = ctx->d_core_tab;
   prm.lnprob = lnprob;
   prm.tickets = (unsigned int*)((char*)workspace + lay.tickets);
@@ -1577,9 +1646,10 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   // from the batch size.  Sightline mode: each walker sees only its own instrument (identical geometry).
   size_t smem = 0;
   int stream_wd = 0, stream_ctas = 0;
-  const int stream_ranges = stream_geometry(ctx, W, prm.geom, &stream_wd, &stream_ctas, sl ? 1 : (size_t)-1);
+  const int Wg = std::max(W, W_hint);
+  const int stream_ranges = stream_geometry(ctx, Wg, prm.geom, &stream_wd, &stream_ctas, sl ? 1 : (size_t)-1);
   if (stream_ranges > 0) prm.n_tiles = stream_ranges;
-  else prm.n_tiles = choose_geometry(ctx, W, prm.geom, &smem, sl ? 1 : (size_t)-1);
+  else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
   dim3 pgrid((unsigned)W, (unsigned)((prm.n_lines_total + 127) / 128));
@@ -1592,7 +1662,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   prm.inst_in_params = !sl && ctx->inst.size() <= (size_t)kMaxInst;
   if (prm.inst_in_params)
     for (size_t k = 0; k < ctx->inst.size(); ++k) prm.inst_v[k] = ctx->inst[k].dev;
-  prm.separate_finalize = (long long)W * prm.n_tiles >= 8LL * RBV_MIN_CTAS * ctx->sm_count;
+  prm.separate_finalize = (long long)Wg * prm.n_tiles >= 8LL * RBV_MIN_CTAS * ctx->sm_count;
   if (ctx->tune.force_finalize >= 0) prm.separate_finalize = ctx->tune.force_finalize;
   if (stream_ranges > 0) {
     // persistent warps pull (walker, range) items from a global counter; lnprob always by finalize_kernel
@@ -1624,6 +1694,12 @@ int rbv_lnprob_batch(RbvContext* ctx, const double* theta, int W, double* lnprob
   return launch_lnprob(ctx, theta, W, 0, lnprob, workspace, workspace_bytes, stream, "rbv_lnprob_batch");
 }
 
+int rbv_lnlike_batch(RbvContext* ctx, const double* theta, int W, double* lnlike, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return launch_lnprob(ctx, theta, W, 0, lnlike, workspace, workspace_bytes, stream, "rbv_lnlike_batch", nullptr, -1,
+                       nullptr, 0, false);
+}
+
 int rbv_lnprob_batch_sightlines(RbvContext* ctx, const double* theta, int W, int walkers_per_sightline,
                                 double* lnprob, void* workspace, size_t workspace_bytes, void* stream) {
   if (walkers_per_sightline <= 0) return fail(RBV_EINVAL, "rbv_lnprob_batch_sightlines: walkers_per_sightline <= 0");
@@ -1648,6 +1724,7 @@ int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, doub
 }
 
 // ------------------------------------------------------------------------------------------ device-resident sampler
+constexpr int kMaxRanks = 64;   // ranks of one communicator (rows of a half-step are padded to world x chunk)
 struct StretchLayout {
   size_t prop, lnp_prop, factors, walker_of, ctr, lnprob_ws, total;
 };
@@ -1657,8 +1734,8 @@ static StretchLayout stretch_layout(const RbvContext* ctx, int W) {
   StretchLayout lay;
   lay.prop = 0;
   lay.lnp_prop = up(h * std::max(ctx->ndim, 1) * sizeof(double));
-  lay.factors = lay.lnp_prop + up(h * sizeof(double));
-  lay.walker_of = lay.factors + up(h * sizeof(double));
+  lay.factors = lay.lnp_prop + up((h + kMaxRanks) * sizeof(double));   // padded to world x chunk rows: the in-place
+  lay.walker_of = lay.factors + up(h * sizeof(double));                //   all-gather of the multi-GPU form
   lay.ctr = lay.walker_of + up(h * sizeof(int));
   lay.lnprob_ws = lay.ctr + 256;
   lay.total = lay.lnprob_ws + workspace_layout(ctx, (int)h, false).total;
@@ -1800,7 +1877,7 @@ int rbv_stretch_propose_eval(RbvContext* ctx, const double* coords, int n_walker
   if (row_hi == row_lo) return RBV_OK;
   return launch_lnprob(ctx, P.prop + (size_t)row_lo * ctx->ndim, row_hi - row_lo, 0, lnprob_rows + row_lo,
                        (char*)workspace + lay.lnprob_ws, workspace_bytes - lay.lnprob_ws, stream,
-                       "rbv_stretch_propose_eval");
+                       "rbv_stretch_propose_eval", nullptr, -1, nullptr, nS);   // geometry of the whole half-step
 }
 
 int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, double a,
@@ -1828,6 +1905,173 @@ int rbv_stretch_accept(RbvContext* ctx, double* coords, double* lnprob, int n_wa
   stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, (cudaStream_t)stream>>>(P, split);
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
+  return RBV_OK;
+}
+
+
+// ---- multi-GPU entry points: the lnprob all-gather is issued by the library on its own stream ---------------------
+int rbv_comm_unique_id(unsigned char* out_id128) {
+  if (!out_id128) return fail(RBV_EINVAL, "rbv_comm_unique_id: null argument");
+  int rc = load_nccl();
+  if (rc != RBV_OK) return rc;
+  RbvNcclUniqueId id;
+  RBV_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out_id128, id.internal, sizeof(id.internal));
+  return RBV_OK;
+}
+
+int rbv_comm_init(RbvContext* ctx, const unsigned char* id128, int rank, int world) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(RBV_EINVAL, "rbv_comm_init: bad argument");
+  if (world > kMaxRanks) return fail(RBV_EINVAL, "rbv_comm_init: more than 64 ranks");
+  int rc = load_nccl();
+  if (rc != RBV_OK) return rc;
+  RBV_ON_DEVICE(ctx);
+  if (ctx->comm) {
+    g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  RbvNcclUniqueId id;
+  memcpy(id.internal, id128, sizeof(id.internal));
+  RBV_NCCL(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return RBV_OK;
+}
+
+int rbv_comm_info(const RbvContext* ctx, int* rank, int* world, int* nccl_version) {
+  if (!ctx) return fail(RBV_EINVAL, "rbv_comm_info: null context");
+  if (rank) *rank = ctx->comm ? ctx->comm_rank : 0;
+  if (world) *world = ctx->comm ? ctx->comm_world : 1;
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (g_nccl.GetVersion) g_nccl.GetVersion(nccl_version);
+  }
+  return RBV_OK;
+}
+
+// rows [lo, hi) of n rows owned by `rank` when every rank owns `chunk` = ceil(n / world) consecutive rows
+static void rank_rows(int n, int rank, int world, int* lo, int* hi, int* chunk) {
+  const int c = (n + world - 1) / world;
+  *chunk = c;
+  *lo = std::min(rank * c, n);
+  *hi = std::min(*lo + c, n);
+}
+
+// in-place all-gather of `chunk` doubles per rank: rank r's chunk sits at buf + r * chunk
+static int allgather_rows(RbvContext* ctx, double* buf, int chunk, cudaStream_t st) {
+  if (!ctx->comm || ctx->comm_world == 1 || chunk == 0) return RBV_OK;
+  RBV_NCCL(g_nccl.AllGather(buf + (size_t)ctx->comm_rank * chunk, buf, (size_t)chunk, kNcclFloat64, ctx->comm, st));
+  return RBV_OK;
+}
+
+int rbv_lnprob_batch_allgather(RbvContext* ctx, const double* theta, int W, double* lnprob, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, "rbv_lnprob_batch_allgather: null argument");
+  if (W <= 0) return W == 0 ? RBV_OK : fail(RBV_EINVAL, "negative n_walkers");
+  int lo, hi, chunk;
+  rank_rows(W, ctx->comm ? ctx->comm_rank : 0, ctx->comm ? ctx->comm_world : 1, &lo, &hi, &chunk);
+  if (hi > lo) {
+    int rc = launch_lnprob(ctx, theta + (size_t)lo * ctx->ndim, hi - lo, 0, lnprob + lo, workspace, workspace_bytes,
+                           stream, "rbv_lnprob_batch_allgather", nullptr, -1, nullptr, W);
+    if (rc != RBV_OK) return rc;
+  }
+  RBV_ON_DEVICE(ctx);
+  return allgather_rows(ctx, lnprob, chunk, (cudaStream_t)stream);
+}
+
+int rbv_stretch_run_dist(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                         unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                         int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                         void* stream) {
+  if (!ctx || !coords || !lnprob || !n_accepted || !flag)
+    return fail(RBV_EINVAL, "rbv_stretch_run_dist: null argument");
+  if (n_steps < 0 || !(a > 1.0)) return fail(RBV_EINVAL, "rbv_stretch_run_dist: n_steps < 0 or stretch scale a <= 1");
+  StretchParams P;
+  StretchLayout lay;
+  int rc = stretch_params(ctx, n_walkers, workspace, workspace_bytes, "rbv_stretch_run_dist", &P, &lay);
+  if (rc != RBV_OK) return rc;
+  if (n_steps == 0) return RBV_OK;
+  RBV_ON_DEVICE(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  P.coords = coords;
+  P.lnp = lnprob;
+  P.chain = chain;
+  P.lnp_chain = lnprob_chain;
+  P.n_accepted = n_accepted;
+  P.flag = flag;
+  P.step_ctr = (unsigned long long*)(ws + lay.ctr);     // the step index lives on the device: one graph, replayed
+  P.ticket = (unsigned int*)(ws + lay.ctr + 64);
+  P.first_step = first_step;
+  P.seed = seed;
+  P.a = a;
+  RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
+  const int rank = ctx->comm ? ctx->comm_rank : 0, world = ctx->comm ? ctx->comm_world : 1;
+  const int h = (n_walkers + 1) / 2;
+
+  // one half-step: every rank builds all proposals (replicated state, counter-based streams), evaluates its rows,
+  // the ranks all-gather the 8-byte lnprob values in place over NCCL, every rank applies the same accept/reject
+  auto one_step = [&]() -> int {
+    for (int split = 0; split < 2; ++split) {
+      const int nS = split == 0 ? h : n_walkers - h;
+      int lo, hi, chunk;
+      rank_rows(nS, rank, world, &lo, &hi, &chunk);
+      stretch_propose_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+      if (hi > lo) {
+        int rc2 = launch_lnprob(ctx, P.prop + (size_t)lo * ctx->ndim, hi - lo, 0, P.lnp_prop + lo,
+                                ws + lay.lnprob_ws, workspace_bytes - lay.lnprob_ws, stream, "rbv_stretch_run_dist",
+                                nullptr, -1, nullptr, nS);
+        if (rc2 != RBV_OK) return rc2;
+      }
+      int rc2 = allgather_rows(ctx, P.lnp_prop, chunk, st);
+      if (rc2 != RBV_OK) return rc2;
+      stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    return RBV_OK;
+  };
+
+  if (use_graph && st != nullptr && n_steps >= 4) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const long long launches_before = ctx->launches;
+    for (int split = 0; split < 2; ++split) {   // NCCL sets up its buffers on the first collective of a size: not
+      int lo, hi, chunk;                        // inside a capture (lnp_prop is scratch here)
+      rank_rows(split == 0 ? h : n_walkers - h, rank, world, &lo, &hi, &chunk);
+      rc = allgather_rows(ctx, P.lnp_prop, chunk, st);
+      if (rc != RBV_OK) return rc;
+    }
+    RBV_CUDA(cudaStreamSynchronize(st));
+    RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = one_step();
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != RBV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    const long long per_step = ctx->launches - launches_before;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    for (int s2 = 0; s2 < n_steps && e == cudaSuccess; ++s2) e = cudaGraphLaunch(exec, st);
+    ctx->launches = launches_before + per_step * n_steps;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("rbv_stretch_run_dist (graph): ") + cudaGetErrorString(e));
+    return RBV_OK;
+  }
+  for (int s2 = 0; s2 < n_steps; ++s2) {
+    rc = one_step();
+    if (rc != RBV_OK) return rc;
+  }
+  RBV_CUDA(cudaStreamSynchronize(st));
   return RBV_OK;
 }
 
@@ -1926,7 +2170,7 @@ static SliceLayout slice_layout(const RbvContext* ctx, int W) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += up(bytes); return at; };
   lay.cand = take(2 * row);                       // two rows per walker while it widens its bracket
-  lay.lnp_cand = take(2 * h * sizeof(double));
+  lay.lnp_cand = take((2 * h + kMaxRanks) * sizeof(double));   // padded for the in-place all-gather
   lay.dir = take(row);
   lay.z0 = take(h * sizeof(double));
   lay.lo = take(h * sizeof(double));
@@ -2008,9 +2252,19 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
     const unsigned rows_grid = (unsigned)((nS + 3) / 4);
     slice_candidate_kernel<<<rows_grid, 128, 0, st>>>(P, split, loop, use_loop);
     RBV_CUDA(cudaGetLastError());
-    int rc = launch_lnprob(ctx, P.cand, rows, 0, P.lnp_cand, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
-                           "rbv_slice_run", nullptr, -1, P.skip);
-    if (rc != RBV_OK) return rc;
+    // multi-GPU (rbv_comm_init): this rank evaluates its share of the rows, in-place all-gather of their lnprob
+    int lo = 0, hi = rows, chunk = rows;
+    const bool dist = ctx->comm && ctx->comm_world > 1;
+    if (dist) rank_rows(rows, ctx->comm_rank, ctx->comm_world, &lo, &hi, &chunk);
+    if (hi > lo) {
+      int rc = launch_lnprob(ctx, P.cand + (size_t)lo * ctx->ndim, hi - lo, 0, P.lnp_cand + lo, ws + lay.lnprob_ws,
+                             lnprob_ws_bytes, stream, "rbv_slice_run", nullptr, -1, P.skip + lo, rows);
+      if (rc != RBV_OK) return rc;
+    }
+    if (dist) {
+      int rc = allgather_rows(ctx, P.lnp_cand, chunk, st);
+      if (rc != RBV_OK) return rc;
+    }
     slice_update_kernel<<<rows_grid, 128, 0, st>>>(P, split, loop, use_loop);
     RBV_CUDA(cudaGetLastError());
     return RBV_OK;
@@ -2031,6 +2285,21 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
 
   int rc = RBV_OK;
   long long per_iteration = 0;
+  const bool dist_run = ctx->comm && ctx->comm_world > 1;
+  if (dist_run) {
+    // multi-GPU: NCCL sets up its buffers on the first collective of a size -- do that outside any capture
+    // (lnp_cand is scratch here).  The WHILE-node loop with a collective in its body is opt-in
+    // (RBVFIT_B200_SLICE_DIST_GRAPH=1); by default the host-polled loop runs: every rank reads the same replicated
+    // counters and therefore enqueues the same iterations.
+    for (int split = 0; split < 2; ++split) {
+      int lo, hi, chunk;
+      rank_rows(2 * (split == 0 ? h : n_walkers - h), ctx->comm_rank, ctx->comm_world, &lo, &hi, &chunk);
+      rc = allgather_rows(ctx, P.lnp_cand, chunk, st);
+      if (rc != RBV_OK) return rc;
+    }
+    RBV_CUDA(cudaStreamSynchronize(st));
+    if (!ctx->tune.slice_dist_graph) use_graph = 0;
+  }
   if (use_graph && st != nullptr) {
     // Graph mode: per half a graph whose only node is a WHILE node; its body is one iteration, captured from the
     // stream, and slice_update_kernel sets the condition.  A step = begin, graph, begin, graph, record -- five

@@ -42,6 +42,35 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def replicate_seed(seed, rank: int, world: int, group=None) -> int:
+    """The 64-bit sampler seed every rank must share: rank 0's (drawn from OS entropy when ``seed`` is None) is
+    broadcast.  Device samplers run replicated from counter-based random streams -- ranks with different seeds would
+    build different proposals and apply all-gathered lnprob values to rows they were not computed for."""
+    s = int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
+    if world == 1:
+        return s
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([s >> 32, s & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    hi, lo = (int(v) for v in t.cpu().tolist())
+    return (hi << 32) | lo
+
+
+def replicate_array(arr, rank: int, world: int, group=None) -> np.ndarray:
+    """Rank 0's copy of a float64 array (initial ensemble) on every rank."""
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    if world == 1:
+        return a
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.as_tensor(a).to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return t.cpu().numpy()
+
+
 class WalkerPartition:
     """Row partition of a [W, ndim] batch over the ranks of a process group."""
 
@@ -130,8 +159,13 @@ class DistributedLikelihood:
         self._theta_dev = None
 
     def lnprob_device(self, theta_t):
-        """Device-resident: every rank holds the full theta tensor, evaluates its rows, gathers lnprob."""
+        """Device-resident: every rank holds the full theta tensor, evaluates its rows, gathers lnprob.  With a
+        communicator attached to the engine (``Engine.comm_init``) the all-gather is issued by the library itself
+        (``rbv_lnprob_batch_allgather``): one C call, no torch.distributed op on the hot path."""
         W = int(theta_t.shape[0])
+        eng = getattr(self.like, "engine", None)
+        if eng is not None and getattr(eng, "has_comm", False) and eng.comm_world == self.part.world:
+            return eng.lnprob_allgather_device(theta_t)
         lo, hi = self.part.rows(W)
         local = self.like.lnprob_device(theta_t[lo:hi].contiguous()) if hi > lo else theta_t.new_empty(0)
         return self.part.gather(local, W)

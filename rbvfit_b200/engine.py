@@ -31,6 +31,17 @@ def _dptr(a: np.ndarray):
 class Engine:
     """One likelihood context on one device."""
 
+    def _dev_tensor(self, t, dtype, what: str, shape=None):
+        """Every tensor whose ``data_ptr()`` crosses the C ABI: right dtype, contiguous, on this engine's device
+        (anything else would be read as raw doubles / ints by the library)."""
+        if t is None:
+            return None
+        if t.dtype != dtype or not t.is_contiguous() or t.device != self.tdev:
+            raise ValueError(f"{what} must be a contiguous {dtype} tensor on {self.tdev}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
     def __init__(self, device: Optional[int] = None):
         torch = _torch()
         self.lib = _lib.load()
@@ -49,6 +60,7 @@ class Engine:
         self._ws_sightlines = False
         self._stretch_ws = None               # workspace of the device-resident sampler
         self._slice_ws = None                 # workspace of the device-resident slice sampler
+        self.comm_rank, self.comm_world = 0, 1   # rbv_comm_init (multi-GPU: the library issues the all-gather)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -163,17 +175,31 @@ class Engine:
     def lnprob_device(self, theta_t, out_t=None):
         """DEVICE theta tensor [W, ndim] (float64, contiguous) -> DEVICE lnprob tensor [W]; asynchronous."""
         torch = _torch()
-        if theta_t.dtype != torch.float64 or not theta_t.is_contiguous() or theta_t.device != self.tdev:
-            raise ValueError("theta must be a contiguous float64 tensor on the engine's device")
+        self._dev_tensor(theta_t, torch.float64, "theta")
         W, ndim = theta_t.shape
         if ndim != self.ndim:
             raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
         self._reserve(W, ndim, sightlines=False)
         if out_t is None:
             out_t = torch.empty(W, dtype=torch.float64, device=self.tdev)
+        self._dev_tensor(out_t, torch.float64, "out", (W,))
         check(self.lib.rbv_lnprob_batch(self._h, theta_t.data_ptr(), W, out_t.data_ptr(), self._ws.data_ptr(),
                                         self._ws_bytes, self._stream()), "rbv_lnprob_batch")
         return out_t
+
+    def lnlike_host(self, theta: np.ndarray) -> np.ndarray:
+        """HOST theta [W, ndim] -> HOST lnlike [W] (``rbv_lnlike_batch``: the same launch without the prior)."""
+        torch = _torch()
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        W, ndim = theta.shape
+        if ndim != self.ndim:
+            raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
+        self._reserve(W, ndim, sightlines=False)
+        th = torch.as_tensor(theta, device=self.tdev)
+        out = torch.empty(W, dtype=torch.float64, device=self.tdev)
+        check(self.lib.rbv_lnlike_batch(self._h, th.data_ptr(), W, out.data_ptr(), self._ws.data_ptr(), self._ws_bytes,
+                                        self._stream()), "rbv_lnlike_batch")
+        return out.cpu().numpy()
 
     def lnprob_sightlines_host(self, theta: np.ndarray, wps: int) -> np.ndarray:
         """HOST theta [S * wps, ndim] (wps consecutive rows per sightline) -> HOST lnprob [S * wps]."""
@@ -183,12 +209,14 @@ class Engine:
 
     def lnprob_sightlines_device(self, theta_t, wps: int, out_t=None):
         torch = _torch()
+        self._dev_tensor(theta_t, torch.float64, "theta")
         W, ndim = theta_t.shape
         if ndim != self.ndim:
             raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
         self._reserve(W, ndim, sightlines=True)
         if out_t is None:
             out_t = torch.empty(W, dtype=torch.float64, device=self.tdev)
+        self._dev_tensor(out_t, torch.float64, "out", (W,))
         check(self.lib.rbv_lnprob_batch_sightlines(self._h, theta_t.data_ptr(), W, int(wps), out_t.data_ptr(),
                                                    self._ws.data_ptr(), self._ws_bytes, self._stream()),
               "rbv_lnprob_batch_sightlines")
@@ -206,6 +234,8 @@ class Engine:
                       (flag_t, torch.int32)):
             if t.dtype != dt or not t.is_contiguous() or t.device != self.tdev:
                 raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
+        self._dev_tensor(chain_t, torch.float64, "chain", (int(n_steps), W, ndim))
+        self._dev_tensor(lnp_chain_t, torch.float64, "lnprob chain", (int(n_steps), W))
         nbytes = C.c_size_t(0)
         check(self.lib.rbv_stretch_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_stretch_workspace_bytes")
         if self._stretch_ws is None or self._stretch_ws.numel() < nbytes.value:
@@ -230,6 +260,9 @@ class Engine:
                              lnp_rows_t):
         """Multi-GPU half-step, first part (rbv_stretch_propose_eval): all proposals of the half, lnprob of rows
         [row_lo, row_hi) into ``lnp_rows_t``; asynchronous on the current stream."""
+        torch = _torch()
+        self._dev_tensor(coords_t, torch.float64, "coords")
+        self._dev_tensor(lnp_rows_t, torch.float64, "lnprob rows")
         ws = self._stretch_workspace(coords_t.shape[0])
         check(self.lib.rbv_stretch_propose_eval(self._h, coords_t.data_ptr(), coords_t.shape[0], float(a),
                                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), int(split), int(row_lo),
@@ -239,6 +272,15 @@ class Engine:
     def stretch_accept(self, coords_t, lnp_t, a: float, seed: int, step: int, split: int, lnp_rows_t, chain_row_t,
                        lnp_chain_row_t, n_accepted_t, flag_t):
         """Multi-GPU half-step, second part (rbv_stretch_accept), after the all-gather of ``lnp_rows_t``."""
+        torch = _torch()
+        W = coords_t.shape[0]
+        self._dev_tensor(coords_t, torch.float64, "coords")
+        self._dev_tensor(lnp_t, torch.float64, "lnprob", (W,))
+        self._dev_tensor(lnp_rows_t, torch.float64, "lnprob rows")
+        self._dev_tensor(chain_row_t, torch.float64, "chain row", (W, coords_t.shape[1]))
+        self._dev_tensor(lnp_chain_row_t, torch.float64, "lnprob chain row", (W,))
+        self._dev_tensor(n_accepted_t, torch.int32, "n_accepted", (W,))
+        self._dev_tensor(flag_t, torch.int32, "flag")
         ws = self._stretch_workspace(coords_t.shape[0])
         check(self.lib.rbv_stretch_accept(self._h, coords_t.data_ptr(), lnp_t.data_ptr(), coords_t.shape[0], float(a),
                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), int(split),
@@ -247,6 +289,72 @@ class Engine:
                                           lnp_chain_row_t.data_ptr() if lnp_chain_row_t is not None else None,
                                           n_accepted_t.data_ptr(), flag_t.data_ptr(), ws.data_ptr(), ws.numel(),
                                           self._stream()), "rbv_stretch_accept")
+
+    # ------------------------------------------------------------------ multi-GPU (collective inside the library)
+    def comm_init(self, group=None):
+        """Collective over the ranks of ``group`` (default: the world group): attach this context to an NCCL
+        communicator of its own (``rbv_comm_init``).  Rank 0 creates the unique id; it travels through
+        ``torch.distributed.broadcast``.  Afterwards ``lnprob_allgather_device`` / ``stretch_run_dist`` /
+        ``slice_run`` split their rows over the ranks and all-gather inside the library."""
+        torch = _torch()
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return False
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(self.lib.rbv_comm_unique_id(ident), "rbv_comm_unique_id")
+        t = torch.tensor(list(ident), dtype=torch.uint8)
+        on_gpu = dist.get_backend(group) == "nccl"
+        if on_gpu:
+            t = t.to(self.tdev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        check(self.lib.rbv_comm_init(self._h, ident, rank, world), "rbv_comm_init")
+        self.comm_rank, self.comm_world = rank, world
+        return True
+
+    @property
+    def has_comm(self) -> bool:
+        return self.comm_world > 1
+
+    def lnprob_allgather_device(self, theta_t):
+        """Replicated DEVICE theta [W, ndim] -> DEVICE lnprob [W], complete on every rank: this rank evaluates its
+        rows, NCCL all-gather in place inside the library (``rbv_lnprob_batch_allgather``); asynchronous."""
+        torch = _torch()
+        self._dev_tensor(theta_t, torch.float64, "theta")
+        W, ndim = theta_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
+        chunk = -(-W // self.comm_world)
+        self._reserve(chunk, ndim, sightlines=False)
+        out_t = torch.empty(chunk * self.comm_world, dtype=torch.float64, device=self.tdev)
+        check(self.lib.rbv_lnprob_batch_allgather(self._h, theta_t.data_ptr(), W, out_t.data_ptr(), self._ws.data_ptr(),
+                                                  self._ws_bytes, self._stream()), "rbv_lnprob_batch_allgather")
+        return out_t[:W]
+
+    def stretch_run_dist(self, coords_t, lnp_t, n_steps: int, a: float, seed: int, first_step: int, chain_t,
+                         lnp_chain_t, n_accepted_t, flag_t, use_graph: bool = True):
+        """``stretch_run`` over all ranks of the communicator (``rbv_stretch_run_dist``): replicated state, rows of
+        every half-step split over the ranks, the lnprob all-gather inside the captured step."""
+        torch = _torch()
+        W, ndim = coords_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"coords has {ndim} columns, bounds were set for ndim={self.ndim}")
+        self._dev_tensor(coords_t, torch.float64, "coords")
+        self._dev_tensor(lnp_t, torch.float64, "lnprob", (W,))
+        self._dev_tensor(chain_t, torch.float64, "chain", (int(n_steps), W, ndim))
+        self._dev_tensor(lnp_chain_t, torch.float64, "lnprob chain", (int(n_steps), W))
+        self._dev_tensor(n_accepted_t, torch.int32, "n_accepted", (W,))
+        self._dev_tensor(flag_t, torch.int32, "flag")
+        ws = self._stretch_workspace(W)
+        check(self.lib.rbv_stretch_run_dist(
+            self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), float(a),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_step),
+            chain_t.data_ptr() if chain_t is not None else None,
+            lnp_chain_t.data_ptr() if lnp_chain_t is not None else None,
+            n_accepted_t.data_ptr(), flag_t.data_ptr(), ws.data_ptr(), ws.numel(), int(bool(use_graph)),
+            self._stream()), "rbv_stretch_run_dist")
 
     def stretch_run_sightlines(self, coords_t, lnp_t, n_steps: int, a: float, seed: int, first_step: int, chain_t,
                                lnp_chain_t, n_accepted_t, flag_t):
@@ -260,6 +368,10 @@ class Engine:
                       (flag_t, torch.int32)):
             if t.dtype != dt or not t.is_contiguous() or t.device != self.tdev:
                 raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
+        self._dev_tensor(lnp_t, torch.float64, "lnprob", (S, W))
+        self._dev_tensor(chain_t, torch.float64, "chain", (int(n_steps), S, W, ndim))
+        self._dev_tensor(lnp_chain_t, torch.float64, "lnprob chain", (int(n_steps), S, W))
+        self._dev_tensor(n_accepted_t, torch.int32, "n_accepted", (S, W))
         nbytes = C.c_size_t(0)
         check(self.lib.rbv_stretch_workspace_bytes_sightlines(self._h, W, C.byref(nbytes)),
               "rbv_stretch_workspace_bytes_sightlines")
@@ -286,6 +398,9 @@ class Engine:
         for t, dt in ((coords_t, torch.float64), (lnp_t, torch.float64), (flag_t, torch.int32)):
             if t.dtype != dt or not t.is_contiguous() or t.device != self.tdev:
                 raise ValueError("sampler state tensors must be contiguous, on the engine's device, f64 / i32")
+        self._dev_tensor(lnp_t, torch.float64, "lnprob", (W,))
+        self._dev_tensor(chain_t, torch.float64, "chain", (int(n_steps), W, ndim))
+        self._dev_tensor(lnp_chain_t, torch.float64, "lnprob chain", (int(n_steps), W))
         nbytes = C.c_size_t(0)
         check(self.lib.rbv_slice_workspace_bytes(self._h, W, C.byref(nbytes)), "rbv_slice_workspace_bytes")
         if self._slice_ws is None or self._slice_ws.numel() < nbytes.value:

@@ -83,6 +83,16 @@ class GpuLikelihood:
 
     __call__ = lnprob
 
+    def lnlike(self, theta):
+        """The likelihood without the prior (``vfit.lnlike``, vfit_mcmc.py:297-319): rows outside the bounds are
+        evaluated like any other.  One launch, no shared state touched."""
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim == 1:
+            return float(self.engine.lnlike_host(theta[None, :])[0])
+        if theta.shape[0] == 0:
+            return np.zeros(0)
+        return self.engine.lnlike_host(theta)
+
     def lnprior(self, theta):
         theta = np.asarray(theta, dtype=np.float64)
         bad = np.any(theta < self.lb, axis=-1) | np.any(theta > self.ub, axis=-1)

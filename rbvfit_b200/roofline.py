@@ -19,7 +19,7 @@ algorithmic work of THAT algorithm (the honest numerator for its roofline); the 
                       + sum over the lines NOT in the far field of c(x_lp)           (same tiers as above)
                       + 2 K + 32
     line l is in the far field of a super-chunk when min |z|^2 >= 576 over it (6-term series valid) and
-        72 |kappa_l| (hw / (2 xm))^8 / xm^2 <= 1e-13 / L,   kappa = N f K a / sqrt(pi),  xm = min |x|, hw = half width in x
+        72 |kappa_l| (hw / (2 xm))^8 / xm^2 <= 1e-12 / L,   kappa = N f K a / sqrt(pi),  xm = min |x|, hw = half width in x
 """
 from __future__ import annotations
 
@@ -59,7 +59,7 @@ def flops_per_walker_pixel(data, theta, wave, n_taps):
 
 SUPER_PIX = 1024
 FF_NODES = 8
-FF_EPS = 1e-13
+FF_EPS = 1e-12
 
 
 def flops_farfield(data, theta, wave, n_taps):

@@ -101,8 +101,33 @@ def walkers_independent(coords) -> bool:
     return np.linalg.cond(C.astype(float)) <= 1e8
 
 
+class _ChunkedHistory:
+    """Chain / log-prob history as a list of per-run chunks, concatenated once when it is first read: appending the
+    chain of a run must not re-copy everything sampled so far (a C5a-scale ensemble writes 2.3 MB per step)."""
+
+    def _hist_get(self, name):
+        chunks = self.__dict__["_hist_" + name]
+        if len(chunks) > 1:
+            chunks[:] = [np.concatenate(chunks, axis=0)]
+        return chunks[0]
+
+    def _hist_set(self, name, value):
+        self.__dict__["_hist_" + name] = [value]
+
+    def _hist_append(self, chain, lps):
+        for name, arr in (("chain", chain), ("log_prob", lps)):
+            chunks = self.__dict__["_hist_" + name]
+            if len(chunks) == 1 and len(chunks[0]) == 0:
+                chunks[:] = [arr]
+            else:
+                chunks.append(arr)
+
+    _chain = property(lambda self: self._hist_get("chain"), lambda self, v: self._hist_set("chain", v))
+    _log_prob = property(lambda self: self._hist_get("log_prob"), lambda self, v: self._hist_set("log_prob", v))
+
+
 # ------------------------------------------------------------------------------------------ sampler
-class EnsembleSampler:
+class EnsembleSampler(_ChunkedHistory):
     """Stretch-move ensemble sampler; ``log_prob_fn`` must map ``(n, ndim) -> (n,)``."""
 
     def __init__(self, nwalkers: int, ndim: int, log_prob_fn: Callable, a: float = 2.0, pool=None,
@@ -195,8 +220,7 @@ class EnsembleSampler:
             self._accepted += acc
             chain[i] = coords
             lps[i] = log_prob
-        self._chain = np.concatenate([self._chain, chain], axis=0)
-        self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self._hist_append(chain, lps)
         self.iteration += nsteps
         self._last = (coords, log_prob)
         return coords, log_prob
@@ -269,11 +293,7 @@ class DeviceEnsembleSampler(EnsembleSampler):
         chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
         nacc = nacc_t.cpu().numpy()
         self._accepted += nacc
-        if len(self._chain) == 0:
-            self._chain, self._log_prob = chain, lps
-        else:
-            self._chain = np.concatenate([self._chain, chain], axis=0)
-            self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self._hist_append(chain, lps)
         n = chain.shape[0]
         self.iteration += n
         if n:
@@ -325,25 +345,43 @@ class DeviceEnsembleSampler(EnsembleSampler):
 
 
 class DistributedDeviceSampler(DeviceEnsembleSampler):
-    """The device-resident stretch move over several GPUs (one process per GPU, ``torch.distributed``): the
-    ensemble state is replicated, every half-step each rank evaluates its rows of the proposals
-    (``rbv_stretch_propose_eval``), the ranks all-gather the 8-byte lnprob values over NCCL / NVLink, and every rank
-    applies the same accept/reject (``rbv_stretch_accept``) -- the random streams are counter based, so the chain is
-    the one ``DeviceEnsembleSampler`` produces on a single GPU with the same seed (up to the last-bit differences of
-    lnprob between tile geometries).  Nothing but the lnprob values crosses the wire; no host synchronisation inside
-    a run."""
+    """The device-resident stretch move over several GPUs (one process per GPU): the ensemble state is replicated,
+    every half-step each rank evaluates its rows of the proposals, the ranks all-gather the 8-byte lnprob values over
+    NCCL / NVLink, and every rank applies the same accept/reject -- the random streams are counter based, so the
+    chain is the one ``DeviceEnsembleSampler`` produces on a single GPU with the same seed, bit for bit (the launch
+    geometry of a rank's share is chosen as for the whole half-step).  Nothing but lnprob values crosses the wire.
+
+    With a communicator attached to the engine (``Engine.comm_init``, done here when ``torch.distributed`` runs on
+    NCCL) the whole run is ONE C call: ``rbv_stretch_run_dist`` captures a step -- proposals, this rank's likelihood
+    launch, the in-place NCCL all-gather, accept/reject -- in a CUDA graph and replays it; no Python and no host
+    synchronisation inside the run.  Without one (gloo in the CPU tests, a stub engine) the half-step is driven from
+    here: ``rbv_stretch_propose_eval`` -> ``torch.distributed.all_gather_into_tensor`` -> ``rbv_stretch_accept``.
+
+    Every rank must run with the same seed and the same initial ensemble: ``seed`` (None = OS entropy) and
+    ``initial_state`` are taken from rank 0 and broadcast."""
 
     def __init__(self, nwalkers: int, ndim: int, likelihood, partition, a: float = 2.0, seed: Optional[int] = None,
-                 **_ignored):
-        super().__init__(nwalkers, ndim, likelihood, a=a, seed=seed, use_graph=False)
+                 use_graph: bool = True, **_ignored):
+        super().__init__(nwalkers, ndim, likelihood, a=a, seed=seed, use_graph=use_graph)
         self.partition = partition
+        from .dist import replicate_seed
+        self._seed = replicate_seed(seed, partition.rank, partition.world, partition.group)
+        eng = likelihood.engine
+        if partition.world > 1 and not getattr(eng, "has_comm", True):
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_backend(partition.group) == "nccl":
+                eng.comm_init(partition.group)
 
     def run_mcmc(self, initial_state, nsteps, progress=False, skip_initial_state_check=False, **_ignored):
         import torch
+        from .dist import replicate_array
         eng = self.likelihood.engine
         dev = eng.tdev
         part = self.partition
         W, nd = self.nwalkers, self.ndim
+        in_library = bool(getattr(eng, "has_comm", False)) and eng.comm_world == part.world
+        if in_library and self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
         if initial_state is None:
             if self._state is None:
                 raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
@@ -352,17 +390,37 @@ class DistributedDeviceSampler(DeviceEnsembleSampler):
             coords = np.array(initial_state, dtype=np.float64, copy=True)
             if coords.shape != (W, nd):
                 raise ValueError("incompatible input dimensions {0}".format(coords.shape))
+            coords = replicate_array(coords, part.rank, part.world, part.group)      # rank 0's ensemble everywhere
             if not np.all(np.isfinite(coords)):
                 raise ValueError("At least one parameter value was infinite or NaN")
             if not skip_initial_state_check and not walkers_independent(coords):
                 raise ValueError("Initial state has a large condition number. Make sure that your walkers are "
                                  "linearly independent for the best performance")
             coords_t = torch.as_tensor(coords, device=dev)
-            lo, hi = part.rows(W)
-            local = eng.lnprob_device(coords_t[lo:hi].contiguous()) if hi > lo else coords_t.new_empty(0)
-            lnp_t = part.gather(local, W).contiguous()
+            if in_library:
+                lnp_t = eng.lnprob_allgather_device(coords_t).contiguous()
+            else:
+                lo, hi = part.rows(W)
+                local = eng.lnprob_device(coords_t[lo:hi].contiguous()) if hi > lo else coords_t.new_empty(0)
+                lnp_t = part.gather(local, W).contiguous()
             if bool(torch.isnan(lnp_t).any()):
                 raise ValueError("Probability function returned NaN")
+        if in_library:
+            torch.cuda.current_stream(dev).synchronize()
+            with torch.cuda.stream(self._stream):
+                chain_t = torch.empty((nsteps, W, nd), dtype=torch.float64, device=dev)
+                lps_t = torch.empty((nsteps, W), dtype=torch.float64, device=dev)
+                nacc_t = torch.zeros(W, dtype=torch.int32, device=dev)
+                flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
+                eng.stretch_run_dist(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t,
+                                     nacc_t, flag_t, use_graph=self.use_graph)
+                self._stream.synchronize()
+            if int(flag_t.item()) & 1:
+                raise ValueError("Probability function returned NaN")
+            self._state = (coords_t, lnp_t)
+            self.n_logp_calls += 2 * nsteps
+            self.n_logp_rows += W * nsteps
+            return self._append(chain_t, lps_t, nacc_t)
         chain_t = torch.empty((nsteps, W, nd), dtype=torch.float64, device=dev)
         lps_t = torch.empty((nsteps, W), dtype=torch.float64, device=dev)
         nacc_t = torch.zeros(W, dtype=torch.int32, device=dev)
@@ -432,7 +490,7 @@ class _SightlineView:
         return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
 
 
-class SightlineEnsembleSampler:
+class SightlineEnsembleSampler(_ChunkedHistory):
     """Survey mode (BASELINE.json config 5): one stretch-move ensemble PER SIGHTLINE of a ``SightlineBatch``, all S
     ensembles advancing in lockstep on the device (``rbv_stretch_run_sightlines``) -- the reference would run S
     separate ``vfit(...).runmcmc()`` calls one after the other (vfit_mcmc.py:492-561).  Per half-step: one proposal
@@ -505,11 +563,7 @@ class SightlineEnsembleSampler:
             self._state = (coords_t, lnp_t)
             chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
             self._accepted += nacc_t.cpu().numpy()
-        if len(self._chain) == 0:
-            self._chain, self._log_prob = chain, lps
-        else:
-            self._chain = np.concatenate([self._chain, chain], axis=0)
-            self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self._hist_append(chain, lps)
         self.iteration += nsteps
         if nsteps:
             self._last = (chain[-1].copy(), lps[-1].copy())

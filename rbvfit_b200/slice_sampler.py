@@ -25,10 +25,10 @@ from typing import Callable, Optional
 
 import numpy as np
 
-from .sampler import integrated_time
+from .sampler import _ChunkedHistory, integrated_time
 
 
-class EnsembleSliceSampler:
+class EnsembleSliceSampler(_ChunkedHistory):
     def __init__(self, nwalkers: int, ndim: int, log_prob_fn: Callable, mu: float = 1.0, tune: bool = True,
                  tolerance: float = 0.05, patience: int = 5, maxsteps: int = 10000, maxiter: int = 10000,
                  pool=None, vectorize: bool = True, seed: Optional[int] = None):
@@ -154,8 +154,7 @@ class EnsembleSliceSampler:
                 if good > self.patience:
                     self.tune = False
             chain[i], lps[i] = X, Z
-        self._chain = np.concatenate([self._chain, chain], axis=0)
-        self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self._hist_append(chain, lps)
         self.iteration += nsteps
         self._last = (X, Z)
         return X, Z
@@ -273,12 +272,35 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
             self.ncon += int(tuning.n_contractions)
             self._state = (coords_t, lnp_t)
             chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
-        if len(self._chain) == 0:
-            self._chain, self._log_prob = chain, lps
-        else:
-            self._chain = np.concatenate([self._chain, chain], axis=0)
-            self._log_prob = np.concatenate([self._log_prob, lps], axis=0)
+        self._hist_append(chain, lps)
         self.iteration += nsteps
         if nsteps:
             self._last = (chain[-1].copy(), lps[-1].copy())
         return self._last
+
+
+class DistributedDeviceSliceSampler(DeviceEnsembleSliceSampler):
+    """The device-resident ensemble slice sampler over several GPUs (one process per GPU, NCCL): with a communicator
+    attached to the engine (``Engine.comm_init``, done here) ``rbv_slice_run`` splits the rows of every iteration's
+    masked likelihood batch over the ranks and all-gathers their lnprob in place inside the library; walker state,
+    directions, brackets and the adaptation of mu are replicated, every rank takes the same decisions from the same
+    counter-based random streams, so the chain is the single-GPU chain bit for bit.  The seed (None = OS entropy) and
+    the initial ensemble are taken from rank 0 and broadcast.  The per-half-step loop is host-polled by default (every
+    rank reads the same replicated counters); ``RBVFIT_B200_SLICE_DIST_GRAPH=1`` keeps it a CUDA-graph WHILE node."""
+
+    def __init__(self, nwalkers: int, ndim: int, likelihood, partition, **kwargs):
+        from .dist import replicate_seed
+        seed = kwargs.pop("seed", None)
+        super().__init__(nwalkers, ndim, likelihood, seed=seed, **kwargs)
+        self.partition = partition
+        self._seed = replicate_seed(seed, partition.rank, partition.world, partition.group)
+        eng = likelihood.engine
+        if partition.world > 1 and not eng.has_comm:
+            eng.comm_init(partition.group)
+
+    def run_mcmc(self, start, nsteps, progress=False, **kw):
+        from .dist import replicate_array
+        if start is not None:
+            p = self.partition
+            start = replicate_array(start, p.rank, p.world, p.group)
+        return super().run_mcmc(start, nsteps, progress=progress, **kw)

@@ -21,6 +21,21 @@ from .likelihood import GpuLikelihood
 from .sampler import DeviceEnsembleSampler, EnsembleSampler
 
 
+def gelman_rubin(chains) -> np.ndarray:
+    """Gelman-Rubin potential scale reduction per parameter; ``chains`` is [n_chains, n_steps, ndim] (the walkers as
+    chains, the call the reference makes: zeus.diagnostics.gelman_rubin(chain.transpose(1, 0, 2)), vfit_mcmc.py:637-639).
+    W = mean within-chain variance, B/n = variance of the chain means, V = (n-1)/n W + B/n + B/(n m), R = sqrt(V / W)."""
+    x = np.asarray(chains, dtype=np.float64)
+    m, n = x.shape[0], x.shape[1]
+    if m < 2 or n < 2:
+        raise ValueError("need at least two chains of at least two steps")
+    means = x.mean(axis=1)
+    W = x.var(axis=1, ddof=1).mean(axis=0)
+    B_over_n = means.var(axis=0, ddof=1)
+    V = (n - 1.0) / n * W + B_over_n + B_over_n / m
+    return np.sqrt(V / W)
+
+
 class vfit:
     def __init__(self, instrument_data: Dict, theta, lb, ub, no_of_Chain=50, no_of_steps=1000,
                  perturbation=1e-4, sampler="emcee", skip_initial_state_check=False, device=None, seed=None,
@@ -100,19 +115,9 @@ class vfit:
         return self._like.lnprob(theta)
 
     def lnlike(self, theta):
-        """lnlike alone (no prior): evaluated with the bounds opened, exceptions -> -inf as in the reference."""
-        theta = np.asarray(theta, dtype=np.float64)
-        lp = self.lnprob(theta)
-        prior = self.lnprior(theta)
-        if np.all(np.isfinite(prior)):
-            return lp
-        # out-of-bounds rows: the reference's lnlike still evaluates them
-        eng = self._like.engine
-        try:
-            eng.set_bounds(np.full(self.ndim, -np.inf), np.full(self.ndim, np.inf))
-            return self._like.lnprob(theta)
-        finally:
-            eng.set_bounds(self.lb, self.ub)
+        """lnlike alone (vfit_mcmc.py:297-319): the reference's lnlike does not look at the bounds, so rows outside
+        them are evaluated too (``rbv_lnlike_batch``: the lnprob launch without the prior, no shared state touched)."""
+        return self._like.lnlike(theta)
 
     # ------------------------------------------------------------------ optimiser (vfit_mcmc.py:355-360)
     def optimize_guess(self, theta):
@@ -261,14 +266,47 @@ class vfit:
         return sampler.acceptance_fraction
 
     def _print_diagnostics(self):
+        """vfit_mcmc.py:589-655: acceptance fraction, emcee's integrated auto-correlation time, zeus's Gelman-Rubin
+        statistic (zeus.diagnostics.gelman_rubin is not vendored in the reference; `gelman_rubin` below restates the
+        standard estimator on the walkers as chains)."""
         print("\n" + "=" * 60 + "\nMCMC DIAGNOSTICS\n" + "=" * 60)
-        af = np.mean(self._get_acceptance_fraction(self.sampler))
-        print(f"Mean acceptance fraction: {af:.3f}")
         try:
-            tau = self.sampler.get_autocorr_time()
-            print(f"Mean auto-correlation time: {np.nanmean(tau):.3f} steps")
+            af = np.mean(self._get_acceptance_fraction(self.sampler))
+            print(f"Mean acceptance fraction: {af:.3f}")
+            if af < 0.2:
+                print("⚠️  Low acceptance fraction (<0.2). Consider reducing step size.")
+            elif af > 0.7:
+                print("⚠️  High acceptance fraction (>0.7). Consider increasing step size.")
+            else:
+                print("✅ Good acceptance fraction (0.2-0.7)")
         except Exception:
-            print("⚠️  Warning: Could not calculate auto-correlation time")
+            print("Acceptance fraction not available")
+        if self.sampler_name == "emcee":
+            try:
+                tau = np.nanmean(self.sampler.get_autocorr_time())
+                print(f"Mean auto-correlation time: {tau:.3f} steps")
+                if self.no_of_steps < 50 * tau:
+                    print("⚠️  Warning: Chain may be too short for reliable results")
+                    print(f"   Recommended: >{50 * tau:.0f} steps")
+                else:
+                    print("✅ Chain length adequate")
+            except Exception:
+                print("⚠️  Warning: Could not calculate auto-correlation time")
+        if self.sampler_name == "zeus":
+            try:
+                max_rhat = float(np.max(gelman_rubin(self.sampler.get_chain().transpose(1, 0, 2))))
+                print(f"Gelman-Rubin R-hat: {max_rhat:.3f}")
+                if max_rhat > 1.1:
+                    print("⚠️  Warning: R-hat > 1.1, chains may not have converged")
+                else:
+                    print("✅ Good convergence (R-hat < 1.1)")
+            except Exception:
+                print("Could not calculate Gelman-Rubin diagnostic")
+        if self.best_theta is not None:
+            print("\nParameter Summary:")
+            print(f"Best-fit parameters: {len(self.best_theta)} values")
+            if self.samples is not None:
+                print(f"Effective samples: {len(self.samples)}")
         print("=" * 60)
 
     def chi_squared(self, theta=None, instrument_name=None):

@@ -326,3 +326,21 @@ def test_product_lowering_matches_live_reference():
             _, rlb, rub = mc.set_bounds(list(n), list(b), list(v))
             _, olb, oub = set_bounds(list(n), list(b), list(v))
         assert np.array_equal(np.asarray(olb), np.asarray(rlb)) and np.array_equal(np.asarray(oub), np.asarray(rub))
+
+
+def test_gelman_rubin_statistic():
+    """vfit._print_diagnostics' R-hat (vfit_mcmc.py:631-647): ~1 for chains of one distribution, > 1.1 when the
+    chains sit in different places; the closed form on a tiny case."""
+    from rbvfit_b200.vfit_mcmc import gelman_rubin
+    rng = np.random.default_rng(0)
+    same = rng.standard_normal((16, 2000, 3))
+    r = gelman_rubin(same)
+    assert r.shape == (3,) and np.all(np.abs(r - 1.0) < 0.01)
+    apart = same + np.arange(16)[:, None, None]
+    assert np.all(gelman_rubin(apart) > 1.1)
+    x = np.array([[[0.0], [2.0]], [[1.0], [5.0]]])           # m = 2 chains, n = 2 steps
+    W, B_over_n = (2.0 + 8.0) / 2, 2.0                        # within-chain variances 2 and 8; means 1 and 3
+    V = 0.5 * W + B_over_n + B_over_n / 2
+    assert np.allclose(gelman_rubin(x), np.sqrt(V / W))
+    with pytest.raises(ValueError):
+        gelman_rubin(np.zeros((1, 10, 2)))

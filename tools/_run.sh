@@ -1,15 +1,4 @@
 set -x
-RBVFIT_B200_STREAM=1 python -m pytest tests -m gpu -q > gpurun_out/r02i_pytest_stream.log 2>&1; echo "rc=$?" >> gpurun_out/r02i_pytest_stream.log
-python -m pytest tests -m gpu -q > gpurun_out/r02i_pytest_default.log 2>&1; echo "rc=$?" >> gpurun_out/r02i_pytest_default.log
-{
-python tools/profile_step.py --walkers 2048
-python tools/profile_step.py --walkers 8192
-python tools/profile_step.py --walkers 1024
-RBVFIT_B200_STREAM=0 python tools/profile_step.py --walkers 1024
-python tools/profile_step.py --walkers 700
-python tools/profile_sightlines.py 256
-python tools/profile_sightlines.py 64
-RBVFIT_B200_STREAM=0 python tools/profile_sightlines.py 64
-python tools/profile_step.py --workload C2 --walkers 1024
-python tools/profile_step.py --workload C4 --walkers 1024
-} > gpurun_out/r02i_perf.log 2>&1
+python -m pytest tests -m gpu -q > gpurun_out/r02k_pytest_default.log 2>&1; echo "rc=$?" >> gpurun_out/r02k_pytest_default.log
+( time python bench.py ) > gpurun_out/r02k_bench.json 2> gpurun_out/r02k_bench.err
+( time python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/r02k_bench_ref.json 2> gpurun_out/r02k_bench_ref.err
