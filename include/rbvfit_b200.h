@@ -209,6 +209,27 @@ int rbv_stretch_run_dist(RbvContext* ctx, double* coords, double* lnprob, int n_
                          double* lnprob_chain, int* n_accepted, int* flag, void* workspace, size_t workspace_bytes,
                          int use_graph, void* stream);
 
+/* The same runs with the chain handed to the HOST while the run goes on (what emcee's backend stores: every step,
+ * every walker -- 2.3 MB per step at 8000 walkers x 36 parameters).  The device keeps a ring of 2 x block_steps
+ * steps; after each block the finished half is copied to page-locked staging on a second stream and from there into
+ * the caller's arrays by the calling thread, while the device already runs the next block: the hand-off costs no
+ * device time and no pageable-memory copy from the device.  distributed != 0: rbv_stretch_run_dist's step.
+ *   chain_host / lnprob_chain_host  HOST [n_steps, n_walkers, ndim] / [n_steps, n_walkers] (any memory), may be NULL
+ *   ring_dev     DEVICE, 2 * block_steps * n_walkers * (ndim + 1) doubles
+ *   ring_pinned  HOST page-locked, same size
+ * Needs a non-default stream and n_steps >= 4; returns after the run has finished and every row has been delivered. */
+typedef struct RbvChainSink {
+  double* chain_host;
+  double* lnprob_chain_host;
+  double* ring_dev;
+  double* ring_pinned;
+  int block_steps;
+} RbvChainSink;
+int rbv_stretch_run_sink(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                         unsigned long long seed, unsigned long long first_step, const RbvChainSink* sink,
+                         int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int distributed,
+                         void* stream);
+
 /* Survey mode of the same sampler: the context holds S sightlines (see rbv_lnprob_batch_sightlines) and every
  * sightline has its OWN ensemble of walkers_per_sightline walkers -- what the reference does as S separate
  * vfit(...).runmcmc() calls, one after the other (vfit_mcmc.py:492-561).  The S ensembles advance in lockstep: a

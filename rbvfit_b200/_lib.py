@@ -33,6 +33,11 @@ class RbvSliceTuning(C.Structure):
                 ("n_batches", C.c_ulonglong)]
 
 
+class RbvChainSink(C.Structure):
+    _fields_ = [("chain_host", C.c_void_p), ("lnprob_chain_host", C.c_void_p), ("ring_dev", C.c_void_p),
+                ("ring_pinned", C.c_void_p), ("block_steps", C.c_int)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "rbv_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -68,6 +73,9 @@ EXPORTS = {
                                              C.c_void_p]),
     "rbv_stretch_run_dist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                        C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "rbv_stretch_run_sink": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                       C.c_ulonglong, C.c_ulonglong, C.POINTER(RbvChainSink), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "rbv_stretch_workspace_bytes_sightlines": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
     "rbv_stretch_run_sightlines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,

@@ -1123,6 +1123,8 @@ struct RbvContext {
   long long launches = 0;
   int last_kernel = -1;
   RbvNcclComm comm = nullptr;   // rbv_comm_init: one rank per context
+  cudaStream_t sink_stream = nullptr;                        // rbv_stretch_run_sink: D2H copies of the chain ring
+  cudaEvent_t sink_done[2] = {nullptr, nullptr}, sink_copied[2] = {nullptr, nullptr};
   int comm_rank = 0, comm_world = 1;
   std::vector<HostInst> inst;
   InstDev* d_inst = nullptr;
@@ -1227,6 +1229,11 @@ void rbv_destroy(RbvContext* ctx) {
     cudaFree(hi.d_taps);
   }
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  for (int k = 0; k < 2; ++k) {
+    if (ctx->sink_done[k]) cudaEventDestroy(ctx->sink_done[k]);
+    if (ctx->sink_copied[k]) cudaEventDestroy(ctx->sink_copied[k]);
+  }
+  if (ctx->sink_stream) cudaStreamDestroy(ctx->sink_stream);
   cudaFree(ctx->d_inst);
   cudaFree(ctx->d_lb);
   cudaFree(ctx->d_ub);
@@ -1748,22 +1755,163 @@ int rbv_stretch_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* by
   return RBV_OK;
 }
 
-int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
-                    unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
-                    int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
-                    void* stream) {
-  if (!ctx || !coords || !lnprob || !n_accepted || !flag)
-    return fail(RBV_EINVAL, "rbv_stretch_run: null argument");
-  if (n_walkers < 2) return fail(RBV_EINVAL, "rbv_stretch_run: need at least two walkers");
-  if (n_steps < 0 || !(a > 1.0)) return fail(RBV_EINVAL, "rbv_stretch_run: n_steps < 0 or stretch scale a <= 1");
-  if (ctx->inst.empty() || ctx->ndim == 0) return fail(RBV_ESTATE, "rbv_stretch_run: context not set up");
+// forward declarations (multi-GPU helpers, defined with the communicator entry points below)
+static void rank_rows(int n, int rank, int world, int* lo, int* hi, int* chunk);
+static int allgather_rows(RbvContext* ctx, double* buf, int chunk, cudaStream_t st);
+
+// The run loop shared by rbv_stretch_run / rbv_stretch_run_dist / rbv_stretch_run_sink.  One step is captured in a
+// CUDA graph (the step index lives in device memory) and replayed.
+//   dist   rows of every half-step split over the ranks of the context's communicator, in-place NCCL all-gather of
+//          their lnprob inside the captured step (separate propose / accept kernels); otherwise the fused single-GPU
+//          step (proposal in the prep kernel, accept/reject in the finalisation)
+//   sink   chain hand-off to the host while the run goes on: P.chain / P.lnp_chain are device RINGS of
+//          2 x block_steps steps; after every block the finished half is copied to page-locked staging on a second
+//          stream and from there by this thread into the caller's arrays, while the device runs the next block
+static int stretch_run_impl(RbvContext* ctx, StretchParams& P, const StretchLayout& lay, char* ws,
+                            size_t workspace_bytes, int n_walkers, int n_steps, bool dist, const RbvChainSink* sink,
+                            int use_graph, cudaStream_t st, const char* who) {
+  RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
+  const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
+  const int h = (n_walkers + 1) / 2;
+  const int rank = (dist && ctx->comm) ? ctx->comm_rank : 0, world = (dist && ctx->comm) ? ctx->comm_world : 1;
+  void* stream = (void*)st;
+
+  auto one_step = [&]() -> int {
+    for (int split = 0; split < 2; ++split) {
+      const int nS = split == 0 ? h : n_walkers - h;
+      if (!dist) {
+        // two launches per half-step: prep_propose_kernel (proposal + line constants) and the lnprob kernel, whose
+        // per-walker finalisation also applies accept/reject and appends the walker's row to the chain
+        int rc = launch_lnprob(ctx, P.prop, nS, 0, P.lnp_prop, ws + lay.lnprob_ws, lnprob_ws_bytes, stream, who, &P,
+                               split);
+        if (rc != RBV_OK) return rc;
+        continue;
+      }
+      // every rank builds all proposals (replicated state, counter-based streams), evaluates its rows, the ranks
+      // all-gather the 8-byte lnprob values in place over NCCL, every rank applies the same accept/reject
+      int lo, hi, chunk;
+      rank_rows(nS, rank, world, &lo, &hi, &chunk);
+      stretch_propose_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+      if (hi > lo) {
+        int rc = launch_lnprob(ctx, P.prop + (size_t)lo * ctx->ndim, hi - lo, 0, P.lnp_prop + lo, ws + lay.lnprob_ws,
+                               lnprob_ws_bytes, stream, who, nullptr, -1, nullptr, nS);
+        if (rc != RBV_OK) return rc;
+      }
+      int rc = allgather_rows(ctx, P.lnp_prop, chunk, st);
+      if (rc != RBV_OK) return rc;
+      stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
+      RBV_CUDA(cudaGetLastError());
+      ctx->launches++;
+    }
+    return RBV_OK;
+  };
+
+  const bool graph_ok = use_graph && st != nullptr && n_steps >= 4;
+  if (sink && !graph_ok) return fail(RBV_EINVAL, std::string(who) + ": the chain sink needs use_graph, a non-default "
+                                                                    "stream and at least 4 steps");
+  if (!graph_ok) {
+    for (int s2 = 0; s2 < n_steps; ++s2) {
+      int rc = one_step();
+      if (rc != RBV_OK) return rc;
+    }
+    if (dist) RBV_CUDA(cudaStreamSynchronize(st));
+    return RBV_OK;
+  }
+  if (dist && world > 1) {
+    for (int split = 0; split < 2; ++split) {   // NCCL sets up its buffers on the first collective of a size: not
+      int lo, hi, chunk;                        // inside a capture (lnp_prop is scratch here)
+      rank_rows(split == 0 ? h : n_walkers - h, rank, world, &lo, &hi, &chunk);
+      int rc = allgather_rows(ctx, P.lnp_prop, chunk, st);
+      if (rc != RBV_OK) return rc;
+    }
+    RBV_CUDA(cudaStreamSynchronize(st));
+  }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const long long launches_before = ctx->launches;
+  RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = one_step();
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc != RBV_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  const long long per_step = ctx->launches - launches_before;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  }
+  ctx->launches = launches_before + per_step * n_steps;
+  if (!sink) {
+    for (int s2 = 0; s2 < n_steps && e == cudaSuccess; ++s2) e = cudaGraphLaunch(exec, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  } else {
+    // ---- pipelined hand-off: block b runs on the device while block b - 1 travels device ring -> pinned staging
+    // (copy stream) -> the caller's host arrays (this thread)
+    const int K = sink->block_steps;
+    const size_t row_c = (size_t)n_walkers * ctx->ndim, row_l = (size_t)n_walkers;     // doubles per step
+    const int n_blocks = (n_steps + K - 1) / K;
+    auto steps_of = [&](int b) { return std::min(K, n_steps - b * K); };
+    auto drain = [&](int b) -> cudaError_t {       // pinned half of block b -> host arrays
+      cudaError_t e2 = cudaEventSynchronize(ctx->sink_copied[b & 1]);
+      if (e2 != cudaSuccess) return e2;
+      const int half = b & 1, ns = steps_of(b);
+      if (sink->chain_host)
+        memcpy(sink->chain_host + (size_t)b * K * row_c, sink->ring_pinned + (size_t)half * K * row_c,
+               (size_t)ns * row_c * sizeof(double));
+      if (sink->lnprob_chain_host)
+        memcpy(sink->lnprob_chain_host + (size_t)b * K * row_l,
+               sink->ring_pinned + 2 * (size_t)K * row_c + (size_t)half * K * row_l, (size_t)ns * row_l * sizeof(double));
+      return cudaSuccess;
+    };
+    for (int b = 0; b < n_blocks && e == cudaSuccess; ++b) {
+      const int half = b & 1, ns = steps_of(b);
+      if (b >= 2) e = cudaStreamWaitEvent(st, ctx->sink_copied[half], 0);      // the ring half is free again
+      for (int k = 0; k < ns && e == cudaSuccess; ++k) e = cudaGraphLaunch(exec, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->sink_done[half], st);
+      if (e == cudaSuccess && b >= 1) e = drain(b - 1);      // frees pinned half (b - 1) & 1 for block b + 1's copy
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sink_stream, ctx->sink_done[half], 0);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(sink->ring_pinned + (size_t)half * K * row_c, sink->ring_dev + (size_t)half * K * row_c,
+                            (size_t)ns * row_c * sizeof(double), cudaMemcpyDeviceToHost, ctx->sink_stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(sink->ring_pinned + 2 * (size_t)K * row_c + (size_t)half * K * row_l,
+                            sink->ring_dev + 2 * (size_t)K * row_c + (size_t)half * K * row_l,
+                            (size_t)ns * row_l * sizeof(double), cudaMemcpyDeviceToHost, ctx->sink_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->sink_copied[half], ctx->sink_stream);
+    }
+    if (e == cudaSuccess) e = drain(n_blocks - 1);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(RBV_ECUDA, std::string(who) + " (graph): " + cudaGetErrorString(e));
+  return RBV_OK;
+}
+
+static int stretch_run_entry(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                             unsigned long long seed, unsigned long long first_step, double* chain,
+                             double* lnprob_chain, const RbvChainSink* sink, int* n_accepted, int* flag,
+                             void* workspace, size_t workspace_bytes, bool dist, int use_graph, void* stream,
+                             const char* who) {
+  if (!ctx || !coords || !lnprob || !n_accepted || !flag) return fail(RBV_EINVAL, std::string(who) + ": null argument");
+  if (n_walkers < 2) return fail(RBV_EINVAL, std::string(who) + ": need at least two walkers");
+  if (n_steps < 0 || !(a > 1.0)) return fail(RBV_EINVAL, std::string(who) + ": n_steps < 0 or stretch scale a <= 1");
+  if (ctx->inst.empty() || ctx->ndim == 0) return fail(RBV_ESTATE, std::string(who) + ": context not set up");
+  if (sink && (sink->block_steps < 1 || !sink->ring_dev || !sink->ring_pinned))
+    return fail(RBV_EINVAL, std::string(who) + ": incomplete chain sink");
   if (n_steps == 0) return RBV_OK;
   const StretchLayout lay = stretch_layout(ctx, n_walkers);
-  if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, "rbv_stretch_run: workspace too small");
+  if (!workspace || workspace_bytes < lay.total) return fail(RBV_ENOMEM, std::string(who) + ": workspace too small");
   RBV_ON_DEVICE(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   StretchParams P;
+  memset(&P, 0, sizeof(P));
   P.coords = coords;
   P.lnp = lnprob;
   P.prop = (double*)(ws + lay.prop);
@@ -1772,6 +1920,18 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
   P.walker_of = (int*)(ws + lay.walker_of);
   P.chain = chain;
   P.lnp_chain = lnprob_chain;
+  if (sink) {
+    P.ring_steps = 2 * sink->block_steps;
+    P.chain = sink->ring_dev;
+    P.lnp_chain = sink->ring_dev + (size_t)P.ring_steps * n_walkers * ctx->ndim;
+    if (!ctx->sink_stream) {
+      RBV_CUDA(cudaStreamCreateWithFlags(&ctx->sink_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        RBV_CUDA(cudaEventCreateWithFlags(&ctx->sink_done[k], cudaEventDisableTiming));
+        RBV_CUDA(cudaEventCreateWithFlags(&ctx->sink_copied[k], cudaEventDisableTiming));
+      }
+    }
+  }
   P.n_accepted = n_accepted;
   P.flag = flag;
   P.step_ctr = (unsigned long long*)(ws + lay.ctr);
@@ -1782,54 +1942,34 @@ int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walke
   P.W = n_walkers;
   P.ndim = ctx->ndim;
   P.S = 1;
-  RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
-  const size_t lnprob_ws_bytes = workspace_bytes - lay.lnprob_ws;
-  const int h = (n_walkers + 1) / 2;
+  return stretch_run_impl(ctx, P, lay, ws, workspace_bytes, n_walkers, n_steps, dist, sink, use_graph, st, who);
+}
 
-  // one step = two half-steps of two launches each: prep_propose_kernel (proposal + line constants) and the tile
-  // kernel, whose per-walker finalisation also applies accept/reject and appends the walker's row to the chain
-  auto one_step = [&]() -> int {
-    for (int split = 0; split < 2; ++split) {
-      const int nS = split == 0 ? h : n_walkers - h;
-      int rc = launch_lnprob(ctx, P.prop, nS, 0, P.lnp_prop, ws + lay.lnprob_ws, lnprob_ws_bytes, stream,
-                             "rbv_stretch_run", &P, split);
-      if (rc != RBV_OK) return rc;
-    }
-    return RBV_OK;
-  };
+int rbv_stretch_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                    unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                    int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                    void* stream) {
+  return stretch_run_entry(ctx, coords, lnprob, n_walkers, n_steps, a, seed, first_step, chain, lnprob_chain, nullptr,
+                           n_accepted, flag, workspace, workspace_bytes, false, use_graph, stream, "rbv_stretch_run");
+}
 
-  if (use_graph && st != nullptr && n_steps >= 4) {
-    // one step captured once, replayed n_steps times (the step index lives in device memory)
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    const long long launches_before = ctx->launches;
-    RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = one_step();
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
-    if (rc != RBV_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    const long long per_step = ctx->launches - launches_before;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e != cudaSuccess) {
-      cudaGraphDestroy(graph);
-      return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-    }
-    for (int s = 0; s < n_steps && e == cudaSuccess; ++s) e = cudaGraphLaunch(exec, st);
-    ctx->launches = launches_before + per_step * n_steps;
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("rbv_stretch_run (graph): ") + cudaGetErrorString(e));
-    return RBV_OK;
-  }
-  for (int s = 0; s < n_steps; ++s) {
-    int rc = one_step();
-    if (rc != RBV_OK) return rc;
-  }
-  return RBV_OK;
+int rbv_stretch_run_dist(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                         unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
+                         int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
+                         void* stream) {
+  return stretch_run_entry(ctx, coords, lnprob, n_walkers, n_steps, a, seed, first_step, chain, lnprob_chain, nullptr,
+                           n_accepted, flag, workspace, workspace_bytes, true, use_graph, stream,
+                           "rbv_stretch_run_dist");
+}
+
+int rbv_stretch_run_sink(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
+                         unsigned long long seed, unsigned long long first_step, const RbvChainSink* sink,
+                         int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int distributed,
+                         void* stream) {
+  if (!sink) return fail(RBV_EINVAL, "rbv_stretch_run_sink: null sink");
+  return stretch_run_entry(ctx, coords, lnprob, n_walkers, n_steps, a, seed, first_step, nullptr, nullptr, sink,
+                           n_accepted, flag, workspace, workspace_bytes, distributed != 0, 1, stream,
+                           "rbv_stretch_run_sink");
 }
 
 // ---- multi-GPU form of the sampler: half-step = propose_eval | caller's all-gather of lnprob | accept ----------
@@ -1977,102 +2117,6 @@ int rbv_lnprob_batch_allgather(RbvContext* ctx, const double* theta, int W, doub
   }
   RBV_ON_DEVICE(ctx);
   return allgather_rows(ctx, lnprob, chunk, (cudaStream_t)stream);
-}
-
-int rbv_stretch_run_dist(RbvContext* ctx, double* coords, double* lnprob, int n_walkers, int n_steps, double a,
-                         unsigned long long seed, unsigned long long first_step, double* chain, double* lnprob_chain,
-                         int* n_accepted, int* flag, void* workspace, size_t workspace_bytes, int use_graph,
-                         void* stream) {
-  if (!ctx || !coords || !lnprob || !n_accepted || !flag)
-    return fail(RBV_EINVAL, "rbv_stretch_run_dist: null argument");
-  if (n_steps < 0 || !(a > 1.0)) return fail(RBV_EINVAL, "rbv_stretch_run_dist: n_steps < 0 or stretch scale a <= 1");
-  StretchParams P;
-  StretchLayout lay;
-  int rc = stretch_params(ctx, n_walkers, workspace, workspace_bytes, "rbv_stretch_run_dist", &P, &lay);
-  if (rc != RBV_OK) return rc;
-  if (n_steps == 0) return RBV_OK;
-  RBV_ON_DEVICE(ctx);
-  cudaStream_t st = (cudaStream_t)stream;
-  char* ws = (char*)workspace;
-  P.coords = coords;
-  P.lnp = lnprob;
-  P.chain = chain;
-  P.lnp_chain = lnprob_chain;
-  P.n_accepted = n_accepted;
-  P.flag = flag;
-  P.step_ctr = (unsigned long long*)(ws + lay.ctr);     // the step index lives on the device: one graph, replayed
-  P.ticket = (unsigned int*)(ws + lay.ctr + 64);
-  P.first_step = first_step;
-  P.seed = seed;
-  P.a = a;
-  RBV_CUDA(cudaMemsetAsync(ws + lay.ctr, 0, 256, st));
-  const int rank = ctx->comm ? ctx->comm_rank : 0, world = ctx->comm ? ctx->comm_world : 1;
-  const int h = (n_walkers + 1) / 2;
-
-  // one half-step: every rank builds all proposals (replicated state, counter-based streams), evaluates its rows,
-  // the ranks all-gather the 8-byte lnprob values in place over NCCL, every rank applies the same accept/reject
-  auto one_step = [&]() -> int {
-    for (int split = 0; split < 2; ++split) {
-      const int nS = split == 0 ? h : n_walkers - h;
-      int lo, hi, chunk;
-      rank_rows(nS, rank, world, &lo, &hi, &chunk);
-      stretch_propose_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
-      RBV_CUDA(cudaGetLastError());
-      ctx->launches++;
-      if (hi > lo) {
-        int rc2 = launch_lnprob(ctx, P.prop + (size_t)lo * ctx->ndim, hi - lo, 0, P.lnp_prop + lo,
-                                ws + lay.lnprob_ws, workspace_bytes - lay.lnprob_ws, stream, "rbv_stretch_run_dist",
-                                nullptr, -1, nullptr, nS);
-        if (rc2 != RBV_OK) return rc2;
-      }
-      int rc2 = allgather_rows(ctx, P.lnp_prop, chunk, st);
-      if (rc2 != RBV_OK) return rc2;
-      stretch_accept_kernel<<<(nS + 3) / 4, 128, 0, st>>>(P, split);
-      RBV_CUDA(cudaGetLastError());
-      ctx->launches++;
-    }
-    return RBV_OK;
-  };
-
-  if (use_graph && st != nullptr && n_steps >= 4) {
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    const long long launches_before = ctx->launches;
-    for (int split = 0; split < 2; ++split) {   // NCCL sets up its buffers on the first collective of a size: not
-      int lo, hi, chunk;                        // inside a capture (lnp_prop is scratch here)
-      rank_rows(split == 0 ? h : n_walkers - h, rank, world, &lo, &hi, &chunk);
-      rc = allgather_rows(ctx, P.lnp_prop, chunk, st);
-      if (rc != RBV_OK) return rc;
-    }
-    RBV_CUDA(cudaStreamSynchronize(st));
-    RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = one_step();
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
-    if (rc != RBV_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    const long long per_step = ctx->launches - launches_before;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e != cudaSuccess) {
-      cudaGraphDestroy(graph);
-      return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-    }
-    for (int s2 = 0; s2 < n_steps && e == cudaSuccess; ++s2) e = cudaGraphLaunch(exec, st);
-    ctx->launches = launches_before + per_step * n_steps;
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("rbv_stretch_run_dist (graph): ") + cudaGetErrorString(e));
-    return RBV_OK;
-  }
-  for (int s2 = 0; s2 < n_steps; ++s2) {
-    rc = one_step();
-    if (rc != RBV_OK) return rc;
-  }
-  RBV_CUDA(cudaStreamSynchronize(st));
-  return RBV_OK;
 }
 
 // ---- survey mode: one stretch-move ensemble per sightline, all advancing in lockstep -------------------------

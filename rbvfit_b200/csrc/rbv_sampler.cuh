@@ -41,6 +41,8 @@ struct StretchParams {
   unsigned long long seed;
   double a;
   int W, ndim;
+  int ring_steps;        // 0: chain / lnp_chain hold every step of the run; > 0: they are rings of that many steps
+                         // (rbv_stretch_run_sink: blocks of the ring are copied to the host while the run goes on)
   int S;                 // independent ensembles of W walkers each that advance in lockstep (survey mode: one per
                          // sightline, rbv_stretch_run_sightlines); 1 everywhere else.  Ensemble e owns walkers
                          // e W .. e W + W - 1 of coords / lnp / n_accepted and rows e n_S .. of the half-step buffers;
@@ -128,7 +130,8 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
   const bool accept = log(u01(r.x, r.y)) < lnpdiff;
   const double* __restrict__ src = accept ? P.prop + (size_t)k * P.ndim : P.coords + (size_t)i * P.ndim;
   double* __restrict__ x = P.coords + (size_t)i * P.ndim;
-  double* __restrict__ row = P.chain ? P.chain + (s * P.S * P.W + i) * (size_t)P.ndim : nullptr;
+  const unsigned long long srow = P.ring_steps ? s % (unsigned long long)P.ring_steps : s;   // row of the chain buffers
+  double* __restrict__ row = P.chain ? P.chain + (srow * P.S * P.W + i) * (size_t)P.ndim : nullptr;
   for (int d = lane; d < P.ndim; d += 32) {
     const double v = src[d];
     if (accept) x[d] = v;
@@ -141,7 +144,7 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
       P.lnp[i] = new_lp;
       P.n_accepted[i] += 1;
     }
-    if (P.lnp_chain) P.lnp_chain[s * P.S * P.W + i] = accept ? new_lp : old_lp;
+    if (P.lnp_chain) P.lnp_chain[srow * P.S * P.W + i] = accept ? new_lp : old_lp;
     if (!P.step_ctr) return;                                 // host-driven steps: no device counters
     __threadfence();
     if (atomicAdd(P.ticket, 1u) == (unsigned)nS - 1u) {      // last walker of this half-step

@@ -182,6 +182,15 @@ class DistributedLikelihood:
             return float(out[0]) if single else out
         lo, hi = self.part.rows(W)
         eng = self.like.engine
+        if getattr(eng, "has_comm", False) and eng.comm_world == self.part.world:
+            # collective inside the library: only this rank's rows cross PCIe (into their place of the replicated
+            # device buffer -- the library reads nothing else), then one C call evaluates and all-gathers
+            eng._reserve(W, th.shape[1])
+            if hi > lo:
+                eng._theta_pin_np[lo:hi] = th[lo:hi]
+                eng._theta_dev[lo:hi].copy_(eng._theta_pin[lo:hi], non_blocking=True)
+            out = eng.lnprob_allgather_device(eng._theta_dev[:W]).cpu().numpy()
+            return float(out[0]) if single else out
         if hi > lo:
             eng._reserve(hi - lo, th.shape[1])
             eng._theta_pin_np[: hi - lo] = th[lo:hi]

@@ -11,7 +11,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import RbvError, RbvLineTable, RbvSpectrum, check
+from ._lib import RbvChainSink, RbvError, RbvLineTable, RbvSpectrum, check
 
 VOIGT_METHODS = {"wofz": 0, "fast": 1}
 
@@ -61,6 +61,7 @@ class Engine:
         self._stretch_ws = None               # workspace of the device-resident sampler
         self._slice_ws = None                 # workspace of the device-resident slice sampler
         self.comm_rank, self.comm_world = 0, 1   # rbv_comm_init (multi-GPU: the library issues the all-gather)
+        self._sink_ring = None                # (block_steps, device ring, pinned ring) of rbv_stretch_run_sink
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -355,6 +356,39 @@ class Engine:
             lnp_chain_t.data_ptr() if lnp_chain_t is not None else None,
             n_accepted_t.data_ptr(), flag_t.data_ptr(), ws.data_ptr(), ws.numel(), int(bool(use_graph)),
             self._stream()), "rbv_stretch_run_dist")
+
+    def stretch_run_to_host(self, coords_t, lnp_t, n_steps: int, a: float, seed: int, first_step: int,
+                            n_accepted_t, flag_t, distributed: bool = False):
+        """``stretch_run`` / ``stretch_run_dist`` with the chain delivered to the HOST while the run goes on
+        (``rbv_stretch_run_sink``): returns (chain [n_steps, W, ndim], lnprob chain [n_steps, W]) as numpy arrays.
+        The device only holds a ring of two blocks of steps; its halves travel through page-locked staging on a copy
+        stream and are unpacked by this thread under the next block's kernels -- no pageable device-to-host copy
+        (2 GB/s, measured) and no device time."""
+        torch = _torch()
+        W, ndim = coords_t.shape
+        if ndim != self.ndim:
+            raise ValueError(f"coords has {ndim} columns, bounds were set for ndim={self.ndim}")
+        self._dev_tensor(coords_t, torch.float64, "coords")
+        self._dev_tensor(lnp_t, torch.float64, "lnprob", (W,))
+        self._dev_tensor(n_accepted_t, torch.int32, "n_accepted", (W,))
+        self._dev_tensor(flag_t, torch.int32, "flag")
+        row = W * (ndim + 1)
+        K = int(min(256, max(1, (16 << 20) // (row * 8)), max(1, (int(n_steps) + 1) // 2)))
+        need = 2 * K * row
+        if self._sink_ring is None or self._sink_ring[0] != K or self._sink_ring[1].numel() < need:
+            self._sink_ring = (K, torch.empty(need, dtype=torch.float64, device=self.tdev),
+                               torch.empty(need, dtype=torch.float64, pin_memory=True))
+        _k, ring_dev, ring_pin = self._sink_ring
+        chain = np.empty((int(n_steps), W, ndim), dtype=np.float64)
+        lps = np.empty((int(n_steps), W), dtype=np.float64)
+        sink = RbvChainSink(chain.ctypes.data, lps.ctypes.data, ring_dev.data_ptr(), ring_pin.data_ptr(), K)
+        ws = self._stretch_workspace(W)
+        check(self.lib.rbv_stretch_run_sink(
+            self._h, coords_t.data_ptr(), lnp_t.data_ptr(), W, int(n_steps), float(a),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_step), C.byref(sink), n_accepted_t.data_ptr(),
+            flag_t.data_ptr(), ws.data_ptr(), ws.numel(), int(bool(distributed)), self._stream()),
+            "rbv_stretch_run_sink")
+        return chain, lps
 
     def stretch_run_sightlines(self, coords_t, lnp_t, n_steps: int, a: float, seed: int, first_step: int, chain_t,
                                lnp_chain_t, n_accepted_t, flag_t):

@@ -290,7 +290,8 @@ class DeviceEnsembleSampler(EnsembleSampler):
     def _append(self, chain_t, lps_t, nacc_t):
         """Device chain of one run -> host, appended without re-copying the first run.  (A pinned staging buffer was
         measured slower here: allocating 100 MB of page-locked memory per run costs more than the pageable copy.)"""
-        chain, lps = chain_t.cpu().numpy(), lps_t.cpu().numpy()
+        chain = chain_t if isinstance(chain_t, np.ndarray) else chain_t.cpu().numpy()
+        lps = lps_t if isinstance(lps_t, np.ndarray) else lps_t.cpu().numpy()
         nacc = nacc_t.cpu().numpy()
         self._accepted += nacc
         self._hist_append(chain, lps)
@@ -329,12 +330,17 @@ class DeviceEnsembleSampler(EnsembleSampler):
                 self.n_logp_rows += self.nwalkers
                 if bool(torch.isnan(lnp_t).any()):
                     raise ValueError("Probability function returned NaN")
-            chain_t = torch.empty((nsteps, self.nwalkers, self.ndim), dtype=torch.float64, device=dev)
-            lps_t = torch.empty((nsteps, self.nwalkers), dtype=torch.float64, device=dev)
             nacc_t = torch.zeros(self.nwalkers, dtype=torch.int32, device=dev)
             flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
-            eng.stretch_run(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t, nacc_t,
-                            flag_t, use_graph=self.use_graph)
+            if self.use_graph and nsteps >= 4:
+                # the chain streams to the host in blocks while the run goes on (rbv_stretch_run_sink)
+                chain_t, lps_t = eng.stretch_run_to_host(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration,
+                                                         nacc_t, flag_t)
+            else:
+                chain_t = torch.empty((nsteps, self.nwalkers, self.ndim), dtype=torch.float64, device=dev)
+                lps_t = torch.empty((nsteps, self.nwalkers), dtype=torch.float64, device=dev)
+                eng.stretch_run(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t, nacc_t,
+                                flag_t, use_graph=self.use_graph)
             self._stream.synchronize()
             if int(flag_t.item()) & 1:
                 raise ValueError("Probability function returned NaN")
@@ -408,12 +414,16 @@ class DistributedDeviceSampler(DeviceEnsembleSampler):
         if in_library:
             torch.cuda.current_stream(dev).synchronize()
             with torch.cuda.stream(self._stream):
-                chain_t = torch.empty((nsteps, W, nd), dtype=torch.float64, device=dev)
-                lps_t = torch.empty((nsteps, W), dtype=torch.float64, device=dev)
                 nacc_t = torch.zeros(W, dtype=torch.int32, device=dev)
                 flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
-                eng.stretch_run_dist(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t,
-                                     nacc_t, flag_t, use_graph=self.use_graph)
+                if self.use_graph and nsteps >= 4:
+                    chain_t, lps_t = eng.stretch_run_to_host(coords_t, lnp_t, nsteps, self.a, self._seed,
+                                                             self.iteration, nacc_t, flag_t, distributed=True)
+                else:
+                    chain_t = torch.empty((nsteps, W, nd), dtype=torch.float64, device=dev)
+                    lps_t = torch.empty((nsteps, W), dtype=torch.float64, device=dev)
+                    eng.stretch_run_dist(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t,
+                                         nacc_t, flag_t, use_graph=self.use_graph)
                 self._stream.synchronize()
             if int(flag_t.item()) & 1:
                 raise ValueError("Probability function returned NaN")
