@@ -69,6 +69,7 @@ struct TileGeom {
   int n_super;     // super-chunks (kSuperPix flux slots) per CTA
 };
 constexpr int kMaxInst = 16;
+constexpr int kMaxStreamRanges = 128;   // slots (ranges of all instruments) of one streaming launch
 
 struct LaunchParams {
   const InstDev* inst;
@@ -98,6 +99,9 @@ struct LaunchParams {
   int inst_in_params;    // 1 = inst_v holds the instruments (joint fits: no global round trip in the CTA prologue)
   StretchParams sp;
   InstDev inst_v[kMaxInst];
+  // streaming kernel: slot s (a range of one instrument, see TileGeom::first_tile) covers the 1024-pixel segments
+  // [range_lo[s], range_hi[s]) of its instrument
+  unsigned short range_lo[kMaxStreamRanges], range_hi[kMaxStreamRanges];
 };
 
 __device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
@@ -1347,8 +1351,8 @@ static int stream_warp_doubles(const RbvContext* ctx, size_t n_inst_used) {
 }
 
 // Ranges per instrument for a batch of W walkers; returns the number of ranges (0 = use the tile kernel).
-static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_doubles, int* ctas_per_sm,
-                           size_t n_inst_used) {
+static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, unsigned short* range_lo, unsigned short* range_hi,
+                           int* warp_doubles, int* ctas_per_sm, size_t n_inst_used) {
   if (ctx->tune.stream == 0 || ctx->precision != RBV_PRECISION_FP64) return 0;
   const int wd = stream_warp_doubles(ctx, n_inst_used);
   const size_t smem = (size_t)wd * kStreamWarps * sizeof(double);
@@ -1369,28 +1373,44 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, int* warp_dou
   compute_geometry(ctx, 0, g0, nullptr, n_used);     // the workspace holds one partial per level-0 tile
   long long segs = 0;
   for (size_t k = 0; k < n_used; ++k) segs += (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix;
-  // Segments per item: long ranges amortise the item start (line constants, taps, the K-1 leading flux values
-  // evaluated line by line: about one row's worth of instructions), short ones balance the tail of the launch.
-  // The choice depends on the spectra only, never on the batch size, so a walker's lnprob is bit-identical in
-  // every batch that takes this path.
-  const int seg = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
-                                            : (int)std::min<long long>(16, std::max<long long>(4, segs / 12));
+  // Ranges per instrument, longest first (the counter hands items out in slot order, so the launch ends on short
+  // items: guided self-scheduling).  Long ranges amortise the item start (line constants, taps, the K-1 leading flux
+  // values evaluated line by line: about one row's worth of instructions per item), short ones balance the tail;
+  // the longest range is half a warp's average share of the launch (16 segments at most).  The schedule
+  // depends on the spectra and on W (the WHOLE batch in a multi-GPU call), so a walker's lnprob is bit-identical for
+  // a given batch size, on any number of ranks.  RBVFIT_B200_STREAM_SEGS=n: uniform ranges of n segments.
+  // too little work per resident warp: the tile kernel wins (measured crossovers: 28 segments per warp on a long
+  // spectrum, where the tile kernel runs its biggest tiles; 6 on short ones -- C2's 20 000 px, a sightline batch)
+  long long seg_max = 0;
+  for (size_t k = 0; k < n_used; ++k) seg_max = std::max<long long>(seg_max, (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix);
+  if (ctx->tune.stream < 0 && (long long)W * segs < (seg_max > 32 ? 28 : 6) * warps) return 0;
+  const int len_max = (int)std::min<long long>(16, std::max<long long>(2, (long long)W * segs / (2 * warps)));
   int total = 0;
   for (size_t k = 0; k < n_used; ++k) {
     const InstDev& I = ctx->inst[k].dev;
+    const int n_seg = (I.P + kSuperPix - 1) / kSuperPix;
     const int min_seg = (g0[k].tile + kSuperPix - 1) / kSuperPix;   // never more ranges than level-0 tiles
     TileGeom g;
-    g.tile = std::max(seg, min_seg) * kSuperPix;
+    g.tile = 0;
     g.ext_alloc = 0;
     g.n_super = 0;
     g.first_tile = total;
-    g.n_tiles = (I.P + g.tile - 1) / g.tile;
-    total += g.n_tiles;
+    int at = 0;
+    while (at < n_seg) {
+      const int rem = n_seg - at;
+      int len = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
+                                          : std::min(len_max, std::max(std::min(2, rem), (rem + 2) / 3));
+      len = std::min(std::max(len, min_seg), rem);
+      if (total >= kMaxStreamRanges) return 0;
+      range_lo[total] = (unsigned short)at;
+      range_hi[total] = (unsigned short)(at + len);
+      at += len;
+      ++total;
+    }
+    g.n_tiles = total - g.first_tile;
     geom[k] = g;
   }
   if ((long long)W * total >= 0x7fffffffLL) return 0;
-  // enough items to keep every resident warp busy a few times over, else the tile kernel's small tiles win
-  if (ctx->tune.stream < 0 && (long long)W * total < 2 * warps) return 0;
   *warp_doubles = wd;
   *ctas_per_sm = ctas;
   return total;
@@ -1437,9 +1457,10 @@ static int rebuild_tables(RbvContext* ctx) {
   }
   if (n <= (size_t)kMaxInst) {   // occupancy of the streaming kernel for a joint launch and for a sightline launch
     TileGeom g[kMaxInst];
+    unsigned short lo[kMaxStreamRanges], hi[kMaxStreamRanges];
     int wd = 0, nb = 0;
-    stream_geometry(ctx, 1 << 20, g, &wd, &nb, kMaxInst);
-    stream_geometry(ctx, 1 << 20, g, &wd, &nb, 1);
+    stream_geometry(ctx, 1 << 20, g, lo, hi, &wd, &nb, kMaxInst);
+    stream_geometry(ctx, 1 << 20, g, lo, hi, &wd, &nb, 1);
   }
   return RBV_OK;
 }
@@ -1654,7 +1675,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   size_t smem = 0;
   int stream_wd = 0, stream_ctas = 0;
   const int Wg = std::max(W, W_hint);
-  const int stream_ranges = stream_geometry(ctx, Wg, prm.geom, &stream_wd, &stream_ctas, sl ? 1 : (size_t)-1);
+  const int stream_ranges = stream_geometry(ctx, Wg, prm.geom, prm.range_lo, prm.range_hi, &stream_wd, &stream_ctas,
+                                            sl ? 1 : (size_t)-1);
   if (stream_ranges > 0) prm.n_tiles = stream_ranges;
   else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);

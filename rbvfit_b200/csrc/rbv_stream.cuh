@@ -306,8 +306,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
       } else {
         while (k + 1 < prm.n_inst && slot >= prm.geom[k + 1].first_tile) ++k;
       }
-      const int gk = prm.wps > 0 ? 0 : k;
-      const int range_len = prm.geom[gk].tile, first_slot = prm.geom[gk].first_tile;
+
       InstDev I;
       if (prm.inst_in_params) I = prm.inst_v[k];
       else I = prm.inst[k];
@@ -319,7 +318,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
       unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + wbase + S.lists);
       const float ff_eps = prm.farfield ? (float)(prm.ff_budget / (double)I.L) : 0.f;
       const int h = I.K >> 1, halo = I.K - 1;
-      const int o_lo = (slot - first_slot) * range_len, o_hi = min(o_lo + range_len, I.P);
+      const int o_lo = (int)prm.range_lo[slot] * kSuperPix, o_hi = min((int)prm.range_hi[slot] * kSuperPix, I.P);
 
       // ---- item start: line constants, taps, slack, leading flux values
       {

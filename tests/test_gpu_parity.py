@@ -142,10 +142,11 @@ def test_headline_geometry_vs_golden(case, kernel, monkeypatch):
     fin = np.isfinite(ref)
     rel = np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])
     assert rel.max() <= LNPROB_RTOL, rel.max()
-    # bit-identical repeats; the stream kernel's range decomposition does not depend on the batch size
+    # bit-identical repeats; another batch size may pick another partition (tile size / range schedule, i.e. other
+    # far-field intervals and another order of the chi^2 additions): same values to rounding
     assert np.array_equal(like.lnprob(batch), got_all)
-    if kernel == "stream":
-        assert np.array_equal(like.lnprob(batch[: pos[3] + 1])[pos[:4]], got[:4])
+    sub = like.lnprob(batch[: pos[3] + 1])[pos[:4]]
+    assert np.max(np.abs(sub - got[:4]) / np.abs(got[:4])) <= 1e-13
     # model flux of two fixture rows on the fixture's pixel subset (flux mode of the tile kernel)
     comp = models[n].compile()
     flux = comp.model_flux(g.thetas[g.flux_rows], wave)
