@@ -50,6 +50,8 @@ struct InstDev {
   const double* zfac;      // [L]
   const int* comp;         // [L]
   const double2* ublk;     // [ceil(P / 256)] (min, max) of 1/wave over aligned 256-pixel blocks
+  const double2* useg;     // [ceil(P / 1024)] (min, max) of 1/wave over pixels K/2 + 1024 s .. + 1023 (clamped): the
+                           // super-chunks of the streaming kernel
   const double* taps_rev;  // [Kpad] flipped taps, zero padded to a multiple of R
   double sum_log_inv_sigma2;   // sum_p log_inv_sigma2[p] (theta-independent part of lnlike), fixed order
   const double2* obs_w;        // (flux, inv_sigma2) pairs re-ordered per 256-pixel block so that phase 2 loads them
@@ -147,9 +149,16 @@ __device__ __forceinline__ void prep_line_wofz(const InstDev& I, int l, const do
 }
 
 // FP32 copies of the far-tier constants (A, a^2, Q1..Q3) for the gated FP32 path
-__device__ __forceinline__ void fill_fp32_constants(double* __restrict__ lc) {
+// ... and the far-field gate of the streaming kernel's phase 0 solved for the distance: the a-priori bound
+// 8 (m + 1) kappa (hw / (2 xm))^m / xm^2 <= eps with hw = |A| du / 2 (classify_lines) holds exactly when
+// xm >= G du^(m / (m + 2)),  G = [8 (m + 1) |kappa| (|A| / 4)^m / eps]^(1 / (m + 2))  -- one number per (walker, line).
+__device__ __forceinline__ void fill_fp32_constants(double* __restrict__ lc, double ff_eps) {
   float4 fa = make_float4((float)lc[LC_A], (float)lc[LC_A2], (float)lc[LC_Q], (float)lc[LC_Q + 1]);
-  float2 fb = make_float2((float)lc[LC_Q + 2], 0.f);
+  const double G = (ff_eps > 0.0)
+      ? exp2((log2(8.0 * (RBV_FF_M + 1) * 1.001 * fabs(lc[LC_AUX]) / ff_eps) + RBV_FF_M * log2(0.25 * fabs(lc[LC_A]))) /
+             (RBV_FF_M + 2))
+      : CUDART_INF;
+  float2 fb = make_float2((float)lc[LC_Q + 2], (float)G * 1.0001f);       // rounded to the conservative side
   *reinterpret_cast<float4*>(lc + LC_F32A) = fa;
   *reinterpret_cast<float2*>(lc + LC_F32B) = fb;
 }
@@ -328,7 +337,21 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
       un[k] = fma(uh, c_ff_nodes[k], um);
       S[k] = 0.0;
     }
-    for (int i = lane; i < n_ff; i += 32) accum_asym_line<kNQMid, 8>(lc_off + (int)listff[i] * LC_STRIDE, un, S);
+    if (lane < n_ff) accum_asym_line<kNQMid, 8>(lc_off + (int)listff[lane] * LC_STRIDE, un, S);
+    // lines beyond the first 32 (L = 33 is a common case: one line would cost a whole second round of 8 node
+    // evaluations per lane): one (line, node) pair per lane -- node = lane & 7, lines 32 + (lane >> 3) + 4 i --
+    // summed over the four lane groups in fixed order into column 32 of the transpose scratch
+    double rest = 0.0;
+    if (n_ff > 32) {
+      double un1[1], v[1];
+      un1[0] = fma(uh, c_ff_nodes[lane & 7], um);
+      v[0] = 0.0;
+      for (int i = 32 + (lane >> 3); i < n_ff; i += 4) accum_asym_line<kNQMid, 1>(lc_off + (int)listff[i] * LC_STRIDE, un1, v);
+      rest = v[0];
+      rest += __shfl_xor_sync(0xffffffffu, rest, 8);
+      rest += __shfl_xor_sync(0xffffffffu, rest, 16);
+    }
+    if (lane < 8) smem[scratch_off + lane * 33 + 32] = rest;
   }
   // transpose-reduce through shared memory (the flux tile is still unused in phase 0): lane writes its 8 node
   // values, then lane (k = lane >> 2, q = lane & 3) adds the values of lanes 8q .. 8q+7 for node k in lane order and
@@ -342,6 +365,7 @@ __device__ __forceinline__ void farfield_coefficients(int lc_off, const unsigned
     const int rd = base + (lane >> 2) * 33 + (lane & 3) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) T1 += smem[rd + i];
+    if ((lane & 3) == 0) T1 += smem[base + (lane >> 2) * 33 + 32];      // the lines beyond the first 32
     T1 += __shfl_xor_sync(0xffffffffu, T1, 1);
     T1 += __shfl_xor_sync(0xffffffffu, T1, 2);     // every lane: S_k of node k = lane >> 2
     __syncwarp();
@@ -545,7 +569,7 @@ __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w
     prep_line_wofz(I, l, th, lc);
 #pragma unroll
     for (int p = 0; p < kNQNear; ++p) lc[LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
-    fill_fp32_constants(lc);
+    fill_fp32_constants(lc, prm.farfield ? prm.ff_budget / (double)I.L : 0.0);
   }
   double2* dst = reinterpret_cast<double2*>(prm.lc + ((size_t)w * prm.n_lines_total + g) * LC_STRIDE);
 #pragma unroll
@@ -667,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   for (int i = tid; i < I.Kpad; i += kThreads) s_taps[i] = I.taps_rev[i];
   int oob = 0;
   const bool fast = (I.method == RBV_VOIGT_FAST);
-  if (MODE == 0 || prm.lc != nullptr) {
+  if (prm.lc != nullptr) {
     // ---- per-line constants and the prior flag were computed once per walker by prep_kernel; the copy does not
     // wait for the flag (an out-of-bounds row's constants are finite or NaN, never read)
     {
@@ -680,24 +704,64 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     if (MODE == 0) oob = prm.oob[w];
     __syncthreads();
   } else {
-    // ---- flux mode without a workspace: the CTA prepares its own constants
-    const double* th_g = prm.theta + (size_t)w * ndim;
-    for (int i = tid; i < ndim; i += kThreads) s_theta[i] = th_g[i];
-    __syncthreads();
-    for (int l = tid; l < I.L; l += kThreads) {
-      if (fast) prep_line_fast(I, l, s_theta, s_lc + l * LC_STRIDE);
-      else prep_line_wofz(I, l, s_theta, s_lc + l * LC_STRIDE);
-    }
-    __syncthreads();
-    if (!fast) {
-      for (int t = tid; t < I.L * kNQNear; t += kThreads) {
-        int l = t / kNQNear, p = t - l * kNQNear;
-        const double* lc = s_lc + l * LC_STRIDE;
-        s_lc[l * LC_STRIDE + LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
+    // ---- the CTA prepares its own constants: flux mode without a workspace, and the lnprob launch of a small
+    // batch (prm.lc == NULL: no prep_kernel in front -- one launch less on the latency path; every CTA of the walker
+    // repeats the ~400 dependent FP64 instructions per line, which costs nothing while the GPU is mostly empty)
+    __shared__ int s_ij[2];
+    __shared__ double s_zz;
+    if (MODE == 0 && prm.sampler_split >= 0) {
+      // device-resident sampler: row w of the batch is the stretch proposal of the w-th walker of the active half
+      // (what prep_propose_kernel builds); the walker's first CTA also stores it for the accept step
+      const StretchParams& P = prm.sp;
+      if (tid == 0) {
+        int i, j;
+        double zz;
+        stretch_propose_row(P, prm.sampler_split, w, i, j, zz);
+        s_ij[0] = i;
+        s_ij[1] = j;
+        s_zz = zz;
+        if (tile_id == 0) {
+          P.factors[w] = (P.ndim - 1.0) * log(zz);
+          P.walker_of[w] = i;
+        }
       }
       __syncthreads();
-      for (int l = tid; l < I.L; l += kThreads) fill_fp32_constants(s_lc + l * LC_STRIDE);
+      const double* sp = P.coords + (size_t)s_ij[0] * P.ndim;
+      const double* cp = P.coords + (size_t)s_ij[1] * P.ndim;
+      const double zz = s_zz;
+      for (int d = tid; d < ndim; d += kThreads) {
+        const double q = __dsub_rn(cp[d], __dmul_rn(__dsub_rn(cp[d], sp[d]), zz));
+        s_theta[d] = q;
+        if (tile_id == 0) P.prop[(size_t)w * ndim + d] = q;
+      }
+    } else {
+      const double* th_g = prm.theta + (size_t)w * ndim;
+      for (int i = tid; i < ndim; i += kThreads) s_theta[i] = th_g[i];
+    }
+    __syncthreads();
+    if (MODE == 0) {   // uniform prior (vfit.lnprior, vfit_mcmc.py:291-295) and the slice sampler's row mask
+      int bad = (prm.row_skip != nullptr && prm.row_skip[w] != 0);
+      if (prm.lb != nullptr)
+        for (int i = tid; i < ndim; i += kThreads) bad |= (s_theta[i] < prm.lb[i]) || (s_theta[i] > prm.ub[i]);
+      oob = __syncthreads_or(bad);
+    }
+    if (!oob) {
+      for (int l = tid; l < I.L; l += kThreads) {
+        if (fast) prep_line_fast(I, l, s_theta, s_lc + l * LC_STRIDE);
+        else prep_line_wofz(I, l, s_theta, s_lc + l * LC_STRIDE);
+      }
       __syncthreads();
+      if (!fast) {
+        for (int t = tid; t < I.L * kNQNear; t += kThreads) {
+          int l = t / kNQNear, p = t - l * kNQNear;
+          const double* lc = s_lc + l * LC_STRIDE;
+          s_lc[l * LC_STRIDE + LC_Q + p] = asym_coef(p + 1, lc[LC_A2], lc[LC_AUX]);
+        }
+        __syncthreads();
+        for (int l = tid; l < I.L; l += kThreads)
+          fill_fp32_constants(s_lc + l * LC_STRIDE, prm.farfield ? prm.ff_budget / (double)I.L : 0.0);
+        __syncthreads();
+      }
     }
   }
 
@@ -877,6 +941,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       prev = __shfl_sync(0xffffffffu, prev, 0);
       if (prev != (unsigned int)(prm.n_tiles - 1)) return;
       finalize_walker(prm, w, inst_id, oob, lane);
+      if (lane == 0) prm.tickets[w] = 0u;     // re-armed for a launch without prep_kernel (harmless otherwise)
     }
   }
 }
@@ -908,6 +973,36 @@ __global__ void __launch_bounds__(256) block_range_kernel(const double* __restri
   const int i = blockIdx.x * 256 + threadIdx.x;
   double v = inv_wave[min(i, n - 1)];
   double lo = v, hi = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      lo = fmin(lo, s_lo[k]);
+      hi = fmax(hi, s_hi[k]);
+    }
+    out[blockIdx.x] = make_double2(lo, hi);
+  }
+}
+
+// (min, max) of 1/wave over the streaming kernel's super-chunks: pixels first + 1024 s .. first + 1024 s + 1023,
+// indices clamped to the spectrum (edge replication)
+__global__ void __launch_bounds__(256) segment_range_kernel(const double* __restrict__ inv_wave,
+                                                            double2* __restrict__ out, int n, int first) {
+  __shared__ double s_lo[8], s_hi[8];
+  double lo = CUDART_INF, hi = -CUDART_INF;
+  for (int i = threadIdx.x; i < kSuperPix; i += 256) {
+    const double v = inv_wave[min(max(first + blockIdx.x * kSuperPix + i, 0), n - 1)];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -1029,6 +1124,7 @@ struct Tuning {
   int stream_ctas = 0;      // RBVFIT_B200_STREAM_CTAS=n: CTAs per SM of the streaming kernel (0: occupancy)
   double ff_budget = kFFEps;   // RBVFIT_B200_FF_EPS=x: far-field error budget (experiments only)
   int slice_dist_graph = 0;    // RBVFIT_B200_SLICE_DIST_GRAPH=1: multi-GPU slice sampler as a CUDA-graph WHILE loop
+  int inline_prep = -1;        // RBVFIT_B200_INLINE_PREP=0|1: line constants prepared by prep_kernel / in the CTA prologue
 };
 
 // Every entry point runs on the context's device and leaves the caller's current device as it found it.
@@ -1194,6 +1290,8 @@ int rbv_create(int device, RbvContext** out) {
     ctx->tune.stream_segs = e ? std::max(atoi(e), 0) : 0;
     e = getenv("RBVFIT_B200_STREAM_CTAS");
     ctx->tune.stream_ctas = e ? std::max(atoi(e), 0) : 0;
+    e = getenv("RBVFIT_B200_INLINE_PREP");
+    ctx->tune.inline_prep = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_SLICE_DIST_GRAPH");
     ctx->tune.slice_dist_graph = e ? atoi(e) : 0;
     e = getenv("RBVFIT_B200_FF_EPS");
@@ -1434,6 +1532,17 @@ static int rebuild_tables(RbvContext* ctx) {
     RBV_CUDA(upload(&hi.d_taps, rev.data(), rev.size()));
     I.taps_rev = hi.d_taps;
     I.line_base = (k == 0) ? 0 : ctx->inst[k - 1].dev.line_base + ctx->inst[k - 1].dev.L;
+    {
+      const int n_seg = (I.P + kSuperPix - 1) / kSuperPix;
+      double2* d_seg = nullptr;
+      RBV_CUDA(cudaMalloc((void**)&d_seg, (size_t)n_seg * sizeof(double2)));
+      hi.owned.push_back(d_seg);
+      segment_range_kernel<<<n_seg, 256>>>(I.inv_wave, d_seg, I.P, I.K >> 1);
+      RBV_CUDA(cudaGetLastError());
+      RBV_CUDA(cudaDeviceSynchronize());     // set-up runs on the default stream, the batches on the caller's
+      I.useg = d_seg;
+      ctx->launches++;
+    }
   }
   TileGeom geom[kMaxInst];
   // smallest tiles = most tiles: sizes the workspace (joint fits use <= 16 instruments; larger contexts are
@@ -1681,11 +1790,6 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
-  dim3 pgrid((unsigned)W, (unsigned)((prm.n_lines_total + 127) / 128));
-  if (sampler) prep_propose_kernel<<<pgrid, 128, (size_t)prm.ndim * sizeof(double), st>>>(prm);
-  else prep_kernel<<<pgrid, 128, 0, st>>>(prm);
-  RBV_CUDA(cudaGetLastError());
-  ctx->launches++;
   // the walker's last CTA finalises in-kernel when the grid is small (one launch less on the latency path); big
   // grids use a separate tiny launch instead, so that no CTA waits for the ticket round trip
   prm.inst_in_params = !sl && ctx->inst.size() <= (size_t)kMaxInst;
@@ -1693,6 +1797,24 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
     for (size_t k = 0; k < ctx->inst.size(); ++k) prm.inst_v[k] = ctx->inst[k].dev;
   prm.separate_finalize = (long long)Wg * prm.n_tiles >= 8LL * RBV_MIN_CTAS * ctx->sm_count;
   if (ctx->tune.force_finalize >= 0) prm.separate_finalize = ctx->tune.force_finalize;
+  // Small grids (the 25-walker half-steps of an MCMC run, the slice sampler's iterations): no prep launch at all --
+  // every CTA prepares the walker's line constants (and, for the fused sampler, its proposal row) in its prologue.
+  // The tickets then have to be zero on entry: a memset node instead of a kernel.
+  int max_lines = 0;
+  for (size_t k = 0; k < (sl ? (size_t)1 : ctx->inst.size()); ++k) max_lines = std::max(max_lines, ctx->inst[k].dev.L);
+  bool inline_prep = stream_ranges == 0 && !prm.separate_finalize && max_lines <= 256 &&
+                     (long long)Wg * prm.n_tiles <= 2LL * RBV_MIN_CTAS * ctx->sm_count;
+  if (ctx->tune.inline_prep >= 0) inline_prep = ctx->tune.inline_prep != 0 && stream_ranges == 0 && !prm.separate_finalize;
+  if (inline_prep) {
+    prm.lc = nullptr;
+    RBV_CUDA(cudaMemsetAsync(prm.tickets, 0, (size_t)W * sizeof(unsigned int), st));
+  } else {
+    dim3 pgrid((unsigned)W, (unsigned)((prm.n_lines_total + 127) / 128));
+    if (sampler) prep_propose_kernel<<<pgrid, 128, (size_t)prm.ndim * sizeof(double), st>>>(prm);
+    else prep_kernel<<<pgrid, 128, 0, st>>>(prm);
+    RBV_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
   if (stream_ranges > 0) {
     // persistent warps pull (walker, range) items from a global counter; lnprob always by finalize_kernel
     prm.separate_finalize = 1;

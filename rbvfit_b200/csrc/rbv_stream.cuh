@@ -192,19 +192,17 @@ __device__ __noinline__ void stream_exp_store(double* fo, int step, double t0, d
 // super-chunk from the block table, then per line (lane = line) far field or direct -- the a-priori gate of
 // classify_lines, rbv_kernels.cu, without its tiers (stream_direct_line takes the series length per row) -- then
 // the far-field record.  list: directly evaluated lines (bit 15: a >= 1), listff: far-field lines.
-__device__ __noinline__ void stream_prepare(const double2* __restrict__ ublk, int L, int lc_off, int rec_off,
+__device__ __noinline__ void stream_prepare(const double2* __restrict__ useg, int seg, int L, int lc_off, int rec_off,
                                             unsigned short* __restrict__ list, unsigned short* __restrict__ listff,
-                                            float ff_eps, int plo, int phi, int scratch_off, int lane) {
-  int hlo = 0x7fffffff, hhi = 0;
-  for (int b = (plo >> 8) + lane; b <= (phi >> 8); b += 32) {
-    const double2 mm = ublk[b];
-    hlo = min(hlo, __double2hiint(mm.x));
-    hhi = max(hhi, __double2hiint(mm.y));
-  }
-  hlo = __reduce_min_sync(0xffffffffu, hlo);       // 1/lambda > 0: the high words order like the values
-  hhi = __reduce_max_sync(0xffffffffu, hhi);
-  const double umin = __hiloint2double(hlo, 0), umax = __hiloint2double(hhi, (int)0xffffffff);
+                                            bool farfield, int scratch_off, int lane) {
+  // range of 1/lambda over the super-chunk (set-up table), widened to the high words: 1/lambda > 0
+  const double2 mm = __ldg(useg + seg);
+  const double umin = __hiloint2double(__double2hiint(mm.x), 0),
+               umax = __hiloint2double(__double2hiint(mm.y), (int)0xffffffff);
   const double du = umax - umin;
+  // gate distance: xm >= G_l du^(m / (m + 2)) (fill_fp32_constants); the power through the FP32 special-function
+  // unit, rounded up by more than its error
+  const float dup = __powf((float)du, (float)RBV_FF_M / (float)(RBV_FF_M + 2)) * 1.001f;
   const unsigned lt = (1u << lane) - 1u;
   int n_dir = 0, n_ff = 0;
   for (int l0 = 0; l0 < L; l0 += 32) {
@@ -218,14 +216,10 @@ __device__ __noinline__ void stream_prepare(const double2* __restrict__ ublk, in
       const bool crosses = ((__double2hiint(x1) ^ __double2hiint(x2)) < 0);   // line centre inside the super-chunk
       const int hmin = min(__double2hiint(fma(x1, x1, a2)), __double2hiint(fma(x2, x2, a2)));
       general = __double2hiint(a2) >= 0x3ff00000;                             // a >= 1
-      if (ff_eps > 0.f && !general && !crosses && hmin >= kHiNear) {           // |z|^2 >= 576: 6-term series exact
+      if (farfield && !general && !crosses && hmin >= kHiNear) {               // |z|^2 >= 576: 6-term series exact
         const float xm = fminf(fabsf((float)x1), fabsf((float)x2)) * 0.99999f;     // rounded towards the line
-        const float hw = (float)(0.5 * fabs(A) * du) * 1.00001f;
-        const float r = __fdividef(hw, 2.f * xm) * 1.00001f;
-        const float r2 = r * r, r4 = r2 * r2;
-        const float bound = (8.f * (RBV_FF_M + 1) * 1.001f) * fabsf((float)smem[off + LC_AUX]) *
-                            __fdividef(r4 * r4, xm * xm);
-        ff = bound <= ff_eps;                      // NaN fails the comparison and stays on the direct path
+        const float G = reinterpret_cast<const float2*>(smem + off + LC_F32B)->y;
+        ff = xm >= G * dup;                        // NaN fails the comparison and stays on the direct path
       }
     }
     const unsigned ff_mask = __ballot_sync(0xffffffffu, valid && ff);
@@ -316,7 +310,6 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
                 rec_off = wbase + S.rec;
       const int list_stride = (I.L + 3) & ~3;
       unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + wbase + S.lists);
-      const float ff_eps = prm.farfield ? (float)(prm.ff_budget / (double)I.L) : 0.f;
       const int h = I.K >> 1, halo = I.K - 1;
       const int o_lo = (int)prm.range_lo[slot] * kSuperPix, o_hi = min((int)prm.range_hi[slot] * kSuperPix, I.P);
 
@@ -355,10 +348,8 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
       for (int r = 0; r < n_rows; ++r) {
         const int pf = o_lo + h + r * kStreamRow;      // first pixel of the row's new flux values
         if (!fast && (r % kStreamRowsPerRecord) == 0) {
-          const int plo = min(max(pf, 0), I.P - 1);
-          const int phi = min(max(pf + kSuperPix - 1, 0), I.P - 1);
-          stream_prepare(I.ublk, I.L, lc_off, rec_off, s_list, s_list + list_stride, ff_eps, plo, phi,
-                         wbase + S.scratch, lane);
+          stream_prepare(I.useg, (o_lo + r * kStreamRow) / kSuperPix, I.L, lc_off, rec_off, s_list, s_list + list_stride,
+                         prm.farfield != 0, wbase + S.scratch, lane);
           __syncwarp();
         }
         // ---- phase 1: 8 pixels per lane
