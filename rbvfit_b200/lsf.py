@@ -12,14 +12,11 @@ import math
 import numpy as np
 
 
-def gaussian_taps(fwhm_pixels) -> np.ndarray:
-    """Gaussian1DKernel(stddev=FWHM/2.355).array  (voigt_model.py:462-464)."""
+def gaussian_taps_restated(fwhm_pixels) -> np.ndarray:
+    """astropy >= 5.3's ``Gaussian1DKernel(stddev)`` restated: odd size >= ceil(8 sigma), centre-sampled Gaussian,
+    normalised to sum 1.  Parity against astropy itself is pinned wherever astropy is importable
+    (tests/test_reference_contract.py); it is not in the build image nor on the GPU pool."""
     sigma = float(fwhm_pixels) / 2.355
-    try:  # pragma: no cover - astropy is absent in the build image
-        from astropy.convolution import Gaussian1DKernel
-        return np.asarray(Gaussian1DKernel(stddev=sigma).array, dtype=np.float64)
-    except ImportError:
-        pass
     size = int(math.ceil(8 * sigma))
     if size % 2 == 0:
         size += 1
@@ -27,6 +24,16 @@ def gaussian_taps(fwhm_pixels) -> np.ndarray:
     x = np.arange(-half, half + 1, dtype=np.float64)
     arr = (1.0 / (np.sqrt(2 * np.pi) * sigma)) * np.exp(-0.5 * (x / sigma) ** 2)
     return arr / arr.sum()
+
+
+def gaussian_taps(fwhm_pixels) -> np.ndarray:
+    """Gaussian1DKernel(stddev=FWHM/2.355).array  (voigt_model.py:462-464): astropy's own array whenever astropy is
+    importable (so the taps cannot drift from the reference's), else the restated construction."""
+    try:  # pragma: no cover - astropy is absent in the build image
+        from astropy.convolution import Gaussian1DKernel
+        return np.asarray(Gaussian1DKernel(stddev=float(fwhm_pixels) / 2.355).array, dtype=np.float64)
+    except ImportError:
+        return gaussian_taps_restated(fwhm_pixels)
 
 
 def cos_taps(grating, life_position, cen_wave) -> np.ndarray:

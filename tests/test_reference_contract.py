@@ -103,3 +103,109 @@ def test_reference_vfit_drives_gpu_model(workload):
     assert np.max(np.abs(ora[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-9
     # the reference's optimiser entry (vfit_mcmc.py:355-360) runs on the GPU-backed model as well
     assert np.isfinite(ref_fitter.lnprob(w["theta_true"]))
+
+
+def _reference_and_gpu_fitters(workload="C1", theta0_shift=None):
+    """The same spectrum fitted by the reference's own vfit (its CPU VoigtModel) and by this package's vfit."""
+    import contextlib
+    import io
+    from oracle import refshim
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.model import GpuVoigtModel
+    from rbvfit_b200.vfit_mcmc import vfit as gpu_vfit
+    RefConfig, RefModel, mc, _vm = refshim.import_reference()
+    w = wl.get_workload(workload)
+    rcfg, cfg = RefConfig(), FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        rcfg.add_system(z=z, ion=ion, transitions=list(trans), components=comps)
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    (name, inst), = w["instruments"].items()
+    rmodel = RefModel(rcfg, FWHM=inst["FWHM"])
+    rcomp = rmodel.compile()
+    s = wl.make_spectra(w, lambda n, th, wave: rcomp.model_flux(th, wave))[name]
+    theta0 = w["theta_true"] + (theta0_shift if theta0_shift is not None else 0.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = mc.vfit({name: dict(model=rmodel, **s)}, theta0, w["lb"], w["ub"])
+    ours = gpu_vfit({name: dict(model=GpuVoigtModel(cfg, FWHM=inst["FWHM"]), **s)}, theta0, w["lb"], w["ub"])
+    return w, ref, ours, theta0
+
+
+@pytest.mark.gpu
+def test_optimizer_and_quick_fit_match_the_reference():
+    """`vfit.optimize_guess` (vfit_mcmc.py:355-360) and `vfit.fit_quick`
+    (core/quick_fit_interface.py:10-128) against the reference's own implementations driving its CPU model on the
+    same data: L-BFGS-B from the same start with the same 2-point differences.  Both sides difference lnprob with
+    h = 1e-8, so their gradients carry ~1e-2 of rounding noise and the two runs stop at slightly different points of
+    the same flat optimum: the optima must agree in lnprob to 1e-6 relative and in the parameters to 1e-3 of the
+    prior width, the 1-sigma errors of the quick fit to 1e-3 relative."""
+    shift = np.array([0.05, -0.04, 3.0, -2.0, 2.0, -3.0])
+    w, ref, ours, theta0 = _reference_and_gpu_fitters("C1", shift)
+    width = w["ub"] - w["lb"]
+    p_ref = ref.optimize_guess(theta0)
+    p_gpu = ours.optimize_guess(theta0)
+    l_ref, l_gpu = ours.lnprob(np.vstack([p_ref, p_gpu]))
+    assert abs(l_gpu - l_ref) <= 1e-6 * abs(l_ref), (l_gpu, l_ref)
+    assert np.max(np.abs(p_gpu - p_ref) / width) <= 1e-3, (p_gpu, p_ref)
+    assert l_gpu > ours.lnprob(theta0) + 1.0
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        b_ref, e_ref = ref.fit_quick(verbose=False)
+    b_gpu, e_gpu = ours.fit_quick(verbose=False)
+    c_ref, c_gpu = ours._chi2_batch(np.vstack([b_ref, b_gpu]))
+    assert abs(c_gpu - c_ref) <= 1e-6 * abs(c_ref), (c_gpu, c_ref)
+    assert np.max(np.abs(b_gpu - b_ref) / width) <= 1e-3, (b_gpu, b_ref)
+    assert np.all(e_ref > 0) and np.max(np.abs(e_gpu - e_ref) / e_ref) <= 1e-3, (e_gpu, e_ref)
+
+
+@pytest.mark.gpu
+def test_kernel_taps_and_samplers_against_the_real_packages_when_present():
+    """SURVEY 8(a10/f1): wherever astropy / emcee / zeus ARE importable, pin this package against them (the build
+    container and the GPU pool have none of them: then this test records that and skips).
+      astropy  lsf.gaussian_taps_restated(FWHM) == Gaussian1DKernel(stddev=FWHM / 2.355).array, bit for bit
+      emcee    posterior mean / covariance of DeviceEnsembleSampler vs emcee.EnsembleSampler on C1 within Monte-Carlo
+               error (both driven by the GPU lnprob)
+      zeus     the same for DeviceEnsembleSliceSampler vs zeus.EnsembleSampler"""
+    import importlib
+    real = {}
+    for name in ("astropy", "emcee", "zeus"):
+        try:
+            mod = importlib.import_module(name)
+            if getattr(mod, "__file__", None):          # the oracle's shim modules have no file
+                real[name] = mod
+        except Exception:
+            pass
+    if not real:
+        pytest.skip("astropy, emcee and zeus are not installed on this box: kernel taps and samplers stay pinned "
+                    "against the restated algorithms only (DESIGN.md: parity unpinned)")
+    from rbvfit_b200 import lsf
+    if "astropy" in real:
+        from astropy.convolution import Gaussian1DKernel
+        for fwhm in (2.2, 2.394991274145626, 3.0, 4.0, 4.285, 6.5):
+            assert np.array_equal(lsf.gaussian_taps_restated(fwhm), Gaussian1DKernel(stddev=fwhm / 2.355).array)
+    w, ref, ours, theta0 = _reference_and_gpu_fitters("C1")
+    like = ours._like
+    p0 = ours._initialize_walkers(w["theta_true"])
+
+    def moments(chain):
+        flat = chain.reshape(-1, chain.shape[-1])
+        return flat.mean(axis=0), flat.std(axis=0)
+
+    if "emcee" in real:
+        import emcee
+        from rbvfit_b200.sampler import DeviceEnsembleSampler
+        es = emcee.EnsembleSampler(50, 6, like.lnprob, vectorize=True)
+        es.run_mcmc(p0, 3000)
+        ds = DeviceEnsembleSampler(50, 6, like, seed=1)
+        ds.run_mcmc(p0, 3000)
+        (m1, s1), (m2, s2) = moments(es.get_chain(discard=500)), moments(ds.get_chain(discard=500))
+        assert np.all(np.abs(m1 - m2) < 0.25 * s1) and np.all(np.abs(s1 - s2) < 0.25 * s1)
+    if "zeus" in real:
+        import zeus
+        from rbvfit_b200.slice_sampler import DeviceEnsembleSliceSampler
+        zs = zeus.EnsembleSampler(20, 6, like.lnprob, vectorize=True, verbose=False)
+        zs.run_mcmc(p0[:20], 1500, progress=False)
+        ds = DeviceEnsembleSliceSampler(20, 6, like, seed=1)
+        ds.run_mcmc(p0[:20], 1500)
+        (m1, s1), (m2, s2) = moments(zs.get_chain(discard=300)), moments(ds.get_chain(discard=300))
+        assert np.all(np.abs(m1 - m2) < 0.25 * s1) and np.all(np.abs(s1 - s2) < 0.25 * s1)
