@@ -1,3 +1,5 @@
 set -x
-python -m pytest tests -m gpu -q > gpurun_out/r02t_pytest_default.log 2>&1; echo "rc=$?" >> gpurun_out/r02t_pytest_default.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02t_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/r02t_smoke.log
+python bench.py > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/r02_final_bench_n1.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_final_bench_ref.json 2> gpurun_out/r02_final_bench_ref.err
+python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/r02_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launch_list_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > gpurun_out/r02_ncu_launches.log 2>&1
