@@ -648,7 +648,7 @@ def fp32_gated_leg(like, theta_dev, thetas, W, total_px, steps, flush):
     return out
 
 
-def mcmc_large_leg(like, w, thetas, total_px, rank=0, world=1, nsteps=12):
+def mcmc_large_leg(like, w, thetas, total_px, rank=0, world=1, nsteps=48):
     """MCMC steps/s at the bench workload's own scale (C5a: ~8000 walkers x 100 000 px) on all N GPUs: the
     device-resident stretch move on the in-bounds rows of the bench ensemble; one step = every walker updated once =
     one full ensemble evaluation.  N = 1: rbv_stretch_run (one CUDA graph per step).  N > 1: rbv_stretch_run_dist --
