@@ -373,7 +373,7 @@ class Engine:
         self._dev_tensor(n_accepted_t, torch.int32, "n_accepted", (W,))
         self._dev_tensor(flag_t, torch.int32, "flag")
         row = W * (ndim + 1)
-        K = int(min(256, max(1, (16 << 20) // (row * 8)), max(1, (int(n_steps) + 1) // 2)))
+        K = int(min(256, max(1, (6 << 20) // (row * 8)), max(1, (int(n_steps) + 1) // 2)))   # ~6 MB blocks
         need = 2 * K * row
         if self._sink_ring is None or self._sink_ring[0] != K or self._sink_ring[1].numel() < need:
             self._sink_ring = (K, torch.empty(need, dtype=torch.float64, device=self.tdev),

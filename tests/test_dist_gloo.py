@@ -236,3 +236,44 @@ def test_slice_sampler_over_partitioned_likelihood_gloo():
         assert np.array_equal(chain, ref.get_chain()) and np.array_equal(lps, ref.get_log_prob())
         assert mu == ref.mu and ncall == ref.ncall
     assert ret[0][4] + ret[1][4] == ref.ncall and ret[0][4] > 0 and ret[1][4] > 0     # every row evaluated once
+
+
+def _replicate_worker(rank, world, port, W, nsteps, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.cuda
+    torch.cuda.synchronize = lambda *a, **k: None            # no device in this test
+    from rbvfit_b200 import dist as rdist
+    from rbvfit_b200.sampler import DistributedDeviceSampler
+    r, w, _ = rdist.init_from_env("gloo")
+    s0 = rdist.replicate_seed(1000 + r, r, w)                # ranks ask for different seeds: rank 0's wins
+    a0 = rdist.replicate_array(np.full((2, 3), float(r)), r, w)
+    like = _StubLikelihood()
+    smp = DistributedDeviceSampler(W, 3, like, rdist.WalkerPartition(r, w), seed=None)    # OS entropy on rank 0
+    p0 = MU + 0.1 * np.random.default_rng(5 + r).standard_normal((W, 3))                  # rank-dependent start
+    smp.run_mcmc(p0, nsteps)
+    ret[rank] = (s0, a0, smp._seed, smp.get_chain().copy(), like.engine.rows_evaluated)
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_seed_and_initial_state_are_replicated_from_rank0_gloo():
+    """Device samplers run replicated from counter-based random streams: with seed=None (each rank would draw its
+    own OS entropy) or rank-dependent initial states the ranks would apply all-gathered lnprob values to proposals
+    they were not computed for.  Rank 0's seed and ensemble are broadcast instead; every rank ends with rank 0's
+    chain, which is the single-process chain for that seed and start."""
+    from oracle import stretch_replay as sr
+    world, W, nsteps = 2, 10, 9
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_replicate_worker, args=(world, port, W, nsteps, ret), nprocs=world, join=True)
+    assert ret[0][0] == ret[1][0] and ret[0][0] == int(np.random.SeedSequence(1000).generate_state(1, dtype=np.uint64)[0])
+    assert np.array_equal(ret[0][1], np.zeros((2, 3))) and np.array_equal(ret[1][1], np.zeros((2, 3)))
+    assert ret[0][2] == ret[1][2]
+    assert np.array_equal(ret[0][3], ret[1][3])
+    p0 = MU + 0.1 * np.random.default_rng(5).standard_normal((W, 3))         # rank 0's start
+    chain, _lps, _nacc = sr.run(_gauss, p0, _gauss(p0), nsteps, ret[0][2])
+    assert np.array_equal(ret[0][3], chain)
+    assert ret[0][4] + ret[1][4] == nsteps * W
