@@ -620,7 +620,8 @@ __global__ void __launch_bounds__(128) prep_propose_kernel(const LaunchParams pr
 // Sum of a walker's tile partials in fixed order -> lnprob (and, for the device-resident sampler, accept/reject).
 // Called by a whole warp: the partials are loaded lane-parallel and added by lane 0 in tile order (the same
 // order whatever path or geometry calls it), the sampler step uses all lanes.
-__device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, int inst_id, int oob, int lane) {
+__device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, int inst_id, int oob, int lane,
+                                                int split) {
   double total;
   if (oob) {
     total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
@@ -642,15 +643,17 @@ __device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, 
     }
   }
   if (lane == 0) prm.lnprob[w] = total;
-  if (prm.sampler_split >= 0) stretch_accept_record(prm.sp, prm.sampler_split, w, total, lane);
+  if (split >= 0) stretch_accept_record(prm.sp, split, w, total, lane);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
 // MODE 0: lnprob (chi^2 partial + ticket finalisation); MODE 1: model flux out.
 // PPT = pixels per lane in phase 1: 8 for big tiles (ILP), 2 when a tile has only a few chunks per warp, so that
 // the chunks that hold line cores (several times the cost of a far-wing chunk) can be balanced over the warps.
+// The work of one CTA on one (walker w, tile) -- the body of voigt_tile_kernel, and of every half-step of
+// voigt_mcmc_kernel.  split: -1, or the half of the stretch move whose proposal row w is (fused sampler).
 template <int LOGR, int MODE, int PPT>
-__global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(const LaunchParams prm) {
+__device__ __forceinline__ void tile_body(const LaunchParams& prm, const int w, const int tile_blk, const int split) {
   constexpr int R = 1 << LOGR;
   constexpr int kWarpPix = 32 * PPT;                  // pixels per chunk
   constexpr int kSuperChunks = kSuperPix / kWarpPix;  // chunks per super-chunk
@@ -658,8 +661,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
   __shared__ int s_next;   // dynamic chunk counter of phase 1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int w = blockIdx.x;
-  const int tile_id = (MODE == 0) ? blockIdx.y : prm.tile_base + blockIdx.y;
+  const int tile_id = (MODE == 0) ? tile_blk : prm.tile_base + tile_blk;
   int inst_id = 0;
   if (prm.wps > 0) {
     inst_id = w / prm.wps;                 // sightline mode: every instrument shares geom[0]
@@ -709,14 +711,14 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
     // repeats the ~400 dependent FP64 instructions per line, which costs nothing while the GPU is mostly empty)
     __shared__ int s_ij[2];
     __shared__ double s_zz;
-    if (MODE == 0 && prm.sampler_split >= 0) {
+    if (MODE == 0 && split >= 0) {
       // device-resident sampler: row w of the batch is the stretch proposal of the w-th walker of the active half
       // (what prep_propose_kernel builds); the walker's first CTA also stores it for the accept step
       const StretchParams& P = prm.sp;
       if (tid == 0) {
         int i, j;
         double zz;
-        stretch_propose_row(P, prm.sampler_split, w, i, j, zz);
+        stretch_propose_row(P, split, w, i, j, zz);
         s_ij[0] = i;
         s_ij[1] = j;
         s_zz = zz;
@@ -730,7 +732,8 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       const double* cp = P.coords + (size_t)s_ij[1] * P.ndim;
       const double zz = s_zz;
       for (int d = tid; d < ndim; d += kThreads) {
-        const double q = __dsub_rn(cp[d], __dmul_rn(__dsub_rn(cp[d], sp[d]), zz));
+        const double cd = __ldcg(cp + d), sd = __ldcg(sp + d);       // L2: written by other CTAs (persistent launch)
+        const double q = __dsub_rn(cd, __dmul_rn(__dsub_rn(cd, sd), zz));
         s_theta[d] = q;
         if (tile_id == 0) P.prop[(size_t)w * ndim + d] = q;
       }
@@ -940,8 +943,51 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
       if (prm.separate_finalize) return;
       prev = __shfl_sync(0xffffffffu, prev, 0);
       if (prev != (unsigned int)(prm.n_tiles - 1)) return;
-      finalize_walker(prm, w, inst_id, oob, lane);
+      finalize_walker(prm, w, inst_id, oob, lane, split);
       if (lane == 0) prm.tickets[w] = 0u;     // re-armed for a launch without prep_kernel (harmless otherwise)
+    }
+  }
+}
+
+template <int LOGR, int MODE, int PPT>
+__global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(const LaunchParams prm) {
+  tile_body<LOGR, MODE, PPT>(prm, blockIdx.x, blockIdx.y, prm.sampler_split);
+}
+
+// Grid-wide barrier of a cooperative launch: one counter that only grows (target = generation x CTAs).  A bounded
+// spin: if the grid were ever not co-resident the launch ends with flag bit 2 set instead of hanging the device.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target, int* flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(bar) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > (4LL << 30)) {       // ~2 s at 2 GHz
+        atomicOr(flag, 4);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// The whole stretch-move loop of a SMALL ensemble as ONE cooperative launch: grid = (walkers of a half, tiles), every
+// CTA runs the tile body of its (proposal row, tile) -- proposal and line constants in the prologue, accept/reject
+// by the walker's last CTA -- then all CTAs meet at a grid barrier, half-step after half-step.  Per half-step this
+// replaces two kernel launches of a CUDA graph (~19 us on the README problem) by the body plus one barrier.
+template <int LOGR, int PPT>
+__global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_mcmc_kernel(const __grid_constant__ LaunchParams prm,
+                                                                           const int n_steps, unsigned int* bar) {
+  const int n_ctas = gridDim.x * gridDim.y, h = (prm.sp.W + 1) / 2;
+  unsigned int gen = 0u;
+  for (int s = 0; s < n_steps; ++s) {
+    for (int split = 0; split < 2; ++split) {
+      const int nS = split == 0 ? h : prm.sp.W - h;
+      if ((int)blockIdx.x < nS) tile_body<LOGR, 0, PPT>(prm, blockIdx.x, blockIdx.y, split);
+      grid_barrier(bar, ++gen * (unsigned int)n_ctas, prm.sp.flag);
     }
   }
 }
@@ -952,7 +998,7 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_tile_kernel(cons
 __global__ void __launch_bounds__(128) finalize_kernel(const LaunchParams prm) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // one warp per walker
   if (w >= prm.W) return;
-  finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31);
+  finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31, prm.sampler_split);
 }
 
 }  // namespace rbv
@@ -1125,6 +1171,7 @@ struct Tuning {
   double ff_budget = kFFEps;   // RBVFIT_B200_FF_EPS=x: far-field error budget (experiments only)
   int slice_dist_graph = 0;    // RBVFIT_B200_SLICE_DIST_GRAPH=1: multi-GPU slice sampler as a CUDA-graph WHILE loop
   int inline_prep = -1;        // RBVFIT_B200_INLINE_PREP=0|1: line constants prepared by prep_kernel / in the CTA prologue
+  int mcmc_persistent = -1;    // RBVFIT_B200_MCMC_PERSISTENT=0|1: small-ensemble stretch move as one cooperative launch
 };
 
 // Every entry point runs on the context's device and leaves the caller's current device as it found it.
@@ -1234,6 +1281,7 @@ struct RbvContext {
   double* d_ub = nullptr;
   double* d_core_tab = nullptr;
   double* d_unit_taps = nullptr;        // {1, 0 x 7}: the 'no convolution' LSF of rbv_model_flux_batch(convolve = 0)
+  unsigned int* d_grid_bar = nullptr;   // grid-barrier counter of voigt_mcmc_kernel
   size_t max_smem_lnprob[2] = {0, 0};  // per LOGR in {2,3}
   // rbv_slice_run: pinned landing slots + events for the per-iteration read-back of the counters
   SliceCounters* h_poll = nullptr;     // [2], page-locked
@@ -1290,6 +1338,8 @@ int rbv_create(int device, RbvContext** out) {
     ctx->tune.stream_segs = e ? std::max(atoi(e), 0) : 0;
     e = getenv("RBVFIT_B200_STREAM_CTAS");
     ctx->tune.stream_ctas = e ? std::max(atoi(e), 0) : 0;
+    e = getenv("RBVFIT_B200_MCMC_PERSISTENT");
+    ctx->tune.mcmc_persistent = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_INLINE_PREP");
     ctx->tune.inline_prep = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_SLICE_DIST_GRAPH");
@@ -1316,6 +1366,9 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_mcmc_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_mcmc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaMalloc((void**)&ctx->d_grid_bar, 256));
   RBV_CUDA(cudaMallocHost((void**)&ctx->h_poll, 2 * sizeof(SliceCounters)));
   for (int k = 0; k < 2; ++k) RBV_CUDA(cudaEventCreateWithFlags(&ctx->poll_ev[k], cudaEventDisableTiming));
   guard.c = nullptr;
@@ -1341,6 +1394,7 @@ void rbv_destroy(RbvContext* ctx) {
   cudaFree(ctx->d_ub);
   cudaFree(ctx->d_core_tab);
   cudaFree(ctx->d_unit_taps);
+  cudaFree(ctx->d_grid_bar);
   if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
   for (int k = 0; k < 2; ++k)
     if (ctx->poll_ev[k]) cudaEventDestroy(ctx->poll_ev[k]);
@@ -1717,6 +1771,18 @@ int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t*
   return RBV_OK;
 }
 
+// What rbv_stretch_run needs to run the sampler's half-steps as ONE cooperative launch (voigt_mcmc_kernel): the
+// parameters launch_lnprob would hand to the tile kernel with the constants prepared in the CTA prologue, and the
+// launch shape.  launch_lnprob(plan != NULL) fills it and launches nothing; ok = false when the batch does not
+// qualify (stream kernel, separate finalisation, too many lines).
+struct LaunchPlan {
+  LaunchParams prm;
+  dim3 grid;
+  size_t smem = 0;
+  bool small = false;    // 2 pixels per lane in phase 1 (voigt_tile_kernel<3, 0, 2>)
+  bool ok = false;
+};
+
 // W_hint (>= W, 0 = W): the launch geometry (kernel, tile size / ranges) is chosen as for a batch of W_hint rows.
 // The multi-GPU entry points pass the size of the WHOLE batch here, so that a rank evaluating 1/N of the rows uses
 // the partition -- far-field super-chunks, order of the chi^2 additions -- the single-GPU launch uses, and every
@@ -1724,7 +1790,8 @@ int rbv_workspace_bytes_sightlines(const RbvContext* ctx, int n_walkers, size_t*
 static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, double* lnprob, void* workspace,
                          size_t workspace_bytes, void* stream, const char* who,
                          const StretchParams* sampler = nullptr, int sampler_split = -1,
-                         const int* row_skip = nullptr, int W_hint = 0, bool with_prior = true) {
+                         const int* row_skip = nullptr, int W_hint = 0, bool with_prior = true,
+                         LaunchPlan* plan = nullptr) {
   if (!ctx || !theta || !lnprob) return fail(RBV_EINVAL, std::string(who) + ": null argument");
   if (W < 0) return fail(RBV_EINVAL, std::string(who) + ": negative n_walkers");
   if (W == 0) return RBV_OK;
@@ -1784,8 +1851,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   size_t smem = 0;
   int stream_wd = 0, stream_ctas = 0;
   const int Wg = std::max(W, W_hint);
-  const int stream_ranges = stream_geometry(ctx, Wg, prm.geom, prm.range_lo, prm.range_hi, &stream_wd, &stream_ctas,
-                                            sl ? 1 : (size_t)-1);
+  const int stream_ranges = plan ? 0 : stream_geometry(ctx, Wg, prm.geom, prm.range_lo, prm.range_hi, &stream_wd,
+                                                       &stream_ctas, sl ? 1 : (size_t)-1);
   if (stream_ranges > 0) prm.n_tiles = stream_ranges;
   else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
@@ -1806,6 +1873,15 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   // prologue's dependent chain replaces the prep launch one for one -- and 3 % slower on the C2 slice move)
   const bool inline_prep = ctx->tune.inline_prep > 0 && stream_ranges == 0 && !prm.separate_finalize &&
                            max_lines <= 256 && (long long)Wg * prm.n_tiles <= 2LL * RBV_MIN_CTAS * ctx->sm_count;
+  if (plan) {
+    plan->ok = !prm.separate_finalize && max_lines <= 256;
+    prm.lc = nullptr;                    // constants (and the proposal) in the CTA prologue
+    plan->prm = prm;
+    plan->grid = grid;
+    plan->smem = smem;
+    plan->small = small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst);
+    return RBV_OK;
+  }
   if (inline_prep) {
     prm.lc = nullptr;
     RBV_CUDA(cudaMemsetAsync(prm.tickets, 0, (size_t)W * sizeof(unsigned int), st));
@@ -1956,6 +2032,43 @@ static int stretch_run_impl(RbvContext* ctx, StretchParams& P, const StretchLayo
   const bool graph_ok = use_graph && st != nullptr && n_steps >= 4;
   if (sink && !graph_ok) return fail(RBV_EINVAL, std::string(who) + ": the chain sink needs use_graph, a non-default "
                                                                     "stream and at least 4 steps");
+  // ---- small ensembles: the whole loop as cooperative launches of voigt_mcmc_kernel (one per block of steps)
+  LaunchPlan plan;
+  bool persistent = false;
+  if (graph_ok && !dist && ctx->tune.mcmc_persistent != 0) {
+    int rc0 = launch_lnprob(ctx, P.prop, h, 0, P.lnp_prop, ws + lay.lnprob_ws, lnprob_ws_bytes, stream, who, &P, 0,
+                            nullptr, 0, true, &plan);
+    if (rc0 != RBV_OK) return rc0;
+    if (plan.ok) {
+      int per_sm = 0;      // resident CTAs per SM at this launch's shared-memory size (a query, not a stream call)
+      cudaError_t eo = plan.small
+          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voigt_mcmc_kernel<3, 2>, kThreads, plan.smem)
+          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voigt_mcmc_kernel<3, 8>, kThreads, plan.smem);
+      if (eo != cudaSuccess) per_sm = 0;
+      persistent = (long long)plan.grid.x * plan.grid.y <= (long long)per_sm * ctx->sm_count;
+    }
+  }
+  auto run_persistent = [&](int ns) -> cudaError_t {      // ns steps, enqueued on st
+    int n = ns;
+    unsigned int* bar = ctx->d_grid_bar;
+    void* args[] = {(void*)&plan.prm, (void*)&n, (void*)&bar};
+    cudaError_t e2 = cudaMemsetAsync(ctx->d_grid_bar, 0, sizeof(unsigned int), st);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(plan.prm.tickets, 0, (size_t)h * sizeof(unsigned int), st);
+    if (e2 != cudaSuccess) return e2;
+    ctx->launches++;
+    ctx->last_kernel = RBV_KERNEL_TILE;
+    return plan.small ? cudaLaunchCooperativeKernel((void*)voigt_mcmc_kernel<3, 2>, plan.grid, dim3(kThreads), args,
+                                                    plan.smem, st)
+                      : cudaLaunchCooperativeKernel((void*)voigt_mcmc_kernel<3, 8>, plan.grid, dim3(kThreads), args,
+                                                    plan.smem, st);
+  };
+  if (persistent && !sink) {
+    cudaError_t e2 = cudaSuccess;
+    for (int done = 0; done < n_steps && e2 == cudaSuccess; done += 1024) e2 = run_persistent(std::min(1024, n_steps - done));
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+    if (e2 != cudaSuccess) return fail(RBV_ECUDA, std::string(who) + " (cooperative launch): " + cudaGetErrorString(e2));
+    return RBV_OK;
+  }
   if (!graph_ok) {
     for (int s2 = 0; s2 < n_steps; ++s2) {
       int rc = one_step();
@@ -1975,22 +2088,25 @@ static int stretch_run_impl(RbvContext* ctx, StretchParams& P, const StretchLayo
   }
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  const long long launches_before = ctx->launches;
-  RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  int rc = one_step();
-  cudaError_t e = cudaStreamEndCapture(st, &graph);
-  if (rc != RBV_OK) {
-    if (graph) cudaGraphDestroy(graph);
-    return rc;
+  cudaError_t e = cudaSuccess;
+  if (!persistent) {
+    const long long launches_before = ctx->launches;
+    RBV_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = one_step();
+    e = cudaStreamEndCapture(st, &graph);
+    if (rc != RBV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    const long long per_step = ctx->launches - launches_before;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    ctx->launches = launches_before + per_step * n_steps;
   }
-  if (e != cudaSuccess) return fail(RBV_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-  const long long per_step = ctx->launches - launches_before;
-  e = cudaGraphInstantiate(&exec, graph, 0);
-  if (e != cudaSuccess) {
-    cudaGraphDestroy(graph);
-    return fail(RBV_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-  }
-  ctx->launches = launches_before + per_step * n_steps;
   if (!sink) {
     for (int s2 = 0; s2 < n_steps && e == cudaSuccess; ++s2) e = cudaGraphLaunch(exec, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -2016,7 +2132,8 @@ static int stretch_run_impl(RbvContext* ctx, StretchParams& P, const StretchLayo
     for (int b = 0; b < n_blocks && e == cudaSuccess; ++b) {
       const int half = b & 1, ns = steps_of(b);
       if (b >= 2) e = cudaStreamWaitEvent(st, ctx->sink_copied[half], 0);      // the ring half is free again
-      for (int k = 0; k < ns && e == cudaSuccess; ++k) e = cudaGraphLaunch(exec, st);
+      if (persistent) e = (e == cudaSuccess) ? run_persistent(ns) : e;
+      else for (int k = 0; k < ns && e == cudaSuccess; ++k) e = cudaGraphLaunch(exec, st);
       if (e == cudaSuccess) e = cudaEventRecord(ctx->sink_done[half], st);
       if (e == cudaSuccess && b >= 1) e = drain(b - 1);      // frees pinned half (b - 1) & 1 for block b + 1's copy
       if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sink_stream, ctx->sink_done[half], 0);
@@ -2032,8 +2149,8 @@ static int stretch_run_impl(RbvContext* ctx, StretchParams& P, const StretchLayo
     if (e == cudaSuccess) e = drain(n_blocks - 1);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
-  cudaGraphExecDestroy(exec);
-  cudaGraphDestroy(graph);
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
   if (e != cudaSuccess) return fail(RBV_ECUDA, std::string(who) + " (graph): " + cudaGetErrorString(e));
   return RBV_OK;
 }

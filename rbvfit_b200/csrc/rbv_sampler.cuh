@@ -122,7 +122,7 @@ __device__ __forceinline__ void stretch_accept_record(const StretchParams& P, in
                                                       int lane, int e = 0) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
-  const unsigned long long s = P.step_ctr ? *P.step_ctr : 0ull, step = P.first_step + s;
+  const unsigned long long s = P.step_ctr ? __ldcg(P.step_ctr) : 0ull, step = P.first_step + s;   // L2: see below
   const int i = e * P.W + P.walker_of[k];              // k: row of the half-step buffers, i: global walker
   const uint4 r = stretch_rand(P, step, (uint32_t)i, 3u + (uint32_t)split);
   const double old_lp = P.lnp[i];
@@ -163,7 +163,8 @@ __device__ __forceinline__ void stretch_propose_row(const StretchParams& P, int 
                                                     int& j_out, double& zz_out, int e = 0) {
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
-  const unsigned long long step = P.first_step + (P.step_ctr ? *P.step_ctr : 0ull);
+  // (the counter is advanced by another CTA of the SAME launch in voigt_mcmc_kernel: read it from L2)
+  const unsigned long long step = P.first_step + (P.step_ctr ? __ldcg(P.step_ctr) : 0ull);
   uint32_t pa, pb;
   stretch_perm(P, step, pa, pb);
   const int i = walker_at(pa, pb, P.W, offS + k);

@@ -342,7 +342,10 @@ class DeviceEnsembleSampler(EnsembleSampler):
                 eng.stretch_run(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t, nacc_t,
                                 flag_t, use_graph=self.use_graph)
             self._stream.synchronize()
-            if int(flag_t.item()) & 1:
+            flag = int(flag_t.item())
+            if flag & 4:
+                raise RuntimeError("rbv_stretch_run: grid barrier timed out (cooperative launch not co-resident)")
+            if flag & 1:
                 raise ValueError("Probability function returned NaN")
             self._state = (coords_t, lnp_t)
             self.n_logp_calls += 2 * nsteps
