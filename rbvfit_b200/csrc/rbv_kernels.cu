@@ -2035,7 +2035,8 @@ static int stretch_run_impl(RbvContext* ctx, StretchParams& P, const StretchLayo
   // ---- small ensembles: the whole loop as cooperative launches of voigt_mcmc_kernel (one per block of steps)
   LaunchPlan plan;
   bool persistent = false;
-  if (graph_ok && !dist && ctx->tune.mcmc_persistent != 0) {
+  if (graph_ok && !dist && ctx->tune.mcmc_persistent != 0 && ctx->tune.stream != 1) {   // (STREAM=1: tests force the
+                                                                                         // stream kernel everywhere)
     int rc0 = launch_lnprob(ctx, P.prop, h, 0, P.lnp_prop, ws + lay.lnprob_ws, lnprob_ws_bytes, stream, who, &P, 0,
                             nullptr, 0, true, &plan);
     if (rc0 != RBV_OK) return rc0;
