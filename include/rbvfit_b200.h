@@ -189,6 +189,21 @@ int rbv_comm_unique_id(unsigned char* out_id128);
 int rbv_comm_init(RbvContext* ctx, const unsigned char* id128, int rank, int world);
 int rbv_comm_info(const RbvContext* ctx, int* rank, int* world, int* nccl_version);
 
+/* The same all-gather as ONE kernel over NVLink peer memory (optional, after rbv_comm_init; 2..16 ranks of one node).
+ * Every rank owns an exchange block and maps the others' through CUDA IPC; a call pushes the rank's rows into every
+ * other block with 8-byte stores and waits for the others' rows in its own: an empty slot holds a reserved NaN
+ * pattern, so the arrival of a value is its own signal (no flags, no fences) -- one launch and one NVLink hop
+ * instead of a NCCL collective (the payload is 8 B per walker: the cost of the exchange is latency).  Payloads above
+ * 65536 doubles keep using NCCL.
+ *   rbv_peer_export  allocates the block (first call) and returns its 64-byte CUDA IPC handle; the caller
+ *                    all-gathers the handles (torch.distributed in the Python layer)
+ *   rbv_peer_attach  handles = world x 64 bytes in rank order; opens every peer's block
+ *   rbv_peer_info    attached: 1 when the all-gather runs over peer memory; error: 1 after a wait that saw
+ *                    nothing for 10 s (a rank died or skipped a call) */
+int rbv_peer_export(RbvContext* ctx, unsigned char* out_handle64);
+int rbv_peer_attach(RbvContext* ctx, const unsigned char* handles, int rank, int world);
+int rbv_peer_info(RbvContext* ctx, int* attached, int* error);
+
 /* rbv_lnprob_batch over all ranks of the communicator: every rank passes the SAME theta [n_walkers, ndim] (replicated
  * ensemble), evaluates its own rows and the ranks all-gather in place; lnprob must hold world * ceil(n_walkers/world)
  * doubles and ends up complete on every rank.  The launch geometry is chosen as for the whole batch, so each row's

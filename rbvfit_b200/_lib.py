@@ -69,6 +69,9 @@ EXPORTS = {
     "rbv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "rbv_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "rbv_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rbv_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rbv_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "rbv_peer_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rbv_lnprob_batch_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                              C.c_void_p]),
     "rbv_stretch_run_dist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,

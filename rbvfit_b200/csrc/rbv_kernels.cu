@@ -104,6 +104,11 @@ struct LaunchParams {
   // streaming kernel: slot s (a range of one instrument, see TileGeom::first_tile) covers the 1024-pixel segments
   // [range_lo[s], range_hi[s]) of its instrument
   unsigned short range_lo[kMaxStreamRanges], range_hi[kMaxStreamRanges];
+  // streaming kernel: boundary records [W, n_tiles, bnd_stride]: record (w, s) = the 2 (K - 1) flux values around the
+  // first output of range s -- the K - 1 in front written by range s - 1 (its last carry), the K - 1 behind by range
+  // s (the head of its first row); finalize adds the K - 1 outputs that straddle the boundary.  NULL otherwise.
+  double* bnd;
+  int bnd_stride;
 };
 
 __device__ __forceinline__ int smem_pos(int i, int logR) { return i + (i >> logR); }
@@ -550,6 +555,7 @@ __device__ __forceinline__ void prep_walker_lines(const LaunchParams& prm, int w
     if (threadIdx.x == 0) {
       prm.oob[w] = bad;
       prm.tickets[w] = 0u;   // the workspace layout depends on W: never trust ticket state from an earlier call
+      if (w == 0) prm.tickets[prm.W] = 0u;     // work-queue counter of the streaming kernel
     }
   }
   if (g >= prm.n_lines_total || skipped) return;
@@ -620,8 +626,12 @@ __global__ void __launch_bounds__(128) prep_propose_kernel(const LaunchParams pr
 // Sum of a walker's tile partials in fixed order -> lnprob (and, for the device-resident sampler, accept/reject).
 // Called by a whole warp: the partials are loaded lane-parallel and added by lane 0 in tile order (the same
 // order whatever path or geometry calls it), the sampler step uses all lanes.
+// BND (finalize_kernel after the streaming kernel): E = the calling warp's shared memory, cap doubles of it for
+// boundary records + 72 for the taps behind them.
+constexpr int kFinalizeBndDoubles = 1024;
+template <bool BND>
 __device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, int inst_id, int oob, int lane,
-                                                int split) {
+                                                int split, double* E = nullptr, int cap = 0) {
   double total;
   if (oob) {
     total = -CUDART_INF;                                          // vfit_mcmc.py:350-352
@@ -638,6 +648,45 @@ __device__ __forceinline__ void finalize_walker(const LaunchParams& prm, int w, 
         for (int t = 0; t < m; ++t) s += __shfl_sync(0xffffffffu, v, t);
       }
       const int ki = (prm.wps > 0) ? inst_id : k;
+      if (BND && prm.bnd != nullptr && n > 1) {
+        // streaming kernel: the K - 1 outputs behind every range boundary, from the flux values the two ranges left
+        // in the boundary records (same tap order as the kernel's LSF).  Records of consecutive slots are contiguous:
+        // chunks of them go through the warp's shared memory with one coalesced pass; (boundary, output) pairs are
+        // dealt to the lanes in index order, one fixed-order sum per instrument.
+        double* tp = E + cap;
+        const InstDev& I = prm.inst_in_params ? prm.inst_v[ki] : prm.inst[ki];
+        const int K = I.K, halo = K - 1, stride = prm.bnd_stride;
+        // asynchronous copies (every 8-byte piece in flight at once; records are only 8-byte aligned in general)
+        __syncwarp();
+        const unsigned tdst = (unsigned)__cvta_generic_to_shared(tp);
+        for (int m = lane; m < K; m += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tdst + 8u * (unsigned)m), "l"(I.taps_rev + m) : "memory");
+        const int per_chunk = max(1, cap / stride);
+        double part = 0.0;
+        for (int t0 = 1; t0 < n; t0 += per_chunk) {
+          const int nt = min(per_chunk, n - t0);
+          const double* src = prm.bnd + ((size_t)w * prm.n_tiles + first + t0) * stride;
+          __syncwarp();
+          const unsigned edst = (unsigned)__cvta_generic_to_shared(E);
+          for (int i = lane; i < nt * stride; i += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(edst + 8u * (unsigned)i), "l"(src + i) : "memory");
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          __syncwarp();
+          for (int idx = lane; idx < nt * halo; idx += 32) {
+            const int t = idx / halo, q = idx - t * halo;
+            const int slot = first + t0 + t;
+            const int o = (int)prm.range_lo[slot] * kSuperPix + q;
+            if (o < min((int)prm.range_hi[slot] * kSuperPix, I.P)) {
+              const double* e = E + t * stride + q;
+              double acc = 0.0;
+              for (int m = 0; m < K; ++m) acc = fma(tp[m], e[m], acc);
+              const double resid = __ldg(I.flux + o) - acc;
+              part = fma(resid * resid, __ldg(I.inv_sigma2 + o), part);
+            }
+          }
+        }
+        s += __shfl_sync(0xffffffffu, warp_sum(part), 0);
+      }
       const double slog = prm.inst_in_params ? prm.inst_v[ki].sum_log_inv_sigma2 : prm.inst[ki].sum_log_inv_sigma2;
       total += -0.5 * (s - slog);                                   // vfit_mcmc.py:309-313
     }
@@ -943,7 +992,7 @@ __device__ __forceinline__ void tile_body(const LaunchParams& prm, const int w, 
       if (prm.separate_finalize) return;
       prev = __shfl_sync(0xffffffffu, prev, 0);
       if (prev != (unsigned int)(prm.n_tiles - 1)) return;
-      finalize_walker(prm, w, inst_id, oob, lane, split);
+      finalize_walker<false>(prm, w, inst_id, oob, lane, split);
       if (lane == 0) prm.tickets[w] = 0u;     // re-armed for a launch without prep_kernel (harmless otherwise)
     }
   }
@@ -998,7 +1047,16 @@ __global__ void __launch_bounds__(kThreads, RBV_MIN_CTAS) voigt_mcmc_kernel(cons
 __global__ void __launch_bounds__(128) finalize_kernel(const LaunchParams prm) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);       // one warp per walker
   if (w >= prm.W) return;
-  finalize_walker(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31, prm.sampler_split);
+  finalize_walker<false>(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31, prm.sampler_split);
+}
+
+// ... after the streaming kernel: + the outputs behind the range boundaries (records through shared memory)
+__global__ void __launch_bounds__(128) finalize_stream_kernel(const LaunchParams prm) {
+  __shared__ double s_bnd[4][kFinalizeBndDoubles + 72];
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= prm.W) return;
+  finalize_walker<true>(prm, w, prm.wps > 0 ? w / prm.wps : 0, prm.oob[w], threadIdx.x & 31, prm.sampler_split,
+                        s_bnd[threadIdx.x >> 5], kFinalizeBndDoubles);
 }
 
 }  // namespace rbv
@@ -1168,6 +1226,8 @@ struct Tuning {
   int stream = -1;          // RBVFIT_B200_STREAM=0|1: streaming kernel never / whenever eligible (-1: by batch size)
   int stream_segs = 0;      // RBVFIT_B200_STREAM_SEGS=n: 1024-pixel segments per work item of the streaming kernel
   int stream_ctas = 0;      // RBVFIT_B200_STREAM_CTAS=n: CTAs per SM of the streaming kernel (0: occupancy)
+  int stream_cap = 16;      // RBVFIT_B200_STREAM_CAP=n: longest range of the streaming kernel's schedule (segments)
+  int stream_div = 3;       // RBVFIT_B200_STREAM_DIV=n: a range is 1/n of what is left of the spectrum
   double ff_budget = kFFEps;   // RBVFIT_B200_FF_EPS=x: far-field error budget (experiments only)
   int slice_dist_graph = 0;    // RBVFIT_B200_SLICE_DIST_GRAPH=1: multi-GPU slice sampler as a CUDA-graph WHILE loop
   int inline_prep = -1;        // RBVFIT_B200_INLINE_PREP=0|1: line constants prepared by prep_kernel / in the CTA prologue
@@ -1270,6 +1330,10 @@ struct RbvContext {
   long long launches = 0;
   int last_kernel = -1;
   RbvNcclComm comm = nullptr;   // rbv_comm_init: one rank per context
+  // rbv_peer_export / rbv_peer_attach: the all-gather as ONE kernel over NVLink peer memory (push + flags)
+  void* peer_block = nullptr;            // this rank's exchange block (call counter | 2 x kPeerCap slots)
+  void* peer_open[16] = {nullptr};       // the other ranks' blocks, opened through CUDA IPC
+  int peer_world = 0;                    // > 0: attached
   cudaStream_t sink_stream = nullptr;                        // rbv_stretch_run_sink: D2H copies of the chain ring
   cudaEvent_t sink_done[2] = {nullptr, nullptr}, sink_copied[2] = {nullptr, nullptr};
   int comm_rank = 0, comm_world = 1;
@@ -1336,6 +1400,10 @@ int rbv_create(int device, RbvContext** out) {
     ctx->tune.stream = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_STREAM_SEGS");
     ctx->tune.stream_segs = e ? std::max(atoi(e), 0) : 0;
+    e = getenv("RBVFIT_B200_STREAM_CAP");
+    if (e && atoi(e) > 0) ctx->tune.stream_cap = atoi(e);
+    e = getenv("RBVFIT_B200_STREAM_DIV");
+    if (e && atoi(e) > 0) ctx->tune.stream_div = atoi(e);
     e = getenv("RBVFIT_B200_STREAM_CTAS");
     ctx->tune.stream_ctas = e ? std::max(atoi(e), 0) : 0;
     e = getenv("RBVFIT_B200_MCMC_PERSISTENT");
@@ -1384,6 +1452,9 @@ void rbv_destroy(RbvContext* ctx) {
     cudaFree(hi.d_taps);
   }
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  for (int r = 0; r < 16; ++r)
+    if (ctx->peer_open[r]) cudaIpcCloseMemHandle(ctx->peer_open[r]);
+  cudaFree(ctx->peer_block);
   for (int k = 0; k < 2; ++k) {
     if (ctx->sink_done[k]) cudaEventDestroy(ctx->sink_done[k]);
     if (ctx->sink_copied[k]) cudaEventDestroy(ctx->sink_copied[k]);
@@ -1502,7 +1573,67 @@ static int stream_warp_doubles(const RbvContext* ctx, size_t n_inst_used) {
   return need;
 }
 
-// Ranges per instrument for a batch of W walkers; returns the number of ranges (0 = use the tile kernel).
+// Ranges of every instrument of a launch (lo/hi/geom may be NULL: count only); 0 = the spectra do not fit the
+// streaming kernel.  Longest first (the counter hands items out in slot order, so the launch ends on short items:
+// guided self-scheduling): 16 segments while more than 48 are left, then a third of the remainder, down to single
+// segments (C5a: 16 16 16 16 11 7 5 3 2 2 1 1 1 1).  An item start costs the line constants, the taps and ~750
+// scalar instructions -- 5 us of warp time, measured through the schedule (14 / 22 / 26 / 31 items per walker:
+// 5.38 / 5.51 / 5.56 / 5.67 ms at C5a) -- so finer schedules lose more in item starts than they win at the end of
+// the launch, even on a 1024-row share (0.75 ms with this schedule, 0.79 ms with 22 items per walker whose idle
+// tail is 4 % instead of 10 %).  The schedule depends on the spectra ONLY: a walker's lnprob is bit-identical in
+// every batch that takes this kernel, on any number of ranks.  RBVFIT_B200_STREAM_SEGS=n: uniform ranges of n
+// segments; RBVFIT_B200_STREAM_CAP / _DIV: longest range / divisor of the remainder (experiments).
+static int stream_schedule(const RbvContext* ctx, size_t n_inst_used, TileGeom* geom, unsigned short* range_lo,
+                           unsigned short* range_hi) {
+  const size_t n_used = std::min(ctx->inst.size(), n_inst_used);
+  if (n_used == 0 || n_used > (size_t)kMaxInst) return 0;
+  TileGeom g0[kMaxInst];
+  compute_geometry(ctx, 0, g0, nullptr, n_used);     // the workspace holds one partial per level-0 tile
+  for (int cap = ctx->tune.stream_cap; cap <= 512; cap *= 2) {
+    int total = 0;
+    bool fits = true;
+    for (size_t k = 0; k < n_used && fits; ++k) {
+      const InstDev& I = ctx->inst[k].dev;
+      const int n_seg = (I.P + kSuperPix - 1) / kSuperPix;
+      const int min_seg = (g0[k].tile + kSuperPix - 1) / kSuperPix;   // never more ranges than level-0 tiles
+      const int first = total;
+      int at = 0;
+      while (at < n_seg) {
+        const int rem = n_seg - at;
+        int len = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
+                                            : (n_seg <= 2 ? n_seg : std::min(cap, std::max(1, rem / ctx->tune.stream_div)));
+        len = std::min(std::max(len, min_seg), rem);
+        if (total >= kMaxStreamRanges) { fits = false; break; }
+        if (range_lo) {
+          range_lo[total] = (unsigned short)at;
+          range_hi[total] = (unsigned short)(at + len);
+        }
+        at += len;
+        ++total;
+      }
+      if (geom) {
+        TileGeom g;
+        g.tile = 0;
+        g.ext_alloc = 0;
+        g.n_super = 0;
+        g.first_tile = first;
+        g.n_tiles = total - first;
+        geom[k] = g;
+      }
+    }
+    if (fits) return total;
+  }
+  return 0;
+}
+
+// doubles per boundary record of a streaming launch: 2 (K - 1), K the widest LSF of the instruments used
+static int stream_bnd_stride(const RbvContext* ctx, size_t n_inst_used) {
+  int halo = 0;
+  for (size_t k = 0; k < std::min(ctx->inst.size(), n_inst_used); ++k) halo = std::max(halo, ctx->inst[k].dev.K - 1);
+  return 2 * std::max(halo, 1);
+}
+
+// Streaming kernel for a batch of W walkers?  Returns the number of ranges (0 = use the tile kernel).
 static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, unsigned short* range_lo, unsigned short* range_hi,
                            int* warp_doubles, int* ctas_per_sm, size_t n_inst_used) {
   if (ctx->tune.stream == 0 || ctx->precision != RBV_PRECISION_FP64) return 0;
@@ -1521,48 +1652,17 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, unsigned shor
   if (ctx->tune.stream_ctas > 0) ctas = std::min(ctas, ctx->tune.stream_ctas);
   const long long warps = (long long)ctas * kStreamWarps * ctx->sm_count;
   const size_t n_used = std::min(ctx->inst.size(), n_inst_used);
-  TileGeom g0[kMaxInst];
-  compute_geometry(ctx, 0, g0, nullptr, n_used);     // the workspace holds one partial per level-0 tile
-  long long segs = 0;
-  for (size_t k = 0; k < n_used; ++k) segs += (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix;
-  // Ranges per instrument, longest first (the counter hands items out in slot order, so the launch ends on short
-  // items: guided self-scheduling).  Long ranges amortise the item start (line constants, taps, the K-1 leading flux
-  // values evaluated line by line: about one row's worth of instructions per item), short ones balance the tail;
-  // the longest range is half a warp's average share of the launch (16 segments at most).  The schedule
-  // depends on the spectra and on W (the WHOLE batch in a multi-GPU call), so a walker's lnprob is bit-identical for
-  // a given batch size, on any number of ranks.  RBVFIT_B200_STREAM_SEGS=n: uniform ranges of n segments.
+  long long segs = 0, seg_max = 0;
+  for (size_t k = 0; k < n_used; ++k) {
+    const long long n_seg = (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix;
+    segs += n_seg;
+    seg_max = std::max(seg_max, n_seg);
+  }
   // too little work per resident warp: the tile kernel wins (measured crossovers: 28 segments per warp on a long
   // spectrum, where the tile kernel runs its biggest tiles; 6 on short ones -- C2's 20 000 px, a sightline batch)
-  long long seg_max = 0;
-  for (size_t k = 0; k < n_used; ++k) seg_max = std::max<long long>(seg_max, (ctx->inst[k].dev.P + kSuperPix - 1) / kSuperPix);
   if (ctx->tune.stream < 0 && (long long)W * segs < (seg_max > 32 ? 28 : 6) * warps) return 0;
-  const int len_max = (int)std::min<long long>(16, std::max<long long>(2, (long long)W * segs / (2 * warps)));
-  int total = 0;
-  for (size_t k = 0; k < n_used; ++k) {
-    const InstDev& I = ctx->inst[k].dev;
-    const int n_seg = (I.P + kSuperPix - 1) / kSuperPix;
-    const int min_seg = (g0[k].tile + kSuperPix - 1) / kSuperPix;   // never more ranges than level-0 tiles
-    TileGeom g;
-    g.tile = 0;
-    g.ext_alloc = 0;
-    g.n_super = 0;
-    g.first_tile = total;
-    int at = 0;
-    while (at < n_seg) {
-      const int rem = n_seg - at;
-      int len = ctx->tune.stream_segs > 0 ? ctx->tune.stream_segs
-                                          : std::min(len_max, std::max(std::min(2, rem), (rem + 2) / 3));
-      len = std::min(std::max(len, min_seg), rem);
-      if (total >= kMaxStreamRanges) return 0;
-      range_lo[total] = (unsigned short)at;
-      range_hi[total] = (unsigned short)(at + len);
-      at += len;
-      ++total;
-    }
-    g.n_tiles = total - g.first_tile;
-    geom[k] = g;
-  }
-  if ((long long)W * total >= 0x7fffffffLL) return 0;
+  const int total = stream_schedule(ctx, n_inst_used, geom, range_lo, range_hi);
+  if (total == 0 || (long long)W * total >= 0x7fffffffLL) return 0;
   *warp_doubles = wd;
   *ctas_per_sm = ctas;
   return total;
@@ -1737,25 +1837,33 @@ int rbv_set_bounds(RbvContext* ctx, const double* lb, const double* ub, int ndim
 }
 
 struct WorkspaceLayout {
-  size_t tickets, oob, partials, lc, total;   // byte offsets
+  size_t tickets, oob, partials, lc, bnd, total;   // byte offsets
 };
 
 // [tickets u32 x W][oob i32 x W][partials f64 x W x n_tiles][line constants f64 x W x n_lines x LC_STRIDE]
-static WorkspaceLayout workspace_layout_raw(int W, int tiles_per_walker, int lines_per_walker) {
+// [boundary records f64 x W x bnd_doubles (streaming kernel: ranges x 2 (K - 1))]
+static WorkspaceLayout workspace_layout_raw(int W, int tiles_per_walker, int lines_per_walker, size_t bnd_doubles = 0) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   WorkspaceLayout lay;
   lay.tickets = 0;
-  lay.oob = up((size_t)W * sizeof(unsigned int));
+  lay.oob = up(((size_t)W + 1) * sizeof(unsigned int));   // + the streaming kernel's work-queue counter
   lay.partials = lay.oob + up((size_t)W * sizeof(int));
   lay.lc = lay.partials + up((size_t)W * std::max(tiles_per_walker, 1) * sizeof(double));
-  lay.total = lay.lc + up((size_t)W * std::max(lines_per_walker, 1) * LC_STRIDE * sizeof(double));
+  lay.bnd = lay.lc + up((size_t)W * std::max(lines_per_walker, 1) * LC_STRIDE * sizeof(double));
+  lay.total = lay.bnd + up((size_t)W * bnd_doubles * sizeof(double));
   return lay;
 }
+static size_t stream_bnd_doubles(const RbvContext* ctx, size_t n_inst_used) {
+  if (ctx->inst.empty() || stream_warp_doubles(ctx, n_inst_used) == 0) return 0;
+  return (size_t)stream_schedule(ctx, n_inst_used, nullptr, nullptr, nullptr) * stream_bnd_stride(ctx, n_inst_used);
+}
 static WorkspaceLayout workspace_layout(const RbvContext* ctx, int W, bool sightlines) {
-  if (!sightlines) return workspace_layout_raw(W, ctx->n_tiles, ctx->n_lines_total);
+  if (!sightlines)
+    return workspace_layout_raw(W, ctx->n_tiles, ctx->n_lines_total,
+                                ctx->inst.size() <= (size_t)kMaxInst ? stream_bnd_doubles(ctx, (size_t)-1) : 0);
   TileGeom g[1];
   int tiles = compute_geometry(ctx, 0, g, nullptr, 1);
-  return workspace_layout_raw(W, tiles, ctx->inst.empty() ? 1 : ctx->inst[0].dev.L);
+  return workspace_layout_raw(W, tiles, ctx->inst.empty() ? 1 : ctx->inst[0].dev.L, stream_bnd_doubles(ctx, 1));
 }
 
 int rbv_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes) {
@@ -1853,8 +1961,11 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   const int Wg = std::max(W, W_hint);
   const int stream_ranges = plan ? 0 : stream_geometry(ctx, Wg, prm.geom, prm.range_lo, prm.range_hi, &stream_wd,
                                                        &stream_ctas, sl ? 1 : (size_t)-1);
-  if (stream_ranges > 0) prm.n_tiles = stream_ranges;
-  else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
+  if (stream_ranges > 0) {
+    prm.n_tiles = stream_ranges;
+    prm.bnd = (double*)((char*)workspace + lay.bnd);
+    prm.bnd_stride = stream_bnd_stride(ctx, sl ? 1 : (size_t)-1);
+  } else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
   // the walker's last CTA finalises in-kernel when the grid is small (one launch less on the latency path); big
@@ -1893,7 +2004,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
     ctx->launches++;
   }
   if (stream_ranges > 0) {
-    // persistent warps pull (walker, range) items from a global counter; lnprob always by finalize_kernel
+    // persistent warps pull (walker, range) items from a global counter; lnprob always by finalize_kernel (a
+    // per-walker ticket + in-kernel finalisation by the last range to finish was measured 5 % slower at C5a)
     prm.separate_finalize = 1;
     const long long items = (long long)W * stream_ranges;
     const unsigned ctas = (unsigned)std::min<long long>((long long)stream_ctas * ctx->sm_count,
@@ -1910,7 +2022,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   if (prm.separate_finalize) {
-    finalize_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
+    if (stream_ranges > 0) finalize_stream_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
+    else finalize_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
     RBV_CUDA(cudaGetLastError());
     ctx->launches++;
   }
@@ -2360,10 +2473,145 @@ static void rank_rows(int n, int rank, int world, int* lo, int* hi, int* chunk) 
   *hi = std::min(*lo + c, n);
 }
 
+// ---- the all-gather as one kernel over peer memory (NVLink / NVSwitch) ---------------------------------------------
+// Every rank owns an exchange block [epoch u64 | err i32 | pad -> 256 B][2 x kPeerCap slots of 8 bytes] and maps the
+// others' through CUDA IPC.  One CTA per rank and call: PUSH the rank's rows into the block of every other rank
+// (8-byte stores over NVLink), then wait for every other rank's rows in the own block and copy them out.  There
+// are no flags and no fences: an empty slot holds the bit pattern 0xFFFF...F (a NaN no arithmetic produces; a value
+// with exactly these bits is sent as the default NaN), an 8-byte store is indivisible, so the arrival of a value IS
+// its signal (the idea of NCCL's low-latency protocol); the receiver puts the empty pattern back once it has read a
+// slot.  The two halves of the block alternate from call to call: a rank can be at most one call ahead of a peer
+// (to finish a call it needs that peer's rows of the same call), so the half it writes next is never one the peer
+// still reads or has not yet emptied.  The call counter lives in device memory: the kernel replays inside a CUDA
+// graph.  A lnprob all-gather is 8 B per walker -- the cost of the exchange is latency: this is one launch and one
+// NVLink hop.  A wait that sees nothing for 10 s sets the block's error word and gives up (rbv_peer_info reports
+// it) instead of hanging the device.
+constexpr int kPeerMaxWorld = 16;
+constexpr size_t kPeerCap = 1u << 16;          // slots per half: world * chunk above this goes through NCCL
+constexpr size_t kPeerHeader = 256;            // bytes
+constexpr unsigned long long kPeerEmpty = 0xFFFFFFFFFFFFFFFFull;
+struct PeerDev {
+  unsigned char* block[kPeerMaxWorld];
+  int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long peer_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(1024) peer_allgather_kernel(const PeerDev d, double* __restrict__ buf, const int chunk) {
+  unsigned char* mine = d.block[d.rank];
+  unsigned long long* my_epoch = reinterpret_cast<unsigned long long*>(mine);
+  int* my_err = reinterpret_cast<int*>(my_epoch + 1);
+  const unsigned long long e = *my_epoch + 1ull;       // every thread reads it; thread 0 writes it back at the end
+  const size_t half = (size_t)(e & 1ull) * kPeerCap;
+  const int total = chunk * d.world;
+  // push: this rank's rows into every other rank's block
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / chunk, j = i - r * chunk;
+    if (r == d.rank) continue;
+    unsigned long long v = (unsigned long long)__double_as_longlong(buf[(size_t)d.rank * chunk + j]);
+    if (v == kPeerEmpty) v = 0x7ff8000000000000ull;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.block[r] + kPeerHeader) + half + (size_t)d.rank * chunk + j;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+  }
+  // receive: the other ranks' rows out of the own block; every slot is emptied again once read
+  unsigned long long* got = reinterpret_cast<unsigned long long*>(mine + kPeerHeader) + half;
+  const unsigned long long t0 = peer_timer_ns();
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    if (i / chunk == d.rank) continue;
+    unsigned long long v;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(got + i) : "memory");
+      if (v != kPeerEmpty) break;
+      if (peer_timer_ns() - t0 > 10000000000ull) {
+        *my_err = 1;
+        break;
+      }
+    }
+    buf[i] = __longlong_as_double((long long)v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(got + i), "l"(kPeerEmpty) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *my_epoch = e;
+}
+
 // in-place all-gather of `chunk` doubles per rank: rank r's chunk sits at buf + r * chunk
 static int allgather_rows(RbvContext* ctx, double* buf, int chunk, cudaStream_t st) {
   if (!ctx->comm || ctx->comm_world == 1 || chunk == 0) return RBV_OK;
+  if (ctx->peer_world == ctx->comm_world && (size_t)chunk * ctx->comm_world <= kPeerCap) {
+    PeerDev d;
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < ctx->comm_world; ++r)
+      d.block[r] = (unsigned char*)(r == ctx->comm_rank ? ctx->peer_block : ctx->peer_open[r]);
+    d.rank = ctx->comm_rank;
+    d.world = ctx->comm_world;
+    peer_allgather_kernel<<<1, 1024, 0, st>>>(d, buf, chunk);
+    RBV_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return RBV_OK;
+  }
   RBV_NCCL(g_nccl.AllGather(buf + (size_t)ctx->comm_rank * chunk, buf, (size_t)chunk, kNcclFloat64, ctx->comm, st));
+  return RBV_OK;
+}
+
+int rbv_peer_export(RbvContext* ctx, unsigned char* out_handle64) {
+  if (!ctx || !out_handle64) return fail(RBV_EINVAL, "rbv_peer_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  RBV_ON_DEVICE(ctx);
+  if (!ctx->peer_block) {
+    const size_t bytes = kPeerHeader + 2 * kPeerCap * sizeof(double);
+    RBV_CUDA(cudaMalloc(&ctx->peer_block, bytes));
+    RBV_CUDA(cudaMemset(ctx->peer_block, 0xFF, bytes));         // every slot empty
+    RBV_CUDA(cudaMemset(ctx->peer_block, 0, kPeerHeader));      // call counter, error word
+    RBV_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  RBV_CUDA(cudaIpcGetMemHandle(&h, ctx->peer_block));
+  memcpy(out_handle64, &h, sizeof(h));
+  return RBV_OK;
+}
+
+int rbv_peer_attach(RbvContext* ctx, const unsigned char* handles, int rank, int world) {
+  if (!ctx || !handles) return fail(RBV_EINVAL, "rbv_peer_attach: null argument");
+  if (!ctx->peer_block) return fail(RBV_ESTATE, "rbv_peer_attach: call rbv_peer_export first");
+  if (world < 2 || world > kPeerMaxWorld || rank < 0 || rank >= world)
+    return fail(RBV_EINVAL, "rbv_peer_attach: 2..16 ranks");
+  if (ctx->peer_world > 0) return fail(RBV_ESTATE, "rbv_peer_attach: already attached");
+  RBV_ON_DEVICE(ctx);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_open[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < world; ++q)
+        if (ctx->peer_open[q]) {
+          cudaIpcCloseMemHandle(ctx->peer_open[q]);
+          ctx->peer_open[q] = nullptr;
+        }
+      cudaGetLastError();
+      return fail(RBV_ECUDA, std::string("rbv_peer_attach: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+  }
+  ctx->peer_world = world;
+  return RBV_OK;
+}
+
+// 1 = the all-gather runs over peer memory; *error = the exchange block's error word (a spin that timed out)
+int rbv_peer_info(RbvContext* ctx, int* attached, int* error) {
+  if (!ctx) return fail(RBV_EINVAL, "rbv_peer_info: null context");
+  if (attached) *attached = ctx->peer_world > 0;
+  if (error) {
+    *error = 0;
+    if (ctx->peer_block) {
+      RBV_ON_DEVICE(ctx);
+      RBV_CUDA(cudaMemcpy(error, (char*)ctx->peer_block + sizeof(unsigned long long), sizeof(int),
+                          cudaMemcpyDeviceToHost));
+    }
+  }
   return RBV_OK;
 }
 
@@ -2823,6 +3071,14 @@ int rbv_measure_fp64_peak(RbvContext* ctx, double millis, double* tflops) {
   *tflops = best;
   return RBV_OK;
 }
+
+#ifdef RBV_STREAM_TIMELINE
+// experiments only: per-warp timeline of the last voigt_stream_kernel launch (4 u64 per warp)
+int rbv_debug_stream_timeline(unsigned long long* out, int n_u64) {
+  return cudaMemcpyFromSymbol(out, g_stream_timeline, (size_t)n_u64 * sizeof(unsigned long long)) == cudaSuccess
+             ? RBV_OK : RBV_ECUDA;
+}
+#endif
 
 // max relative error of the device reciprocal used in the asymptotic tiers (test hook)
 int rbv_selftest_rcp(RbvContext* ctx, double* max_rel_err) {

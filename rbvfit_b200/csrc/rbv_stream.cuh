@@ -7,21 +7,24 @@
 // it row by row (256 pixels = 8 per lane) with no CTA-wide synchronisation at all:
 //
 //   item start   line constants of the walker (written by prep_kernel) and the flipped taps -> the warp's private
-//                shared memory; the K-1 flux values in front of the first row are evaluated directly (every line,
-//                tier chosen per pixel) -- the only recomputation between neighbouring ranges
+//                shared memory (asynchronous copies); the K-1 flux values in front of the first row are evaluated
+//                directly only for the FIRST range of a spectrum (edge replication).  Any other range leaves the
+//                K-1 outputs that need its predecessor's flux to finalize_stream_kernel: it stores the head of
+//                its first row, its predecessor stores its last carry (boundary records), nothing is recomputed
 //   every 4 rows phase 0 of voigt_tile_kernel for the next 1024 pixels (prepare_super_chunk: tier lists + far-field
 //                record, one lane per line)
 //   every row    tau (far-field polynomial + listed lines, tau_wofz<8>) -> exp(-tau) -> private flux buffer
 //                [carry K-1 | row 256];  __syncwarp;  LSF for the row's 256 outputs (8 consecutive outputs per lane,
 //                sliding register window, same code as phase 2 of the tile kernel) -> chi^2 terms accumulated per
 //                lane;  the last K-1 flux values move to the front of the buffer (the next row's carry)
-//   item end     warp-shuffle sum of the lanes' chi^2 -> partials[walker, range]; finalize_kernel adds the ranges
-//                in fixed order and writes lnprob (and applies the sampler's accept/reject when fused)
+//   item end     warp-shuffle sum of the lanes' chi^2 -> partials[walker, range]; finalize_stream_kernel adds the
+//                ranges and the boundary outputs in fixed order and writes lnprob (and applies the sampler's
+//                accept/reject when fused)
 //
 // Items are numbered range-major (all walkers of range 0, then range 1, ...) and handed out through one global
 // counter, so the warps resident on an SM work on the same pixels of different walkers at about the same time and
-// share the 1/lambda and (flux, inv_sigma2) rows through L1.  The range decomposition depends on the spectrum and
-// the LSF only, not on the batch size: a walker's lnprob is bit-identical in every batch that takes this path.
+// share the 1/lambda and (flux, inv_sigma2) rows through L1.  The range decomposition depends on the spectra only,
+// not on the batch size: a walker's lnprob is bit-identical in every batch that takes this path.
 #pragma once
 
 namespace rbv {
@@ -274,6 +277,16 @@ __device__ __forceinline__ void stream_lsf(int fw, int taps_off, int n_blocks, d
   }
 }
 
+#ifdef RBV_STREAM_TIMELINE
+// experiments only (tools/stream_timeline.py): per warp {first ticket drawn, last item finished, items, segments}
+__device__ unsigned long long g_stream_timeline[4 * 148 * 4 * 8];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 template <int LOGR>
 __global__ void __launch_bounds__(kStreamThreads, RBV_STREAM_MIN_CTAS)
 voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_doubles) {
@@ -283,8 +296,12 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
   const int lane = threadIdx.x & 31;
   const int wbase = (threadIdx.x >> 5) * warp_doubles;
   const unsigned n_items = (unsigned)prm.W * (unsigned)prm.n_tiles;
-  unsigned int* queue = prm.tickets;       // tickets[0]: zeroed by prep_kernel, unused otherwise on this path
+  unsigned int* queue = prm.tickets + prm.W;   // zeroed by prep_kernel, like the per-walker tickets
 
+#ifdef RBV_STREAM_TIMELINE
+  const unsigned long long tl_t0 = global_ns();
+  unsigned long long tl_items = 0, tl_segs = 0;
+#endif
   unsigned next = 0u;
   if (lane == 0) next = atomicAdd(queue, 1u);
   next = __shfl_sync(kFull, next, 0);
@@ -317,20 +334,36 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
       {
         const double2* src = reinterpret_cast<const double2*>(
             prm.lc + ((size_t)w * prm.n_lines_total + (prm.wps > 0 ? 0 : I.line_base)) * LC_STRIDE);
-        double2* dst = reinterpret_cast<double2*>(smem + lc_off);
-        for (int i = lane; i < I.L * (LC_STRIDE / 2); i += 32) dst[i] = src[i];
-        for (int i = lane; i < I.Kpad; i += 32) smem[taps_off + i] = __ldg(I.taps_rev + i);
+        // asynchronous copies (LDGSTS): every 16-byte piece is in flight at once -- a register-staged loop keeps one
+        // load per lane in flight and cost 6 us of warp time per item (measured through the schedule: 8 more items
+        // per walker = +3 % at C5a)
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + lc_off);
+        for (int i = lane; i < I.L * (LC_STRIDE / 2); i += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(src + i) : "memory");
+        const unsigned tdst = (unsigned)__cvta_generic_to_shared(smem + taps_off);
+        for (int i = lane; i < I.Kpad; i += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tdst + 8u * (unsigned)i), "l"(I.taps_rev + i) : "memory");
         if (lane < 16) smem[flux_off + smem_pos(halo + kStreamRow + lane, LOGR)] = 0.0;
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
       __syncwarp();
-      // the K-1 flux values in front of the first row (the only recomputation between neighbouring ranges), every
-      // line evaluated on its own.  (Running them through the row machinery with one pixel per lane was measured
-      // 2 % slower at C5a: the second instantiation costs registers and instruction cache in the row loop.)
-      for (int i = lane; i < halo; i += 32) {
-        const int p = min(max(o_lo - h + i, 0), I.P - 1);
-        const double tau = tau_direct_pixel(lc_off, I.L, fast, __ldg(I.inv_wave + p), prm.core_tab);
-        smem[flux_off + smem_pos(i, LOGR)] = exp_flux(-tau);
+      // The K-1 flux values in front of the first row.  First range of a spectrum: pixels -h .. h-1 (edge
+      // replicated), every line evaluated on its own.  Any other range: they are the previous range's last carry,
+      // which another warp computes at some other time -- so the K-1 outputs that need them are left out here
+      // (q_first) and added by finalize from the boundary record: the previous range's carry + this range's head.
+      // An item start therefore costs the line constants and the taps, nothing else, and the partition into ranges
+      // is free to be fine (the launch ends on one-segment items).
+      const bool first_range = (slot == prm.geom[prm.wps > 0 ? 0 : k].first_tile);
+      if (first_range) {
+        for (int i = lane; i < halo; i += 32) {
+          const int p = min(max(o_lo - h + i, 0), I.P - 1);
+          const double tau = tau_direct_pixel(lc_off, I.L, fast, __ldg(I.inv_wave + p), prm.core_tab);
+          smem[flux_off + smem_pos(i, LOGR)] = exp_flux(-tau);
+        }
+      } else {
+        for (int i = lane; i < halo; i += 32) smem[flux_off + smem_pos(i, LOGR)] = 0.0;
       }
+      int q_first = first_range ? 0 : halo;      // outputs of the first row in front of this index: finalize's
       double part = 0.0;
       const int n_rows = (o_hi - o_lo + kStreamRow - 1) / kStreamRow;
       double* fo = smem + flux_off + smem_pos(halo + lane, LOGR);     // slot(halo + 32 j + lane) = fo[36 j]
@@ -379,6 +412,10 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
           }
         }
         __syncwarp();
+        if (q_first > 0) {   // first row of a range that has a predecessor: its head -> boundary record
+          double* bnd_rec = prm.bnd + ((size_t)w * prm.n_tiles + slot) * prm.bnd_stride;
+          for (int i = lane; i < halo; i += 32) bnd_rec[halo + i] = smem[flux_off + smem_pos(halo + i, LOGR)];
+        }
         // ---- phase 2: M_p = sum_m taps_rev[m] * E[o + m] for the lane's outputs o = 8 lane .. 8 lane + 7
         double acc[R];
         {
@@ -393,7 +430,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         }
         const int n_out = o_hi - o_row;     // outputs of this row (>= 256 except in the last row)
         const int e0 = lane << LOGR;
-        if (e0 + R <= n_out) {
+        if (e0 + R <= n_out && e0 >= q_first) {
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             const double resid = obs[q] - acc[q];                   // vfit_mcmc.py:310
@@ -402,12 +439,13 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         } else {
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            if (e0 + q < n_out) {
+            if (e0 + q < n_out && e0 + q >= q_first) {
               const double resid = obs[q] - acc[q];
               part = fma(resid * resid, wgt[q], part);
             }
           }
         }
+        q_first = 0;
         __syncwarp();
         // the row's last K-1 flux values become the next row's carry (element i <- i + 256: slot + 288)
         for (int i = lane; i < halo; i += 32) {
@@ -416,11 +454,30 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         }
         __syncwarp();
       }
+      if (o_hi < I.P) {   // the last carry = the K-1 flux values in front of the next range's first output
+        double* bnd_next = prm.bnd + ((size_t)w * prm.n_tiles + slot + 1) * prm.bnd_stride;
+        for (int i = lane; i < halo; i += 32) bnd_next[i] = smem[flux_off + smem_pos(i, LOGR)];
+      }
       part = warp_sum(part);
       if (lane == 0) prm.partials[(size_t)w * prm.n_tiles + slot] = part;
+#ifdef RBV_STREAM_TIMELINE
+      tl_items++;
+      tl_segs += (unsigned long long)(prm.range_hi[slot] - prm.range_lo[slot]);
+#endif
     }
     next = __shfl_sync(kFull, next, 0);
   }
+#ifdef RBV_STREAM_TIMELINE
+  if (lane == 0) {
+    const unsigned gw = blockIdx.x * (kStreamThreads / 32) + (threadIdx.x >> 5);
+    if (gw < 148 * 4 * 8) {
+      g_stream_timeline[4 * gw] = tl_t0;
+      g_stream_timeline[4 * gw + 1] = global_ns();
+      g_stream_timeline[4 * gw + 2] = tl_items;
+      g_stream_timeline[4 * gw + 3] = tl_segs;
+    }
+  }
+#endif
 }
 
 }  // namespace rbv

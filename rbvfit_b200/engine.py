@@ -6,6 +6,7 @@ handle, and (in ``rbvfit_b200.dist``) torch.distributed.  All arithmetic happens
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -61,6 +62,7 @@ class Engine:
         self._stretch_ws = None               # workspace of the device-resident sampler
         self._slice_ws = None                 # workspace of the device-resident slice sampler
         self.comm_rank, self.comm_world = 0, 1   # rbv_comm_init (multi-GPU: the library issues the all-gather)
+        self.peer_attached = False               # rbv_peer_attach: the all-gather over NVLink peer memory
         self._sink_ring = None                # (block_steps, device ring, pinned ring) of rbv_stretch_run_sink
 
     # ------------------------------------------------------------------ lifetime
@@ -313,7 +315,41 @@ class Engine:
         ident = (C.c_ubyte * 128)(*t.cpu().tolist())
         check(self.lib.rbv_comm_init(self._h, ident, rank, world), "rbv_comm_init")
         self.comm_rank, self.comm_world = rank, world
+        self._peer_attach(group, rank, world, on_gpu)
         return True
+
+    def _peer_attach(self, group, rank, world, on_gpu):
+        """The all-gather as one kernel over NVLink peer memory (``rbv_peer_export`` / ``rbv_peer_attach``): every
+        rank's exchange block is mapped into every other rank through CUDA IPC; the 64-byte handles travel through
+        ``torch.distributed.all_gather``.  Every rank takes the same decision (the outcome of the attach is reduced
+        over the group): peer memory on all ranks or NCCL on all ranks.  ``RBVFIT_B200_PEER=0`` keeps NCCL."""
+        torch = _torch()
+        import torch.distributed as dist
+        self.peer_attached = False
+        if os.environ.get("RBVFIT_B200_PEER", "1") == "0" or not on_gpu or world > 16:
+            return
+        handle = (C.c_ubyte * 64)()
+        ok = self.lib.rbv_peer_export(self._h, handle) == 0
+        mine = torch.tensor(list(handle) + [1 if ok else 0], dtype=torch.uint8, device=self.tdev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        rows = [g.cpu().tolist() for g in gathered]
+        if not all(r[64] for r in rows):
+            return
+        flat = (C.c_ubyte * (64 * world))(*[b for r in rows for b in r[:64]])
+        ok = self.lib.rbv_peer_attach(self._h, flat, rank, world) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.tdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 1:
+            self.peer_attached = True
+        elif ok:
+            raise RbvError("rbv_peer_attach succeeded on this rank but failed on another: set RBVFIT_B200_PEER=0")
+
+    def peer_error(self) -> int:
+        """1 after a peer-memory all-gather gave up waiting for a rank (10 s without progress)."""
+        att, err = C.c_int(0), C.c_int(0)
+        check(self.lib.rbv_peer_info(self._h, C.byref(att), C.byref(err)), "rbv_peer_info")
+        return int(err.value)
 
     @property
     def has_comm(self) -> bool:

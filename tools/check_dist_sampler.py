@@ -111,7 +111,8 @@ def main():
     out.update(c5a_walkers=int(W), c5a_pixels=int(like.total_pixels), c5a_stretch_steps_per_sec=sps,
                c5a_stretch_runs=rates, c5a_walker_pixel_per_sec=sps * W * like.total_pixels,
                c5a_acceptance=float(dsm.acceptance_fraction.mean()), c5a_chain_digest=repr(digest),
-               kernel=like.engine.last_kernel)
+               kernel=like.engine.last_kernel, peer_memory_allgather=bool(like.engine.peer_attached),
+               peer_error=like.engine.peer_error() if world > 1 else 0)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
