@@ -292,9 +292,10 @@ typedef struct RbvSliceTuning {
   int patience;
   int maxsteps;     /* stepping-out budget per walker and step, shared between the two sides             */
   int maxiter;      /* iterations per half-step before RBV_ESTATE is returned                            */
-  int reserved;
+  int depth;        /* logical iterations evaluated per launch: 1, or 2 (also 0: the default) -- the second one's
+                     * candidates are speculative; chains, mu and the counters below do not depend on it */
   unsigned long long n_expansions, n_contractions; /* out */
-  unsigned long long n_calls;                      /* out: lnprob rows evaluated                        */
+  unsigned long long n_calls;                      /* out: lnprob rows the sequential algorithm evaluates */
   unsigned long long n_batches;                    /* out: lnprob launches                               */
 } RbvSliceTuning;
 int rbv_slice_workspace_bytes(const RbvContext* ctx, int n_walkers, size_t* bytes);

@@ -28,7 +28,7 @@ class RbvSpectrum(C.Structure):
 
 class RbvSliceTuning(C.Structure):
     _fields_ = [("mu", C.c_double), ("tolerance", C.c_double), ("tune", C.c_int), ("good", C.c_int),
-                ("patience", C.c_int), ("maxsteps", C.c_int), ("maxiter", C.c_int), ("reserved", C.c_int),
+                ("patience", C.c_int), ("maxsteps", C.c_int), ("maxiter", C.c_int), ("depth", C.c_int),
                 ("n_expansions", C.c_ulonglong), ("n_contractions", C.c_ulonglong), ("n_calls", C.c_ulonglong),
                 ("n_batches", C.c_ulonglong)]
 

@@ -1230,6 +1230,7 @@ struct Tuning {
   int stream_div = 3;       // RBVFIT_B200_STREAM_DIV=n: a range is 1/n of what is left of the spectrum
   double ff_budget = kFFEps;   // RBVFIT_B200_FF_EPS=x: far-field error budget (experiments only)
   int slice_dist_graph = 0;    // RBVFIT_B200_SLICE_DIST_GRAPH=1: multi-GPU slice sampler as a CUDA-graph WHILE loop
+  int slice_depth = 0;         // RBVFIT_B200_SLICE_DEPTH=1|2: logical iterations per launch of the slice sampler
   int inline_prep = -1;        // RBVFIT_B200_INLINE_PREP=0|1: line constants prepared by prep_kernel / in the CTA prologue
   int mcmc_persistent = -1;    // RBVFIT_B200_MCMC_PERSISTENT=0|1: small-ensemble stretch move as one cooperative launch
 };
@@ -1412,6 +1413,8 @@ int rbv_create(int device, RbvContext** out) {
     ctx->tune.inline_prep = e ? atoi(e) : -1;
     e = getenv("RBVFIT_B200_SLICE_DIST_GRAPH");
     ctx->tune.slice_dist_graph = e ? atoi(e) : 0;
+    e = getenv("RBVFIT_B200_SLICE_DEPTH");
+    ctx->tune.slice_depth = e ? atoi(e) : 0;
     e = getenv("RBVFIT_B200_FF_EPS");
     if (e && atof(e) > 0.0) ctx->tune.ff_budget = atof(e);
   }
@@ -1891,7 +1894,7 @@ struct LaunchPlan {
   bool ok = false;
 };
 
-// W_hint (>= W, 0 = W): the launch geometry (kernel, tile size / ranges) is chosen as for a batch of W_hint rows.
+// W_hint (0 = W): the launch geometry (kernel, tile size / ranges) is chosen as for a batch of W_hint rows.
 // The multi-GPU entry points pass the size of the WHOLE batch here, so that a rank evaluating 1/N of the rows uses
 // the partition -- far-field super-chunks, order of the chi^2 additions -- the single-GPU launch uses, and every
 // row's lnprob is bit-identical whatever the number of ranks.
@@ -1958,7 +1961,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   // from the batch size.  Sightline mode: each walker sees only its own instrument (identical geometry).
   size_t smem = 0;
   int stream_wd = 0, stream_ctas = 0;
-  const int Wg = std::max(W, W_hint);
+  const int Wg = W_hint > 0 ? W_hint : W;
   const int stream_ranges = plan ? 0 : stream_geometry(ctx, Wg, prm.geom, prm.range_lo, prm.range_hi, &stream_wd,
                                                        &stream_ctas, sl ? 1 : (size_t)-1);
   if (stream_ranges > 0) {
@@ -2716,7 +2719,7 @@ int rbv_stretch_run_sightlines(RbvContext* ctx, double* coords, double* lnprob, 
 
 // ---- device-resident ensemble slice sampler (zeus's differential move), rbv_slice.cuh ------------------------
 struct SliceLayout {
-  size_t cand, lnp_cand, dir, z0, lo, hi, tcur, jbudget, kbudget, phase, skip, walker_of, ctr, lnprob_ws, total;
+  size_t cand, lnp_cand, dir, z0, lo, hi, tcur, jbudget, kbudget, phase, lit, skip, walker_of, ctr, lnprob_ws, total;
 };
 static SliceLayout slice_layout(const RbvContext* ctx, int W) {
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -2724,21 +2727,22 @@ static SliceLayout slice_layout(const RbvContext* ctx, int W) {
   SliceLayout lay;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += up(bytes); return at; };
-  lay.cand = take(2 * row);                       // two rows per walker while it widens its bracket
-  lay.lnp_cand = take((2 * h + kMaxRanks) * sizeof(double));   // padded for the in-place all-gather
+  lay.cand = take(4 * row);                       // two rows per walker and logical iteration (depth 2)
+  lay.lnp_cand = take((4 * h + kMaxRanks) * sizeof(double));   // padded for the in-place all-gather
   lay.dir = take(row);
   lay.z0 = take(h * sizeof(double));
   lay.lo = take(h * sizeof(double));
   lay.hi = take(h * sizeof(double));
-  lay.tcur = take(h * sizeof(double));
+  lay.tcur = take(2 * h * sizeof(double));
   lay.jbudget = take(h * sizeof(int));
   lay.kbudget = take(h * sizeof(int));
   lay.phase = take(h * sizeof(int));
-  lay.skip = take(2 * h * sizeof(int));
+  lay.lit = take(h * sizeof(int));
+  lay.skip = take(4 * h * sizeof(int));
   lay.walker_of = take(h * sizeof(int));
   lay.ctr = take(sizeof(SliceCounters));
   lay.lnprob_ws = o;
-  lay.total = o + workspace_layout(ctx, (int)(2 * h), false).total;
+  lay.total = o + workspace_layout(ctx, (int)(4 * h), false).total;
   return lay;
 }
 
@@ -2776,6 +2780,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   P.jbudget = (int*)(ws + lay.jbudget);
   P.kbudget = (int*)(ws + lay.kbudget);
   P.phase = (int*)(ws + lay.phase);
+  P.lit = (int*)(ws + lay.lit);
   P.skip = (int*)(ws + lay.skip);
   P.walker_of = (int*)(ws + lay.walker_of);
   P.flag = flag;
@@ -2787,6 +2792,10 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   P.maxsteps = tuning->maxsteps;
   P.maxiter = tuning->maxiter;
   P.patience = tuning->patience;
+  // logical iterations per launch (rbv_slice.cuh, "Speculation"): chains and counters do not depend on it
+  P.depth = tuning->depth == 1 ? 1 : 2;
+  if (ctx->tune.slice_depth > 0) P.depth = std::min(ctx->tune.slice_depth, 2);
+  const int rows_per_walker = 2 * P.depth;
   {   // loop state: everything zero except mu and its adaptation state (the host slot is reused by the polls below)
     SliceCounters init;
     memset(&init, 0, sizeof(init));
@@ -2801,7 +2810,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   const int h = (n_walkers + 1) / 2;
   const long long launches_before = ctx->launches;
 
-  // one iteration of half `split`: candidates -> lnprob of the 2 n_S rows (masked rows skipped) -> update
+  // one iteration of half `split`: candidates -> lnprob of the 2 depth n_S rows (masked rows skipped) -> update
   auto iteration = [&](int split, int rows, cudaGraphConditionalHandle loop, int use_loop) -> int {
     const int nS = split == 0 ? h : n_walkers - h;
     const unsigned rows_grid = (unsigned)((nS + 3) / 4);
@@ -2812,8 +2821,11 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
     const bool dist = ctx->comm && ctx->comm_world > 1;
     if (dist) rank_rows(rows, ctx->comm_rank, ctx->comm_world, &lo, &hi, &chunk);
     if (hi > lo) {
+      // geometry as for the 2 n_S rows of one logical iteration, whatever the depth: about half the rows of a launch
+      // are masked, and the two depths then produce the same bits (measured at C2, depth 2: 1.70k steps/s with the
+      // 4096-pixel tiles this picks, 1.58k with the 8192-pixel tiles picked for 4 n_S rows)
       int rc = launch_lnprob(ctx, P.cand + (size_t)lo * ctx->ndim, hi - lo, 0, P.lnp_cand + lo, ws + lay.lnprob_ws,
-                             lnprob_ws_bytes, stream, "rbv_slice_run", nullptr, -1, P.skip + lo, rows);
+                             lnprob_ws_bytes, stream, "rbv_slice_run", nullptr, -1, P.skip + lo, 2 * nS);
       if (rc != RBV_OK) return rc;
     }
     if (dist) {
@@ -2848,7 +2860,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
     // counters and therefore enqueues the same iterations.
     for (int split = 0; split < 2; ++split) {
       int lo, hi, chunk;
-      rank_rows(2 * (split == 0 ? h : n_walkers - h), ctx->comm_rank, ctx->comm_world, &lo, &hi, &chunk);
+      rank_rows(rows_per_walker * (split == 0 ? h : n_walkers - h), ctx->comm_rank, ctx->comm_world, &lo, &hi, &chunk);
       rc = allgather_rows(ctx, P.lnp_cand, chunk, st);
       if (rc != RBV_OK) return rc;
     }
@@ -2880,7 +2892,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
                                         cudaStreamCaptureModeThreadLocal);
       if (e != cudaSuccess) break;
       const long long l0 = ctx->launches;
-      rc = iteration(split, 2 * nS, loop, 1);
+      rc = iteration(split, rows_per_walker * nS, loop, 1);
       per_iteration = ctx->launches - l0 + 2;
       cudaGraph_t captured = nullptr;
       e = cudaStreamEndCapture(st, &captured);
@@ -2914,7 +2926,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
         bool done = false;
         for (int it = 0; !done; ++it) {
           const long long l0 = ctx->launches;
-          rc = iteration(split, 2 * nS, 0, 0);
+          rc = iteration(split, rows_per_walker * nS, 0, 0);
           if (rc != RBV_OK) return rc;
           per_iteration = ctx->launches - l0 + 2;
           RBV_CUDA(cudaMemcpyAsync(&ctx->h_poll[it & 1], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost, st));

@@ -26,6 +26,18 @@
 // iteration it).  All floating-point steps that decide the chain are written with explicitly rounded operations so
 // that oracle/slice_replay.py reproduces them bit for bit in numpy.
 //
+// Speculation (depth 2, the default).  One launch can serve TWO logical iterations of a walker, because the second
+// one's candidates do not depend on the first one's lnprob values, only on WHICH case they select: while widening,
+// the next test point of an open end is one unit further out (rows 2 n_S + k and 3 n_S + k hold X + (L - 1) eta and
+// X + (R + 1) eta; used only if the first test succeeds); while shrinking, a rejected draw t_1 moves the end on its
+// own side, whatever lnprob was, so t_2 is drawn from the bracket that rejection would leave (row 2 n_S + k; used
+// only if t_1 is rejected).  slice_update_kernel then replays the two logical iterations in order with exactly the
+// rules of the sequential algorithm; rows it does not reach are dropped (not counted, not flagged).  Every walker
+// keeps its own logical iteration index (lit), which keys the shrink draws -- in the sequential run every unfinished
+// walker's index IS the iteration number -- so chains, mu, and the expansion / contraction / call counters are
+// bit-identical for depth 1 and 2; only the number of launches per step drops (C2: 17.4 -> see DESIGN.md).  The
+// extra rows cost next to nothing: the batch is far below one wave of CTAs either way.
+//
 // Who drives the loop.  Everything the loop needs -- step, iteration index, mu and its adaptation state, the count of
 // unfinished walkers -- lives in one device struct (SliceCounters).  Graph mode: the iteration is the body of a CUDA
 // graph WHILE node and the last warp of slice_update_kernel sets the loop condition (cudaGraphSetConditional), so a
@@ -43,6 +55,7 @@ struct SliceCounters {          // device; the loop state of rbv_slice_run
   unsigned int it;              // iteration index within the half-step
   unsigned int ticket;          // warps of slice_update_kernel that have finished the current iteration
   unsigned int guard;           // iterations started in this half-step (second, independent loop bound)
+  unsigned int over;            // unfinished walkers whose logical iteration index has passed maxiter
   int error;                    // 1 = a half-step needed more than maxiter iterations
   unsigned long long step;      // global index of the step being sampled
   unsigned long long ncall;     // likelihood rows evaluated in this run
@@ -64,7 +77,8 @@ struct SliceParams {
   double* z0;            // [h] slice levels
   double* lo;            // [h] bracket
   double* hi;            // [h]
-  double* tcur;          // [h] the shrink draw that produced the current candidate
+  double* tcur;          // [2 h] the shrink draws that produced the current candidates (second: speculative)
+  int* lit;              // [h] logical iterations the walker has consumed in this half-step
   int* jbudget;          // [h] expansions left on the left / right side
   int* kbudget;          // [h]
   int* phase;            // [h] kSlice* state
@@ -75,6 +89,7 @@ struct SliceParams {
   unsigned long long seed;
   double tolerance;
   int W, ndim, maxsteps, maxiter, patience;
+  int depth;             // logical iterations per launch: 1 or 2 (rows per launch: 2 depth n_S)
 };
 
 // Start of a half-step: direction, slice level, bracket and budgets of every walker of the half (warp per row).
@@ -113,6 +128,7 @@ __global__ void __launch_bounds__(128) slice_begin_kernel(const SliceParams P, u
     P.jbudget[k] = J;
     P.kbudget[k] = P.maxsteps - 1 - J;
     P.phase[k] = kSliceLeft | kSliceRight;
+    P.lit[k] = 0;
     P.walker_of[k] = i;
   }
 }
@@ -127,10 +143,10 @@ __global__ void __launch_bounds__(128) slice_candidate_kernel(const SliceParams 
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   if (k >= nS) return;
-  const unsigned long long step = P.ctr->step;
-  const unsigned int it = P.ctr->it;                  // both written by earlier launches
+  const unsigned long long step = P.ctr->step;     // written by an earlier launch
   if (k == 0 && lane == 0) {      // every block of this iteration's update kernel runs later
     P.ctr->remaining = 0u;
+    P.ctr->over = 0u;
     const unsigned int g = P.ctr->guard + 1u;
     P.ctr->guard = g;
     if (g > (unsigned)P.maxiter + 8u) {
@@ -140,26 +156,52 @@ __global__ void __launch_bounds__(128) slice_candidate_kernel(const SliceParams 
   }
   const int ph = P.phase[k];
   const bool rowA = (ph & (kSliceLeft | kSliceShrink)) != 0, rowB = (ph & kSliceRight) != 0;
+  // second logical iteration (speculative): shrinking -- always; widening -- an end that still has budget
+  const bool rowA2 = P.depth > 1 && rowA && ((ph & kSliceShrink) || P.jbudget[k] >= 1);
+  const bool rowB2 = P.depth > 1 && rowB && P.kbudget[k] >= 1;
   if (lane == 0) {
     P.skip[k] = !rowA;
     P.skip[nS + k] = !rowB;
+    if (P.depth > 1) {
+      P.skip[2 * nS + k] = !rowA2;
+      P.skip[3 * nS + k] = !rowB2;
+    }
   }
   if (!rowA && !rowB) return;
   const int i = P.walker_of[k];
   const double* x = P.coords + (size_t)i * P.ndim;
   const double* e = P.dir + (size_t)k * P.ndim;
   if (rowA) {
-    double s = P.lo[k];
+    double s = P.lo[k], s2;
     if (ph & kSliceShrink) {
-      const uint4 r = sampler_rand(P.seed, step, (uint32_t)i, 16u + 2u * it + (uint32_t)split);
-      s = __dadd_rn(s, __dmul_rn(u01(r.x, r.y), __dsub_rn(P.hi[k], s)));
-      if (lane == 0) P.tcur[k] = s;
+      const unsigned int lit = (unsigned int)P.lit[k];
+      const double left = s, right = P.hi[k];
+      const uint4 r = sampler_rand(P.seed, step, (uint32_t)i, 16u + 2u * lit + (uint32_t)split);
+      s = __dadd_rn(left, __dmul_rn(u01(r.x, r.y), __dsub_rn(right, left)));
+      // the draw that follows if s is rejected: the end on s's side moves to s
+      const double left2 = (s < 0.0) ? s : left, right2 = (s < 0.0) ? right : s;
+      const uint4 r2 = sampler_rand(P.seed, step, (uint32_t)i, 16u + 2u * (lit + 1u) + (uint32_t)split);
+      s2 = __dadd_rn(left2, __dmul_rn(u01(r2.x, r2.y), __dsub_rn(right2, left2)));
+      if (lane == 0) {
+        P.tcur[k] = s;
+        P.tcur[nS + k] = s2;
+      }
+    } else {
+      s2 = __dsub_rn(s, 1.0);
     }
     for (int d = lane; d < P.ndim; d += 32) P.cand[(size_t)k * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s, e[d]));
+    if (rowA2)
+      for (int d = lane; d < P.ndim; d += 32)
+        P.cand[(size_t)(2 * nS + k) * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s2, e[d]));
   }
   if (rowB) {
     const double s = P.hi[k];
     for (int d = lane; d < P.ndim; d += 32) P.cand[(size_t)(nS + k) * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s, e[d]));
+    if (rowB2) {
+      const double s2 = __dadd_rn(s, 1.0);
+      for (int d = lane; d < P.ndim; d += 32)
+        P.cand[(size_t)(3 * nS + k) * P.ndim + d] = __dadd_rn(x[d], __dmul_rn(s2, e[d]));
+    }
   }
 }
 
@@ -174,58 +216,78 @@ __global__ void __launch_bounds__(128) slice_update_kernel(const SliceParams P, 
   int ph = P.phase[k];
   if (!(ph & kSliceDone)) {
     const double z0 = P.z0[k];
+    int lit = P.lit[k];
     if (ph & kSliceShrink) {
-      const double zs = P.lnp_cand[k];
-      if (zs >= z0) {                                    // accepted: the candidate becomes the walker
-        const int i = P.walker_of[k];
-        for (int d = lane; d < P.ndim; d += 32) P.coords[(size_t)i * P.ndim + d] = P.cand[(size_t)k * P.ndim + d];
-        if (lane == 0) P.lnp[i] = zs;
-        ph = kSliceDone;
-      } else if (lane == 0) {                            // NaN: outside (and flagged)
-        const double t = P.tcur[k];
-        if (t < 0.0) P.lo[k] = t;
-        else P.hi[k] = t;
-        atomicAdd(&P.ctr->ncon, 1u);
+      // up to `depth` logical iterations: draw d is looked at only if every earlier one was rejected
+      unsigned int ncon = 0u, ncall = 0u;
+      bool nan = false;
+      for (int d = 0; d < P.depth; ++d) {
+        const int row = 2 * d * nS + k;
+        const double zs = P.lnp_cand[row];
+        ++ncall;
+        ++lit;
+        nan |= (zs != zs);
+        if (zs >= z0) {                                  // accepted: the candidate becomes the walker
+          const int i = P.walker_of[k];
+          for (int q = lane; q < P.ndim; q += 32) P.coords[(size_t)i * P.ndim + q] = P.cand[(size_t)row * P.ndim + q];
+          if (lane == 0) P.lnp[i] = zs;
+          ph = kSliceDone;
+          break;
+        }
+        if (lane == 0) {                                 // NaN: outside (and flagged)
+          const double t = P.tcur[d * nS + k];
+          if (t < 0.0) P.lo[k] = t;
+          else P.hi[k] = t;
+        }
+        ++ncon;
       }
       if (lane == 0) {
-        if (zs != zs) atomicOr(P.flag, 1);               // zeus / emcee: "Probability function returned NaN"
-        atomicAdd(&P.ctr->ncall, 1ull);
+        if (nan) atomicOr(P.flag, 1);                    // zeus / emcee: "Probability function returned NaN"
+        if (ncon) atomicAdd(&P.ctr->ncon, ncon);
+        atomicAdd(&P.ctr->ncall, (unsigned long long)ncall);
       }
     } else if (lane == 0) {
       unsigned int widened = 0u, evaluated = 0u;
-      if (ph & kSliceLeft) {
-        const double zs = P.lnp_cand[k];
-        const int b = P.jbudget[k];
-        if (zs != zs) atomicOr(P.flag, 1);
-        if (zs >= z0 && b >= 1) {
-          P.lo[k] = __dsub_rn(P.lo[k], 1.0);
-          P.jbudget[k] = b - 1;
-          ++widened;
-        } else {
-          ph &= ~kSliceLeft;
+      for (int d = 0; d < P.depth && ph != kSliceShrink; ++d) {
+        if (ph & kSliceLeft) {
+          const double zs = P.lnp_cand[2 * d * nS + k];
+          const int b = P.jbudget[k];
+          if (zs != zs) atomicOr(P.flag, 1);
+          if (zs >= z0 && b >= 1) {
+            P.lo[k] = __dsub_rn(P.lo[k], 1.0);
+            P.jbudget[k] = b - 1;
+            ++widened;
+          } else {
+            ph &= ~kSliceLeft;
+          }
+          ++evaluated;
         }
-        ++evaluated;
-      }
-      if (ph & kSliceRight) {
-        const double zs = P.lnp_cand[nS + k];
-        const int b = P.kbudget[k];
-        if (zs != zs) atomicOr(P.flag, 1);
-        if (zs >= z0 && b >= 1) {
-          P.hi[k] = __dadd_rn(P.hi[k], 1.0);
-          P.kbudget[k] = b - 1;
-          ++widened;
-        } else {
-          ph &= ~kSliceRight;
+        if (ph & kSliceRight) {
+          const double zs = P.lnp_cand[(2 * d + 1) * nS + k];
+          const int b = P.kbudget[k];
+          if (zs != zs) atomicOr(P.flag, 1);
+          if (zs >= z0 && b >= 1) {
+            P.hi[k] = __dadd_rn(P.hi[k], 1.0);
+            P.kbudget[k] = b - 1;
+            ++widened;
+          } else {
+            ph &= ~kSliceRight;
+          }
+          ++evaluated;
         }
-        ++evaluated;
+        ++lit;
+        if (ph == 0) ph = kSliceShrink;
       }
       if (widened) atomicAdd(&P.ctr->nexp, widened);
       atomicAdd(&P.ctr->ncall, (unsigned long long)evaluated);
-      if (ph == 0) ph = kSliceShrink;
     }
     if (lane == 0) {
       P.phase[k] = ph;
-      if (!(ph & kSliceDone)) atomicAdd(&P.ctr->remaining, 1u);
+      P.lit[k] = lit;
+      if (!(ph & kSliceDone)) {
+        atomicAdd(&P.ctr->remaining, 1u);
+        if (lit > P.maxiter) atomicAdd(&P.ctr->over, 1u);
+      }
     }
   }
   __syncwarp();
@@ -238,7 +300,7 @@ __global__ void __launch_bounds__(128) slice_update_kernel(const SliceParams P, 
       P.ctr->it = it;
       P.ctr->batches += 1ull;
       bool go = rem > 0u;
-      if (go && it > (unsigned)P.maxiter) {                         // zeus: "Number of contractions exceeded ..."
+      if (go && atomicAdd(&P.ctr->over, 0u) > 0u) {                 // zeus: "Number of contractions exceeded ..."
         P.ctr->error = 1;
         go = false;
       }

@@ -204,11 +204,13 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
     chain is copied to the host once per ``run_mcmc`` call.  ``likelihood`` is a ``GpuLikelihood``; random numbers
     come from the counter-based Philox streams of the device stretch move, so a run is reproducible and can be
     continued (``run_mcmc(None, n)``) without changing the stream of one long run (``oracle/slice_replay.py``
-    restates it in numpy for the tests)."""
+    restates it in numpy for the tests).  ``depth``: logical iterations served per launch (1 or 2, default 2 -- the
+    second one's candidates are evaluated speculatively, ``csrc/rbv_slice.cuh``); chains, ``mu`` and the counters
+    ``ncall`` / ``nexp`` / ``ncon`` do not depend on it, only ``nbatches`` does."""
 
     def __init__(self, nwalkers: int, ndim: int, likelihood, mu: float = 1.0, tune: bool = True,
                  tolerance: float = 0.05, patience: int = 5, maxsteps: int = 10000, maxiter: int = 10000,
-                 seed: Optional[int] = None, use_graph: bool = True, **_ignored):
+                 seed: Optional[int] = None, use_graph: bool = True, depth: int = 2, **_ignored):
         if not hasattr(likelihood, "engine"):
             raise TypeError("DeviceEnsembleSliceSampler needs a GpuLikelihood (the log-probability must run on "
                             "the device)")
@@ -220,6 +222,9 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
         self._state = None
         self.good = 0
         self.use_graph = bool(use_graph)
+        if depth not in (1, 2):
+            raise ValueError("depth must be 1 or 2")
+        self.depth = int(depth)
         super().__init__(nwalkers, ndim, likelihood.lnprob, mu=mu, tune=tune, tolerance=tolerance,
                          patience=patience, maxsteps=maxsteps, maxiter=maxiter, seed=seed)
 
@@ -256,7 +261,8 @@ class DeviceEnsembleSliceSampler(EnsembleSliceSampler):
             lps_t = torch.empty((nsteps, self.nwalkers), dtype=torch.float64, device=dev)
             flag_t = torch.zeros(1, dtype=torch.int32, device=dev)
             tuning = RbvSliceTuning(mu=self.mu, tolerance=self.tolerance, tune=int(self.tune), good=int(self.good),
-                                    patience=self.patience, maxsteps=self.maxsteps, maxiter=self.maxiter)
+                                    patience=self.patience, maxsteps=self.maxsteps, maxiter=self.maxiter,
+                                    depth=self.depth)
             mus = eng.slice_run(coords_t, lnp_t, nsteps, tuning, self._seed, self.iteration, chain_t, lps_t, flag_t,
                                 use_graph=self.use_graph)
             self._stream.synchronize()

@@ -276,7 +276,8 @@ def test_no_writes_outside_caller_buffers():
         assert torch.all(torch.isfinite(b[PAD:PAD + n])) and not torch.any(b[PAD:PAD + n] == SENT), name
     assert torch.all(big_ws[:PAD] == SENT) and torch.all(big_ws[PAD + nws:] == SENT)
     assert mus[0] == SENT and mus[-1] == SENT and np.all(mus[1:-1] > 0) and int(flag.item()) == 0
-    assert tuning.n_calls >= 3 * W * nsteps and tuning.n_batches >= 2 * 3 * nsteps and tuning.mu == mus[-2]
+    # (at least one widening and one shrinking launch per half-step: two logical iterations per launch by default)
+    assert tuning.n_calls >= 3 * W * nsteps and tuning.n_batches >= 2 * 2 * nsteps and tuning.mu == mus[-2]
     # argument checks of the entry point
     assert lib.rbv_slice_run(eng._h, bufs["coords"][PAD:].data_ptr(), bufs["lnp"][PAD:].data_ptr(), 3, nsteps,
                              C.byref(tuning), 99, 0, None, None, None, flag.data_ptr(), big_ws[PAD:].data_ptr(),

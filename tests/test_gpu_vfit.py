@@ -279,7 +279,7 @@ def test_device_slice_sampler_matches_numpy_replay():
     rng = np.random.default_rng(8)
     for W, nsteps in ((12, 40), (16, 25)):
         p0 = np.clip(w["theta_true"] + 1e-3 * rng.standard_normal((W, 6)), w["lb"], w["ub"])
-        dev = DeviceEnsembleSliceSampler(W, 6, like, seed=77)
+        dev = DeviceEnsembleSliceSampler(W, 6, like, seed=77, depth=1)
         dev.run_mcmc(p0, nsteps)
         ref = sl.run(like.lnprob, p0, like.lnprob(p0), nsteps, dev._seed)
         assert np.allclose(dev.get_chain(), ref["chain"], rtol=0, atol=1e-9)
@@ -287,12 +287,25 @@ def test_device_slice_sampler_matches_numpy_replay():
         assert (dev.nexp, dev.ncon) == (ref["nexp"], ref["ncon"])
         assert dev.ncall == W + ref["ncall"] and dev.nbatches == 1 + ref["nbatches"]
         assert dev.mu == ref["mu"] and dev.tune == ref["tune"] and np.array_equal(dev.mus, ref["mus"][:len(dev.mus)])
-        poll = DeviceEnsembleSliceSampler(W, 6, like, seed=77, use_graph=False)      # host-polled loop: same chain
+        poll = DeviceEnsembleSliceSampler(W, 6, like, seed=77, use_graph=False, depth=1)   # host-polled loop: same chain
         poll.run_mcmc(p0, nsteps)
         assert np.array_equal(poll.get_chain(), dev.get_chain()) and np.array_equal(poll.get_log_prob(),
                                                                                     dev.get_log_prob())
         assert (poll.mu, poll.ncall, poll.nexp, poll.ncon) == (dev.mu, dev.ncall, dev.nexp, dev.ncon)
         assert poll.nbatches == dev.nbatches + 2 * nsteps        # one masked batch per half-step
+        # two logical iterations per launch (the default: the second one's candidates are speculative): the chain, mu
+        # and every counter of the sequential algorithm bit for bit, in fewer launches -- graph mode and host-polled
+        for graph in (True, False):
+            spec = DeviceEnsembleSliceSampler(W, 6, like, seed=77, use_graph=graph)
+            assert spec.depth == 2
+            spec.run_mcmc(p0, nsteps)
+            assert np.array_equal(spec.get_chain(), dev.get_chain())
+            assert np.array_equal(spec.get_log_prob(), dev.get_log_prob())
+            assert (spec.mu, spec.ncall, spec.nexp, spec.ncon, spec.tune) == (dev.mu, dev.ncall, dev.nexp, dev.ncon,
+                                                                              dev.tune)
+            assert np.array_equal(spec.mus, dev.mus)
+            ref_batches = dev.nbatches if graph else poll.nbatches
+            assert spec.nbatches < ref_batches and 2 * (spec.nbatches - 1) >= dev.nbatches - 1 - 2 * nsteps
 
 
 def test_device_slice_sampler_bookkeeping_continuation_and_posterior():
