@@ -6,7 +6,8 @@
 One "step" = one lnprob evaluation of the whole walker ensemble of the workload (default C5a: 8192 walkers x
 100 000 px, L = 33 lines, K = 23 LSF taps -- the configuration the metric is quoted on; it fits one GPU).
 With N > 1 (launched by torchrun, one rank per GPU) the ensemble is split by walkers (strong scaling: the
-total work per step is fixed) and every step ends with the NCCL all-gather of lnprob.
+total work per step is fixed) and every step ends with the all-gather of lnprob issued by the library: one kernel
+over NVLink peer memory (`config.collective`; NCCL when the peer attach is unavailable or RBVFIT_B200_PEER=0).
 
 `value`  device-resident throughput: theta already in HBM, CUDA events around each step on the launch
          stream, L2 flushed (untimed) between steps, max over ranks.
@@ -255,7 +256,7 @@ def measure_workload(workload, rank, world, local, steps, warmup, far_field="che
     w, models, like, thetas, spectra = build_problem(workload, local)
     part = rdist.WalkerPartition(rank, world)
     if world > 1:
-        like.engine.comm_init()                 # the lnprob all-gather is issued by the library (NCCL, in-stream)
+        like.engine.comm_init()                 # the lnprob all-gather is issued by the library, in-stream
     dlike = rdist.DistributedLikelihood(like, part)
     W, ndim = thetas.shape
     total_px = like.total_pixels
@@ -299,7 +300,7 @@ def measure_workload(workload, rank, world, local, steps, warmup, far_field="che
     for k in range(steps):
         flush.zero_()                                     # untimed L2 flush
         ev[k][0].record()
-        out = dlike.lnprob_device(theta_dev)              # prep + lnprob kernel + finalize (+ NCCL all-gather, N > 1)
+        out = dlike.lnprob_device(theta_dev)              # prep + lnprob kernel + finalize (+ all-gather, N > 1)
         ev[k][1].record()
     barrier()
     launches = like.engine.launch_count - launches0
@@ -326,13 +327,23 @@ def measure_workload(workload, rank, world, local, steps, warmup, far_field="che
     else:
         k_ms = float("nan")
 
-    # e2e through the public API (host buffers)
+    # e2e through the public API (host buffers): theta sits in page-locked host memory, as the contract asks, so the
+    # H2D copy reads it in place (a pageable array costs a staging copy on top -- reported as e2e.pageable)
+    thetas_pin = like.pinned_theta(W)
+    thetas_pin[:] = thetas
     for _ in range(min(warmup, 3)):
+        dlike.lnprob(thetas_pin)
         dlike.lnprob(thetas)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = dlike.lnprob(thetas)
+        res_pageable = dlike.lnprob(thetas)
+    torch.cuda.synchronize(dev)
+    e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / steps
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = dlike.lnprob(thetas_pin)
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -350,12 +361,18 @@ def measure_workload(workload, rank, world, local, steps, warmup, far_field="che
         "config": {"workload": workload, "walkers": W, "pixels": total_px, "ndim": ndim,
                    "lines": int(sum(models[n].compile().data.n_lines for n in like.names)), "lsf_taps": n_taps,
                    "partition": f"walkers/{world}",
+                   "collective": ("none (one rank)" if world == 1 else
+                                  "all-gather of lnprob: one kernel over NVLink peer memory (rbv_peer_attach)"
+                                  if like.engine.peer_attached else "all-gather of lnprob: ncclAllGather in-stream"),
                    "l2": "flushed between timed steps (256 MiB memset, untimed)",
                    "walkers_out_of_bounds": int(np.count_nonzero(np.isneginf(lnp))),
                    "value_counts": "all walkers, the out-of-bounds rows included (they return -inf unevaluated); "
                                    "roofline.achieved counts the evaluated rows only"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8)},
+                "h2d_bytes_per_step": int(n_local * ndim * 8), "d2h_bytes_per_step": int(W * 8),
+                "input": "page-locked host array (GpuLikelihood.pinned_theta), read in place by the H2D copy",
+                "pageable": {"value": W * total_px / (e2e_pageable_ms * 1e-3), "ms_per_step": e2e_pageable_ms,
+                             "note": "this rank's wall clock with a pageable numpy theta (staging copy included)"}},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "kernel": f"voigt_{kernel}_kernel", "kernel_ms": k_ms,
                      "far_field": far_field, "algorithmic_flops_per_walker_pixel": F, "tiers": tiers,
@@ -397,7 +414,7 @@ def run_gpu(args, rank, world, local):
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": r["config"], "clocks": r["clocks"],
         "e2e": r["e2e"],
-        "gpu_launches": r["launches"],      # prep_kernel + lnprob kernel + finalize_kernel per step
+        "gpu_launches": r["launches"],      # prep_kernel + lnprob kernel + finalize kernel (+ all-gather kernel) per step
         "roofline": roof,
     }
     extras = not args.no_extras
@@ -513,13 +530,15 @@ def sightline_leg(args, rank, world, local, fp64_peak=None, flush=None, steps=No
         torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
     ms = float(total_ms.item())
     value = n_sightlines * Ws * P / (ms * 1e-3)
-    # e2e: host theta -> host lnprob through SightlineBatch.lnprob
+    # e2e: host theta (page-locked, read in place by the H2D copy) -> host lnprob through SightlineBatch.lnprob
+    thetas_pin = batch.pinned_theta(Ws)
+    thetas_pin[:] = thetas
     for _ in range(2):
-        batch.lnprob(thetas)
+        batch.lnprob(thetas_pin)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = batch.lnprob(thetas)
+        res = batch.lnprob(thetas_pin)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
@@ -682,7 +701,7 @@ def mcmc_large_leg(like, w, thetas, total_px, rank=0, world=1, nsteps=48):
             "acceptance": float(smp.acceptance_fraction.mean()),
             "chain_digest_first_4_steps": repr(digest),
             "sampler": "rbv_stretch_run (CUDA graph)" if world == 1 else
-                       "rbv_stretch_run_dist (CUDA graph incl. the in-place NCCL all-gather of lnprob per half-step)",
+                       "rbv_stretch_run_dist (CUDA graph incl. the in-place all-gather of lnprob per half-step)",
             "note": "median of 3 runs, max over ranks; includes the D2H copy of the chain (W x ndim x 8 B per step)"}
 
 

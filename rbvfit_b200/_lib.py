@@ -69,6 +69,7 @@ EXPORTS = {
     "rbv_comm_unique_id": (C.c_int, [C.c_void_p]),
     "rbv_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "rbv_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rbv_host_pinned": (C.c_int, [C.c_void_p]),
     "rbv_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rbv_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "rbv_peer_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -2025,7 +2025,8 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   if (prm.separate_finalize) {
-    if (stream_ranges > 0) finalize_stream_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
+    // (boundary outputs only where a spectrum has more than one range: a sightline batch of 2048-pixel spectra has none)
+    if (stream_ranges > (sl ? 1 : prm.n_inst)) finalize_stream_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
     else finalize_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
     RBV_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -2049,6 +2050,18 @@ int rbv_lnprob_batch_sightlines(RbvContext* ctx, const double* theta, int W, int
   if (walkers_per_sightline <= 0) return fail(RBV_EINVAL, "rbv_lnprob_batch_sightlines: walkers_per_sightline <= 0");
   return launch_lnprob(ctx, theta, W, walkers_per_sightline, lnprob, workspace, workspace_bytes, stream,
                        "rbv_lnprob_batch_sightlines");
+}
+
+// 1 = p points into page-locked host memory (cudaMallocHost / cudaHostRegister / a pinned torch tensor): an
+// asynchronous H2D copy can read it in place, no staging copy needed
+int rbv_host_pinned(const void* p) {
+  if (!p) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 int rbv_lnprob_batch_host(RbvContext* ctx, const double* theta_host, int W, double* lnprob_host,

@@ -187,8 +187,11 @@ class DistributedLikelihood:
             # device buffer -- the library reads nothing else), then one C call evaluates and all-gathers
             eng._reserve(W, th.shape[1])
             if hi > lo:
-                eng._theta_pin_np[lo:hi] = th[lo:hi]
-                eng._theta_dev[lo:hi].copy_(eng._theta_pin[lo:hi], non_blocking=True)
+                if th.flags.c_contiguous and eng.lib.rbv_host_pinned(th.ctypes.data):
+                    eng._theta_dev[lo:hi].copy_(torch.from_numpy(th[lo:hi]), non_blocking=True)   # page-locked: in place
+                else:
+                    eng._theta_pin_np[lo:hi] = th[lo:hi]
+                    eng._theta_dev[lo:hi].copy_(eng._theta_pin[lo:hi], non_blocking=True)
             out = eng.lnprob_allgather_device(eng._theta_dev[:W]).cpu().numpy()
             return float(out[0]) if single else out
         if hi > lo:

@@ -168,12 +168,27 @@ class Engine:
         if ndim != self.ndim:
             raise ValueError(f"theta has {ndim} columns, bounds were set for ndim={self.ndim}")
         self._reserve(W, ndim, sightlines=False)
-        self._theta_pin_np[:W] = theta
-        check(self.lib.rbv_lnprob_batch_host(self._h, self._theta_pin.data_ptr(), W, self._lnp_pin.data_ptr(),
+        src = self._theta_pin.data_ptr()
+        if (theta.dtype == np.float64 and theta.flags.c_contiguous
+                and self.lib.rbv_host_pinned(theta.ctypes.data)):
+            src = theta.ctypes.data            # page-locked already (pinned_theta, a pinned torch tensor): DMA in place
+        else:
+            self._theta_pin_np[:W] = theta     # staging copy of a pageable array
+        check(self.lib.rbv_lnprob_batch_host(self._h, src, W, self._lnp_pin.data_ptr(),
                                              self._theta_dev.data_ptr(), self._lnp_dev.data_ptr(),
                                              self._ws.data_ptr(), self._ws_bytes, self._stream()),
               "rbv_lnprob_batch_host")
         return self._lnp_pin_np[:W].copy()
+
+    def pinned_theta(self, W: int) -> np.ndarray:
+        """A page-locked float64 array [W, ndim] the caller can fill in place: ``lnprob_host`` on it (or on any other
+        page-locked array) skips the staging copy.  The array owns its memory (a pinned torch tensor behind it)."""
+        torch = _torch()
+        t = torch.empty((int(W), self.ndim), dtype=torch.float64, pin_memory=True)
+        a = t.numpy()
+        self._pinned_keep = getattr(self, "_pinned_keep", [])
+        self._pinned_keep.append(t)
+        return a
 
     def lnprob_device(self, theta_t, out_t=None):
         """DEVICE theta tensor [W, ndim] (float64, contiguous) -> DEVICE lnprob tensor [W]; asynchronous."""
@@ -206,9 +221,17 @@ class Engine:
 
     def lnprob_sightlines_host(self, theta: np.ndarray, wps: int) -> np.ndarray:
         """HOST theta [S * wps, ndim] (wps consecutive rows per sightline) -> HOST lnprob [S * wps]."""
-        out = self.lnprob_sightlines_device(_torch().as_tensor(np.ascontiguousarray(theta, dtype=np.float64),
-                                                               device=self.tdev), wps)
-        return out.cpu().numpy()
+        torch = _torch()
+        th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64))
+        # a page-locked array (pinned_theta) is read in place by the copy engine; a pageable one is staged by the driver
+        out = self.lnprob_sightlines_device(th.to(self.tdev, non_blocking=True), wps)
+        W = out.shape[0]
+        if getattr(self, "_sl_out_pin", None) is None or self._sl_out_pin.shape[0] < W:
+            self._sl_out_pin = torch.empty(W, dtype=torch.float64, pin_memory=True)
+        host = self._sl_out_pin[:W]
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.tdev).synchronize()
+        return host.numpy().copy()
 
     def lnprob_sightlines_device(self, theta_t, wps: int, out_t=None):
         torch = _torch()

@@ -83,6 +83,11 @@ class GpuLikelihood:
 
     __call__ = lnprob
 
+    def pinned_theta(self, n: int) -> np.ndarray:
+        """Page-locked [n, ndim] array for ensembles that are evaluated repeatedly: ``lnprob`` reads a page-locked
+        theta in place (no staging copy on the host)."""
+        return self.engine.pinned_theta(n)
+
     def lnlike(self, theta):
         """The likelihood without the prior (``vfit.lnlike``, vfit_mcmc.py:297-319): rows outside the bounds are
         evaluated like any other.  One launch, no shared state touched."""
@@ -182,6 +187,11 @@ class SightlineBatch:
             raise ValueError(f"theta must be [{self.n_sightlines}, walkers_per_sightline, {self.ndim}]")
         S, Ws, nd = theta.shape
         return self.engine.lnprob_sightlines_host(theta.reshape(S * Ws, nd), Ws).reshape(S, Ws)
+
+    def pinned_theta(self, walkers_per_sightline: int) -> np.ndarray:
+        """Page-locked [S, walkers_per_sightline, ndim] array: ``lnprob`` copies it to the device in place."""
+        a = self.engine.pinned_theta(self.n_sightlines * int(walkers_per_sightline))
+        return a.reshape(self.n_sightlines, int(walkers_per_sightline), self.ndim)
 
     def lnprob_device(self, theta_t, wps: int, out_t=None):
         return self.engine.lnprob_sightlines_device(theta_t, wps, out_t)

@@ -63,6 +63,14 @@ def test_c5a_batching_permutation_and_tile_geometry_invariance():
     perm = np.random.default_rng(1).permutation(700)
     assert np.array_equal(like.lnprob(thetas[perm]), full[perm], equal_nan=True)     # bit-exact
     assert np.array_equal(like.lnprob(thetas), full, equal_nan=True)                 # run-to-run
+    # a page-locked theta is copied to the device in place (no staging copy): same bits, and the query tells them apart
+    pin = like.pinned_theta(700)
+    pin[:] = thetas
+    assert like.engine.lib.rbv_host_pinned(pin.ctypes.data) == 1
+    assert like.engine.lib.rbv_host_pinned(thetas.ctypes.data) == 0
+    assert np.array_equal(like.lnprob(pin), full, equal_nan=True)
+    pin[3] = thetas[5]                                                               # refilled in place between calls
+    assert like.lnprob(pin)[3] == full[5]
 
 
 def test_additivity_over_pixel_ranges_without_lsf():
@@ -166,6 +174,9 @@ def test_sightline_batch_equals_individual_fits():
     same = np.array([singles[s].lnprob(np.tile(thetas[s], (S, 1)))[:Ws] for s in range(0, S, 5)])
     assert np.array_equal(got[0:S:5], same, equal_nan=True)
     assert len(set(np.round(ref[np.isfinite(ref)], 3))) > S     # sightlines really differ
+    pin = batch.pinned_theta(Ws)                     # page-locked input: same values
+    pin[:] = thetas
+    assert np.array_equal(batch.lnprob(pin), got, equal_nan=True)
     with pytest.raises(ValueError):
         batch.lnprob(thetas[:5])
 
