@@ -2823,12 +2823,11 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   const int h = (n_walkers + 1) / 2;
   const long long launches_before = ctx->launches;
 
-  // one iteration of half `split`: candidates -> lnprob of the 2 depth n_S rows (masked rows skipped) -> update
+  // one iteration of half `split`: lnprob of the 2 depth n_S candidate rows (masked rows skipped) -> update + the
+  // candidates of the next iteration
   auto iteration = [&](int split, int rows, cudaGraphConditionalHandle loop, int use_loop) -> int {
     const int nS = split == 0 ? h : n_walkers - h;
     const unsigned rows_grid = (unsigned)((nS + 3) / 4);
-    slice_candidate_kernel<<<rows_grid, 128, 0, st>>>(P, split, loop, use_loop);
-    RBV_CUDA(cudaGetLastError());
     // multi-GPU (rbv_comm_init): this rank evaluates its share of the rows, in-place all-gather of their lnprob
     int lo = 0, hi = rows, chunk = rows;
     const bool dist = ctx->comm && ctx->comm_world > 1;
@@ -2852,6 +2851,8 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   auto begin = [&](unsigned long long step, int split) -> int {
     const int nS = split == 0 ? h : n_walkers - h;
     slice_begin_kernel<<<(unsigned)((nS + 3) / 4), 128, 0, st>>>(P, step, split);
+    RBV_CUDA(cudaGetLastError());
+    slice_candidate_kernel<<<(unsigned)((nS + 3) / 4), 128, 0, st>>>(P, split);     // the first candidates
     RBV_CUDA(cudaGetLastError());
     return RBV_OK;
   };
@@ -2882,8 +2883,8 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   }
   if (use_graph && st != nullptr) {
     // Graph mode: per half a graph whose only node is a WHILE node; its body is one iteration, captured from the
-    // stream, and slice_update_kernel sets the condition.  A step = begin, graph, begin, graph, record -- five
-    // asynchronous launches whatever the number of iterations, and no host synchronisation inside the run.
+    // stream, and slice_update_kernel sets the condition.  A step = (begin, first candidates, graph) x 2, record --
+    // seven asynchronous launches whatever the number of iterations, and no host synchronisation inside the run.
     cudaGraph_t graph[2] = {nullptr, nullptr};
     cudaGraphExec_t exec[2] = {nullptr, nullptr};
     cudaError_t e = cudaSuccess;
@@ -2906,7 +2907,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
       if (e != cudaSuccess) break;
       const long long l0 = ctx->launches;
       rc = iteration(split, rows_per_walker * nS, loop, 1);
-      per_iteration = ctx->launches - l0 + 2;
+      per_iteration = ctx->launches - l0 + 1;
       cudaGraph_t captured = nullptr;
       e = cudaStreamEndCapture(st, &captured);
       if (e != cudaSuccess || rc != RBV_OK) break;
@@ -2941,13 +2942,13 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
           const long long l0 = ctx->launches;
           rc = iteration(split, rows_per_walker * nS, 0, 0);
           if (rc != RBV_OK) return rc;
-          per_iteration = ctx->launches - l0 + 2;
+          per_iteration = ctx->launches - l0 + 1;
           RBV_CUDA(cudaMemcpyAsync(&ctx->h_poll[it & 1], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost, st));
           RBV_CUDA(cudaEventRecord(ctx->poll_ev[it & 1], st));
           if (it >= 1) {
             RBV_CUDA(cudaEventSynchronize(ctx->poll_ev[(it - 1) & 1]));
             const SliceCounters& c = ctx->h_poll[(it - 1) & 1];
-            if (c.remaining == 0u || c.error) done = true;
+            if (c.pending == 0u || c.error) done = true;
           }
         }
       }
@@ -2958,7 +2959,7 @@ int rbv_slice_run(RbvContext* ctx, double* coords, double* lnprob, int n_walkers
   }
   RBV_CUDA(cudaMemcpy(&ctx->h_poll[0], P.ctr, sizeof(SliceCounters), cudaMemcpyDeviceToHost));
   const SliceCounters& c = ctx->h_poll[0];
-  ctx->launches = launches_before + (long long)c.batches * per_iteration + 3LL * n_steps;
+  ctx->launches = launches_before + (long long)c.batches * per_iteration + 5LL * n_steps;   // + begin, candidates (x 2), record
   tuning->mu = c.mu;
   tuning->tune = c.tune;
   tuning->good = c.good;

@@ -15,8 +15,9 @@
 //
 // Here every walker of the half is a small state machine (widening: either end of the bracket still open;
 // shrinking; finished) and one ITERATION advances every unfinished walker by one step of it:
-//   slice_candidate_kernel  ->  the lnprob launch over the half (masked rows are skipped through row_skip)
-//                           ->  slice_update_kernel
+//   the lnprob launch over the half (masked rows are skipped through row_skip)
+//                           ->  slice_update_kernel (state machines, then the candidates of the next launch;
+//                               slice_candidate_kernel writes the first candidates of a half-step)
 // While a walker widens, BOTH ends of its bracket are evaluated in the same iteration (row k = X + L eta, row
 // n_S + k = X + R eta; the two sides have independent budgets, so this is zeus's left-then-right loop run
 // concurrently); while it shrinks only row k is live.  The number of device batches per half-step is therefore the
@@ -56,6 +57,8 @@ struct SliceCounters {          // device; the loop state of rbv_slice_run
   unsigned int ticket;          // warps of slice_update_kernel that have finished the current iteration
   unsigned int guard;           // iterations started in this half-step (second, independent loop bound)
   unsigned int over;            // unfinished walkers whose logical iteration index has passed maxiter
+  unsigned int pending;         // `remaining` of the last finished iteration (what the host-polled loop reads:
+                                // `remaining` itself is re-armed by the warp that closes an iteration)
   int error;                    // 1 = a half-step needed more than maxiter iterations
   unsigned long long step;      // global index of the step being sampled
   unsigned long long ncall;     // likelihood rows evaluated in this run
@@ -133,27 +136,11 @@ __global__ void __launch_bounds__(128) slice_begin_kernel(const SliceParams P, u
   }
 }
 
-// Candidates of the current iteration: widening walkers put X + L eta into row k and X + R eta into row n_S + k (open
-// ends only), shrinking walkers X + t eta with t drawn from (L, R) into row k; every other row is masked.
-// `loop` is the WHILE node's handle in graph mode (use_loop != 0): should slice_update_kernel ever fail to end the
-// loop, the iteration count kept HERE ends it.
-__global__ void __launch_bounds__(128) slice_candidate_kernel(const SliceParams P, int split,
-                                                              cudaGraphConditionalHandle loop, int use_loop) {
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  int offS, nS, offC, nC;
-  split_geometry(P.W, split, offS, nS, offC, nC);
-  if (k >= nS) return;
-  const unsigned long long step = P.ctr->step;     // written by an earlier launch
-  if (k == 0 && lane == 0) {      // every block of this iteration's update kernel runs later
-    P.ctr->remaining = 0u;
-    P.ctr->over = 0u;
-    const unsigned int g = P.ctr->guard + 1u;
-    P.ctr->guard = g;
-    if (g > (unsigned)P.maxiter + 8u) {
-      P.ctr->error = 1;
-      if (use_loop) cudaGraphSetConditional(loop, 0u);
-    }
-  }
+// Candidates of walker-row k for the next launch (a whole warp): widening walkers put X + L eta into row k and
+// X + R eta into row n_S + k (open ends only), shrinking walkers X + t eta with t drawn from (L, R) into row k, the
+// speculative second iteration goes into rows 2 n_S + k and 3 n_S + k; every other row is masked.
+__device__ __forceinline__ void slice_candidates(const SliceParams& P, int split, int nS, int k, int lane,
+                                                 unsigned long long step) {
   const int ph = P.phase[k];
   const bool rowA = (ph & (kSliceLeft | kSliceShrink)) != 0, rowB = (ph & kSliceRight) != 0;
   // second logical iteration (speculative): shrinking -- always; widening -- an end that still has budget
@@ -205,14 +192,33 @@ __global__ void __launch_bounds__(128) slice_candidate_kernel(const SliceParams 
   }
 }
 
-// Advance every unfinished walker's state machine with the lnprob of its candidate(s).  The last warp to finish
-// closes the iteration: iteration index, batch count and -- in graph mode -- the WHILE node's condition.
+// First candidates of a half-step (launched once, after slice_begin_kernel; every later iteration gets its candidates
+// from slice_update_kernel itself).
+__global__ void __launch_bounds__(128) slice_candidate_kernel(const SliceParams P, int split) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  int offS, nS, offC, nC;
+  split_geometry(P.W, split, offS, nS, offC, nC);
+  if (k >= nS) return;
+  if (k == 0 && lane == 0) {      // every warp of the first update kernel runs later
+    P.ctr->pending = (unsigned)nS;
+    P.ctr->remaining = 0u;
+    P.ctr->over = 0u;
+    P.ctr->guard = 1u;
+  }
+  slice_candidates(P, split, nS, k, lane, P.ctr->step);
+}
+
+// Advance every unfinished walker's state machine with the lnprob of its candidate(s), then write its candidates for
+// the next launch (one kernel less per iteration than a separate candidate launch).  The last warp to finish closes
+// the iteration: iteration index, batch count, the counters of the next iteration and -- in graph mode -- the WHILE
+// node's condition (`loop`, use_loop != 0).
 __global__ void __launch_bounds__(128) slice_update_kernel(const SliceParams P, int split,
                                                            cudaGraphConditionalHandle loop, int use_loop) {
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   int offS, nS, offC, nC;
   split_geometry(P.W, split, offS, nS, offC, nC);
   if (k >= nS) return;
+  const unsigned long long step = P.ctr->step;     // written by an earlier launch
   int ph = P.phase[k];
   if (!(ph & kSliceDone)) {
     const double z0 = P.z0[k];
@@ -290,19 +296,33 @@ __global__ void __launch_bounds__(128) slice_update_kernel(const SliceParams P, 
       }
     }
   }
+  __syncwarp();                       // lane 0's state of this walker -> the whole warp
+  slice_candidates(P, split, nS, k, lane, step);      // (a finished walker masks all its rows)
   __syncwarp();
   if (lane == 0) {
     __threadfence();
     if (atomicAdd(&P.ctr->ticket, 1u) == (unsigned)nS - 1u) {      // every row of the half has been updated
       P.ctr->ticket = 0u;
       const unsigned int rem = atomicAdd(&P.ctr->remaining, 0u);
+      const unsigned int over = atomicAdd(&P.ctr->over, 0u);
+      P.ctr->pending = rem;
+      P.ctr->remaining = 0u;                                        // counters of the next iteration: its update
+      P.ctr->over = 0u;                                             // kernel is a later launch
       const unsigned int it = P.ctr->it + 1u;
       P.ctr->it = it;
       P.ctr->batches += 1ull;
       bool go = rem > 0u;
-      if (go && atomicAdd(&P.ctr->over, 0u) > 0u) {                 // zeus: "Number of contractions exceeded ..."
+      if (go && over > 0u) {                                        // zeus: "Number of contractions exceeded ..."
         P.ctr->error = 1;
         go = false;
+      }
+      if (go) {                                                     // second, independent loop bound
+        const unsigned int g = P.ctr->guard + 1u;
+        P.ctr->guard = g;
+        if (g > (unsigned)P.maxiter + 8u) {
+          P.ctr->error = 1;
+          go = false;
+        }
       }
       if (use_loop) cudaGraphSetConditional(loop, go ? 1u : 0u);
       __threadfence();
