@@ -306,6 +306,11 @@ def test_device_slice_sampler_matches_numpy_replay():
             assert np.array_equal(spec.mus, dev.mus)
             ref_batches = dev.nbatches if graph else poll.nbatches
             assert spec.nbatches < ref_batches and 2 * (spec.nbatches - 1) >= dev.nbatches - 1 - 2 * nsteps
+        ref2 = sl.run(like.lnprob, p0, like.lnprob(p0), nsteps, dev._seed, depth=2)     # the replay's own depth 2
+        graph2 = DeviceEnsembleSliceSampler(W, 6, like, seed=77)
+        graph2.run_mcmc(p0, nsteps)
+        assert graph2.nbatches == 1 + ref2["nbatches"] and graph2.ncall == W + ref2["ncall"]
+        assert np.allclose(graph2.get_chain(), ref2["chain"], rtol=0, atol=1e-9)
 
 
 def test_device_slice_sampler_bookkeeping_continuation_and_posterior():

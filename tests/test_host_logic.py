@@ -243,6 +243,26 @@ def test_slice_replay_recovers_gaussian_and_tunes_mu():
     # a tiny stepping-out budget still samples correctly (the bracket just cannot widen)
     c = sl.run(lnp, p0, lnp(p0), 50, seed=3, mu=0.01, maxsteps=1, tune=False)
     assert c["nexp"] == 0 and np.all(np.isfinite(c["lnp_chain"]))
+    # two logical iterations per batch (the device default: the second one's candidates are speculative): the chain,
+    # mu and every counter of the sequential algorithm, in between half and all of its batches -- also with a
+    # stepping-out budget that runs out, and with an lnprob that is -inf outside a box (rejections on one side)
+    spec = sl.run(lnp, p0, lnp(p0), 700, seed=20260, mu=1.0, depth=2)
+    for key in ("chain", "lnp_chain", "mus"):
+        assert np.array_equal(spec[key], out[key]), key
+    assert [spec[k] for k in ("mu", "tune", "good", "nexp", "ncon", "ncall")] == \
+           [out[k] for k in ("mu", "tune", "good", "nexp", "ncon", "ncall")]
+    assert out["nbatches"] / 2 <= spec["nbatches"] < 0.75 * out["nbatches"]
+
+    def boxed(x):
+        x = np.atleast_2d(x)
+        return np.where(np.all(np.abs(x - mu) < 3.0, axis=1), lnp(x), -np.inf)
+
+    for kw in (dict(maxsteps=3, mu=0.05, tune=False), dict(mu=5.0)):
+        one = sl.run(boxed, p0, boxed(p0), 120, seed=11, **kw)
+        two = sl.run(boxed, p0, boxed(p0), 120, seed=11, depth=2, **kw)
+        assert np.array_equal(one["chain"], two["chain"]) and np.array_equal(one["lnp_chain"], two["lnp_chain"])
+        assert (one["mu"], one["nexp"], one["ncon"], one["ncall"]) == (two["mu"], two["nexp"], two["ncon"], two["ncall"])
+        assert two["nbatches"] < one["nbatches"]
 
 
 def test_sightline_sampler_accessors_without_device():
