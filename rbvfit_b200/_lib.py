@@ -117,6 +117,8 @@ def load():
             "(or __graft_entry__.build()).  rbvfit_b200 has no CPU fallback.")
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in EXPORTS.items():
+        if path != LIB_PATH and not hasattr(lib, name):
+            continue                # an experiment's build of an older source tree: newer entry points are absent
         fn = getattr(lib, name)     # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

@@ -1436,7 +1436,8 @@ int rbv_create(int device, RbvContext** out) {
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-  RBV_CUDA(cudaFuncSetAttribute(voigt_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_stream_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  RBV_CUDA(cudaFuncSetAttribute(voigt_stream_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_mcmc_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaFuncSetAttribute(voigt_mcmc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   RBV_CUDA(cudaMalloc((void**)&ctx->d_grid_bar, 256));
@@ -1562,6 +1563,7 @@ static int choose_geometry(const RbvContext* ctx, int W, TileGeom* geom, size_t*
 }
 
 // ---- streaming kernel (rbv_stream.cuh): work items = (walker, range of whole 1024-pixel segments of one instrument)
+constexpr int kStreamBndMinLines = 8;   // fewer lines: a range evaluates its K-1 leading flux values itself (cheap)
 constexpr int kStreamMaxHalo = 64;      // wider LSFs stay on the tile kernel (its LSF loop is unrolled 3 x 8 taps)
 constexpr int kStreamWarps = kStreamThreads / 32;
 
@@ -1647,7 +1649,7 @@ static int stream_geometry(RbvContext* ctx, int W, TileGeom* geom, unsigned shor
   for (auto& e : ctx->stream_ctas_cache)
     if (e.first == (int)smem) ctas = e.second;
   if (ctas < 0) {   // first use of this size (rebuild_tables warms the cache: no query while a stream is capturing)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, voigt_stream_kernel<3>, kStreamThreads, smem) != cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, voigt_stream_kernel<3, true>, kStreamThreads, smem) != cudaSuccess)
       ctas = 0;
     ctx->stream_ctas_cache.emplace_back((int)smem, ctas);
   }
@@ -1964,10 +1966,18 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   const int Wg = W_hint > 0 ? W_hint : W;
   const int stream_ranges = plan ? 0 : stream_geometry(ctx, Wg, prm.geom, prm.range_lo, prm.range_hi, &stream_wd,
                                                        &stream_ctas, sl ? 1 : (size_t)-1);
+  bool stream_bnd = false;
   if (stream_ranges > 0) {
     prm.n_tiles = stream_ranges;
-    prm.bnd = (double*)((char*)workspace + lay.bnd);
-    prm.bnd_stride = stream_bnd_stride(ctx, sl ? 1 : (size_t)-1);
+    // boundary records where a spectrum has several ranges AND evaluating the K-1 leading flux values per range
+    // would be expensive (kStreamBndMinLines lines or more); else every range evaluates them itself
+    int max_lines = 0;
+    for (size_t k = 0; k < (sl ? (size_t)1 : ctx->inst.size()); ++k) max_lines = std::max(max_lines, ctx->inst[k].dev.L);
+    stream_bnd = stream_ranges > (sl ? 1 : (int)ctx->inst.size()) && max_lines >= kStreamBndMinLines;
+    if (stream_bnd) {
+      prm.bnd = (double*)((char*)workspace + lay.bnd);
+      prm.bnd_stride = stream_bnd_stride(ctx, sl ? 1 : (size_t)-1);
+    }
   } else prm.n_tiles = choose_geometry(ctx, Wg, prm.geom, &smem, sl ? 1 : (size_t)-1);
   dim3 grid((unsigned)W, (unsigned)prm.n_tiles);
   if (prm.n_tiles > 65535) return fail(RBV_EINVAL, std::string(who) + ": more than 65535 tiles per walker");
@@ -2013,7 +2023,9 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
     const long long items = (long long)W * stream_ranges;
     const unsigned ctas = (unsigned)std::min<long long>((long long)stream_ctas * ctx->sm_count,
                                                         (items + kStreamWarps - 1) / kStreamWarps);
-    voigt_stream_kernel<3><<<ctas, kStreamThreads, (size_t)stream_wd * kStreamWarps * sizeof(double), st>>>(prm, stream_wd);
+    const size_t stream_smem = (size_t)stream_wd * kStreamWarps * sizeof(double);
+    if (stream_bnd) voigt_stream_kernel<3, true><<<ctas, kStreamThreads, stream_smem, st>>>(prm, stream_wd);
+    else voigt_stream_kernel<3, false><<<ctas, kStreamThreads, stream_smem, st>>>(prm, stream_wd);
     ctx->last_kernel = RBV_KERNEL_STREAM;
   } else if (small_chunks(ctx, prm.geom, sl ? 1 : prm.n_inst)) {
     voigt_tile_kernel<3, 0, 2><<<grid, kThreads, smem, st>>>(prm);
@@ -2025,8 +2037,7 @@ static int launch_lnprob(RbvContext* ctx, const double* theta, int W, int wps, d
   RBV_CUDA(cudaGetLastError());
   ctx->launches++;
   if (prm.separate_finalize) {
-    // (boundary outputs only where a spectrum has more than one range: a sightline batch of 2048-pixel spectra has none)
-    if (stream_ranges > (sl ? 1 : prm.n_inst)) finalize_stream_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
+    if (stream_bnd) finalize_stream_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
     else finalize_kernel<<<(W + 3) / 4, 128, 0, st>>>(prm);
     RBV_CUDA(cudaGetLastError());
     ctx->launches++;

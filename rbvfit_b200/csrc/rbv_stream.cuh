@@ -287,7 +287,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 #endif
 
-template <int LOGR>
+// BND = true: range boundaries through boundary records (above).  BND = false: every range evaluates the K-1 flux
+// values in front of its first row itself and owns all its outputs -- cheaper when that evaluation is (few lines), and
+// it keeps the row loop free of the boundary code for spectra that have a single range (a sightline batch): measured
+// against one instantiation for everything, C5a_L4 3.77 -> 3.68 ms, C5b-1024 2.146 -> 2.12 ms.
+template <int LOGR, bool BND>
 __global__ void __launch_bounds__(kStreamThreads, RBV_STREAM_MIN_CTAS)
 voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_doubles) {
   constexpr int R = 1 << LOGR;
@@ -353,7 +357,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
       // (q_first) and added by finalize from the boundary record: the previous range's carry + this range's head.
       // An item start therefore costs the line constants and the taps, nothing else, and the partition into ranges
       // is free to be fine (the launch ends on one-segment items).
-      const bool first_range = (slot == prm.geom[prm.wps > 0 ? 0 : k].first_tile);
+      const bool first_range = !BND || (slot == prm.geom[prm.wps > 0 ? 0 : k].first_tile);
       if (first_range) {
         for (int i = lane; i < halo; i += 32) {
           const int p = min(max(o_lo - h + i, 0), I.P - 1);
@@ -412,7 +416,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
           }
         }
         __syncwarp();
-        if (q_first > 0) {   // first row of a range that has a predecessor: its head -> boundary record
+        if (BND && q_first > 0) {   // first row of a range that has a predecessor: its head -> boundary record
           double* bnd_rec = prm.bnd + ((size_t)w * prm.n_tiles + slot) * prm.bnd_stride;
           for (int i = lane; i < halo; i += 32) bnd_rec[halo + i] = smem[flux_off + smem_pos(halo + i, LOGR)];
         }
@@ -430,7 +434,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         }
         const int n_out = o_hi - o_row;     // outputs of this row (>= 256 except in the last row)
         const int e0 = lane << LOGR;
-        if (e0 + R <= n_out && e0 >= q_first) {
+        if (e0 + R <= n_out && (!BND || e0 >= q_first)) {
 #pragma unroll
           for (int q = 0; q < R; ++q) {
             const double resid = obs[q] - acc[q];                   // vfit_mcmc.py:310
@@ -439,13 +443,13 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         } else {
 #pragma unroll
           for (int q = 0; q < R; ++q) {
-            if (e0 + q < n_out && e0 + q >= q_first) {
+            if (e0 + q < n_out && (!BND || e0 + q >= q_first)) {
               const double resid = obs[q] - acc[q];
               part = fma(resid * resid, wgt[q], part);
             }
           }
         }
-        q_first = 0;
+        if (BND) q_first = 0;
         __syncwarp();
         // the row's last K-1 flux values become the next row's carry (element i <- i + 256: slot + 288)
         for (int i = lane; i < halo; i += 32) {
@@ -454,7 +458,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
         }
         __syncwarp();
       }
-      if (o_hi < I.P) {   // the last carry = the K-1 flux values in front of the next range's first output
+      if (BND && o_hi < I.P) {   // the last carry = the K-1 flux values in front of the next range's first output
         double* bnd_next = prm.bnd + ((size_t)w * prm.n_tiles + slot + 1) * prm.bnd_stride;
         for (int i = lane; i < halo; i += 32) bnd_next[i] = smem[flux_off + smem_pos(i, LOGR)];
       }
