@@ -205,7 +205,7 @@ int rbv_comm_info(const RbvContext* ctx, int* rank, int* world, int* nccl_versio
  *                    all-gathers the handles (torch.distributed in the Python layer)
  *   rbv_peer_attach  handles = world x 64 bytes in rank order; opens every peer's block
  *   rbv_peer_info    attached: 1 when the all-gather runs over peer memory; error: 1 after a wait that saw
- *                    nothing for 10 s (a rank died or skipped a call) */
+ *                    nothing for 30 s (a rank died or skipped a call) */
 int rbv_peer_export(RbvContext* ctx, unsigned char* out_handle64);
 int rbv_peer_attach(RbvContext* ctx, const unsigned char* handles, int rank, int world);
 int rbv_peer_info(RbvContext* ctx, int* attached, int* error);

@@ -2511,8 +2511,8 @@ static void rank_rows(int n, int rank, int world, int* lo, int* hi, int* chunk) 
 // (to finish a call it needs that peer's rows of the same call), so the half it writes next is never one the peer
 // still reads or has not yet emptied.  The call counter lives in device memory: the kernel replays inside a CUDA
 // graph.  A lnprob all-gather is 8 B per walker -- the cost of the exchange is latency: this is one launch and one
-// NVLink hop.  A wait that sees nothing for 10 s sets the block's error word and gives up (rbv_peer_info reports
-// it) instead of hanging the device.
+// NVLink hop.  A wait that sees nothing for 30 s sets the block's error word, hands NaN to the caller for the rows it
+// did not receive and gives up (rbv_peer_info reports it) instead of hanging the device.
 constexpr int kPeerMaxWorld = 16;
 constexpr size_t kPeerCap = 1u << 16;          // slots per half: world * chunk above this goes through NCCL
 constexpr size_t kPeerHeader = 256;            // bytes
@@ -2553,7 +2553,7 @@ __global__ void __launch_bounds__(1024) peer_allgather_kernel(const PeerDev d, d
     for (;;) {
       asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(got + i) : "memory");
       if (v != kPeerEmpty) break;
-      if (peer_timer_ns() - t0 > 10000000000ull) {
+      if (peer_timer_ns() - t0 > 30000000000ull) {
         *my_err = 1;
         break;
       }

@@ -369,7 +369,7 @@ class Engine:
             raise RbvError("rbv_peer_attach succeeded on this rank but failed on another: set RBVFIT_B200_PEER=0")
 
     def peer_error(self) -> int:
-        """1 after a peer-memory all-gather gave up waiting for a rank (10 s without progress)."""
+        """1 after a peer-memory all-gather gave up waiting for a rank (30 s without progress)."""
         att, err = C.c_int(0), C.c_int(0)
         check(self.lib.rbv_peer_info(self._h, C.byref(att), C.byref(err)), "rbv_peer_info")
         return int(err.value)

@@ -21,6 +21,8 @@ from typing import Callable, Optional
 
 import numpy as np
 
+from ._lib import RbvError
+
 
 class AutocorrError(Exception):
     """Raised when the chain is too short for a reliable autocorrelation-time estimate (emcee's name)."""
@@ -428,6 +430,9 @@ class DistributedDeviceSampler(DeviceEnsembleSampler):
                     eng.stretch_run_dist(coords_t, lnp_t, nsteps, self.a, self._seed, self.iteration, chain_t, lps_t,
                                          nacc_t, flag_t, use_graph=self.use_graph)
                 self._stream.synchronize()
+            if getattr(eng, "peer_attached", False) and eng.peer_error():
+                raise RbvError("the peer-memory all-gather gave up waiting for a rank (30 s without its rows): a "
+                               "rank died or ran a different sequence of calls; rows it did not receive are NaN")
             if int(flag_t.item()) & 1:
                 raise ValueError("Probability function returned NaN")
             self._state = (coords_t, lnp_t)

@@ -309,4 +309,9 @@ class DistributedDeviceSliceSampler(DeviceEnsembleSliceSampler):
         if start is not None:
             p = self.partition
             start = replicate_array(start, p.rank, p.world, p.group)
-        return super().run_mcmc(start, nsteps, progress=progress, **kw)
+        out = super().run_mcmc(start, nsteps, progress=progress, **kw)
+        eng = self.likelihood.engine
+        if getattr(eng, "peer_attached", False) and eng.peer_error():
+            from ._lib import RbvError
+            raise RbvError("the peer-memory all-gather gave up waiting for a rank (30 s without its rows)")
+        return out
