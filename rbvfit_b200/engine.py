@@ -182,13 +182,10 @@ class Engine:
 
     def pinned_theta(self, W: int) -> np.ndarray:
         """A page-locked float64 array [W, ndim] the caller can fill in place: ``lnprob_host`` on it (or on any other
-        page-locked array) skips the staging copy.  The array owns its memory (a pinned torch tensor behind it)."""
+        page-locked array) skips the staging copy.  The array owns its memory (a pinned torch tensor behind it, freed
+        with the array)."""
         torch = _torch()
-        t = torch.empty((int(W), self.ndim), dtype=torch.float64, pin_memory=True)
-        a = t.numpy()
-        self._pinned_keep = getattr(self, "_pinned_keep", [])
-        self._pinned_keep.append(t)
-        return a
+        return torch.empty((int(W), self.ndim), dtype=torch.float64, pin_memory=True).numpy()   # the array keeps it alive
 
     def lnprob_device(self, theta_t, out_t=None):
         """DEVICE theta tensor [W, ndim] (float64, contiguous) -> DEVICE lnprob tensor [W]; asynchronous."""
