@@ -241,6 +241,28 @@ def model_flux(m: LoweredModel, theta, wave, convolve=True, return_tau=False):
     return flux
 
 
+def model_flux_piecewise_lsf(models, starts, theta, wave):
+    """Wavelength-dependent LSF (an EXTENSION -- the reference applies one kernel per instrument,
+    core/voigt_model.py:444-464 -- SURVEY 8(f) rank 3), by its definition: output pixel p is the unconvolved model
+    convolved with the kernel of the block p lies in (block b = pixels with starts[b] <= wave < starts[b + 1], the
+    first block from the first pixel), edges of the spectrum replicated.  ``models``: one LoweredModel per block (same
+    lines, its own kernel)."""
+    wave = np.asarray(wave)
+    raw = model_flux(models[0], theta, wave, convolve=False)
+    first = [0] + [int(np.searchsorted(wave, w0, side="left")) for w0 in list(starts)[1:]]
+    edges = first + [wave.size]
+    out = np.empty_like(raw)
+    for b, m in enumerate(models):
+        if m.kernel_taps is None:
+            conv = raw
+        elif m.kernel_kind == "gaussian":
+            conv = ndimage.convolve1d(raw, m.kernel_taps, mode="nearest")
+        else:
+            conv = convolve_extend(raw, m.kernel_taps)
+        out[edges[b]:edges[b + 1]] = conv[edges[b]:edges[b + 1]]
+    return out
+
+
 # --------------------------------------------------------------------------- likelihood
 def compile_instruments(instruments: Dict[str, dict]) -> Dict[str, dict]:
     """vfit._compile_models, vfit_mcmc.py:234-259 -- weights inherit the dtype of ``error``."""

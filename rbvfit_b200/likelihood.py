@@ -52,6 +52,13 @@ class GpuLikelihood:
             if len(flux) != len(wave) or len(error) != len(wave):
                 raise ValueError(f"instrument_data['{name}']: wave, flux, and error must have same length")
             inv_sigma2, log_inv_sigma2 = _weights(error)
+            mask = d.get("weight_mask")
+            if mask is not None:     # extension: pixels with False do not enter the likelihood (both terms exactly 0)
+                mask = np.asarray(mask, dtype=bool)
+                if mask.shape != wave.shape:
+                    raise ValueError(f"instrument_data['{name}']: weight_mask must have the shape of wave")
+                inv_sigma2 = np.where(mask, inv_sigma2, inv_sigma2.dtype.type(0))
+                log_inv_sigma2 = np.where(mask, log_inv_sigma2, log_inv_sigma2.dtype.type(0))
             data = compiled.data
             self.engine.add_instrument(data, wave, flux=flux, inv_sigma2=inv_sigma2,
                                        log_inv_sigma2=log_inv_sigma2, taps=data.kernel,
@@ -60,7 +67,7 @@ class GpuLikelihood:
             self.pixels.append(len(wave))
             self.instrument_data[name] = {"model": compiled.model_flux, "wave": wave, "flux": flux,
                                           "error": error, "inv_sigma2": inv_sigma2,
-                                          "log_inv_sigma2": log_inv_sigma2}
+                                          "log_inv_sigma2": log_inv_sigma2, "weight_mask": mask}
         self.lb = np.asarray(lb, dtype=np.float64)
         self.ub = np.asarray(ub, dtype=np.float64)
         self.engine.set_bounds(self.lb, self.ub)
@@ -171,6 +178,13 @@ class SightlineBatch:
             if len(flux) != len(wave) or len(error) != len(wave):
                 raise ValueError(f"sightline {i}: wave, flux, and error must have same length")
             inv_sigma2, log_inv_sigma2 = _weights(error)
+            mask = d.get("weight_mask")
+            if mask is not None:     # extension: pixels with False do not enter the likelihood (both terms exactly 0)
+                mask = np.asarray(mask, dtype=bool)
+                if mask.shape != wave.shape:
+                    raise ValueError(f"instrument_data['{name}']: weight_mask must have the shape of wave")
+                inv_sigma2 = np.where(mask, inv_sigma2, inv_sigma2.dtype.type(0))
+                log_inv_sigma2 = np.where(mask, log_inv_sigma2, log_inv_sigma2.dtype.type(0))
             data = compiled.data
             self.engine.add_instrument(data, wave, flux=flux, inv_sigma2=inv_sigma2, log_inv_sigma2=log_inv_sigma2,
                                        taps=data.kernel, normalize_taps=data.kernel_normalize)

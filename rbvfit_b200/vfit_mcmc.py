@@ -323,10 +323,12 @@ class vfit:
         for name in names:
             d = self.instrument_data[name]
             model = d["model"](theta, d["wave"])
-            chi2 = float(np.sum(((d["flux"] - model) / d["error"]) ** 2))
-            results[name] = chi2 / max(len(d["wave"]) - len(theta), 1)
+            keep = d.get("weight_mask")             # extension: masked pixels (piecewise-LSF halos) do not count
+            keep = np.ones(len(d["wave"]), dtype=bool) if keep is None else np.asarray(keep, dtype=bool)
+            chi2 = float(np.sum((((d["flux"] - model) / d["error"]) ** 2)[keep]))
+            results[name] = chi2 / max(int(keep.sum()) - len(theta), 1)
             total_chi2 += chi2
-            total_n += len(d["wave"])
+            total_n += int(keep.sum())
         if instrument_name is None and len(names) > 1:
             results["combined"] = total_chi2 / max(total_n - len(theta), 1)
         return results

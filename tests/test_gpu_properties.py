@@ -237,3 +237,48 @@ def test_far_field_stress_strong_lines_and_extreme_widths():
         assert np.max(np.abs(fa - fb)) <= 1e-12, P
         assert np.max(np.abs(la - lb_) / np.abs(la)) <= 1e-11, P
         like.close()
+
+
+def test_wavelength_dependent_lsf_and_weight_mask_vs_oracle():
+    """Extension: a spectrum whose LSF changes along the wavelength axis, run as a joint fit of its
+    blocks with weight-0 halos -- lnprob and the stitched model flux against the oracle's direct definition (every
+    output pixel under the kernel of its own block); plus the weight mask on its own (masked pixels drop out of both
+    likelihood terms exactly)."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_logic import _piecewise_problem
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import lsf, workloads as wl
+    from rbvfit_b200.likelihood import GpuLikelihood
+    w, cfg, wave, flux, error, starts, models, lowered = _piecewise_problem()
+    entries = lsf.piecewise_lsf_instruments("COS", wave, flux, error, list(zip(starts, models)))
+    like = GpuLikelihood(entries, w["lb"], w["ub"])
+    thetas = wl.make_ensemble(w, 40)
+    got = like.lnprob(thetas)
+    ref = np.empty(len(thetas))
+    for i, th in enumerate(thetas):
+        if np.any(th < w["lb"]) or np.any(th > w["ub"]):
+            ref[i] = -np.inf
+            continue
+        m = vo.model_flux_piecewise_lsf(lowered, starts, th, wave)
+        ref[i] = -0.5 * np.sum((flux - m) ** 2 / error ** 2 - np.log(1.0 / error ** 2))
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.isneginf(ref).sum() >= 1
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-9
+    compiled = {n: d["model"].compile() for n, d in entries.items()}
+    stitched = lsf.piecewise_lsf_flux(entries, lambda n, d: compiled[n].model_flux(thetas[0], d["wave"]))
+    assert np.max(np.abs(stitched - vo.model_flux_piecewise_lsf(lowered, starts, thetas[0], wave))) <= 1e-10
+    like.close()
+    # the mask alone: a single-kernel instrument with every third pixel masked == the oracle's sum over the rest
+    keep = (np.arange(wave.size) % 3) != 0
+    like = GpuLikelihood({"COS": dict(model=models[0], wave=wave, flux=flux, error=error, weight_mask=keep)},
+                         w["lb"], w["ub"])
+    got = like.lnprob(thetas[:6])
+    for i, th in enumerate(thetas[:6]):
+        if not np.isfinite(got[i]):
+            continue
+        m = vo.model_flux(lowered[0], th, wave)
+        r = -0.5 * np.sum(((flux - m) ** 2 / error ** 2 - np.log(1.0 / error ** 2))[keep])
+        assert abs(got[i] - r) <= 1e-9 * abs(r)
+    like.close()

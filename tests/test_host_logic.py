@@ -364,3 +364,57 @@ def test_gelman_rubin_statistic():
     assert np.allclose(gelman_rubin(x), np.sqrt(V / W))
     with pytest.raises(ValueError):
         gelman_rubin(np.zeros((1, 10, 2)))
+
+
+def _piecewise_problem():
+    """C1's MgII doublet on a 2400-pixel grid with three LSF blocks: Gaussian FWHM 6.5, Gaussian FWHM 3.0, and an
+    asymmetric 31-tap table (normalised by the convolution, like a CustomKernel)."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.model import GpuVoigtModel
+    w = wl.get_workload("C1")
+    cfg = FitConfiguration()
+    for (z, ion, trans, comps) in w["systems"]:
+        cfg.add_system(z=z, ion=ion, transitions=trans, components=comps)
+    wave = np.linspace(3755.0, 3795.0, 2400)
+    x = np.arange(-15, 16)
+    table = np.exp(-0.5 * (x / 3.0) ** 2) * (1 + 0.4 * (x > 0))
+    specs = [("6.5", None), ("3.0", None), (None, table)]
+    starts = [wave[0], 3768.3, 3781.7]
+    models = [GpuVoigtModel(cfg, FWHM=f, lsf_taps=t) for f, t in specs]
+    lowered = [vo.lower(cfg, FWHM=f if f is not None else "6.5", custom_taps=t) for f, t in specs]
+    rng = np.random.default_rng(5)
+    truth = vo.model_flux_piecewise_lsf(lowered, starts, w["theta_true"], wave)
+    flux = truth + 0.05 * rng.standard_normal(wave.size)
+    error = np.full(wave.size, 0.05)
+    return w, cfg, wave, flux, error, starts, models, lowered
+
+
+def test_piecewise_lsf_split_equals_its_definition():
+    """Wavelength-dependent LSF (extension): the split into sub-instruments with weight-0 halos
+    (rbvfit_b200.lsf.piecewise_lsf_instruments) reproduces the definition -- every output pixel convolved with the
+    kernel of ITS block, spectrum edges replicated (oracle.model_flux_piecewise_lsf) -- on the CPU oracle: the split
+    is host logic, no device involved."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import lsf
+    w, cfg, wave, flux, error, starts, models, lowered = _piecewise_problem()
+    entries = lsf.piecewise_lsf_instruments("COS", wave, flux, error, list(zip(starts, models)))
+    assert list(entries) == ["COS[0]", "COS[1]", "COS[2]"]
+    # every pixel is counted exactly once, halos are K // 2 wide on interior sides only
+    assert np.array_equal(np.concatenate([d["wave"][d["weight_mask"]] for d in entries.values()]), wave)
+    halos = [(int(np.argmax(d["weight_mask"])), int(np.argmax(d["weight_mask"][::-1]))) for d in entries.values()]
+    assert halos == [(0, 11), (5, 5), (15, 0)]
+    theta = w["theta_true"] + np.array([0.05, -0.03, 2.0, -1.5, 3.0, -4.0])
+    direct = vo.model_flux_piecewise_lsf(lowered, starts, theta, wave)
+    by_name = dict(zip(entries, lowered))
+    stitched = lsf.piecewise_lsf_flux(entries, lambda n, d: vo.model_flux(by_name[n], theta, d["wave"]))
+    assert stitched.shape == wave.shape and np.max(np.abs(stitched - direct)) <= 2e-15
+    # a single block is the single-kernel model
+    one = lsf.piecewise_lsf_instruments("COS", wave, flux, error, [(wave[0], models[0])])
+    assert np.all(one["COS[0]"]["weight_mask"]) and len(one["COS[0]"]["wave"]) == wave.size
+    assert np.array_equal(vo.model_flux_piecewise_lsf(lowered[:1], starts[:1], theta, wave),
+                          vo.model_flux(lowered[0], theta, wave))
+    with pytest.raises(ValueError):
+        lsf.piecewise_lsf_instruments("COS", wave, flux, error, [(3780.0, models[0]), (3770.0, models[1])])
+    with pytest.raises(ValueError):
+        lsf.piecewise_lsf_instruments("COS", wave, flux, error, [(wave[0], models[0]), (9999.0, models[1])])
