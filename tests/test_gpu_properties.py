@@ -282,3 +282,51 @@ def test_wavelength_dependent_lsf_and_weight_mask_vs_oracle():
         r = -0.5 * np.sum(((flux - m) ** 2 / error ** 2 - np.log(1.0 / error ** 2))[keep])
         assert abs(got[i] - r) <= 1e-9 * abs(r)
     like.close()
+
+
+def test_sightline_batch_of_long_many_line_spectra():
+    """Survey batch whose spectra are long (several ranges of the stream kernel) and have 8 lines (boundary
+    records): with the stream kernel forced (RBVFIT_B200_STREAM=1, the second run of the GPU suite) this is the
+    sightline launch of voigt_stream_kernel<3, true> + finalize_stream_kernel; by default the tile kernel takes it.
+    Either way: one launch over S sightlines == S separate likelihoods, and the oracle on a few rows."""
+    from oracle import voigt_oracle as vo
+    from rbvfit_b200 import FitConfiguration, workloads as wl
+    from rbvfit_b200.likelihood import GpuLikelihood, SightlineBatch
+    from rbvfit_b200.model import GpuVoigtModel
+    S, Ws = 5, 12
+    base = wl.get_workload("C4")
+    sight, thetas, singles, lowered = [], [], [], []
+    for s in range(S):
+        w = dict(base)
+        w["seed"] = base["seed"] + 31 * s
+        z = 2.5 + 0.004 * s
+        w["systems"] = [(z, ion, trans, comps) for (_z, ion, trans, comps) in base["systems"]]
+        w["instruments"] = {"SPEC": dict(wave=np.linspace(3500.0, 5500.0, 6000) * (1 + 0.004 * s / 3.5), FWHM="6.5",
+                                         lsf=None)}
+        cfg = FitConfiguration()
+        for (zz, ion, trans, comps) in w["systems"]:
+            cfg.add_system(z=zz, ion=ion, transitions=trans, components=comps)
+        m = GpuVoigtModel(cfg, FWHM="6.5")
+        c = m.compile()
+        sp = wl.make_spectra(w, lambda n, th, wave: c.model_flux(th, wave))["SPEC"]
+        sight.append(dict(model=m, **sp))
+        thetas.append(wl.make_ensemble(w, Ws, frac_out_of_bounds=0.1))
+        singles.append(GpuLikelihood({"SPEC": dict(model=m, **sp)}, w["lb"], w["ub"]))
+        lowered.append((vo.lower(cfg, FWHM="6.5"), sp))
+    thetas = np.array(thetas)
+    batch = SightlineBatch(sight, base["lb"], base["ub"])
+    got = batch.lnprob(thetas)
+    ref = np.array([singles[s].lnprob(thetas[s]) for s in range(S)])
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.isneginf(ref).sum() >= S
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-12
+    for s in (0, S - 1):
+        m, sp = lowered[s]
+        comp = vo.compile_instruments({"SPEC": dict(model=m, **sp)})
+        for i in range(3):
+            o = vo.lnprob(comp, thetas[s, i], base["lb"], base["ub"])
+            assert (np.isneginf(o) and np.isneginf(got[s, i])) or abs(got[s, i] - o) <= 1e-9 * abs(o)
+    assert np.array_equal(batch.lnprob(thetas), got, equal_nan=True)
+    batch.close()
+    for one in singles:
+        one.close()
