@@ -118,7 +118,7 @@ class GpuLikelihood:
     def set_far_field(self, mode: str = "chebyshev"):
         """``"chebyshev"`` (default): the summed far wings (lines >= 24 Doppler widths away) of each 1024-pixel
         super-chunk are evaluated at 8 Chebyshev nodes and interpolated; a line takes part only where an
-        a-priori bound keeps its interpolation error <= 1e-13 / L in optical depth.
+        a-priori bound keeps its interpolation error <= 1e-12 / L in optical depth.
         ``"direct"``: every (line, pixel) pair is evaluated on its own."""
         if mode not in ("chebyshev", "direct"):
             raise ValueError("far field mode must be 'chebyshev' or 'direct'")
