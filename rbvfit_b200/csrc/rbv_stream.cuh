@@ -355,8 +355,7 @@ voigt_stream_kernel(const __grid_constant__ LaunchParams prm, const int warp_dou
       // replicated), every line evaluated on its own.  Any other range: they are the previous range's last carry,
       // which another warp computes at some other time -- so the K-1 outputs that need them are left out here
       // (q_first) and added by finalize from the boundary record: the previous range's carry + this range's head.
-      // An item start therefore costs the line constants and the taps, nothing else, and the partition into ranges
-      // is free to be fine (the launch ends on one-segment items).
+      // (BND = false: every range is treated like a first one and evaluates them itself.)
       const bool first_range = !BND || (slot == prm.geom[prm.wps > 0 ? 0 : k].first_tile);
       if (first_range) {
         for (int i = lane; i < halo; i += 32) {
